@@ -1,0 +1,179 @@
+/* scv.h — C ABI of libscv.so, the sm_100a kernel library behind scrubvae_b200.
+ *
+ * The reference (tdunnlab/scrubvae) has no FFI: its hot path is PyTorch library calls.  Each entry
+ * point below replaces the library call sites of one part of the SC-VAE training step; the
+ * reference file:line it replaces is cited per function (paths relative to
+ * /root/reference/src/scrubvae).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every struct field is 8 bytes wide (pointer, int64_t, double)
+ *    so that the ctypes mirror cannot mis-pad;
+ *  - all device buffers are owned by the caller (PyTorch caching allocator); the library never
+ *    allocates, frees or synchronises; every call only enqueues work on `stream` (a cudaStream_t);
+ *  - return value 0 = ok, >0 = cudaError_t, <0 = argument error; scv_last_error() gives the text;
+ *  - activations are fp32, channels-last, halo-padded:  X[b][halo + l][c], halo rows are zero.
+ *    A convolution row (b,l) is then a CONTIGUOUS run of k*C floats, so every conv / transposed
+ *    conv / linear, forward, dgrad and wgrad, is one "overlapping-row GEMM" (scv_gemm / scv_wgrad).
+ */
+#ifndef SCV_H_
+#define SCV_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCV_ACT_NONE 0
+#define SCV_ACT_RELU 1
+#define SCV_ACT_TANH 2
+#define SCV_ACT_RELUMASK 3 /* y = (R > 0) ? y : 0 ; R is a mask, not added */
+
+#define SCV_PREC_FP32 0 /* FFMA, fp32 exact */
+#define SCV_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
+#define SCV_PREC_BF16 2 /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate */
+
+int scv_version(void);
+const char* scv_last_error(void);
+/* number of kernels this library has launched in this process (bench.py: gpu_launches) */
+int64_t scv_launch_count(void);
+
+/* ---- overlapping-row GEMM ---------------------------------------------------------------
+ * Y[b][l][n] = act( out_scale * sum_k A[b*a_bs + l*a_ls + k] * W[n*K + k] + bias[n % bias_mod] + R[b][l][n] )
+ * for b < B, l < Lo, n < N (row l == Lo-1 only for n < n_last).  Optional per-column sums of the
+ * pre-activation value and its square are accumulated into stats[0..N) and stats[N..2N) (double).
+ * Replaces cuDNN conv fprop/dgrad and cuBLAS linear: model/residual.py:78-119 (ResidualBlock),
+ * :136-180 (ResidualBlockTranspose), :198,219-222,264,286 (conv_in, fc_mu/fc_sigma, fc_in,
+ * conv_out), model/disentangle.py:583-632 (MLPEnsemble).
+ */
+typedef struct {
+  const float* A; int64_t a_bs, a_ls;
+  int64_t B, Lo, K, N;
+  const float* W;                       /* packed [N][K], K contiguous */
+  const float* bias; int64_t bias_mod, bias_n; /* bias[n % bias_mod] for n < bias_n; NULL = none */
+  float* Y; int64_t y_bs, y_ls, n_last;
+  const float* R; int64_t r_bs, r_ls;   /* residual (or mask), same (b,l,n) addressing as Y; NULL = none */
+  int64_t act; double out_scale;
+  double* stats;                        /* [2][N] accumulators or NULL */
+  int64_t precision;
+} scv_gemm_t;
+int scv_gemm(const scv_gemm_t* p, void* stream);
+
+/* dW[n][k] += sum_{b,l} dY[b*y_bs + l*y_ls + n] * A[b*a_bs + l*a_ls + k];
+ * dbias[n % bias_mod] += sum_{b,l} dY[..n] (n < bias_n).  dY must hold zeros where invalid.
+ * Replaces cuDNN wgrad / cuBLAS for the same layers (autograd of the sites above). */
+typedef struct {
+  const float* A; int64_t a_bs, a_ls;
+  int64_t B, Lo, K, N;
+  const float* dY; int64_t y_bs, y_ls;
+  float* dW;
+  float* dbias; int64_t bias_mod, bias_n;
+  int64_t precision;
+} scv_wgrad_t;
+int scv_wgrad(const scv_wgrad_t* p, void* stream);
+
+/* ---- input pack: ResVAE.encode model/residual.py:438-451 + normalize_root :428-431 --------
+ * out[b][halo+w][0..nx) = x6d[b][w][:], [nx..nx+3) = 2*(root-a0)/(a1-a0)-1, rest 0 (C floats/row) */
+int scv_pack_input(const float* x6d, const float* root, const float* arena, float* out,
+                   int64_t B, int64_t W, int64_t nx, int64_t C, int64_t halo, void* stream);
+
+/* ---- BatchNorm1d(train/eval) + PReLU (+ x2 linear upsample) -------------------------------
+ * model/residual.py:88-89,112-113,146-147,160,172-174,199.  X rows (b,l) of C floats.
+ * mode bit0: batch-norm present, bit1: PReLU present, bit2: training (batch statistics from
+ * `stats` = column sums / sums of squares over `fold` column groups, `count` elements per channel;
+ * running stats updated with `momentum`), else running statistics are used.
+ * H gets the activated rows; U (optional) gets the 2L rows of nn.Upsample(2,'linear'). */
+typedef struct {
+  const float* X; int64_t x_bs, x_ls;
+  int64_t B, L, C;
+  const double* stats; int64_t fold; double count, eps, momentum;
+  const float* gamma; const float* beta; float* running_mean; float* running_var;
+  const float* slope;
+  float* H; int64_t h_bs, h_ls;
+  float* U; int64_t u_bs, u_ls;
+  int64_t mode;
+} scv_bnact_t;
+int scv_bnact_fwd(const scv_bnact_t* p, void* stream);
+
+/* backward of the above.  dO rows (b,l) are the gradient w.r.t. H; dU (optional) w.r.t. U.
+ * reduce: sums[0..C) += sum g, sums[C..2C) += sum g*xhat, sums[2C] += dslope   (double)
+ * apply : dX rows = BN backward; dgamma/dbeta/dslope (+=) param grads from `sums`. */
+typedef struct {
+  const float* X; int64_t x_bs, x_ls;
+  int64_t B, L, C;
+  const double* stats; int64_t fold; double count, eps;
+  const float* gamma; const float* beta; const float* slope;
+  const float* dO; int64_t o_bs, o_ls;
+  const float* dU; int64_t u_bs, u_ls;
+  double* sums;
+  float* dX; int64_t d_bs, d_ls;
+  float* dgamma; float* dbeta; float* dslope;
+  int64_t mode;
+} scv_bnact_bwd_t;
+int scv_bnact_bwd_reduce(const scv_bnact_bwd_t* p, void* stream);
+int scv_bnact_bwd_apply(const scv_bnact_bwd_t* p, void* stream);
+
+/* ---- CholeskyL + reparameterisation: model/residual.py:39-68, :305-316 ---------------------
+ * ms rows: [mu (z) | sigma raw (z(z+1)/2)] with row stride ms_ld.  Writes mu (B,z), dense L (B,z,z),
+ * zc rows [z | var | 0-pad] (row stride zc_ld; var = B x nvar, may be NULL).  eps NULL => z = mu. */
+int scv_reparam_fwd(const float* ms, int64_t ms_ld, const float* eps, const float* var, int64_t nvar,
+                    float* mu, float* L, float* zc, int64_t zc_ld, int64_t B, int64_t z, void* stream);
+/* dms = backward of the above given dmu (B,z), dz rows (stride dz_ld), dL dense (each may be NULL);
+ * dmu2 (optional, B x z) is added to dmu scaled by dmu2_scale (gradient reversal: -alpha). */
+int scv_reparam_bwd(const float* ms, int64_t ms_ld, const float* eps, const float* dmu, const float* dmu2,
+                    double dmu2_scale, const float* dz, int64_t dz_ld, const float* dL, float* dms,
+                    int64_t dms_ld, int64_t B, int64_t z, void* stream);
+
+/* ---- prior_loss train/losses.py:138-146: loss[0] += KL/B (double, if loss != NULL);
+ * if dmu/dL != NULL they get gscale[0] * dKL/dmu, dKL/dL (gscale: device scalar, NULL = 1) ------*/
+int scv_kl(const float* mu, const float* L, double* loss, const float* gscale, float* dmu, float* dL,
+           int64_t B, int64_t z, void* stream);
+
+/* ---- reconstruction losses on the decoder output xh (B*W rows of ld floats: nx 6-D channels
+ * then 3 normalised root channels, all after tanh):
+ *   jpe  : mpjpe_loss train/losses.py:148-171 -> fwd_kin_cont6d_torch data/dataset.py:83-116 ->
+ *          cont6d_to_matrix data/quaternion.py:337-353;  loss[0] += sum (target-pose)^2/(B*3*J)
+ *   root : train/losses.py:216-219 with inv_normalize_root model/residual.py:433-436;
+ *          loss[1] += sum (root_hat-root)^2 / B;  root_hat (F,3) is written out.
+ * dxh rows get the UNIT gradients d jpe/d xh[..nx) and d root/d xh[nx..nx+3) (pad columns 0).
+ * parents[j] = parent joint (-1 root); chain_id/chain_pos describe kinematic_tree. */
+int scv_recon_loss(const float* xh, int64_t ld, const float* offsets, const float* target,
+                   const float* root, const float* arena, const int32_t* tree, int64_t n_tree,
+                   double* loss, float* root_hat, float* dxh, int64_t F, int64_t B, int64_t J,
+                   void* stream);
+
+/* draw[b][halo+w][c] = (g_jpe*dxh[c<nx] | g_root*dxh[nx<=c<nx+3]) * (1 - xh^2); g_* are device
+ * scalars (NULL = 0).  Backward of tanh at model/residual.py:291 fused with the loss scales. */
+int scv_out_bwd(const float* xh, const float* dxh, int64_t ld, const float* g_jpe, const float* g_root,
+                int64_t nx, float* draw, int64_t d_bs, int64_t d_ls, int64_t B, int64_t W, void* stream);
+
+/* ---- gradient-reversal head loss train/losses.py:267-284 (nested normalisation, quirk i) ------
+ * pred[e] (B x d, row stride ld) for e < n_ens; target (B x d float) or labels (B int64, CE).
+ * loss[0] += sum_e w_e * L_e with w_e = c^-(n_ens-e), c = n_ens*num_keys*B (if loss != NULL);
+ * dpred[e] (if dpred != NULL) = gscale[0] * w_e * dL_e/dpred (gscale: device scalar, NULL = 1). */
+int scv_gr_loss(const float* const* pred, float* const* dpred, int64_t ld, int64_t n_ens,
+                const float* target, const int64_t* labels, int64_t B, int64_t d, int64_t num_keys,
+                double* loss, const float* gscale, void* stream);
+
+/* ---- gather  dst[i] = idx[i] >= 0 ? src[idx[i]] : 0  (weight repack / gradient unpack;
+ * skip_neg != 0 leaves dst[i] untouched where idx[i] < 0) */
+int scv_gather(const float* src, const int32_t* idx, float* dst, int64_t n, int64_t skip_neg, void* stream);
+
+/* ---- step tail train/trainer.py:160-165: clip_grad_norm_(max_norm) + Adam/AdamW/SGD ----------
+ * sumsq[0] += sum g^2 (double).  The update kernel derives the clip coefficient
+ * min(1, max_norm/(sqrt(sumsq)*gscale + 1e-6)) itself; gscale scales grads first (1/world). */
+int scv_sumsq(const float* g, int64_t n, double* sumsq, void* stream);
+typedef struct {
+  float* p; const float* g; float* m; float* v; int64_t n;
+  const double* sumsq; double max_norm, gscale;
+  double lr, beta1, beta2, eps, weight_decay; int64_t step;
+  int64_t kind; /* 0 adam (L2 wd folded in grad), 1 adamw (decoupled), 2 sgd nesterov (m = momentum buf, beta1 = momentum) */
+} scv_optim_t;
+int scv_optim_step(const scv_optim_t* p, void* stream);
+
+/* out[i] = float(in[i]) */
+int scv_d2f(const double* in, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

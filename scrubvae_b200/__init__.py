@@ -1,0 +1,3 @@
+"""scrubvae_b200 — B200-native (sm_100a) SC-VAE training step behind the scrubvae API."""
+from . import model
+from . import get

@@ -1,0 +1,229 @@
+"""ctypes binding of libscv.so (include/scv.h).  This is the ONLY compute backend of the package:
+there is no CPU or PyTorch fallback — if the library is missing or a call fails, an exception is
+raised.
+
+Every method takes `Ref`s (tensor + element offset) for device buffers and enqueues one kernel on
+torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libscv.so")
+
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELUMASK = 0, 1, 2, 3
+PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
+BN, PRELU, TRAIN = 1, 2, 4  # bnact mode bits
+
+
+class Ref:
+    """A device buffer position: tensor `t` (1-D storage view) + element offset."""
+    __slots__ = ("t", "off")
+
+    def __init__(self, t: torch.Tensor, off: int = 0):
+        self.t, self.off = t, int(off)
+
+    def __add__(self, k: int) -> "Ref":
+        return Ref(self.t, self.off + int(k))
+
+
+def _ptr(r: Optional[Ref]):
+    if r is None:
+        return None
+    if isinstance(r, torch.Tensor):
+        return r.data_ptr()
+    return r.t.data_ptr() + r.off * r.t.element_size()
+
+
+_i64, _f64, _vp = C.c_int64, C.c_double, C.c_void_p
+
+
+def _struct(name, fields):
+    return type(name, (C.Structure,), {"_fields_": fields})
+
+
+GemmT = _struct("GemmT", [
+    ("A", _vp), ("a_bs", _i64), ("a_ls", _i64), ("B", _i64), ("Lo", _i64), ("K", _i64), ("N", _i64),
+    ("W", _vp), ("bias", _vp), ("bias_mod", _i64), ("bias_n", _i64),
+    ("Y", _vp), ("y_bs", _i64), ("y_ls", _i64), ("n_last", _i64),
+    ("R", _vp), ("r_bs", _i64), ("r_ls", _i64), ("act", _i64), ("out_scale", _f64),
+    ("stats", _vp), ("precision", _i64)])
+WgradT = _struct("WgradT", [
+    ("A", _vp), ("a_bs", _i64), ("a_ls", _i64), ("B", _i64), ("Lo", _i64), ("K", _i64), ("N", _i64),
+    ("dY", _vp), ("y_bs", _i64), ("y_ls", _i64), ("dW", _vp), ("dbias", _vp), ("bias_mod", _i64),
+    ("bias_n", _i64), ("precision", _i64)])
+BnactT = _struct("BnactT", [
+    ("X", _vp), ("x_bs", _i64), ("x_ls", _i64), ("B", _i64), ("L", _i64), ("C", _i64),
+    ("stats", _vp), ("fold", _i64), ("count", _f64), ("eps", _f64), ("momentum", _f64),
+    ("gamma", _vp), ("beta", _vp), ("running_mean", _vp), ("running_var", _vp), ("slope", _vp),
+    ("H", _vp), ("h_bs", _i64), ("h_ls", _i64), ("U", _vp), ("u_bs", _i64), ("u_ls", _i64), ("mode", _i64)])
+BnactBwdT = _struct("BnactBwdT", [
+    ("X", _vp), ("x_bs", _i64), ("x_ls", _i64), ("B", _i64), ("L", _i64), ("C", _i64),
+    ("stats", _vp), ("fold", _i64), ("count", _f64), ("eps", _f64),
+    ("gamma", _vp), ("beta", _vp), ("slope", _vp),
+    ("dO", _vp), ("o_bs", _i64), ("o_ls", _i64), ("dU", _vp), ("u_bs", _i64), ("u_ls", _i64),
+    ("sums", _vp), ("dX", _vp), ("d_bs", _i64), ("d_ls", _i64),
+    ("dgamma", _vp), ("dbeta", _vp), ("dslope", _vp), ("mode", _i64)])
+OptimT = _struct("OptimT", [
+    ("p", _vp), ("g", _vp), ("m", _vp), ("v", _vp), ("n", _i64), ("sumsq", _vp), ("max_norm", _f64),
+    ("gscale", _f64), ("lr", _f64), ("beta1", _f64), ("beta2", _f64), ("eps", _f64),
+    ("weight_decay", _f64), ("step", _i64), ("kind", _i64)])
+
+_SIGS = {
+    "scv_version": (C.c_int, []),
+    "scv_last_error": (C.c_char_p, []),
+    "scv_launch_count": (_i64, []),
+    "scv_gemm": (C.c_int, [C.POINTER(GemmT), _vp]),
+    "scv_wgrad": (C.c_int, [C.POINTER(WgradT), _vp]),
+    "scv_pack_input": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "scv_bnact_fwd": (C.c_int, [C.POINTER(BnactT), _vp]),
+    "scv_bnact_bwd_reduce": (C.c_int, [C.POINTER(BnactBwdT), _vp]),
+    "scv_bnact_bwd_apply": (C.c_int, [C.POINTER(BnactBwdT), _vp]),
+    "scv_reparam_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "scv_reparam_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _f64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "scv_kl": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "scv_recon_loss": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "scv_out_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "scv_gr_loss": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "scv_gather": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "scv_sumsq": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "scv_optim_step": (C.c_int, [C.POINTER(OptimT), _vp]),
+    "scv_d2f": (C.c_int, [_vp, _vp, _i64, _vp]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"scrubvae_b200: CUDA kernel library not found at {path}. Build it with "
+            "`python -m scrubvae_b200.build` (there is no CPU fallback).")
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is missing
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+class CudaOps:
+    """Thin call layer over the C ABI; one method per exported kernel entry point."""
+
+    name = "cuda"
+
+    def __init__(self, lib: Optional[C.CDLL] = None):
+        self.lib = lib or load_library()
+
+    # -- helpers
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed (rc={rc}): {self.lib.scv_last_error().decode()}")
+
+    def launch_count(self) -> int:
+        return int(self.lib.scv_launch_count())
+
+    # -- kernels
+    def gemm(self, A, a_bs, a_ls, B, Lo, K, N, W, Y, y_bs, y_ls, bias=None, bias_mod=1, bias_n=0, n_last=None,
+             R=None, r_bs=0, r_ls=0, act=ACT_NONE, out_scale=1.0, stats=None, precision=0):
+        p = GemmT(_ptr(A), a_bs, a_ls, B, Lo, K, N, _ptr(W), _ptr(bias), bias_mod, bias_n, _ptr(Y), y_bs, y_ls,
+                  N if n_last is None else n_last, _ptr(R), r_bs, r_ls, act, out_scale, _ptr(stats), precision)
+        self._check(self.lib.scv_gemm(C.byref(p), self._stream()), "scv_gemm")
+
+    def wgrad(self, A, a_bs, a_ls, B, Lo, K, N, dY, y_bs, y_ls, dW, dbias=None, bias_mod=1, bias_n=0, precision=0):
+        p = WgradT(_ptr(A), a_bs, a_ls, B, Lo, K, N, _ptr(dY), y_bs, y_ls, _ptr(dW), _ptr(dbias), bias_mod, bias_n,
+                   precision)
+        self._check(self.lib.scv_wgrad(C.byref(p), self._stream()), "scv_wgrad")
+
+    def pack_input(self, x6d, root, arena, out, B, W, nx, Cc, halo):
+        self._check(self.lib.scv_pack_input(_ptr(x6d), _ptr(root), _ptr(arena), _ptr(out), B, W, nx, Cc, halo,
+                                            self._stream()), "scv_pack_input")
+
+    def bnact_fwd(self, X, x_bs, x_ls, B, L, Cc, mode, stats=None, fold=1, count=1.0, eps=1e-4, momentum=0.1,
+                  gamma=None, beta=None, running_mean=None, running_var=None, slope=None,
+                  H=None, h_bs=0, h_ls=0, U=None, u_bs=0, u_ls=0):
+        p = BnactT(_ptr(X), x_bs, x_ls, B, L, Cc, _ptr(stats), fold, count, eps, momentum, _ptr(gamma), _ptr(beta),
+                   _ptr(running_mean), _ptr(running_var), _ptr(slope), _ptr(H), h_bs, h_ls, _ptr(U), u_bs, u_ls, mode)
+        self._check(self.lib.scv_bnact_fwd(C.byref(p), self._stream()), "scv_bnact_fwd")
+
+    def _bwd_struct(self, X, x_bs, x_ls, B, L, Cc, mode, stats, fold, count, eps, gamma, beta, slope, dO, o_bs, o_ls,
+                    dU, u_bs, u_ls, sums, dX, d_bs, d_ls, dgamma, dbeta, dslope):
+        return BnactBwdT(_ptr(X), x_bs, x_ls, B, L, Cc, _ptr(stats), fold, count, eps, _ptr(gamma), _ptr(beta),
+                         _ptr(slope), _ptr(dO), o_bs, o_ls, _ptr(dU), u_bs, u_ls, _ptr(sums), _ptr(dX), d_bs, d_ls,
+                         _ptr(dgamma), _ptr(dbeta), _ptr(dslope), mode)
+
+    def bnact_bwd_reduce(self, X, x_bs, x_ls, B, L, Cc, mode, sums, stats=None, fold=1, count=1.0, eps=1e-4,
+                         gamma=None, beta=None, slope=None, dO=None, o_bs=0, o_ls=0, dU=None, u_bs=0, u_ls=0):
+        p = self._bwd_struct(X, x_bs, x_ls, B, L, Cc, mode, stats, fold, count, eps, gamma, beta, slope, dO, o_bs,
+                             o_ls, dU, u_bs, u_ls, sums, None, 0, 0, None, None, None)
+        self._check(self.lib.scv_bnact_bwd_reduce(C.byref(p), self._stream()), "scv_bnact_bwd_reduce")
+
+    def bnact_bwd_apply(self, X, x_bs, x_ls, B, L, Cc, mode, sums=None, stats=None, fold=1, count=1.0, eps=1e-4,
+                        gamma=None, beta=None, slope=None, dO=None, o_bs=0, o_ls=0, dU=None, u_bs=0, u_ls=0,
+                        dX=None, d_bs=0, d_ls=0, dgamma=None, dbeta=None, dslope=None):
+        p = self._bwd_struct(X, x_bs, x_ls, B, L, Cc, mode, stats, fold, count, eps, gamma, beta, slope, dO, o_bs,
+                             o_ls, dU, u_bs, u_ls, sums, dX, d_bs, d_ls, dgamma, dbeta, dslope)
+        self._check(self.lib.scv_bnact_bwd_apply(C.byref(p), self._stream()), "scv_bnact_bwd_apply")
+
+    def reparam_fwd(self, ms, ms_ld, eps, var, nvar, mu, L, zc, zc_ld, B, z):
+        self._check(self.lib.scv_reparam_fwd(_ptr(ms), ms_ld, _ptr(eps), _ptr(var), nvar, _ptr(mu), _ptr(L), _ptr(zc),
+                                             zc_ld, B, z, self._stream()), "scv_reparam_fwd")
+
+    def reparam_bwd(self, ms, ms_ld, eps, dmu, dmu2, dmu2_scale, dz, dz_ld, dL, dms, dms_ld, B, z):
+        self._check(self.lib.scv_reparam_bwd(_ptr(ms), ms_ld, _ptr(eps), _ptr(dmu), _ptr(dmu2), float(dmu2_scale),
+                                             _ptr(dz), dz_ld, _ptr(dL), _ptr(dms), dms_ld, B, z, self._stream()),
+                    "scv_reparam_bwd")
+
+    def kl(self, mu, L, loss, gscale, dmu, dL, B, z):
+        self._check(self.lib.scv_kl(_ptr(mu), _ptr(L), _ptr(loss), _ptr(gscale), _ptr(dmu), _ptr(dL), B, z,
+                                    self._stream()), "scv_kl")
+
+    def recon_loss(self, xh, ld, offsets, target, root, arena, tree, n_tree, loss, root_hat, dxh, F, B, J):
+        self._check(self.lib.scv_recon_loss(_ptr(xh), ld, _ptr(offsets), _ptr(target), _ptr(root), _ptr(arena),
+                                            _ptr(tree), n_tree, _ptr(loss), _ptr(root_hat), _ptr(dxh), F, B, J,
+                                            self._stream()), "scv_recon_loss")
+
+    def out_bwd(self, xh, dxh, ld, g_jpe, g_root, nx, draw, d_bs, d_ls, B, W):
+        self._check(self.lib.scv_out_bwd(_ptr(xh), _ptr(dxh), ld, _ptr(g_jpe), _ptr(g_root), nx, _ptr(draw), d_bs,
+                                         d_ls, B, W, self._stream()), "scv_out_bwd")
+
+    def gr_loss(self, preds: Sequence[Ref], dpreds: Optional[Sequence[Ref]], ld, target, labels, B, d, num_keys,
+                loss, gscale):
+        n = len(preds)
+        pa = (_vp * n)(*[_ptr(p) for p in preds])
+        da = (_vp * n)(*[_ptr(p) for p in dpreds]) if dpreds is not None else None
+        self._check(self.lib.scv_gr_loss(pa, da, ld, n, _ptr(target), _ptr(labels), B, d, num_keys, _ptr(loss),
+                                         _ptr(gscale), self._stream()), "scv_gr_loss")
+
+    def gather(self, src, idx, dst, n, skip_neg=False):
+        self._check(self.lib.scv_gather(_ptr(src), _ptr(idx), _ptr(dst), n, int(skip_neg), self._stream()),
+                    "scv_gather")
+
+    def sumsq(self, g, n, out):
+        self._check(self.lib.scv_sumsq(_ptr(g), n, _ptr(out), self._stream()), "scv_sumsq")
+
+    def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind):
+        s = OptimT(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, _ptr(sumsq), max_norm, gscale, lr, beta1, beta2, eps,
+                   weight_decay, step, kind)
+        self._check(self.lib.scv_optim_step(C.byref(s), self._stream()), "scv_optim_step")
+
+    def d2f(self, src, dst, n):
+        self._check(self.lib.scv_d2f(_ptr(src), _ptr(dst), n, self._stream()), "scv_d2f")
+
+
+_OPS: Optional[CudaOps] = None
+
+
+def get_ops() -> CudaOps:
+    """The process-wide CUDA op table; raises if the library is absent."""
+    global _OPS
+    if _OPS is None:
+        _OPS = CudaOps()
+    return _OPS

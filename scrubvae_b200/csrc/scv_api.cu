@@ -1,0 +1,64 @@
+// C-ABI glue: error text, device info, precision dispatch of scv_gemm / scv_wgrad.
+#include <stdarg.h>
+#include "scv_common.cuh"
+
+namespace scv {
+
+static thread_local char g_err[512] = "";
+int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+int gemm_ffma(const scv_gemm_t* p, cudaStream_t st);
+int wgrad_ffma(const scv_wgrad_t* p, cudaStream_t st);
+int gemm_tc(const scv_gemm_t* p, cudaStream_t st);    // returns 1 if the shape is not taken
+int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st);  // returns 1 if the shape is not taken
+
+}  // namespace scv
+
+extern "C" {
+
+int scv_version(void) { return 100; }
+const char* scv_last_error(void) { return scv::g_err; }
+int64_t scv_launch_count(void) { return scv::g_launches; }
+
+int scv_gemm(const scv_gemm_t* p, void* stream) {
+  SCV_REQUIRE(p && p->A && p->W && p->Y, "scv_gemm: null pointer");
+  SCV_REQUIRE(p->B > 0 && p->Lo > 0 && p->K > 0 && p->N > 0, "scv_gemm: empty problem");
+  SCV_REQUIRE(p->n_last >= 0 && p->n_last <= p->N, "scv_gemm: n_last out of range");
+  SCV_REQUIRE(!p->bias || (p->bias_mod > 0 && p->bias_n <= p->N), "scv_gemm: bad bias_mod/bias_n");
+  if (p->precision != SCV_PREC_FP32) {
+    int r = scv::gemm_tc(p, (cudaStream_t)stream);
+    if (r != 1) return r;
+  }
+  return scv::gemm_ffma(p, (cudaStream_t)stream);
+}
+
+int scv_wgrad(const scv_wgrad_t* p, void* stream) {
+  SCV_REQUIRE(p && p->A && p->dY && p->dW, "scv_wgrad: null pointer");
+  SCV_REQUIRE(p->B > 0 && p->Lo > 0 && p->K > 0 && p->N > 0, "scv_wgrad: empty problem");
+  SCV_REQUIRE(!p->dbias || (p->bias_mod > 0 && p->bias_n <= p->N), "scv_wgrad: bad bias_mod/bias_n");
+  if (p->precision != SCV_PREC_FP32) {
+    int r = scv::wgrad_tc(p, (cudaStream_t)stream);
+    if (r != 1) return r;
+  }
+  return scv::wgrad_ffma(p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// Shared helpers for libscv (sm_100a).  No torch headers: the library is a plain C-ABI .so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/scv.h"
+
+namespace scv {
+
+void set_error(const char* fmt, ...);
+extern int64_t g_launches;
+
+inline int check_launch(const char* what) {
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+#define SCV_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      scv::set_error(__VA_ARGS__);        \
+      return -1;                          \
+    }                                     \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int sm_count();
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of a double, result valid in thread 0; `sh` needs 32 doubles
+__device__ __forceinline__ double block_sum_d(double v, double* sh) {
+  v = warp_sum_d(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    v = l < nw ? sh[l] : 0.0;
+    v = warp_sum_d(v);
+  }
+  return v;
+}
+
+}  // namespace scv

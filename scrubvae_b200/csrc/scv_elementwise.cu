@@ -1,0 +1,442 @@
+// HBM-bound elementwise / reduction kernels of the SC-VAE step: input pack, BatchNorm+PReLU(+upsample)
+// forward and backward, gather (weight repack), grad-norm + fused optimizer, small helpers.
+// All kernels are float4-vectorised over the contiguous channel dimension (channels-last rows).
+#include "scv_common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+struct Tile2D {
+  int c;  // float4 column
+  bool cok;
+  int64_t r0, rstep, rend;
+};
+// 256 threads = 8 warps; a warp covers cw float4 columns x (32/cw) rows, so that narrow layers
+// (C = 64 -> 16 float4) still issue full 512-byte warp requests.
+__device__ __forceinline__ Tile2D make_tile(int C4, int cw, int64_t rows, int64_t rows_per_block) {
+  Tile2D t;
+  int lane = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  int rpw = 32 / cw, lx = lane % cw, rsub = lane / cw;
+  t.c = blockIdx.x * cw + lx;
+  t.cok = t.c < C4;
+  int64_t rbeg = (int64_t)blockIdx.y * rows_per_block;
+  t.rend = rbeg + rows_per_block < rows ? rbeg + rows_per_block : rows;
+  t.r0 = rbeg + ly * rpw + rsub;
+  t.rstep = 8 * rpw;
+  return t;
+}
+
+struct Launch2D {
+  dim3 grid;
+  int cw;
+  int64_t rows_per_block;
+};
+Launch2D plan2d(int64_t C4, int64_t rows, int ctas_per_sm) {
+  Launch2D l;
+  int cw = 1;
+  while (cw < 32 && cw < C4) cw <<= 1;
+  l.cw = cw;
+  int64_t gx = (C4 + cw - 1) / cw;
+  int64_t rows_per_iter = 8 * (32 / cw);
+  int64_t target = (int64_t)scv::sm_count() * ctas_per_sm;
+  int64_t gy = target / gx;
+  if (gy < 1) gy = 1;
+  int64_t maxgy = (rows + rows_per_iter - 1) / rows_per_iter;
+  if (gy > maxgy) gy = maxgy;
+  if (gy > 65535) gy = 65535;
+  int64_t rpb = (rows + gy - 1) / gy;
+  rpb = (rpb + rows_per_iter - 1) / rows_per_iter * rows_per_iter;
+  gy = (rows + rpb - 1) / rpb;
+  l.grid = dim3((unsigned)gx, (unsigned)gy);
+  l.rows_per_block = rpb;
+  return l;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
+
+// per-channel affine of BN (scale, shift) and the statistics needed by backward
+struct ChanBN {
+  float scale[4], shift[4], mean[4], rstd[4];
+};
+__device__ __forceinline__ void chan_bn(ChanBN& cb, int ch0, int C, int mode, const double* stats, int fold,
+                                        double count, double eps, const float* gamma, const float* beta,
+                                        const float* rmean, const float* rvar) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int ch = ch0 + q;
+    if (!(mode & 1)) {
+      cb.scale[q] = 1.f; cb.shift[q] = 0.f; cb.mean[q] = 0.f; cb.rstd[q] = 1.f;
+      continue;
+    }
+    double mean, var;
+    if (mode & 4) {
+      double s = 0.0, ss = 0.0;
+      for (int j = 0; j < fold; ++j) { s += stats[ch + j * C]; ss += stats[(int64_t)fold * C + ch + j * C]; }
+      mean = s / count;
+      var = ss / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+    } else {
+      mean = (double)rmean[ch];
+      var = (double)rvar[ch];
+    }
+    double rstd = 1.0 / sqrt(var + eps);
+    cb.mean[q] = (float)mean;
+    cb.rstd[q] = (float)rstd;
+    float g = gamma[ch], b = beta[ch];
+    cb.scale[q] = g * (float)rstd;
+    cb.shift[q] = b - (float)mean * g * (float)rstd;
+  }
+}
+
+__device__ __forceinline__ float4 bn_prelu(float4 x, const ChanBN& cb, bool has_act, float slope) {
+  float v[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float t = fmaf(v[q], cb.scale[q], cb.shift[q]);
+    v[q] = (has_act && t < 0.f) ? slope * t : t;
+  }
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+__global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, const int cw, const int64_t rpb) {
+  const int C = (int)p.C, C4 = C >> 2;
+  const int mode = (int)p.mode;
+  const int64_t rows = p.B * p.L;
+  Tile2D t = make_tile(C4, cw, rows, rpb);
+  if (!t.cok) return;
+  ChanBN cb;
+  chan_bn(cb, t.c * 4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, p.running_mean,
+          p.running_var);
+  const bool has_act = mode & 2;
+  const float slope = has_act ? __ldg(p.slope) : 0.f;
+  // running statistics: one thread per channel group (block row 0, first row lane)
+  if ((mode & 5) == 5 && p.running_mean && blockIdx.y == 0 && t.r0 == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int ch = t.c * 4 + q;
+      double s = 0.0, ss = 0.0;
+      for (int j = 0; j < (int)p.fold; ++j) { s += p.stats[ch + j * C]; ss += p.stats[p.fold * C + ch + j * C]; }
+      double mean = s / p.count, var = ss / p.count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      double unb = p.count > 1.0 ? var * p.count / (p.count - 1.0) : var;
+      p.running_mean[ch] = (float)((1.0 - p.momentum) * (double)p.running_mean[ch] + p.momentum * mean);
+      p.running_var[ch] = (float)((1.0 - p.momentum) * (double)p.running_var[ch] + p.momentum * unb);
+    }
+  }
+  const int64_t L = p.L;
+  for (int64_t r = t.r0; r < t.rend; r += t.rstep) {
+    int64_t b = r / L, l = r - b * L;
+    const float* xr = p.X + b * p.x_bs + l * p.x_ls + t.c * 4;
+    float4 a = bn_prelu(ld4(xr), cb, has_act, slope);
+    if (p.H) st4(p.H + b * p.h_bs + l * p.h_ls + t.c * 4, a);
+    if (p.U) {
+      float4 am = l > 0 ? bn_prelu(ld4(xr - p.x_ls), cb, has_act, slope) : a;
+      float4 ap = l < L - 1 ? bn_prelu(ld4(xr + p.x_ls), cb, has_act, slope) : a;
+      float4 e, o;
+      e.x = 0.25f * am.x + 0.75f * a.x; e.y = 0.25f * am.y + 0.75f * a.y;
+      e.z = 0.25f * am.z + 0.75f * a.z; e.w = 0.25f * am.w + 0.75f * a.w;
+      o.x = 0.75f * a.x + 0.25f * ap.x; o.y = 0.75f * a.y + 0.25f * ap.y;
+      o.z = 0.75f * a.z + 0.25f * ap.z; o.w = 0.75f * a.w + 0.25f * ap.w;
+      float* ur = p.U + b * p.u_bs + (2 * l) * p.u_ls + t.c * 4;
+      st4(ur, e);
+      st4(ur + p.u_ls, o);
+    }
+  }
+}
+
+// gradient w.r.t. the activated output at (b,l): direct part + transpose of the x2 linear upsample
+__device__ __forceinline__ float4 load_dout(const scv_bnact_bwd_t& p, int64_t b, int64_t l, int c4) {
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.dO) g = ld4(p.dO + b * p.o_bs + l * p.o_ls + c4 * 4);
+  if (p.dU) {
+    const int64_t L = p.L;
+    const float* u = p.dU + b * p.u_bs + c4 * 4;
+    float4 e = ld4(u + (2 * l) * p.u_ls), o = ld4(u + (2 * l + 1) * p.u_ls);
+    float4 m = ld4(u + (l > 0 ? 2 * l - 1 : 0) * p.u_ls);
+    float4 n = ld4(u + (l < L - 1 ? 2 * l + 2 : 2 * L - 1) * p.u_ls);
+    g.x += 0.75f * (e.x + o.x) + 0.25f * (m.x + n.x);
+    g.y += 0.75f * (e.y + o.y) + 0.25f * (m.y + n.y);
+    g.z += 0.75f * (e.z + o.z) + 0.25f * (m.z + n.z);
+    g.w += 0.75f * (e.w + o.w) + 0.25f * (m.w + n.w);
+  }
+  return g;
+}
+
+__global__ void __launch_bounds__(NT) bnact_bwd_reduce_kernel(const scv_bnact_bwd_t p, const int cw,
+                                                              const int64_t rpb) {
+  __shared__ float red[8][32][9];
+  __shared__ double shd[32];
+  const int C = (int)p.C, C4 = C >> 2;
+  const int mode = (int)p.mode;
+  const int64_t rows = p.B * p.L, L = p.L;
+  Tile2D t = make_tile(C4, cw, rows, rpb);
+  float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f}, ds = 0.f;
+  if (t.cok) {
+    ChanBN cb;
+    chan_bn(cb, t.c * 4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, nullptr, nullptr);
+    const bool has_act = mode & 2;
+    const float slope = has_act ? __ldg(p.slope) : 0.f;
+    for (int64_t r = t.r0; r < t.rend; r += t.rstep) {
+      int64_t b = r / L, l = r - b * L;
+      float4 x4 = ld4(p.X + b * p.x_bs + l * p.x_ls + t.c * 4);
+      float4 g4 = load_dout(p, b, l, t.c);
+      float x[4] = {x4.x, x4.y, x4.z, x4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v = fmaf(x[q], cb.scale[q], cb.shift[q]);
+        float gg = g[q];
+        if (has_act && v < 0.f) { ds += gg * v; gg *= slope; }
+        sg[q] += gg;
+        sgx[q] += gg * (x[q] - cb.mean[q]) * cb.rstd[q];
+      }
+    }
+  }
+  // reduce over the 8 warps and the row sub-lanes of each warp
+  const int lane = threadIdx.x & 31, ly = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { red[ly][lane][q] = sg[q]; red[ly][lane][4 + q] = sgx[q]; }
+  red[ly][lane][8] = ds;
+  __syncthreads();
+  const int rpw = 32 / cw;
+  if (threadIdx.x < cw) {
+    int c = blockIdx.x * cw + threadIdx.x;
+    if (c < C4) {
+      double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int w = 0; w < 8; ++w)
+        for (int s = 0; s < rpw; ++s)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) a[q] += (double)red[w][s * cw + threadIdx.x][q];
+      if (mode & 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          atomicAdd(p.sums + c * 4 + q, a[q]);
+          atomicAdd(p.sums + C + c * 4 + q, a[4 + q]);
+        }
+      }
+    }
+  }
+  if (mode & 2) {
+    double d = scv::block_sum_d((double)ds, shd);
+    if (threadIdx.x == 0) atomicAdd(p.sums + 2 * C, d);
+  }
+}
+
+__global__ void __launch_bounds__(NT) bnact_bwd_apply_kernel(const scv_bnact_bwd_t p, const int cw,
+                                                             const int64_t rpb) {
+  const int C = (int)p.C, C4 = C >> 2;
+  const int mode = (int)p.mode;
+  const int64_t rows = p.B * p.L, L = p.L;
+  Tile2D t = make_tile(C4, cw, rows, rpb);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (mode & 2) && p.dslope)
+    p.dslope[0] += (float)p.sums[2 * C];
+  if (!t.cok) return;
+  ChanBN cb;
+  chan_bn(cb, t.c * 4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, nullptr, nullptr);
+  const bool has_act = mode & 2;
+  const bool train_bn = (mode & 5) == 5;
+  const float slope = has_act ? __ldg(p.slope) : 0.f;
+  float mg[4] = {0.f, 0.f, 0.f, 0.f}, mgx[4] = {0.f, 0.f, 0.f, 0.f};
+  if (mode & 1) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int ch = t.c * 4 + q;
+      double s = p.sums[ch], sx = p.sums[C + ch];
+      if (train_bn) { mg[q] = (float)(s / p.count); mgx[q] = (float)(sx / p.count); }
+      if (blockIdx.y == 0 && t.r0 == 0) {
+        if (p.dgamma) p.dgamma[ch] += (float)sx;
+        if (p.dbeta) p.dbeta[ch] += (float)s;
+      }
+    }
+  }
+  if (!p.dX) return;
+  for (int64_t r = t.r0; r < t.rend; r += t.rstep) {
+    int64_t b = r / L, l = r - b * L;
+    float4 x4 = ld4(p.X + b * p.x_bs + l * p.x_ls + t.c * 4);
+    float4 g4 = load_dout(p, b, l, t.c);
+    float x[4] = {x4.x, x4.y, x4.z, x4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w}, d[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v = fmaf(x[q], cb.scale[q], cb.shift[q]);
+      float gg = g[q];
+      if (has_act && v < 0.f) gg *= slope;
+      if (mode & 1) {
+        float xh = (x[q] - cb.mean[q]) * cb.rstd[q];
+        d[q] = cb.scale[q] * (gg - mg[q] - xh * mgx[q]);
+      } else {
+        d[q] = gg;
+      }
+    }
+    st4(p.dX + b * p.d_bs + l * p.d_ls + t.c * 4, make_float4(d[0], d[1], d[2], d[3]));
+  }
+}
+
+__global__ void __launch_bounds__(NT) pack_input_kernel(const float* __restrict__ x6d, const float* __restrict__ root,
+                                                        const float* __restrict__ arena, float* __restrict__ out,
+                                                        int64_t rows, int W, int nx, int C, int halo) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
+    int64_t r = i / C;
+    int c = (int)(i - r * C);
+    int64_t b = r / W;
+    int w = (int)(r - b * W);
+    float v = 0.f;
+    if (c < nx) {
+      v = x6d[r * nx + c];
+    } else if (c < nx + 3) {
+      int d = c - nx;
+      float a0 = arena[d], a1 = arena[3 + d];
+      v = 2.f * (root[r * 3 + d] - a0) / (a1 - a0) - 1.f;
+    }
+    out[(b * (W + 2 * halo) + halo + w) * C + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(NT) gather_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                                    float* __restrict__ dst, int64_t n, int skip_neg) {
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * NT) {
+    int32_t j = idx[i];
+    if (j >= 0) dst[i] = __ldg(src + j);
+    else if (!skip_neg) dst[i] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(NT) sumsq_kernel(const float* __restrict__ g, int64_t n, double* out) {
+  __shared__ double sh[32];
+  float acc = 0.f;
+  double dacc = 0.0;
+  int cnt = 0;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (int64_t)gridDim.x * NT) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    if (++cnt == 64) { dacc += (double)acc; acc = 0.f; cnt = 0; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { float v = g[n4 * 4 + threadIdx.x]; acc += v * v; }
+  dacc += (double)acc;
+  double s = scv::block_sum_d(dacc, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+__global__ void __launch_bounds__(NT) optim_kernel(const scv_optim_t p) {
+  // clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6))  (train/trainer.py:164)
+  const float gs = (float)p.gscale;
+  float coef = gs;
+  if (p.sumsq) {
+    double norm = sqrt(p.sumsq[0]) * p.gscale;
+    double c = p.max_norm / (norm + 1e-6);
+    coef = (float)((c < 1.0 ? c : 1.0) * p.gscale);
+  }
+  const float lr = (float)p.lr, b1 = (float)p.beta1, b2 = (float)p.beta2, eps = (float)p.eps,
+              wd = (float)p.weight_decay;
+  const double bc1d = 1.0 - pow(p.beta1, (double)p.step), bc2d = 1.0 - pow(p.beta2, (double)p.step);
+  const float step_size = (float)(p.lr / bc1d), bc2s = (float)sqrt(bc2d);
+  const int kind = (int)p.kind;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * NT) {
+    float g = p.g[i] * coef, w = p.p[i];
+    if (kind == 2) {  // SGD, momentum beta1, nesterov (torch.optim.SGD)
+      float buf = p.step == 1 ? g : b1 * p.m[i] + g;
+      p.m[i] = buf;
+      p.p[i] = w - lr * (g + b1 * buf);
+      continue;
+    }
+    if (kind == 1) w *= 1.f - lr * wd;
+    else if (wd != 0.f) g += wd * w;
+    float m = p.m[i] + (1.f - b1) * (g - p.m[i]);          // torch: exp_avg.lerp_(grad, 1-beta1)
+    float v = b2 * p.v[i] + (1.f - b2) * g * g;
+    p.m[i] = m;
+    p.v[i] = v;
+    float denom = sqrtf(v) / bc2s + eps;
+    p.p[i] = w - step_size * (m / denom);
+  }
+}
+
+__global__ void d2f_kernel(const double* in, float* out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+int grid1d(int64_t n, int per_sm) {
+  int64_t want = (n + NT - 1) / NT;
+  int64_t cap = (int64_t)scv::sm_count() * per_sm;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+}  // namespace
+
+extern "C" {
+
+int scv_pack_input(const float* x6d, const float* root, const float* arena, float* out, int64_t B, int64_t W,
+                   int64_t nx, int64_t C, int64_t halo, void* stream) {
+  SCV_REQUIRE(nx + 3 <= C, "scv_pack_input: C too small");
+  pack_input_kernel<<<grid1d(B * W * C, 8), NT, 0, (cudaStream_t)stream>>>(x6d, root, arena, out, B * W, (int)W,
+                                                                          (int)nx, (int)C, (int)halo);
+  return scv::check_launch("pack_input_kernel");
+}
+
+static int check_rows(const char* who, int64_t C, const void* ptr, int64_t bs, int64_t ls) {
+  SCV_REQUIRE(C % 4 == 0 && bs % 4 == 0 && ls % 4 == 0 && scv::aligned16(ptr), "%s: rows must be float4-aligned", who);
+  return 0;
+}
+
+int scv_bnact_fwd(const scv_bnact_t* p, void* stream) {
+  if (check_rows("scv_bnact_fwd X", p->C, p->X, p->x_bs, p->x_ls)) return -1;
+  if (p->H && check_rows("scv_bnact_fwd H", p->C, p->H, p->h_bs, p->h_ls)) return -1;
+  if (p->U && check_rows("scv_bnact_fwd U", p->C, p->U, p->u_bs, p->u_ls)) return -1;
+  SCV_REQUIRE(!(p->mode & 1) || (p->gamma && p->beta), "scv_bnact_fwd: BN needs gamma/beta");
+  SCV_REQUIRE(!((p->mode & 5) == 5) || p->stats, "scv_bnact_fwd: training BN needs stats");
+  SCV_REQUIRE(!((p->mode & 5) == 1) || (p->running_mean && p->running_var), "scv_bnact_fwd: eval BN needs running stats");
+  Launch2D l = plan2d(p->C / 4, p->B * p->L, 8);
+  bnact_fwd_kernel<<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
+  return scv::check_launch("bnact_fwd_kernel");
+}
+
+int scv_bnact_bwd_reduce(const scv_bnact_bwd_t* p, void* stream) {
+  if (check_rows("scv_bnact_bwd X", p->C, p->X, p->x_bs, p->x_ls)) return -1;
+  if (p->dO && check_rows("scv_bnact_bwd dO", p->C, p->dO, p->o_bs, p->o_ls)) return -1;
+  if (p->dU && check_rows("scv_bnact_bwd dU", p->C, p->dU, p->u_bs, p->u_ls)) return -1;
+  SCV_REQUIRE(p->sums, "scv_bnact_bwd_reduce: sums required");
+  Launch2D l = plan2d(p->C / 4, p->B * p->L, 4);
+  bnact_bwd_reduce_kernel<<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
+  return scv::check_launch("bnact_bwd_reduce_kernel");
+}
+
+int scv_bnact_bwd_apply(const scv_bnact_bwd_t* p, void* stream) {
+  if (check_rows("scv_bnact_bwd X", p->C, p->X, p->x_bs, p->x_ls)) return -1;
+  if (p->dO && check_rows("scv_bnact_bwd dO", p->C, p->dO, p->o_bs, p->o_ls)) return -1;
+  if (p->dU && check_rows("scv_bnact_bwd dU", p->C, p->dU, p->u_bs, p->u_ls)) return -1;
+  if (p->dX && check_rows("scv_bnact_bwd dX", p->C, p->dX, p->d_bs, p->d_ls)) return -1;
+  SCV_REQUIRE(!(p->mode & 3) || p->sums, "scv_bnact_bwd_apply: sums required");
+  Launch2D l = plan2d(p->C / 4, p->B * p->L, 8);
+  bnact_bwd_apply_kernel<<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
+  return scv::check_launch("bnact_bwd_apply_kernel");
+}
+
+int scv_gather(const float* src, const int32_t* idx, float* dst, int64_t n, int64_t skip_neg, void* stream) {
+  if (n <= 0) return 0;
+  gather_kernel<<<grid1d(n, 16), NT, 0, (cudaStream_t)stream>>>(src, idx, dst, n, (int)skip_neg);
+  return scv::check_launch("gather_kernel");
+}
+
+int scv_sumsq(const float* g, int64_t n, double* sumsq, void* stream) {
+  SCV_REQUIRE(scv::aligned16(g), "scv_sumsq: g must be 16-byte aligned");
+  sumsq_kernel<<<grid1d(n / 4 + 1, 4), NT, 0, (cudaStream_t)stream>>>(g, n, sumsq);
+  return scv::check_launch("sumsq_kernel");
+}
+
+int scv_optim_step(const scv_optim_t* p, void* stream) {
+  SCV_REQUIRE(p->kind >= 0 && p->kind <= 2 && p->step >= 1, "scv_optim_step: bad kind/step");
+  optim_kernel<<<grid1d(p->n, 8), NT, 0, (cudaStream_t)stream>>>(*p);
+  return scv::check_launch("optim_kernel");
+}
+
+int scv_d2f(const double* in, float* out, int64_t n, void* stream) {
+  d2f_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(in, out, n);
+  return scv::check_launch("d2f_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+"""`scrubvae_b200.get.model` — same signature and semantics as the reference factory
+get/model.py:4-151, restricted to the methods on the built hot path (conditional + grad_reversal)."""
+import torch
+
+
+def model(model_config, load_model, epoch, disentangle_config, n_keypts, direction_process, loss_config=None,
+          arena_size=None, kinematic_tree=None, bound=False, discrete_classes=None, device="cuda", verbose=1):
+    feat_dim_dict = {
+        "avg_speed": 1, "part_speed": 4, "frame_speed": model_config["window"] - 1, "avg_speed_3d": 3,
+        "heading": 2, "heading_change": 1, "fluorescence": 1,
+    }
+    if discrete_classes is not None:
+        if verbose > 0:
+            print("Discrete Classes: {}".format(discrete_classes))
+        feat_dim_dict.update({k: len(v) for k, v in discrete_classes.items()})
+
+    in_channels = n_keypts * 6
+    if direction_process in ["x360", "midfwd", None]:
+        in_channels += 3
+
+    methods = disentangle_config["method"]
+    for m in methods:
+        if m not in ("conditional", "grad_reversal"):
+            raise NotImplementedError(
+                f"scrubvae_b200.get.model: method '{m}' is outside the built hot path (SURVEY.md §8)")
+    disentangle = {}
+    if "conditional" in methods.keys():
+        conditional_dim = sum([feat_dim_dict[k] for k in methods["conditional"]])
+        conditional_keys = methods["conditional"]
+    else:
+        conditional_keys = None
+        conditional_dim = 0
+
+    if "grad_reversal" in methods.keys():
+        from .. model.disentangle import GRScrubber
+        disentangle["grad_reversal"] = {}
+        for feat in methods["grad_reversal"]:
+            disentangle["grad_reversal"][feat] = GRScrubber(
+                model_config["z_dim"], feat_dim_dict[feat], alpha=disentangle_config["alpha"], bound=bound)
+
+    if model_config["type"] != "rcnn":
+        raise NotImplementedError("scrubvae_b200.get.model: only model type 'rcnn' exists (as in the reference)")
+    from ..model.residual import ResVAE
+    vae = ResVAE(
+        in_channels=in_channels, kernel=model_config["kernel"], z_dim=model_config["z_dim"],
+        window=model_config["window"], activation=model_config["activation"], is_diag=model_config["diag"],
+        conditional_dim=conditional_dim, init_dilation=model_config["init_dilation"], disentangle=disentangle,
+        disentangle_keys=disentangle_config["features"], conditional_keys=conditional_keys, arena_size=arena_size,
+        kinematic_tree=kinematic_tree, prior=model_config["prior"], ch=model_config["channel"],
+        discrete_classes=discrete_classes, precision=model_config.get("precision") or "tf32",
+    )
+    if verbose > 0:
+        print(vae)
+
+    if load_model is not None:
+        load_path = "{}/weights/epoch_{}.pth".format(load_model, epoch)
+        print("Loading Weights from:\n{}".format(load_path))
+        state_dict = torch.load(load_path)
+        missing_keys, unexpected_keys = vae.load_state_dict(state_dict, strict=False)
+        if verbose > 0:
+            print("Missing Keys: {}".format(missing_keys))
+            print("Unexpected Keys: {}".format(unexpected_keys))
+
+    return vae.to(device)

@@ -1,0 +1,378 @@
+"""TEST INFRASTRUCTURE — a torch-on-CPU statement of the *semantics* of every entry point of
+include/scv.h (same method signatures as scrubvae_b200._ops.CudaOps).
+
+Used only by tests: (1) CPU tests inject it into the engine to check the host logic (buffer
+geometry, weight index maps, forward/backward sequencing) against the oracle without a GPU;
+(2) GPU tests compare each CUDA kernel against the matching method on the same inputs.
+The product never imports this file.
+"""
+import math
+
+import torch
+
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELUMASK = 0, 1, 2, 3
+BN, PRELU, TRAIN = 1, 2, 4
+
+
+def _v(ref, shape, strides):
+    if ref is None:
+        return None
+    t, off = (ref, 0) if isinstance(ref, torch.Tensor) else (ref.t, ref.off)
+    return torch.as_strided(t, shape, strides, off)
+
+
+class EmuOps:
+    name = "emu"
+
+    def __init__(self):
+        self.n = 0
+
+    def launch_count(self):
+        return self.n
+
+    def gemm(self, A, a_bs, a_ls, B, Lo, K, N, W, Y, y_bs, y_ls, bias=None, bias_mod=1, bias_n=0, n_last=None,
+             R=None, r_bs=0, r_ls=0, act=ACT_NONE, out_scale=1.0, stats=None, precision=0):
+        self.n += 1
+        n_last = N if n_last is None else n_last
+        a = _v(A, (B, Lo, K), (a_bs, a_ls, 1))
+        w = _v(W, (N, K), (K, 1))
+        y = out_scale * (a.reshape(B * Lo, K) @ w.t()).reshape(B, Lo, N)
+        if bias is not None:
+            bb = _v(bias, (bias_mod,), (1,))
+            n = torch.arange(N)
+            y = y + torch.where(n < bias_n, bb[n % bias_mod], torch.zeros(()))
+        r = _v(R, (B, Lo, N), (r_bs, r_ls, 1)) if R is not None else None
+        valid = torch.ones(B, Lo, N, dtype=torch.bool)
+        valid[:, Lo - 1, n_last:] = False
+        if r is not None and act != ACT_RELUMASK:
+            y = y + torch.where(valid, r, torch.zeros(()))
+        if stats is not None:
+            st = _v(stats, (2, N), (N, 1))
+            yd = torch.where(valid, y, torch.zeros(())).double()
+            st[0] += yd.sum((0, 1))
+            st[1] += (yd * yd).sum((0, 1))
+        if act == ACT_RELU:
+            y = torch.relu(y)
+        elif act == ACT_TANH:
+            y = torch.tanh(y)
+        elif act == ACT_RELUMASK:
+            y = torch.where(torch.where(valid, r, torch.zeros(())) > 0, y, torch.zeros(()))
+        out = _v(Y, (B, Lo, N), (y_bs, y_ls, 1))
+        if n_last == N:
+            out.copy_(y)
+        else:
+            out[:, :Lo - 1].copy_(y[:, :Lo - 1])
+            out[:, Lo - 1, :n_last].copy_(y[:, Lo - 1, :n_last])
+
+    def wgrad(self, A, a_bs, a_ls, B, Lo, K, N, dY, y_bs, y_ls, dW, dbias=None, bias_mod=1, bias_n=0, precision=0):
+        self.n += 1
+        a = _v(A, (B, Lo, K), (a_bs, a_ls, 1)).reshape(B * Lo, K)
+        g = _v(dY, (B, Lo, N), (y_bs, y_ls, 1)).reshape(B * Lo, N)
+        _v(dW, (N, K), (K, 1)).add_(g.t() @ a)
+        if dbias is not None:
+            db = _v(dbias, (bias_mod,), (1,))
+            s = g.sum(0)
+            for n in range(min(N, bias_n)):
+                db[n % bias_mod] += s[n]
+
+    def pack_input(self, x6d, root, arena, out, B, W, nx, Cc, halo):
+        self.n += 1
+        x = _v(x6d, (B, W, nx), (W * nx, nx, 1))
+        r = _v(root, (B, W, 3), (W * 3, 3, 1))
+        a = _v(arena, (2, 3), (3, 1))
+        o = _v(out, (B, W, Cc), ((W + 2 * halo) * Cc, Cc, 1))
+        if not isinstance(out, torch.Tensor):
+            o = torch.as_strided(out.t, (B, W, Cc), ((W + 2 * halo) * Cc, Cc, 1), out.off + halo * Cc)
+        else:
+            o = torch.as_strided(out, (B, W, Cc), ((W + 2 * halo) * Cc, Cc, 1), halo * Cc)
+        o.zero_()
+        o[..., :nx] = x
+        o[..., nx:nx + 3] = 2 * (r - a[0]) / (a[1] - a[0]) - 1
+
+    # ---- BN + PReLU
+    def _chan(self, Cc, mode, stats, fold, count, eps, gamma, beta, rm, rv):
+        if not (mode & BN):
+            one = torch.ones(Cc)
+            return one, torch.zeros(Cc), torch.zeros(Cc), one
+        if mode & TRAIN:
+            st = _v(stats, (2, fold, Cc), (fold * Cc, Cc, 1))
+            mean = st[0].sum(0) / count
+            var = (st[1].sum(0) / count - mean * mean).clamp_min(0)
+        else:
+            mean, var = _v(rm, (Cc,), (1,)).double(), _v(rv, (Cc,), (1,)).double()
+        rstd = 1.0 / torch.sqrt(var + eps)
+        g, b = _v(gamma, (Cc,), (1,)), _v(beta, (Cc,), (1,))
+        meanf, rstdf = mean.float(), rstd.float()
+        scale = g * rstdf
+        shift = b - meanf * g * rstdf
+        return scale, shift, meanf, rstdf
+
+    def bnact_fwd(self, X, x_bs, x_ls, B, L, Cc, mode, stats=None, fold=1, count=1.0, eps=1e-4, momentum=0.1,
+                  gamma=None, beta=None, running_mean=None, running_var=None, slope=None,
+                  H=None, h_bs=0, h_ls=0, U=None, u_bs=0, u_ls=0):
+        self.n += 1
+        scale, shift, _, _ = self._chan(Cc, mode, stats, fold, count, eps, gamma, beta, running_mean, running_var)
+        if (mode & 5) == 5 and running_mean is not None:
+            st = _v(stats, (2, fold, Cc), (fold * Cc, Cc, 1))
+            mean = st[0].sum(0) / count
+            var = (st[1].sum(0) / count - mean * mean).clamp_min(0)
+            unb = var * count / (count - 1.0) if count > 1 else var
+            rm, rv = _v(running_mean, (Cc,), (1,)), _v(running_var, (Cc,), (1,))
+            rm.copy_(((1 - momentum) * rm.double() + momentum * mean).float())
+            rv.copy_(((1 - momentum) * rv.double() + momentum * unb).float())
+        x = _v(X, (B, L, Cc), (x_bs, x_ls, 1))
+        a = x * scale + shift
+        if mode & PRELU:
+            s = _v(slope, (1,), (1,))
+            a = torch.where(a < 0, s * a, a)
+        if H is not None:
+            _v(H, (B, L, Cc), (h_bs, h_ls, 1)).copy_(a)
+        if U is not None:
+            am = torch.cat([a[:, :1], a[:, :-1]], 1)
+            ap = torch.cat([a[:, 1:], a[:, -1:]], 1)
+            u = _v(U, (B, L, 2, Cc), (u_bs, 2 * u_ls, u_ls, 1))
+            u[:, :, 0] = 0.25 * am + 0.75 * a
+            u[:, :, 1] = 0.75 * a + 0.25 * ap
+
+    def _dout(self, B, L, Cc, dO, o_bs, o_ls, dU, u_bs, u_ls):
+        g = torch.zeros(B, L, Cc)
+        if dO is not None:
+            g = g + _v(dO, (B, L, Cc), (o_bs, o_ls, 1))
+        if dU is not None:
+            u = _v(dU, (B, L, 2, Cc), (u_bs, 2 * u_ls, u_ls, 1))
+            e, o = u[:, :, 0], u[:, :, 1]
+            m = torch.cat([e[:, :1], o[:, :-1]], 1)      # dU[2l-1] (l>0) else dU[0]
+            n = torch.cat([e[:, 1:], o[:, -1:]], 1)      # dU[2l+2] (l<L-1) else dU[2L-1]
+            g = g + 0.75 * (e + o) + 0.25 * (m + n)
+        return g
+
+    def _bwd_common(self, X, x_bs, x_ls, B, L, Cc, mode, stats, fold, count, eps, gamma, beta, slope, dO, o_bs, o_ls,
+                    dU, u_bs, u_ls):
+        scale, shift, mean, rstd = self._chan(Cc, mode, stats, fold, count, eps, gamma, beta, None, None)
+        x = _v(X, (B, L, Cc), (x_bs, x_ls, 1))
+        v = x * scale + shift
+        g = self._dout(B, L, Cc, dO, o_bs, o_ls, dU, u_bs, u_ls)
+        ds = torch.zeros((), dtype=torch.double)
+        if mode & PRELU:
+            s = _v(slope, (1,), (1,))
+            ds = torch.where(v < 0, g * v, torch.zeros(())).double().sum()
+            g = torch.where(v < 0, g * s, g)
+        xh = (x - mean) * rstd
+        return g, xh, scale, ds
+
+    def bnact_bwd_reduce(self, X, x_bs, x_ls, B, L, Cc, mode, sums, stats=None, fold=1, count=1.0, eps=1e-4,
+                         gamma=None, beta=None, slope=None, dO=None, o_bs=0, o_ls=0, dU=None, u_bs=0, u_ls=0):
+        self.n += 1
+        g, xh, _, ds = self._bwd_common(X, x_bs, x_ls, B, L, Cc, mode, stats, fold, count, eps, gamma, beta, slope,
+                                        dO, o_bs, o_ls, dU, u_bs, u_ls)
+        sm = _v(sums, (2 * Cc + 1,), (1,))
+        if mode & BN:
+            sm[:Cc] += g.double().sum((0, 1))
+            sm[Cc:2 * Cc] += (g * xh).double().sum((0, 1))
+        if mode & PRELU:
+            sm[2 * Cc] += ds
+
+    def bnact_bwd_apply(self, X, x_bs, x_ls, B, L, Cc, mode, sums=None, stats=None, fold=1, count=1.0, eps=1e-4,
+                        gamma=None, beta=None, slope=None, dO=None, o_bs=0, o_ls=0, dU=None, u_bs=0, u_ls=0,
+                        dX=None, d_bs=0, d_ls=0, dgamma=None, dbeta=None, dslope=None):
+        self.n += 1
+        g, xh, scale, _ = self._bwd_common(X, x_bs, x_ls, B, L, Cc, mode, stats, fold, count, eps, gamma, beta, slope,
+                                           dO, o_bs, o_ls, dU, u_bs, u_ls)
+        sm = _v(sums, (2 * Cc + 1,), (1,)) if sums is not None else None
+        if (mode & PRELU) and dslope is not None:
+            _v(dslope, (1,), (1,)).add_(sm[2 * Cc].float())
+        d = g
+        if mode & BN:
+            if dgamma is not None:
+                _v(dgamma, (Cc,), (1,)).add_(sm[Cc:2 * Cc].float())
+            if dbeta is not None:
+                _v(dbeta, (Cc,), (1,)).add_(sm[:Cc].float())
+            if (mode & 5) == 5:
+                mg, mgx = (sm[:Cc] / count).float(), (sm[Cc:2 * Cc] / count).float()
+                d = scale * (g - mg - xh * mgx)
+            else:
+                d = scale * g
+        if dX is not None:
+            _v(dX, (B, L, Cc), (d_bs, d_ls, 1)).copy_(d)
+
+    # ---- latent
+    def reparam_fwd(self, ms, ms_ld, eps, var, nvar, mu, L, zc, zc_ld, B, z):
+        self.n += 1
+        nsig = z * (z + 1) // 2
+        row = _v(ms, (B, z + nsig), (ms_ld, 1))
+        m, sig = row[:, :z], row[:, z:]
+        idx = torch.tril_indices(z, z)
+        Ld = torch.zeros(B, z, z)
+        Ld[:, idx[0], idx[1]] = sig
+        dg = torch.nn.functional.softplus(torch.diagonal(Ld, dim1=-2, dim2=-1))
+        Ld = Ld - torch.diag_embed(torch.diagonal(Ld, dim1=-2, dim2=-1)) + torch.diag_embed(dg)
+        if mu is not None:
+            _v(mu, (B, z), (z, 1)).copy_(m)
+        if L is not None:
+            _v(L, (B, z, z), (z * z, z, 1)).copy_(Ld)
+        if zc is not None:
+            o = _v(zc, (B, zc_ld), (zc_ld, 1))
+            o.zero_()
+            if eps is not None:
+                e = _v(eps, (B, z), (z, 1))
+                o[:, :z] = (Ld @ e[..., None]).squeeze(-1) + m
+            else:
+                o[:, :z] = m
+            if nvar > 0:
+                o[:, z:z + nvar] = _v(var, (B, nvar), (nvar, 1))
+
+    def reparam_bwd(self, ms, ms_ld, eps, dmu, dmu2, dmu2_scale, dz, dz_ld, dL, dms, dms_ld, B, z):
+        self.n += 1
+        nsig = z * (z + 1) // 2
+        sig = _v(ms, (B, z + nsig), (ms_ld, 1))[:, z:]
+        out = _v(dms, (B, dms_ld), (dms_ld, 1))
+        out.zero_()
+        g = torch.zeros(B, z)
+        if dmu is not None:
+            g = g + _v(dmu, (B, z), (z, 1))
+        if dmu2 is not None:
+            g = g + float(dmu2_scale) * _v(dmu2, (B, z), (z, 1))
+        gz = None
+        if dz is not None:
+            gz = _v(dz, (B, z), (dz_ld, 1))
+            g = g + gz
+        out[:, :z] = g
+        gL = torch.zeros(B, z, z)
+        if dL is not None:
+            gL = gL + _v(dL, (B, z, z), (z * z, z, 1))
+        if gz is not None and eps is not None:
+            e = _v(eps, (B, z), (z, 1))
+            gL = gL + gz[:, :, None] * e[:, None, :]
+        idx = torch.tril_indices(z, z)
+        gs = gL[:, idx[0], idx[1]]
+        isd = idx[0] == idx[1]
+        sp = torch.where(sig > 20, torch.ones(()), torch.sigmoid(sig))
+        gs = torch.where(isd[None, :], gs * sp, gs)
+        out[:, z:z + nsig] = gs
+
+    def kl(self, mu, L, loss, gscale, dmu, dL, B, z):
+        self.n += 1
+        m = _v(mu, (B, z), (z, 1))
+        Lm = _v(L, (B, z, z), (z * z, z, 1))
+        tril = torch.tril(Lm)
+        dg = torch.diagonal(Lm, dim1=-2, dim2=-1)
+        if loss is not None:
+            val = (-0.5 * (1 + 2 * torch.log(dg) - m * m).double().sum() + 0.5 * (tril * tril).double().sum()) / B
+            _v(loss, (1,), (1,)).add_(val)
+        gs = float(_v(gscale, (1,), (1,))) if gscale is not None else 1.0
+        if dmu is not None:
+            _v(dmu, (B, z), (z, 1)).copy_(m * (gs / B))
+        if dL is not None:
+            g = tril - torch.diag_embed(1.0 / dg)
+            _v(dL, (B, z, z), (z * z, z, 1)).copy_(g * (gs / B))
+
+    # ---- reconstruction
+    def recon_loss(self, xh, ld, offsets, target, root, arena, tree, n_tree, loss, root_hat, dxh, F, B, J):
+        self.n += 1
+        from oracle import scvae_oracle as orc  # test infrastructure may use the oracle
+        tr = _v(tree, (n_tree,), (1,)).tolist()
+        chains, pos = [], 1
+        for _ in range(tr[0]):
+            ln = tr[pos]
+            chains.append(tr[pos + 1:pos + 1 + ln])
+            pos += 1 + ln
+        nx = J * 6
+        rows = _v(xh, (F, ld), (ld, 1))
+        x = rows[:, :nx].reshape(F, J, 6).detach().clone().requires_grad_(True)
+        nr = rows[:, nx:nx + 3].detach().clone().requires_grad_(True)
+        off = _v(offsets, (F, J, 3), (J * 3, 3, 1))
+        tgt = _v(target, (F, J, 3), (J * 3, 3, 1))
+        a = _v(arena, (2, 3), (3, 1))
+        pose = orc.fwd_kin(x, off, torch.zeros(F, 3), tree=chains, eps=1e-8)
+        ljpe = ((tgt - pose) ** 2).sum() / (B * 3 * J)
+        rh = 0.5 * (nr + 1) * (a[1] - a[0]) + a[0]
+        lroot = ((rh - _v(root, (F, 3), (3, 1))) ** 2).sum() / B
+        gx, = torch.autograd.grad(ljpe, x)
+        gr, = torch.autograd.grad(lroot, nr)
+        lo = _v(loss, (2,), (1,))
+        lo[0] += ljpe.detach().double()
+        lo[1] += lroot.detach().double()
+        if root_hat is not None:
+            _v(root_hat, (F, 3), (3, 1)).copy_(rh.detach())
+        d = _v(dxh, (F, ld), (ld, 1))
+        d.zero_()
+        d[:, :nx] = gx.reshape(F, nx)
+        d[:, nx:nx + 3] = gr
+
+    def out_bwd(self, xh, dxh, ld, g_jpe, g_root, nx, draw, d_bs, d_ls, B, W):
+        self.n += 1
+        y = _v(xh, (B, W, ld), (W * ld, ld, 1))
+        d = _v(dxh, (B, W, ld), (W * ld, ld, 1))
+        gj = float(_v(g_jpe, (1,), (1,))) if g_jpe is not None else 0.0
+        gr = float(_v(g_root, (1,), (1,))) if g_root is not None else 0.0
+        sc = torch.zeros(ld)
+        sc[:nx] = gj
+        sc[nx:nx + 3] = gr
+        _v(draw, (B, W, ld), (d_bs, d_ls, 1)).copy_(d * sc * (1 - y * y))
+
+    def gr_loss(self, preds, dpreds, ld, target, labels, B, d, num_keys, loss, gscale):
+        self.n += 1
+        n = len(preds)
+        c = float(n * num_keys * B)
+        gs = float(_v(gscale, (1,), (1,))) if gscale is not None else 1.0
+        tot = torch.zeros((), dtype=torch.double)
+        for e in range(n):
+            w = c ** (-(n - e))
+            p = _v(preds[e], (B, d), (ld, 1)).detach().clone().requires_grad_(True)
+            if labels is not None:
+                le = torch.nn.functional.cross_entropy(p, _v(labels, (B,), (1,)), reduction="sum")
+            else:
+                le = ((p - _v(target, (B, d), (d, 1))) ** 2).sum()
+            tot += le.detach().double() * w
+            if dpreds is not None:
+                g, = torch.autograd.grad(le, p)
+                o = _v(dpreds[e], (B, ld), (ld, 1))
+                o.zero_()
+                o[:, :d] = g * (w * gs)
+        if loss is not None:
+            _v(loss, (1,), (1,)).add_(tot)
+
+    def gather(self, src, idx, dst, n, skip_neg=False):
+        self.n += 1
+        i = _v(idx, (n,), (1,)).long()
+        s = src if isinstance(src, torch.Tensor) else src.t[src.off:]
+        o = _v(dst, (n,), (1,))
+        ok = i >= 0
+        vals = s[i.clamp_min(0)]
+        if skip_neg:
+            o[ok] = vals[ok]
+        else:
+            o.copy_(torch.where(ok, vals, torch.zeros(())))
+
+    def sumsq(self, g, n, out):
+        self.n += 1
+        _v(out, (1,), (1,)).add_((_v(g, (n,), (1,)).double() ** 2).sum())
+
+    def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind):
+        self.n += 1
+        P, G = _v(p, (n,), (1,)), _v(g, (n,), (1,))
+        coef = gscale
+        if sumsq is not None:
+            norm = math.sqrt(float(_v(sumsq, (1,), (1,)))) * gscale
+            coef = min(1.0, max_norm / (norm + 1e-6)) * gscale
+        gg = G * coef
+        M = _v(m, (n,), (1,))
+        if kind == 2:
+            buf = gg.clone() if step == 1 else beta1 * M + gg
+            M.copy_(buf)
+            P.sub_(lr * (gg + beta1 * buf))
+            return
+        V = _v(v, (n,), (1,))
+        if kind == 1:
+            P.mul_(1 - lr * weight_decay)
+        elif weight_decay != 0:
+            gg = gg + weight_decay * P
+        M.lerp_(gg, 1 - beta1)
+        V.mul_(beta2).addcmul_(gg, gg, value=1 - beta2)
+        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        denom = V.sqrt() / math.sqrt(bc2) + eps
+        P.addcdiv_(M, denom, value=-(lr / bc1))
+
+    def d2f(self, src, dst, n):
+        self.n += 1
+        _v(dst, (n,), (1,)).copy_(_v(src, (n,), (1,)).float())
