@@ -166,12 +166,21 @@ typedef struct {
   float* p; const float* g; float* m; float* v; int64_t n;
   const double* sumsq; double max_norm, gscale;
   double lr, beta1, beta2, eps, weight_decay; int64_t step;
+  const double* hyper; /* optional device [lr, step]: overrides lr/step (CUDA-graph replay) */
   int64_t kind; /* 0 adam (L2 wd folded in grad), 1 adamw (decoupled), 2 sgd nesterov (m = momentum buf, beta1 = momentum) */
 } scv_optim_t;
 int scv_optim_step(const scv_optim_t* p, void* stream);
 
 /* out[i] = float(in[i]) */
 int scv_d2f(const double* in, float* out, int64_t n, void* stream);
+
+/* get_batch_loss total, train/losses.py:320-322: out[i] = float(acc[i]) for i < n and
+ * out[n] = sum_i scale[i] * acc[i] over scale[i] != 0 (one thread; n <= 64). */
+int scv_loss_finalize(const double* acc, const float* scale, float* out, int64_t n, void* stream);
+
+/* ResVAE.decode model/residual.py:484-489: root_hat[f][d] = inv_normalize_root(xh[f][nx + d]) */
+int scv_unpack_root(const float* xh, int64_t ld, int64_t nx, const float* arena, float* root_hat, int64_t F,
+                    void* stream);
 
 #ifdef __cplusplus
 }

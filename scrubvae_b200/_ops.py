@@ -72,7 +72,7 @@ BnactBwdT = _struct("BnactBwdT", [
 OptimT = _struct("OptimT", [
     ("p", _vp), ("g", _vp), ("m", _vp), ("v", _vp), ("n", _i64), ("sumsq", _vp), ("max_norm", _f64),
     ("gscale", _f64), ("lr", _f64), ("beta1", _f64), ("beta2", _f64), ("eps", _f64),
-    ("weight_decay", _f64), ("step", _i64), ("kind", _i64)])
+    ("weight_decay", _f64), ("step", _i64), ("hyper", _vp), ("kind", _i64)])
 
 _SIGS = {
     "scv_version": (C.c_int, []),
@@ -94,6 +94,8 @@ _SIGS = {
     "scv_sumsq": (C.c_int, [_vp, _i64, _vp, _vp]),
     "scv_optim_step": (C.c_int, [C.POINTER(OptimT), _vp]),
     "scv_d2f": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "scv_loss_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "scv_unpack_root": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _i64, _vp]),
 }
 
 EXPORTS = tuple(_SIGS)
@@ -209,10 +211,19 @@ class CudaOps:
     def sumsq(self, g, n, out):
         self._check(self.lib.scv_sumsq(_ptr(g), n, _ptr(out), self._stream()), "scv_sumsq")
 
-    def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind):
+    def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind,
+                   hyper=None):
         s = OptimT(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, _ptr(sumsq), max_norm, gscale, lr, beta1, beta2, eps,
-                   weight_decay, step, kind)
+                   weight_decay, step, _ptr(hyper), kind)
         self._check(self.lib.scv_optim_step(C.byref(s), self._stream()), "scv_optim_step")
+
+    def loss_finalize(self, acc, scale, out, n):
+        self._check(self.lib.scv_loss_finalize(_ptr(acc), _ptr(scale), _ptr(out), n, self._stream()),
+                    "scv_loss_finalize")
+
+    def unpack_root(self, xh, ld, nx, arena, root_hat, F):
+        self._check(self.lib.scv_unpack_root(_ptr(xh), ld, nx, _ptr(arena), _ptr(root_hat), F, self._stream()),
+                    "scv_unpack_root")
 
     def d2f(self, src, dst, n):
         self._check(self.lib.scv_d2f(_ptr(src), _ptr(dst), n, self._stream()), "scv_d2f")

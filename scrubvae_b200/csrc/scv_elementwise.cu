@@ -329,15 +329,18 @@ __global__ void __launch_bounds__(NT) optim_kernel(const scv_optim_t p) {
     double c = p.max_norm / (norm + 1e-6);
     coef = (float)((c < 1.0 ? c : 1.0) * p.gscale);
   }
-  const float lr = (float)p.lr, b1 = (float)p.beta1, b2 = (float)p.beta2, eps = (float)p.eps,
+  const double lrd = p.hyper ? p.hyper[0] : p.lr;
+  const double stepd = p.hyper ? p.hyper[1] : (double)p.step;
+  const float lr = (float)lrd, b1 = (float)p.beta1, b2 = (float)p.beta2, eps = (float)p.eps,
               wd = (float)p.weight_decay;
-  const double bc1d = 1.0 - pow(p.beta1, (double)p.step), bc2d = 1.0 - pow(p.beta2, (double)p.step);
-  const float step_size = (float)(p.lr / bc1d), bc2s = (float)sqrt(bc2d);
+  const double bc1d = 1.0 - pow(p.beta1, stepd), bc2d = 1.0 - pow(p.beta2, stepd);
+  const float step_size = (float)(lrd / bc1d), bc2s = (float)sqrt(bc2d);
+  const bool first = stepd < 1.5;
   const int kind = (int)p.kind;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * NT) {
     float g = p.g[i] * coef, w = p.p[i];
     if (kind == 2) {  // SGD, momentum beta1, nesterov (torch.optim.SGD)
-      float buf = p.step == 1 ? g : b1 * p.m[i] + g;
+      float buf = first ? g : b1 * p.m[i] + g;
       p.m[i] = buf;
       p.p[i] = w - lr * (g + b1 * buf);
       continue;
@@ -356,6 +359,27 @@ __global__ void __launch_bounds__(NT) optim_kernel(const scv_optim_t p) {
 __global__ void d2f_kernel(const double* in, float* out, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)in[i];
+}
+
+__global__ void loss_finalize_kernel(const double* acc, const float* scale, float* out, int n) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double tot = 0.0;
+  for (int i = 0; i < n; ++i) {
+    out[i] = (float)acc[i];
+    if (scale[i] != 0.f) tot += (double)scale[i] * acc[i];
+  }
+  out[n] = (float)tot;
+}
+
+__global__ void __launch_bounds__(NT) unpack_root_kernel(const float* __restrict__ xh, int64_t ld, int nx,
+                                                         const float* __restrict__ arena,
+                                                         float* __restrict__ root_hat, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
+    int64_t f = i / 3;
+    int d = (int)(i - f * 3);
+    float a0 = arena[d], a1 = arena[3 + d];
+    root_hat[i] = 0.5f * (xh[f * ld + nx + d] + 1.f) * (a1 - a0) + a0;
+  }
 }
 
 int grid1d(int64_t n, int per_sm) {
@@ -429,9 +453,22 @@ int scv_sumsq(const float* g, int64_t n, double* sumsq, void* stream) {
 }
 
 int scv_optim_step(const scv_optim_t* p, void* stream) {
-  SCV_REQUIRE(p->kind >= 0 && p->kind <= 2 && p->step >= 1, "scv_optim_step: bad kind/step");
+  SCV_REQUIRE(p->kind >= 0 && p->kind <= 2 && (p->hyper || p->step >= 1), "scv_optim_step: bad kind/step");
   optim_kernel<<<grid1d(p->n, 8), NT, 0, (cudaStream_t)stream>>>(*p);
   return scv::check_launch("optim_kernel");
+}
+
+int scv_loss_finalize(const double* acc, const float* scale, float* out, int64_t n, void* stream) {
+  SCV_REQUIRE(n >= 1 && n <= 64, "scv_loss_finalize: n out of range");
+  loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, scale, out, (int)n);
+  return scv::check_launch("loss_finalize_kernel");
+}
+
+int scv_unpack_root(const float* xh, int64_t ld, int64_t nx, const float* arena, float* root_hat, int64_t F,
+                    void* stream) {
+  if (F <= 0) return 0;
+  unpack_root_kernel<<<grid1d(F * 3, 8), NT, 0, (cudaStream_t)stream>>>(xh, ld, (int)nx, arena, root_hat, F * 3);
+  return scv::check_launch("unpack_root_kernel");
 }
 
 int scv_d2f(const double* in, float* out, int64_t n, void* stream) {

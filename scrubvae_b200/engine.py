@@ -1,0 +1,788 @@
+"""Kernel sequencing of the SC-VAE training step on libscv.so (include/scv.h).
+
+The engine owns
+  * ONE flat fp32 parameter buffer (the nn.Parameters of the drop-in modules are views into it, so
+    state_dict keys/shapes stay the reference's) and ONE flat gradient buffer (p.grad are views);
+  * the packed K-major weight matrices of every overlapping-row GEMM (forward + dgrad layouts),
+    refreshed from the flat buffer by a single gather kernel (layout.py);
+  * per-batch-size "plans": statically allocated halo-padded channels-last activation buffers and
+    the pre-bound kernel launch lists for forward / loss / backward.  Everything a launch needs is
+    fixed at plan time, so a whole step can be replayed from a CUDA graph.
+
+Reference semantics followed (paths relative to /root/reference/src/scrubvae):
+  ResVAE.forward/encode/decode model/residual.py:318-362,438-491; ResidualEncoder/Decoder
+  :183-292; ResidualBlock(:71-119)/ResidualBlockTranspose(:122-180); CholeskyL :39-68; sampling
+  :305-316; GRScrubber model/disentangle.py:541-660; get_batch_loss train/losses.py:182-324.
+
+There is no PyTorch compute fallback: torch is used for allocation, tiny host-side plumbing
+(one-hot / dtype casts of the conditioning features, RNG for the reparameterisation noise) and
+streams.  `ops` is the C-ABI call table (scrubvae_b200._ops.CudaOps); tests inject a CPU emulation
+of the ABI to check this host logic without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import layout as lay
+from ._ops import ACT_NONE, ACT_RELU, ACT_RELUMASK, ACT_TANH, BN, PREC, PRELU, TRAIN, Ref
+
+FEAT_FLOAT = ("avg_speed", "part_speed", "frame_speed", "avg_speed_3d", "heading", "heading_change", "fluorescence")
+
+
+def pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def pad16(n: int) -> int:
+    return (n + 15) // 16 * 16
+
+
+class Act:
+    """Halo-padded channels-last activation  t[b][hl + l][c]  (halo rows stay zero forever)."""
+
+    def __init__(self, dev, B, L, C, hl=0, hr=0, even=False, slack=0):
+        rows = hl + L + hr
+        if even and rows % 2:
+            rows += 1
+        self.B, self.L, self.C, self.hl, self.rows = B, L, C, hl, rows
+        self.bs, self.ls = rows * C, C
+        self.t = torch.zeros(B * rows * C + slack, device=dev, dtype=torch.float32)
+
+    def at(self, l: int = 0) -> Ref:
+        return Ref(self.t, (self.hl + l) * self.C)
+
+    def view(self) -> torch.Tensor:
+        return self.t[:self.B * self.rows * self.C].view(self.B, self.rows, self.C)[:, self.hl:self.hl + self.L]
+
+
+class GemmW:
+    """One GEMM layer's packed weights: forward matrix [N][K] (+ bias) and optional dgrad matrix."""
+    __slots__ = ("name", "N", "K", "w", "b", "bias_mod", "bias_n", "gw", "gb", "dN", "dK", "wd")
+
+
+class Engine:
+    def __init__(self, model: nn.Module, ops=None):
+        if ops is None:
+            from ._ops import get_ops
+            ops = get_ops()
+        self.ops = ops
+        self.m = model
+        self.precision = PREC[getattr(model, "precision", "tf32")]
+        self.device = next(model.parameters()).device
+        if ops.name == "cuda" and self.device.type != "cuda":
+            raise RuntimeError("scrubvae_b200: the model must live on a CUDA device (there is no CPU path); "
+                               "call .to('cuda') first")
+        self.plans: Dict[int, "Plan"] = {}
+        self._flatten_params()
+        self._build_weights()
+        self.step_count = 0
+
+    # ------------------------------------------------------------------ parameters
+    def invalidate(self):
+        self.m._engine = None
+
+    def _flatten_params(self):
+        dev = self.device
+        names, params = zip(*list(self.m.named_parameters()))
+        offs, tot = [], 0
+        for p in params:
+            if p.dtype != torch.float32:
+                raise RuntimeError("scrubvae_b200: parameters must be float32")
+            offs.append(tot)
+            tot += pad4(p.numel())
+        self.n_flat = tot
+        self.flat = torch.zeros(tot, device=dev)
+        self.gflat = torch.zeros(tot, device=dev)
+        self.poff: Dict[str, int] = {}
+        self.gviews: List[torch.Tensor] = []
+        self.params = list(params)
+        with torch.no_grad():
+            for n, p, o in zip(names, params, offs):
+                v = self.flat[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                p.grad = None
+                self.poff[n] = o
+                self.gviews.append(self.gflat[o:o + p.numel()].view(p.shape))
+        # one counter tensor behind all BatchNorm num_batches_tracked buffers (one add per step)
+        bns = [(n, mod) for n, mod in self.m.named_modules() if isinstance(mod, nn.BatchNorm1d)]
+        self.nbt = torch.zeros(max(1, len(bns)), dtype=torch.long, device=dev)
+        for i, (_, mod) in enumerate(bns):
+            self.nbt[i] = mod.num_batches_tracked.to(dev)
+            mod.num_batches_tracked = self.nbt[i]
+        self.bn_index = {n: i for i, (n, _) in enumerate(bns)}
+
+    def pref(self, name: str) -> Ref:
+        return Ref(self.flat, self.poff[name])
+
+    def gref(self, name: str) -> Ref:
+        return Ref(self.gflat, self.poff[name])
+
+    def _idx(self, name: str) -> torch.Tensor:
+        p = dict(self.m.named_parameters())[name]
+        return (self.poff[name] + torch.arange(p.numel())).view(p.shape)
+
+    # ------------------------------------------------------------------ packed weights
+    def _build_weights(self):
+        m = self.m
+        ch, k, z, W = m.ch, m.kernel, m.z_dim, m.window
+        self.C0 = pad4(m.in_channels)
+        self.nblk = len(ch) - 1
+        self.W: Dict[str, GemmW] = {}
+        self._pack_parts: List[torch.Tensor] = []   # forward matrices + biases (have gradients)
+        self._pack_parts_d: List[torch.Tensor] = []  # dgrad matrices
+        self._n_fwd = 0
+        self._n_d = 0
+        I = self._idx
+
+        def add(name, w_idx, b_idx=None, bias_mod=None, d_idx=None):
+            g = GemmW()
+            g.name = name
+            g.N, g.K = w_idx.shape
+            assert g.K % 4 == 0, (name, g.K)
+            g.w = self._n_fwd
+            self._pack_parts.append(w_idx.reshape(-1))
+            self._n_fwd += pad4(w_idx.numel())
+            if w_idx.numel() % 4:
+                self._pack_parts.append(torch.full((pad4(w_idx.numel()) - w_idx.numel(),), -1, dtype=torch.long))
+            if b_idx is not None:
+                nb = pad4(b_idx.numel())
+                g.b = self._n_fwd
+                g.bias_mod = bias_mod or b_idx.numel()
+                self._pack_parts.append(lay.pad_cols(b_idx.reshape(1, -1), nb).reshape(-1))
+                self._n_fwd += nb
+            else:
+                g.b, g.bias_mod = None, 1
+            if d_idx is not None:
+                g.dN, g.dK = d_idx.shape
+                assert g.dK % 4 == 0, (name, g.dK)
+                g.wd = self._n_d
+                self._pack_parts_d.append(d_idx.reshape(-1))
+                self._n_d += pad4(d_idx.numel())
+                if d_idx.numel() % 4:
+                    self._pack_parts_d.append(torch.full((pad4(d_idx.numel()) - d_idx.numel(),), -1, dtype=torch.long))
+            else:
+                g.wd = None
+            self.W[name] = g
+            return g
+
+        e = "encoder."
+        add("enc.conv_in", lay.conv_fprop(I(e + "conv_in.weight"), self.C0), I(e + "conv_in.bias"))
+        for i in range(self.nblk):
+            b = f"{e}res_layers.{i}."
+            add(f"enc.{i}.skip", lay.conv_fprop(I(b + "skip.weight")), I(b + "skip.bias"),
+                d_idx=lay.conv_dgrad_s2(I(b + "skip.weight")))
+            add(f"enc.{i}.r0", lay.conv_fprop(I(b + "residual.0.weight")), I(b + "residual.0.bias"),
+                d_idx=lay.conv_dgrad_s2(I(b + "residual.0.weight")))
+            add(f"enc.{i}.r3", lay.conv_fprop(I(b + "residual.3.weight")), I(b + "residual.3.bias"),
+                d_idx=lay.conv_dgrad_s1(I(b + "residual.3.weight")))
+        from .model.residual import find_latent_dim, find_out_dim
+        self.Ll = find_latent_dim(W, k, self.nblk)
+        self.Cl = ch[-1]
+        self.nsig = z * (z + 1) // 2
+        self.ms_ld = pad16(z + self.nsig)
+        wf = torch.cat([lay.fc_enc_fprop(I(e + "fc_mu.weight"), self.Cl, self.Ll),
+                        lay.fc_enc_fprop(I(e + "fc_sigma.0.weight"), self.Cl, self.Ll)], 0)
+        wf = lay.pad_rows(wf, self.ms_ld)
+        bf = lay.pad_cols(torch.cat([I(e + "fc_mu.bias"), I(e + "fc_sigma.0.bias")]).reshape(1, -1), self.ms_ld)
+        add("enc.fc", wf, bf.reshape(-1), d_idx=lay.transpose_pad(wf, self.ms_ld))
+
+        d = "decoder."
+        self.cond_dim = m.conditional_dim
+        self.zc_ld = pad4(z + self.cond_dim)
+        wfi = lay.fc_dec_fprop(I(d + "fc_in.weight"), self.Cl, self.Ll, self.zc_ld)
+        add("dec.fc_in", wfi, lay.fc_dec_bias(I(d + "fc_in.bias"), self.Cl, self.Ll),
+            d_idx=lay.transpose_pad(wfi, self.Ll * self.Cl))
+        for i in range(self.nblk):
+            b = f"{d}res_layers.{i}."
+            add(f"dec.{i}.skip", lay.conv_fprop(I(b + "skip.1.weight")), I(b + "skip.1.bias"),
+                d_idx=lay.conv_dgrad_s1(I(b + "skip.1.weight")))
+            add(f"dec.{i}.r0", lay.convT_fprop_s1(I(b + "residual.0.weight"), k // 2), I(b + "residual.0.bias"),
+                d_idx=lay.convT_dgrad(I(b + "residual.0.weight")))
+            co = I(b + "residual.3.bias").numel()
+            add(f"dec.{i}.r3", lay.convT_fprop_s2(I(b + "residual.3.weight")), I(b + "residual.3.bias"), bias_mod=co,
+                d_idx=lay.convT_dgrad(I(b + "residual.3.weight")))
+        self.l_dec = find_out_dim(self.Ll, k, self.nblk)
+        self.kf = W - self.l_dec + 7
+        add("dec.conv_out", lay.convT_fprop_s1(I(d + "conv_out.weight"), 3, self.C0),
+            lay.pad_cols(I(d + "conv_out.bias").reshape(1, -1), self.C0).reshape(-1),
+            d_idx=lay.convT_dgrad(I(d + "conv_out.weight"), self.C0))
+
+        # gradient-reversal heads: model/disentangle.py:583-632
+        self.gr_keys: List[str] = []
+        self.gr_layers: Dict[str, List[List[GemmW]]] = {}
+        self.gr_alpha: Dict[str, float] = {}
+        if "grad_reversal" in m.disentangle:
+            for key, scr in m.disentangle["grad_reversal"].items():
+                self.gr_keys.append(key)
+                self.gr_alpha[key] = float(scr.reversal[0].alpha)
+                pre = f"disentangle.grad_reversal.{key}.reversal.1."
+                mlps = []
+                for mi, mlp in enumerate(scr.reversal[1].members()):
+                    layers = []
+                    for li, mod in enumerate(mlp):
+                        if not isinstance(mod, nn.Linear):
+                            continue
+                        wi = I(f"{pre}mlp{mi + 1}.{li}.weight")
+                        assert wi.shape[1] % 4 == 0, "scrubvae_b200: z_dim must be a multiple of 8"
+                        npad = pad4(wi.shape[0])
+                        g = add(f"gr.{key}.{mi}.{li}", lay.pad_rows(wi, npad),
+                                lay.pad_cols(I(f"{pre}mlp{mi + 1}.{li}.bias").reshape(1, -1), npad).reshape(-1),
+                                d_idx=lay.transpose_pad(lay.pad_rows(wi, npad), npad))
+                        layers.append(g)
+                    mlps.append(layers)
+                self.gr_layers[key] = mlps
+
+        dev = self.device
+        fwd_idx = torch.cat(self._pack_parts)
+        d_idx = torch.cat(self._pack_parts_d) if self._pack_parts_d else torch.zeros(0, dtype=torch.long)
+        assert fwd_idx.numel() == self._n_fwd and d_idx.numel() == self._n_d
+        self.pack_idx = torch.cat([fwd_idx, d_idx]).to(torch.int32).to(dev)
+        self.packed = torch.zeros(self._n_fwd + self._n_d, device=dev)
+        self.gpacked = torch.zeros(self._n_fwd, device=dev)
+        self.inv_idx = lay.inverse_map(fwd_idx, self.n_flat).to(torch.int32).to(dev)
+        del self._pack_parts, self._pack_parts_d
+        self.max_k = max(max(g.K, g.dK if g.wd is not None else 0) for g in self.W.values())
+
+    def wref(self, g: GemmW) -> Ref:
+        return Ref(self.packed, g.w)
+
+    def bref(self, g: GemmW) -> Optional[Ref]:
+        return None if g.b is None else Ref(self.packed, g.b)
+
+    def wdref(self, g: GemmW) -> Ref:
+        return Ref(self.packed, self._n_fwd + g.wd)
+
+    def gwref(self, g: GemmW) -> Ref:
+        return Ref(self.gpacked, g.w)
+
+    def gbref(self, g: GemmW) -> Optional[Ref]:
+        return None if g.b is None else Ref(self.gpacked, g.b)
+
+    def repack(self):
+        self.ops.gather(self.flat, self.pack_idx, self.packed, self.packed.numel(), False)
+
+    # ------------------------------------------------------------------ API
+    def plan(self, B: int) -> "Plan":
+        p = self.plans.get(B)
+        if p is None:
+            p = Plan(self, B)
+            self.plans[B] = p
+        return p
+
+    def forward(self, data, training: bool):
+        B = data["x6d"].shape[0]
+        return self.plan(B).forward(data, training)
+
+    def encode(self, data, training: bool):
+        B = data["x6d"].shape[0]
+        return self.plan(B).forward(data, training, upto="encode")
+
+    def decode(self, z, data, training: bool):
+        B = z.shape[0]
+        return self.plan(B).forward(data, training, z_given=z)
+
+
+class Plan:
+    """Static buffers + launch lists for one batch size."""
+
+    def __init__(self, eng: Engine, B: int):
+        self.eng, self.B = eng, B
+        m, dev, ops = eng.m, eng.device, eng.ops
+        ch, k, z, W = m.ch, m.kernel, m.z_dim, m.window
+        self.J = (m.in_channels - 3) // 6
+        self.nx = self.J * 6
+        C0 = eng.C0
+        prec = eng.precision
+        slack = eng.max_k + 64
+        p2 = k // 2
+        f32 = dict(device=dev, dtype=torch.float32)
+        A = lambda L, C, hl=0, hr=0, even=False: Act(dev, B, L, C, hl, hr, even, slack)  # noqa: E731
+
+        # ---- static inputs
+        self.inp = {
+            "x6d": torch.zeros(B, W, self.J, 6, **f32), "root": torch.zeros(B, W, 3, **f32),
+            "offsets": torch.zeros(B, W, self.J, 3, **f32), "target_pose": torch.zeros(B, W, self.J, 3, **f32),
+        }
+        self.var = torch.zeros(B, max(1, eng.cond_dim), **f32)
+        self.eps = torch.zeros(B, z, **f32)
+        self.gr_target: Dict[str, torch.Tensor] = {}
+        self.gr_labels: Dict[str, torch.Tensor] = {}
+        self.gr_dim: Dict[str, int] = {}
+        for key in eng.gr_keys:
+            dimk = eng.gr_layers[key][0][-1].N  # padded
+            true_d = dict(m.named_parameters())[f"disentangle.grad_reversal.{key}.reversal.1.mlp1.4.bias"].numel()
+            self.gr_dim[key] = true_d
+            if key == "ids":
+                self.gr_labels[key] = torch.zeros(B, dtype=torch.long, device=dev)
+            else:
+                self.gr_target[key] = torch.zeros(B, true_d, **f32)
+        if isinstance(m.kinematic_tree, (list, tuple)) and len(m.kinematic_tree) > 0:
+            tr = [len(m.kinematic_tree)]
+            for chain in m.kinematic_tree:
+                tr += [len(chain)] + [int(j) for j in chain]
+            self.tree = torch.tensor(tr, dtype=torch.int32, device=dev)
+        else:
+            self.tree = None
+        arena = m.arena_size
+
+        # ---- loss bookkeeping: acc (double) / out (float): [jpe, root, prior, gr keys...]
+        self.loss_names = ["jpe", "root", "prior"] + [kk + "_gr" for kk in eng.gr_keys]
+        nl = len(self.loss_names)
+        self.loss_acc = torch.zeros(nl, dtype=torch.double, device=dev)
+        self.loss_out = torch.zeros(nl + 1, **f32)
+        self.anchor = torch.zeros((), device=dev, requires_grad=True)  # autograd attachment point
+        self.loss_scale = torch.zeros(nl, **f32)    # total = sum scale*loss
+        self.gscale = torch.zeros(nl, **f32)        # d total / d loss_k used by backward
+        self._scale_host = None
+
+        # ---- BN statistics / backward sums (double), zeroed once per step
+        nbn = sum(mod.num_features for mod in m.modules() if isinstance(mod, nn.BatchNorm1d))
+        self.stats = torch.zeros(4 * nbn + 8, dtype=torch.double, device=dev)
+        self.sums = torch.zeros(2 * nbn + 2 * ch[0] + 64, dtype=torch.double, device=dev)
+        self._stats_n = 0
+        self._sums_n = 0
+
+        def stats(n):
+            o = self._stats_n
+            self._stats_n += 2 * n
+            assert self._stats_n <= self.stats.numel()
+            return Ref(self.stats, o)
+
+        def sums(c):
+            o = self._sums_n
+            self._sums_n += 2 * c + 1
+            assert self._sums_n <= self.sums.numel()
+            return Ref(self.sums, o)
+
+        F: List = []   # forward launches (training flag read at run time)
+        E: List = []   # encoder part of F ends at this index
+        Bk: List = []  # backward launches, appended in FORWARD order as groups; run reversed
+        self._training = True
+
+        def bn_mode(has_bn=True, has_act=True):
+            return (BN if has_bn else 0) | (PRELU if has_act else 0)
+
+        def gemm(**kw):
+            kw.setdefault("precision", prec)
+            F.append(lambda: ops.gemm(**kw))
+
+        def bnact_fwd(bn_name, slope_name, X, L, Cc, st_off, fold, H=None, U=None):
+            kw = dict(X=X.at(0), x_bs=X.bs, x_ls=X.ls, B=B, L=L, Cc=Cc, fold=fold, count=float(B * L), eps=1e-4,
+                      momentum=0.1, slope=eng.pref(slope_name) if slope_name else None)
+            if bn_name:
+                mod = m.get_submodule(bn_name)
+                kw.update(gamma=eng.pref(bn_name + ".weight"), beta=eng.pref(bn_name + ".bias"),
+                          running_mean=Ref(mod.running_mean), running_var=Ref(mod.running_var), eps=mod.eps,
+                          momentum=mod.momentum)
+            if H is not None:
+                kw.update(H=H.at(0), h_bs=H.bs, h_ls=H.ls)
+            if U is not None:
+                kw.update(U=U.at(0), u_bs=U.bs, u_ls=U.ls)
+            base = bn_mode(bool(bn_name), bool(slope_name))
+
+            def run():
+                mode = base | (TRAIN if (self._training and bn_name) else 0)
+                ops.bnact_fwd(mode=mode, stats=st_off if bn_name else None, **kw)
+            F.append(run)
+
+        def bnact_bwd(bn_name, slope_name, X, L, Cc, st_off, fold, dO, dU, dX, sm_off):
+            """returns the two backward launches (reduce, apply) for the same geometry"""
+            mode = bn_mode(bool(bn_name), bool(slope_name)) | (TRAIN if bn_name else 0)
+            kw = dict(X=X.at(0), x_bs=X.bs, x_ls=X.ls, B=B, L=L, Cc=Cc, mode=mode, fold=fold, count=float(B * L),
+                      eps=1e-4, slope=eng.pref(slope_name) if slope_name else None)
+            if bn_name:
+                kw.update(gamma=eng.pref(bn_name + ".weight"), beta=eng.pref(bn_name + ".bias"),
+                          eps=m.get_submodule(bn_name).eps)
+            if dO is not None:
+                kw.update(dO=dO.at(0), o_bs=dO.bs, o_ls=dO.ls)
+            if dU is not None:
+                kw.update(dU=dU.at(0), u_bs=dU.bs, u_ls=dU.ls)
+            out = []
+            if mode & 3:
+                out.append(lambda: ops.bnact_bwd_reduce(sums=sm_off, stats=st_off if bn_name else None, **kw))
+            akw = dict(kw)
+            akw.update(dX=dX.at(0) if dX is not None else None, d_bs=dX.bs if dX is not None else 0,
+                       d_ls=dX.ls if dX is not None else 0,
+                       dgamma=eng.gref(bn_name + ".weight") if bn_name else None,
+                       dbeta=eng.gref(bn_name + ".bias") if bn_name else None,
+                       dslope=eng.gref(slope_name) if slope_name else None)
+            out.append(lambda: ops.bnact_bwd_apply(sums=sm_off if (mode & 3) else None,
+                                                   stats=st_off if bn_name else None, **akw))
+            return out
+
+        def wgrad(g: GemmW, Aref, a_bs, a_ls, Lo, dY, y_bs, y_ls, bias_n=None):
+            kw = dict(A=Aref, a_bs=a_bs, a_ls=a_ls, B=B, Lo=Lo, K=g.K, N=g.N, dY=dY, y_bs=y_bs, y_ls=y_ls,
+                      dW=eng.gwref(g), dbias=eng.gbref(g), bias_mod=g.bias_mod,
+                      bias_n=(g.N if bias_n is None else bias_n) if g.b is not None else 0, precision=prec)
+            return lambda: ops.wgrad(**kw)
+
+        def dgemm(g: GemmW, Aref, a_bs, a_ls, Lo, Y, y_bs, y_ls, n_last=None, R=None, r_bs=0, r_ls=0, act=ACT_NONE,
+                  out_scale=1.0):
+            kw = dict(A=Aref, a_bs=a_bs, a_ls=a_ls, B=B, Lo=Lo, K=g.dK, N=g.dN, W=eng.wdref(g), Y=Y, y_bs=y_bs,
+                      y_ls=y_ls, n_last=n_last, R=R, r_bs=r_bs, r_ls=r_ls, act=act, out_scale=out_scale,
+                      precision=prec)
+            return lambda: ops.gemm(**kw)
+
+        WG = eng.W
+        # =============================================================== encoder
+        X0 = A(W, C0, 3, 3)
+        self.X0 = X0
+        F.append(lambda: ops.pack_input(self.inp["x6d"], self.inp["root"], arena, X0.t, B, W, self.nx, C0, 3))
+        Y0 = A(W, ch[0])
+        g = WG["enc.conv_in"]
+        gemm(A=X0.at(-3), a_bs=X0.bs, a_ls=C0, B=B, Lo=W, K=g.K, N=g.N, W=eng.wref(g), bias=eng.bref(g),
+             bias_mod=g.bias_mod, bias_n=g.N, Y=Y0.at(0), y_bs=Y0.bs, y_ls=Y0.ls)
+        H = A(W, ch[0], p2, p2, even=True)
+        bnact_fwd(None, "encoder.activation.weight", Y0, W, ch[0], None, 1, H=H)
+        enc_in = dict(Y0=Y0, H0=H, g=g)
+        L = W
+        enc_blocks = []
+        for i in range(eng.nblk):
+            Ci, Co = ch[i], ch[i + 1]
+            Lo = (L + 2 * p2 - k) // 2 + 1
+            pre = f"encoder.res_layers.{i}."
+            gs, g0, g3 = WG[f"enc.{i}.skip"], WG[f"enc.{i}.r0"], WG[f"enc.{i}.r3"]
+            S, R0 = A(Lo, Co), A(Lo, Co // 2)
+            gemm(A=H.at(-p2), a_bs=H.bs, a_ls=2 * Ci, B=B, Lo=Lo, K=gs.K, N=gs.N, W=eng.wref(gs), bias=eng.bref(gs),
+                 bias_mod=gs.bias_mod, bias_n=gs.N, Y=S.at(0), y_bs=S.bs, y_ls=S.ls)
+            st1 = stats(Co // 2)
+            gemm(A=H.at(-p2), a_bs=H.bs, a_ls=2 * Ci, B=B, Lo=Lo, K=g0.K, N=g0.N, W=eng.wref(g0), bias=eng.bref(g0),
+                 bias_mod=g0.bias_mod, bias_n=g0.N, Y=R0.at(0), y_bs=R0.bs, y_ls=R0.ls, stats=st1)
+            R0a = A(Lo, Co // 2, p2, p2)
+            bnact_fwd(pre + "residual.1", pre + "residual.2.weight", R0, Lo, Co // 2, st1, 1, H=R0a)
+            T = A(Lo, Co)
+            st2 = stats(Co)
+            gemm(A=R0a.at(-p2), a_bs=R0a.bs, a_ls=Co // 2, B=B, Lo=Lo, K=g3.K, N=g3.N, W=eng.wref(g3),
+                 bias=eng.bref(g3), bias_mod=g3.bias_mod, bias_n=g3.N, Y=T.at(0), y_bs=T.bs, y_ls=T.ls,
+                 R=S.at(0), r_bs=S.bs, r_ls=S.ls, stats=st2)
+            last = i == eng.nblk - 1
+            Hn = A(Lo, Co) if last else A(Lo, Co, p2, p2, even=True)
+            bnact_fwd(pre + "add.0", pre + "add.1.weight", T, Lo, Co, st2, 1, H=Hn)
+            enc_blocks.append(dict(pre=pre, Hin=H, Lin=L, Ci=Ci, Co=Co, Lo=Lo, S=S, R0=R0, R0a=R0a, T=T, Hn=Hn,
+                                   st1=st1, st2=st2, gs=gs, g0=g0, g3=g3))
+            H, L = Hn, Lo
+        assert L == eng.Ll
+        Hflat = H
+        self.ms = torch.zeros(B, eng.ms_ld, **f32)
+        gfc = WG["enc.fc"]
+        gemm(A=Hflat.at(0), a_bs=Hflat.bs, a_ls=0, B=B, Lo=1, K=gfc.K, N=gfc.N, W=eng.wref(gfc), bias=eng.bref(gfc),
+             bias_mod=gfc.bias_mod, bias_n=gfc.N, Y=self.ms, y_bs=eng.ms_ld, y_ls=0)
+        self.mu = torch.zeros(B, z, **f32)
+        self.Lmat = torch.zeros(B, z, z, **f32)
+        self.zc = torch.zeros(B, eng.zc_ld, **f32)
+
+        def reparam():
+            ops.reparam_fwd(self.ms, eng.ms_ld, self.eps if self._training else None,
+                            self.var if eng.cond_dim > 0 else None, eng.cond_dim, self.mu, self.Lmat, self.zc,
+                            eng.zc_ld, B, z)
+        F.append(reparam)
+        self._n_enc = len(F)
+
+        # =============================================================== decoder
+        Ll, Cl = eng.Ll, eng.Cl
+        gin = WG["dec.fc_in"]
+        H = A(Ll, Cl, p2, p2)
+        gemm(A=self.zc, a_bs=eng.zc_ld, a_ls=0, B=B, Lo=1, K=gin.K, N=gin.N, W=eng.wref(gin), bias=eng.bref(gin),
+             bias_mod=gin.bias_mod, bias_n=gin.N, Y=H.at(0), y_bs=H.bs, y_ls=0)
+        U = A(2 * Ll, Cl, p2, p2)
+        bnact_fwd(None, None, H, Ll, Cl, None, 1, U=U)
+        dec_in = dict(H=H, U=U, g=gin)
+        wl, wr = lay.poly_window(k)
+        hw = max(wl, wr)
+        L = Ll
+        dec_blocks = []
+        for i in range(eng.nblk):
+            Ci, Co = ch[-1 - i], ch[-2 - i]
+            pre = f"decoder.res_layers.{i}."
+            gs, g0, g3 = WG[f"dec.{i}.skip"], WG[f"dec.{i}.r0"], WG[f"dec.{i}.r3"]
+            Lo2 = 2 * L - 1
+            S = A(Lo2, Co)
+            gemm(A=U.at(-p2), a_bs=U.bs, a_ls=Ci, B=B, Lo=Lo2, K=gs.K, N=gs.N, W=eng.wref(gs), bias=eng.bref(gs),
+                 bias_mod=gs.bias_mod, bias_n=gs.N, Y=S.at(0), y_bs=S.bs, y_ls=S.ls)
+            R0 = A(L, Ci // 2)
+            st1 = stats(Ci // 2)
+            gemm(A=H.at(-p2), a_bs=H.bs, a_ls=Ci, B=B, Lo=L, K=g0.K, N=g0.N, W=eng.wref(g0), bias=eng.bref(g0),
+                 bias_mod=g0.bias_mod, bias_n=g0.N, Y=R0.at(0), y_bs=R0.bs, y_ls=R0.ls, stats=st1)
+            R0a = A(L, Ci // 2, hw, hw)
+            bnact_fwd(pre + "residual.1", pre + "residual.2.weight", R0, L, Ci // 2, st1, 1, H=R0a)
+            T = A(Lo2, Co)
+            st2 = stats(2 * Co)
+            gemm(A=R0a.at(-wl), a_bs=R0a.bs, a_ls=Ci // 2, B=B, Lo=L, K=g3.K, N=g3.N, W=eng.wref(g3),
+                 bias=eng.bref(g3), bias_mod=Co, bias_n=2 * Co, Y=T.at(0), y_bs=T.bs, y_ls=2 * Co, n_last=Co,
+                 R=S.at(0), r_bs=S.bs, r_ls=2 * Co, stats=st2)
+            last = i == eng.nblk - 1
+            if last:
+                ho = eng.kf - 1 - 3
+                Hn, Un = A(Lo2, Co, ho, ho), None
+            else:
+                Hn, Un = A(Lo2, Co, p2, p2), A(2 * Lo2, Co, p2, p2)
+            bnact_fwd(pre + "add.0", pre + "add.1.weight", T, Lo2, Co, st2, 2, H=Hn, U=Un)
+            dec_blocks.append(dict(pre=pre, H=H, U=U, L=L, Ci=Ci, Co=Co, Lo2=Lo2, S=S, R0=R0, R0a=R0a, T=T, Hn=Hn,
+                                   Un=Un, st1=st1, st2=st2, gs=gs, g0=g0, g3=g3))
+            H, U, L = Hn, Un, Lo2
+        assert L == eng.l_dec
+        gout = WG["dec.conv_out"]
+        self.xh = torch.zeros(B * W, C0, **f32)
+        ho = eng.kf - 1 - 3
+        gemm(A=H.at(-ho), a_bs=H.bs, a_ls=ch[0], B=B, Lo=W, K=gout.K, N=gout.N, W=eng.wref(gout),
+             bias=eng.bref(gout), bias_mod=gout.bias_mod, bias_n=gout.N, Y=self.xh, y_bs=W * C0, y_ls=C0,
+             act=ACT_TANH)
+        self.root_hat = torch.zeros(B, W, 3, **f32)
+        F.append(lambda: ops.unpack_root(self.xh, C0, self.nx, arena, self.root_hat, B * W))
+        Hlast = H
+
+        # =============================================================== scrubber heads (forward)
+        self.dmu_gr = torch.zeros(B, z, **f32) if eng.gr_keys else None
+        self.gr_act: Dict[str, List[List[torch.Tensor]]] = {}
+        self.gr_dact: Dict[str, List[List[torch.Tensor]]] = {}
+        for key in eng.gr_keys:
+            acts_k, dacts_k = [], []
+            for layers in eng.gr_layers[key]:
+                acts, dacts = [], []
+                hin, kin = self.mu, z
+                for li, gl in enumerate(layers):
+                    out = torch.zeros(B, gl.N, **f32)
+                    lastl = li == len(layers) - 1
+                    gemm(A=hin, a_bs=kin, a_ls=0, B=B, Lo=1, K=gl.K, N=gl.N, W=eng.wref(gl), bias=eng.bref(gl),
+                         bias_mod=gl.bias_mod, bias_n=gl.N, Y=out, y_bs=gl.N, y_ls=0,
+                         act=ACT_NONE if lastl else ACT_RELU, precision=0)
+                    acts.append(out)
+                    dacts.append(torch.zeros(B, gl.N, **f32))
+                    hin, kin = out, gl.N
+                acts_k.append(acts)
+                dacts_k.append(dacts)
+            self.gr_act[key], self.gr_dact[key] = acts_k, dacts_k
+
+        self.F = F
+
+        # =============================================================== loss launches
+        self.dxh = torch.zeros(B * W, C0, **f32)
+        Lk: List = []
+        Lk.append(lambda: self.loss_acc.zero_())
+        self._loss_has = {"jpe": False, "root": False, "prior": False}
+
+        def recon():
+            if self.tree is None:
+                raise RuntimeError("scrubvae_b200: the jpe loss needs model.kinematic_tree")
+            ops.recon_loss(self.xh, C0, self.inp["offsets"], self.inp["target_pose"], self.inp["root"], arena,
+                           self.tree, self.tree.numel(), self.loss_acc, None, self.dxh, B * W, B, self.J)
+        Lk.append(recon)
+        Lk.append(lambda: ops.kl(self.mu, self.Lmat, Ref(self.loss_acc, 2), None, None, None, B, z))
+        for ki, key in enumerate(eng.gr_keys):
+            preds = [Ref(a[-1]) for a in self.gr_act[key]]
+            ld = self.gr_act[key][0][-1].shape[1]
+            Lk.append(lambda preds=preds, ld=ld, key=key, ki=ki: ops.gr_loss(
+                preds, None, ld, self.gr_target.get(key), self.gr_labels.get(key), B, self.gr_dim[key],
+                len(eng.gr_keys), Ref(self.loss_acc, 3 + ki), None))
+        Lk.append(lambda: ops.loss_finalize(self.loss_acc, self.loss_scale, self.loss_out, nl))
+        self.Lk = Lk
+
+        # =============================================================== backward launches
+        Bw: List = []
+
+        def zero_grads():
+            self.sums.zero_()
+            eng.gpacked.zero_()
+            eng.gflat.zero_()
+        Bw.append(zero_grads)
+        # conv_out + tanh
+        dOut = A(W, C0, 3, 3)
+        Bw.append(lambda: ops.out_bwd(self.xh, self.dxh, C0, Ref(self.gscale, 0), Ref(self.gscale, 1), self.nx,
+                                      dOut.at(0), dOut.bs, dOut.ls, B, W))
+        Bw.append(wgrad(gout, Hlast.at(-ho), Hlast.bs, ch[0], W, dOut.at(0), dOut.bs, dOut.ls))
+        dH = A(eng.l_dec, ch[0])
+        Bw.append(dgemm(gout, dOut.at(-3), dOut.bs, C0, eng.l_dec, dH.at(0), dH.bs, dH.ls))
+        dU = None
+        for blk in reversed(dec_blocks):
+            Ci, Co, L, Lo2, pre = blk["Ci"], blk["Co"], blk["L"], blk["Lo2"], blk["pre"]
+            gs, g0, g3 = blk["gs"], blk["g0"], blk["g3"]
+            dT = A(Lo2, Co, k - p2, p2 + 1, even=True)
+            Bw += bnact_bwd(pre + "add.0", pre + "add.1.weight", blk["T"], Lo2, Co, blk["st2"], 2, dH, dU, dT,
+                            sums(Co))
+            # skip conv (k+1, stride 1, pad k//2) on the upsampled input
+            Bw.append(wgrad(gs, blk["U"].at(-p2), blk["U"].bs, Ci, Lo2, dT.at(0), dT.bs, dT.ls))
+            dUin = A(2 * L, Ci)
+            hl_s = (k + 1) - 1 - p2
+            Bw.append(dgemm(gs, dT.at(-hl_s), dT.bs, Co, 2 * L, dUin.at(0), dUin.bs, dUin.ls))
+            # stride-2 transposed conv (polyphase forward; plain strided-window dgrad)
+            Bw.append(wgrad(g3, blk["R0a"].at(-wl), blk["R0a"].bs, Ci // 2, L, dT.at(0), dT.bs, 2 * Co,
+                            bias_n=2 * Co))
+            dR0a = A(L, Ci // 2)
+            Bw.append(dgemm(g3, dT.at(-p2), dT.bs, 2 * Co, L, dR0a.at(0), dR0a.bs, dR0a.ls))
+            dR0 = A(L, Ci // 2, p2, p2)
+            Bw += bnact_bwd(pre + "residual.1", pre + "residual.2.weight", blk["R0"], L, Ci // 2, blk["st1"], 1,
+                            dR0a, None, dR0, sums(Ci // 2))
+            Bw.append(wgrad(g0, blk["H"].at(-p2), blk["H"].bs, Ci, L, dR0.at(0), dR0.bs, dR0.ls))
+            dHin = A(L, Ci)
+            Bw.append(dgemm(g0, dR0.at(-p2), dR0.bs, Ci // 2, L, dHin.at(0), dHin.bs, dHin.ls))
+            dH, dU = dHin, dUin
+        # fc_in (input of decoder block 0 has no BN / activation: only the upsample transpose)
+        dX0 = A(Ll, Cl)
+        Bw += bnact_bwd(None, None, dec_in["H"], Ll, Cl, None, 1, dH, dU, dX0, None)
+        Bw.append(wgrad(gin, self.zc, eng.zc_ld, 0, 1, dX0.at(0), dX0.bs, 0))
+        self.dzc = torch.zeros(B, eng.zc_ld, **f32)
+        Bw.append(dgemm(gin, dX0.at(0), dX0.bs, 0, 1, self.dzc, eng.zc_ld, 0))
+        # scrubber heads
+        for ki, key in enumerate(eng.gr_keys):
+            preds = [Ref(a[-1]) for a in self.gr_act[key]]
+            dpreds = [Ref(d[-1]) for d in self.gr_dact[key]]
+            ld = self.gr_act[key][0][-1].shape[1]
+            Bw.append(lambda preds=preds, dpreds=dpreds, ld=ld, key=key, ki=ki: ops.gr_loss(
+                preds, dpreds, ld, self.gr_target.get(key), self.gr_labels.get(key), B, self.gr_dim[key],
+                len(eng.gr_keys), None, Ref(self.gscale, 3 + ki)))
+            for mi, layers in enumerate(eng.gr_layers[key]):
+                acts, dacts = self.gr_act[key][mi], self.gr_dact[key][mi]
+                for li in range(len(layers) - 1, -1, -1):
+                    gl = layers[li]
+                    hin, kin = (acts[li - 1], layers[li - 1].N) if li > 0 else (self.mu, z)
+                    kw = dict(A=hin, a_bs=kin, a_ls=0, B=B, Lo=1, K=gl.K, N=gl.N, dY=dacts[li], y_bs=gl.N, y_ls=0,
+                              dW=eng.gwref(gl), dbias=eng.gbref(gl), bias_mod=gl.bias_mod, bias_n=gl.N, precision=0)
+                    Bw.append(lambda kw=kw: ops.wgrad(**kw))
+                    if li > 0:
+                        kw2 = dict(A=dacts[li], a_bs=gl.N, a_ls=0, B=B, Lo=1, K=gl.dK, N=gl.dN, W=eng.wdref(gl),
+                                   Y=dacts[li - 1], y_bs=gl.dN, y_ls=0, R=acts[li - 1], r_bs=gl.dN, r_ls=0,
+                                   act=ACT_RELUMASK, precision=0)
+                    else:  # gradient reversal: -alpha * g accumulated over ensemble members and keys
+                        first = ki == 0 and mi == 0
+                        kw2 = dict(A=dacts[li], a_bs=gl.N, a_ls=0, B=B, Lo=1, K=gl.dK, N=gl.dN, W=eng.wdref(gl),
+                                   Y=self.dmu_gr, y_bs=z, y_ls=0, R=None if first else self.dmu_gr, r_bs=z, r_ls=0,
+                                   out_scale=-eng.gr_alpha[key], precision=0)
+                    Bw.append(lambda kw2=kw2: ops.gemm(**kw2))
+        # latent
+        self.dmu_kl = torch.zeros(B, z, **f32)
+        self.dL_kl = torch.zeros(B, z, z, **f32)
+        self.dms = torch.zeros(B, eng.ms_ld, **f32)
+        Bw.append(lambda: ops.kl(self.mu, self.Lmat, None, Ref(self.gscale, 2), self.dmu_kl, self.dL_kl, B, z))
+        Bw.append(lambda: ops.reparam_bwd(self.ms, eng.ms_ld, self.eps, self.dmu_kl, self.dmu_gr, 1.0, self.dzc,
+                                          eng.zc_ld, self.dL_kl, self.dms, eng.ms_ld, B, z))
+        Bw.append(wgrad(gfc, Hflat.at(0), Hflat.bs, 0, 1, self.dms, eng.ms_ld, 0))
+        dH = A(Ll, Cl)
+        Bw.append(dgemm(gfc, self.dms, eng.ms_ld, 0, 1, dH.at(0), dH.bs, 0))
+        for bi, blk in reversed(list(enumerate(enc_blocks))):
+            Ci, Co, Lo, Lin, pre = blk["Ci"], blk["Co"], blk["Lo"], blk["Lin"], blk["pre"]
+            gs, g0, g3 = blk["gs"], blk["g0"], blk["g3"]
+            dT = A(Lo, Co, p2, p2)
+            Bw += bnact_bwd(pre + "add.0", pre + "add.1.weight", blk["T"], Lo, Co, blk["st2"], 1, dH, None, dT,
+                            sums(Co))
+            Bw.append(wgrad(g3, blk["R0a"].at(-p2), blk["R0a"].bs, Co // 2, Lo, dT.at(0), dT.bs, dT.ls))
+            dR0a = A(Lo, Co // 2)
+            Bw.append(dgemm(g3, dT.at(-(k - 1 - p2)), dT.bs, Co, Lo, dR0a.at(0), dR0a.bs, dR0a.ls))
+            dR0 = A(Lo, Co // 2, hw, hw)
+            Bw += bnact_bwd(pre + "residual.1", pre + "residual.2.weight", blk["R0"], Lo, Co // 2, blk["st1"], 1,
+                            dR0a, None, dR0, sums(Co // 2))
+            Hin = blk["Hin"]
+            Bw.append(wgrad(g0, Hin.at(-p2), Hin.bs, 2 * Ci, Lo, dR0.at(0), dR0.bs, dR0.ls))
+            Bw.append(wgrad(gs, Hin.at(-p2), Hin.bs, 2 * Ci, Lo, dT.at(0), dT.bs, dT.ls))
+            dHin = A(Lin, Ci)
+            Lg = (Lin + 1) // 2
+            nlast = Ci if Lin % 2 else 2 * Ci
+            Bw.append(dgemm(gs, dT.at(-wl), dT.bs, Co, Lg, dHin.at(0), dHin.bs, 2 * Ci, n_last=nlast))
+            Bw.append(dgemm(g0, dR0.at(-wl), dR0.bs, Co // 2, Lg, dHin.at(0), dHin.bs, 2 * Ci, n_last=nlast,
+                            R=dHin.at(0), r_bs=dHin.bs, r_ls=2 * Ci))
+            dH = dHin
+        dY0 = A(W, ch[0])
+        Bw += bnact_bwd(None, "encoder.activation.weight", enc_in["Y0"], W, ch[0], None, 1, dH, None, dY0, sums(ch[0]))
+        g = enc_in["g"]
+        Bw.append(wgrad(g, X0.at(-3), X0.bs, C0, W, dY0.at(0), dY0.bs, dY0.ls))
+        Bw.append(lambda: ops.gather(eng.gpacked, eng.inv_idx, eng.gflat, eng.n_flat, True))
+        self.Bw = Bw
+
+    # ------------------------------------------------------------------ running
+    def load_inputs(self, data, need_loss_inputs: bool):
+        """Copies the batch into the static input buffers (skipped for tensors that already ARE them)."""
+        eng, m = self.eng, self.eng.m
+        for kname in ("x6d", "root") + (("offsets", "target_pose") if need_loss_inputs else ()):
+            if kname in data:
+                src = data[kname]
+                if src.data_ptr() != self.inp[kname].data_ptr():
+                    self.inp[kname].copy_(src.reshape(self.inp[kname].shape), non_blocking=True)
+        if eng.cond_dim > 0:
+            parts = []
+            for kk in m.conditional_keys:
+                if kk in m.discrete_classes:
+                    parts.append(torch.nn.functional.one_hot(data[kk].ravel().long(),
+                                                             len(m.discrete_classes[kk])).to(torch.float32))
+                else:
+                    parts.append(data[kk].to(torch.float32))
+            if len(parts) == 1:
+                self.var.copy_(parts[0], non_blocking=True)
+            else:
+                torch.cat(parts, dim=-1, out=self.var)
+
+    def load_targets(self, data):
+        for key in self.eng.gr_keys:
+            if key == "ids":
+                self.gr_labels[key].copy_(data[key].ravel(), non_blocking=True)
+            else:
+                self.gr_target[key].copy_(data[key].reshape(self.gr_target[key].shape), non_blocking=True)
+
+    def forward(self, data, training: bool, upto: Optional[str] = None, z_given=None):
+        eng, m = self.eng, self.eng.m
+        self._training = training
+        if z_given is None:
+            self.load_inputs(data, need_loss_inputs=False)
+            if training:
+                if m._noise is not None:
+                    self.eps.copy_(m._noise)
+                else:
+                    self.eps.normal_()
+                self.stats.zero_()
+                eng.nbt.add_(1)
+            eng.repack()
+            for f in (self.F[:self._n_enc] if upto == "encode" else self.F):
+                f()
+        else:  # decode(z, data): decoder only
+            self.load_inputs(data, need_loss_inputs=False)
+            if training:
+                self.stats.zero_()
+            eng.repack()
+            self.zc.zero_()
+            self.zc[:, :m.z_dim].copy_(z_given)
+            if eng.cond_dim > 0:
+                self.zc[:, m.z_dim:m.z_dim + eng.cond_dim].copy_(self.var)
+            nheads = sum(len(l) for kk in eng.gr_keys for l in eng.gr_layers[kk])
+            for f in self.F[self._n_enc:len(self.F) - nheads]:
+                f()
+        out = {}
+        if z_given is None:
+            out["mu"], out["L"] = self.mu, self.Lmat
+            if upto == "encode":
+                return out
+            out["z"] = self.zc[:, :m.z_dim]
+        if eng.cond_dim > 0:
+            out["var"] = self.var
+        B, W = self.B, m.window
+        out["root"] = self.root_hat
+        out["x6d"] = self.xh.view(B, W, -1)[..., :self.nx].unflatten(-1, (self.J, 6))
+        if z_given is None:
+            out["disentangle"] = {}
+            if eng.gr_keys:
+                out["disentangle"]["grad_reversal"] = {
+                    key: [a[-1][:, :self.gr_dim[key]] for a in self.gr_act[key]] for key in eng.gr_keys}
+            out["_plan"] = self
+        return out
+
+    def set_loss_scale(self, loss_scale: Dict[str, float]):
+        host = tuple(float(loss_scale.get(n, 0.0) or 0.0) for n in self.loss_names)
+        if host != self._scale_host:
+            self._scale_host = host
+            t = torch.tensor(host, dtype=torch.float32)
+            self.loss_scale.copy_(t)
+        return host
+
+    def loss(self, data, loss_scale):
+        self.load_inputs(data, need_loss_inputs=True)
+        self.load_targets(data)
+        self.set_loss_scale(loss_scale)
+        for f in self.Lk:
+            f()
+        return self.loss_out
+
+    def backward(self):
+        """Runs the backward launch list; `self.gscale` must hold d total / d loss_k."""
+        for f in self.Bw:
+            f()

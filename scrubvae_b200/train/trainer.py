@@ -1,0 +1,165 @@
+"""Step loop with the reference's function names, signatures and call order
+(reference train/trainer.py:26-212, :306-399): predict_batch -> get_batch_loss -> zero grads ->
+total.backward() -> clip_grad_norm_(1e6) -> optimizer.step() -> scheduler.step().
+
+Out of scope: test-time sklearn metrics, wandb logging, plotting, the non-GR scrubbers'
+EMA updates and the MI estimator rebuild."""
+from __future__ import annotations
+
+import time
+from pathlib import Path
+
+import torch
+import torch.optim as optim
+
+from .losses import get_batch_loss
+from .optim import FusedOptimizer
+
+
+class CyclicalBetaAnnealing:
+    """Reference train/trainer.py:26-40."""
+
+    def __init__(self, beta_max=1, len_cycle=100, R=0.5):
+        self.beta_max, self.len_cycle, self.R = beta_max, len_cycle, R
+        self.len_increasing = int(len_cycle * R)
+
+    def get(self, epoch):
+        remainder = (epoch - 1) % self.len_cycle
+        if remainder >= self.len_increasing:
+            return self.beta_max
+        return self.beta_max * remainder / self.len_increasing
+
+
+def get_beta_schedule(schedule, beta):
+    """Reference train/trainer.py:43-51."""
+    if schedule == "cyclical":
+        print("Initializing cyclical beta annealing")
+        return CyclicalBetaAnnealing(beta_max=beta)
+    print("No beta annealing selected")
+    return None
+
+
+def get_optimizer_and_lr_scheduler(model, train_config, load_path=None, start_epoch=None):
+    """Reference train/trainer.py:54-89; the optimizers are the fused single-launch versions."""
+    if train_config["optimizer"] == "adam":
+        print("Initializing Adam optimizer ...")
+        optimizer = FusedOptimizer(model, lr=train_config["lr"], kind="adam")
+    elif train_config["optimizer"] == "adamw":
+        print("Initializing AdamW optimizer ...")
+        optimizer = FusedOptimizer(model, lr=train_config["lr"], kind="adamw")
+    elif train_config["optimizer"] == "sgd":
+        print("Initializing SGD optimizer ...")
+        optimizer = FusedOptimizer(model, lr=train_config["lr"], kind="sgd", momentum=0.2)
+    else:
+        raise ValueError("No valid optimizer selected")
+
+    scheduler = None
+    if train_config["lr_schedule"] == "cawr":
+        print("Initializing cosine annealing w/warm restarts learning rate scheduler")
+        scheduler = optim.lr_scheduler.CosineAnnealingWarmRestarts(optimizer, T_0=50)
+    elif train_config["lr_schedule"] is None:
+        print("No learning rate scheduler selected")
+
+    if load_path is not None:
+        ck = Path("{}/checkpoints/epoch_{}.pth".format(load_path, start_epoch))
+        if ck.exists():
+            checkpoint = torch.load(ck, weights_only=False)
+            optimizer.load_state_dict(checkpoint["optimizer"])
+            scheduler = checkpoint["lr_scheduler"]
+    return optimizer, scheduler
+
+
+def clip_grad_norm_(parameters_or_model, max_norm):
+    """torch.nn.utils.clip_grad_norm_ as used at reference train/trainer.py:164.  The global L2 norm
+    is reduced by one kernel over the flat gradient buffer; the clip coefficient
+    min(1, max_norm/(norm+1e-6)) is applied inside the fused optimizer launch that follows."""
+    model = parameters_or_model
+    eng = model.engine
+    if not hasattr(eng, "sumsq"):
+        eng.sumsq = torch.zeros(1, dtype=torch.double, device=eng.device)
+    eng.sumsq.zero_()
+    eng.ops.sumsq(eng.gflat, eng.n_flat, eng.sumsq)
+    eng.clip = (eng.sumsq, float(max_norm))
+    return eng.sumsq
+
+
+def predict_batch(model, data, disentangle_keys=None):
+    """Reference train/trainer.py:92-99."""
+    data_i = {k: v for k, v in data.items() if (k in disentangle_keys) or (k in ["x6d", "root", "var"])}
+    return model(data_i)
+
+
+def train_test_epoch(config, model, loader, device, epoch, optimizer=None, scheduler=None, mode="train"):
+    """Reference train/trainer.py:101-212."""
+    if mode == "train":
+        model.train()
+        grad_env = torch.enable_grad
+    elif mode == "test":
+        model.eval()
+        grad_env = torch.no_grad
+    else:
+        raise ValueError("This mode is not recognized.")
+
+    with grad_env():
+        model.mi_estimator = None
+        epoch_metrics = {k: 0 for k in ["total"] + list(config["loss"].keys())}
+        for batch_idx, data in enumerate(loader):
+            data = {k: v.to(device, non_blocking=True) for k, v in data.items()}
+            data_o = predict_batch(model, data, model.disentangle_keys)
+            batch_loss = get_batch_loss(model, data, data_o, config["loss"], config["disentangle"])
+            if mode == "train":
+                for param in model.parameters():
+                    param.grad = None
+                batch_loss["total"].backward()
+                clip_grad_norm_(model, max_norm=1e6)
+                optimizer.step()
+                if scheduler is not None:
+                    scheduler.step(epoch + batch_idx / len(loader))
+            epoch_metrics = {k: v + batch_loss[k].detach() for k, v in epoch_metrics.items()}
+
+        for k, v in epoch_metrics.items():
+            epoch_metrics[k] = v.item() / len(loader)
+            print("====> Epoch: {} Average {} loss: {:.4f}".format(epoch, k, epoch_metrics[k]))
+    return epoch_metrics
+
+
+def train_epoch(config, model, loader, device, optimizer, scheduler, epoch):
+    """Reference train/trainer.py:306-318."""
+    return train_test_epoch(config, model, loader, device, epoch, optimizer, scheduler, mode="train")
+
+
+def test_epoch(config, model, loader, device="cuda", epoch=0):
+    """Loss part of reference train/trainer.py:215-303 (the sklearn decoders are out of scope)."""
+    return train_test_epoch(config, model, loader, device, epoch, mode="test")
+
+
+def train(config, model, loader_dict, run=None, device="cuda"):
+    """Epoch loop of reference train/trainer.py:321-399: beta annealing, train_epoch, per-epoch
+    re-initialisation of the GR scrubbers, weight / optimizer checkpoints."""
+    optimizer, scheduler = get_optimizer_and_lr_scheduler(
+        model, config["train"], config["model"]["load_model"], config["model"]["start_epoch"])
+    if "prior" in config["loss"].keys():
+        beta_scheduler = get_beta_schedule(config["loss"]["prior"], config["train"]["beta_anneal"])
+    else:
+        beta_scheduler = None
+    start = config["model"]["start_epoch"] or 0
+    metrics = {}
+    for epoch in range(start + 1, config["train"]["num_epochs"] + 1):
+        if beta_scheduler is not None:
+            config["loss"]["prior"] = beta_scheduler.get(epoch)
+            print("Beta schedule: {:.3f}".format(config["loss"]["prior"]))
+        t0 = time.time()
+        metrics = train_epoch(config, model, loader_dict["train"], device, optimizer, scheduler, epoch)
+        if "grad_reversal" in model.disentangle.keys():
+            for key in model.disentangle["grad_reversal"].keys():
+                model.disentangle["grad_reversal"][key].reset_parameters()
+        metrics["time"] = time.time() - t0
+        if epoch % 5 == 0:
+            Path("{}/weights".format(config["out_path"])).mkdir(parents=True, exist_ok=True)
+            torch.save({k: v.cpu() for k, v in model.state_dict().items()},
+                       "{}/weights/epoch_{}.pth".format(config["out_path"], epoch))
+        if epoch % 20 == 0:
+            Path("{}/checkpoints".format(config["out_path"])).mkdir(parents=True, exist_ok=True)
+            torch.save({"optimizer": optimizer.state_dict(), "lr_scheduler": scheduler},
+                       "{}/checkpoints/epoch_{}.pth".format(config["out_path"], epoch))
+    return model, metrics

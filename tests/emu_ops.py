@@ -267,6 +267,7 @@ class EmuOps:
             _v(dL, (B, z, z), (z * z, z, 1)).copy_(g * (gs / B))
 
     # ---- reconstruction
+    @torch.enable_grad()
     def recon_loss(self, xh, ld, offsets, target, root, arena, tree, n_tree, loss, root_hat, dxh, F, B, J):
         self.n += 1
         from oracle import scvae_oracle as orc  # test infrastructure may use the oracle
@@ -310,6 +311,7 @@ class EmuOps:
         sc[nx:nx + 3] = gr
         _v(draw, (B, W, ld), (d_bs, d_ls, 1)).copy_(d * sc * (1 - y * y))
 
+    @torch.enable_grad()
     def gr_loss(self, preds, dpreds, ld, target, labels, B, d, num_keys, loss, gscale):
         self.n += 1
         n = len(preds)
@@ -348,8 +350,12 @@ class EmuOps:
         self.n += 1
         _v(out, (1,), (1,)).add_((_v(g, (n,), (1,)).double() ** 2).sum())
 
-    def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind):
+    def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind,
+                   hyper=None):
         self.n += 1
+        if hyper is not None:
+            hy = _v(hyper, (2,), (1,))
+            lr, step = float(hy[0]), int(round(float(hy[1])))
         P, G = _v(p, (n,), (1,)), _v(g, (n,), (1,))
         coef = gscale
         if sumsq is not None:
@@ -372,6 +378,19 @@ class EmuOps:
         bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
         denom = V.sqrt() / math.sqrt(bc2) + eps
         P.addcdiv_(M, denom, value=-(lr / bc1))
+
+    def loss_finalize(self, acc, scale, out, n):
+        self.n += 1
+        a, sc, o = _v(acc, (n,), (1,)), _v(scale, (n,), (1,)), _v(out, (n + 1,), (1,))
+        o[:n] = a.float()
+        o[n] = torch.where(sc != 0, sc.double() * a, torch.zeros((), dtype=torch.double)).sum().float()
+
+    def unpack_root(self, xh, ld, nx, arena, root_hat, F):
+        self.n += 1
+        a = _v(arena, (2, 3), (3, 1))
+        t, off = (xh, 0) if isinstance(xh, torch.Tensor) else (xh.t, xh.off)
+        nr = torch.as_strided(t, (F, 3), (ld, 1), off + nx)
+        _v(root_hat, (F, 3), (3, 1)).copy_(0.5 * (nr + 1) * (a[1] - a[0]) + a[0])
 
     def d2f(self, src, dst, n):
         self.n += 1

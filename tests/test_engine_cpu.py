@@ -1,0 +1,117 @@
+"""Host logic of the engine (buffer geometry, weight index maps, forward/backward sequencing,
+loss/autograd glue, fused optimizer) checked on CPU against the oracle and the reference-generated
+golden fixtures, with the C-ABI replaced by its torch-on-CPU emulation (tests/emu_ops.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import scrubvae_b200 as sv
+from scrubvae_b200.engine import Engine
+from oracle import scvae_oracle as orc
+from emu_ops import EmuOps
+
+import re
+ZERO_GRAD_BIAS = re.compile(r"res_layers\.\d+\.(residual\.0|residual\.3|skip|skip\.1)\.bias$")
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def build_model(ch, z, cond, gr, dc=None, window=51, device="cpu"):
+    mc = dict(type="rcnn", channel=list(ch), kernel=5, z_dim=z, window=window, activation="prelu", diag=False,
+              init_dilation=None, prior="gaussian", load_model=None, start_epoch=None)
+    dcfg = dict(method={"conditional": list(cond), "grad_reversal": list(gr)},
+                features=sorted(set(cond) | set(gr)), alpha=1.0)
+    m = sv.get.model(mc, None, None, dcfg, 18, "midfwd", arena_size=torch.tensor(orc.ARENA),
+                     kinematic_tree=orc.KINEMATIC_TREE, discrete_classes=dc or {}, device=device, verbose=0)
+    return m, dcfg
+
+
+@pytest.mark.parametrize("name,cond,gr,dc", [
+    ("step_small_heading.npz", ["heading"], ["heading"], None),
+    ("step_small_3head.npz", ["heading", "avg_speed_3d", "ids"], ["heading", "avg_speed_3d", "ids"],
+     {"ids": [0, 1, 2, 3]}),
+])
+def test_engine_step_matches_reference_golden(golden_dir, name, cond, gr, dc):
+    z = np.load(os.path.join(golden_dir, name))
+    g = {k: z[k] for k in z.files}
+    ch, zd, B = [int(c) for c in g["meta_ch"]], int(g["meta_z"]), int(g["meta_B"])
+    m, dcfg = build_model(ch, zd, cond, gr, dc)
+    sd = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd0.")}
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd)
+    m._engine = Engine(m, ops=EmuOps())
+    m.train()
+    data = orc.synth_batch(B, seed=0)
+    m._noise = orc.synth_eps(B, zd, seed=2)
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, **{k + "_gr": 1.0 for k in gr}}
+    cfg = {"loss": scale, "disentangle": dcfg}
+    data_o = sv.train.predict_batch(m, data, m.disentangle_keys)
+    for k in ("mu", "L", "z", "root", "x6d"):
+        assert _rel(data_o[k], g["out." + k]) < 1e-5, k
+    for k in gr:
+        for i, e in enumerate(data_o["disentangle"]["grad_reversal"][k]):
+            assert _rel(e, g[f"out.gr.{k}.{i}"]) < 1e-5
+    losses = sv.train.get_batch_loss(m, data, data_o, cfg["loss"], cfg["disentangle"])
+    for k in scale:
+        assert abs(losses[k].item() - float(g["loss." + k])) <= 2e-5 * abs(float(g["loss." + k])) + 1e-6, k
+    assert abs(losses["total"].item() - float(g["loss.total"])) <= 2e-5 * abs(float(g["loss.total"]))
+    for p in m.parameters():
+        p.grad = None
+    losses["total"].backward()
+    gnorm = np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for k, v in g.items() if k.startswith("grad.")))
+    for n, p in m.named_parameters():
+        ref = torch.from_numpy(g["grad." + n])
+        err = (p.grad.double() - ref.double()).norm().item()
+        assert _rel(p.grad, ref) < 3e-4 or err < 2e-6 * gnorm, (n, _rel(p.grad, ref), err)
+    opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-4, "lr_schedule": None})
+    sv.train.clip_grad_norm_(m, max_norm=1e6)
+    opt.step()
+    new_sd = m.state_dict()
+    for k, v in g.items():
+        if k.startswith("sd1."):
+            assert _rel(new_sd[k[4:]].float(), v.astype(np.float32)) < 1e-5, k
+        if k.startswith("sd1sum."):
+            t = new_sd[k[7:]].double()
+            slack = 2.1e-4 * (t.numel() if ZERO_GRAD_BIAS.search(k) else max(2.0, 1e-3 * t.numel()))
+            assert abs(t.sum().item() - v[0]) <= 1e-4 * (abs(v[0]) + v[1] * 1e-2) + 1e-6 + slack, k
+            assert abs(t.norm().item() - v[1]) <= 1e-5 * v[1] + 1e-7 + slack, k
+
+
+def test_eval_mode_and_encode_decode_match_oracle():
+    torch.manual_seed(3)
+    m, dcfg = build_model([8, 16, 32, 64, 128], 8, ["heading"], ["heading"])
+    m._engine = Engine(m, ops=EmuOps())
+    cfg = orc.Cfg(ch=[8, 16, 32, 64, 128], z_dim=8)
+    B = 3
+    data = orc.synth_batch(B, seed=5)
+    # a training step first so that the running statistics are not the initial ones
+    m.train()
+    m._noise = orc.synth_eps(B, 8, seed=1)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    m(data)
+    ns = {}
+    orc.forward(sd0, data, cfg, m._noise, True, ns)
+    sd1 = dict(sd0)
+    sd1.update(ns)
+    for k, v in m.state_dict().items():
+        assert _rel(v.float(), sd1[k].float()) < 1e-5 or (v.float() - sd1[k].float()).abs().max() < 1e-6, k
+    m.eval()
+    with torch.no_grad():
+        out = m(data)
+        ref = orc.forward(sd1, data, cfg, None, False)
+        for k in ("mu", "L", "z", "root", "x6d", "var"):
+            assert _rel(out[k], ref[k]) < 1e-5, k
+        enc = m.encode(data)
+        assert _rel(enc["mu"], ref["mu"]) < 1e-5
+        zz = torch.randn(B, 8, generator=torch.Generator().manual_seed(4))
+        dec = m.decode(zz, data)
+        zc = torch.cat([zz, data["heading"]], -1)
+        xh = orc.decoder(sd1, zc, cfg, False, None).moveaxis(-1, 1)
+        assert _rel(dec["x6d"].reshape(B, 51, -1), xh[..., :-3]) < 1e-5
