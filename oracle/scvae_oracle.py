@@ -291,24 +291,20 @@ class Cfg:
 
 
 def _bn(x, sd, pre, training, new_stats, eps=1e-4, momentum=0.1):
-    """nn.BatchNorm1d(eps=1e-4): model/residual.py:88,112,146,173; SURVEY App. B."""
-    rm, rv = sd[pre + ".running_mean"], sd[pre + ".running_var"]
-    if training:
-        mean = x.mean(dim=(0, 2))
-        var = x.var(dim=(0, 2), unbiased=False)
-        n = x.shape[0] * x.shape[2]
-        if new_stats is not None:
-            new_stats[pre + ".running_mean"] = (1 - momentum) * rm + momentum * mean.detach()
-            new_stats[pre + ".running_var"] = (1 - momentum) * rv + momentum * var.detach() * n / (n - 1)
-            new_stats[pre + ".num_batches_tracked"] = sd[pre + ".num_batches_tracked"] + 1
-    else:
-        mean, var = rm, rv
-    xh = (x - mean[None, :, None]) / torch.sqrt(var[None, :, None] + eps)
-    return xh * sd[pre + ".weight"][None, :, None] + sd[pre + ".bias"][None, :, None]
+    """nn.BatchNorm1d(eps=1e-4): model/residual.py:88,112,146,173; SURVEY App. B.  F.batch_norm is
+    the functional form of the same torch module (train: batch mean / biased variance, running
+    statistics updated with the unbiased variance)."""
+    rm, rv = sd[pre + ".running_mean"].clone(), sd[pre + ".running_var"].clone()
+    y = F.batch_norm(x, rm, rv, sd[pre + ".weight"], sd[pre + ".bias"], training, momentum, eps)
+    if training and new_stats is not None:
+        new_stats[pre + ".running_mean"] = rm
+        new_stats[pre + ".running_var"] = rv
+        new_stats[pre + ".num_batches_tracked"] = sd[pre + ".num_batches_tracked"] + 1
+    return y
 
 
 def _prelu(x, a):
-    return torch.where(x >= 0, x, a * x)
+    return F.prelu(x, a)
 
 
 def upsample2_linear(x):
@@ -472,13 +468,12 @@ def clip_coef(grads: Sequence[torch.Tensor], max_norm: float = 1e6):
 
 def adam_update(p, g, m, v, step, lr, kind="adamw", b1=0.9, b2=0.999, eps=1e-8, wd=0.01):
     """torch.optim.Adam / AdamW defaults (train/trainer.py:60-65)."""
-    if kind == "adamw":
-        p = p * (1 - lr * wd)
-    m = b1 * m + (1 - b1) * g
-    v = b2 * v + (1 - b2) * g * g
+    p = p * (1 - lr * wd) if kind == "adamw" else p.clone()
+    m = torch.lerp(m, g, 1 - b1)
+    v = (v * b2).addcmul_(g, g, value=1 - b2)
     bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
-    denom = v.sqrt() / math.sqrt(bc2) + eps
-    return p - (lr / bc1) * m / denom, m, v
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    return p.addcdiv_(m, denom, value=-(lr / bc1)), m, v
 
 
 def train_step(sd, data, cfg: Cfg, loss_scale, eps_noise, opt_state=None, lr=1e-4,

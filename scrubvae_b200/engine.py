@@ -60,7 +60,7 @@ class Act:
 
 class GemmW:
     """One GEMM layer's packed weights: forward matrix [N][K] (+ bias) and optional dgrad matrix."""
-    __slots__ = ("name", "N", "K", "w", "b", "bias_mod", "bias_n", "gw", "gb", "dN", "dK", "wd")
+    __slots__ = ("name", "N", "K", "w", "b", "bias_mod", "bias_n", "gw", "gb", "dN", "dK", "wd", "nnz", "nnz_d")
 
 
 class Engine:
@@ -142,6 +142,8 @@ class Engine:
             g = GemmW()
             g.name = name
             g.N, g.K = w_idx.shape
+            g.nnz = int((w_idx >= 0).sum())  # algorithmic MACs per GEMM row (structural zeros excluded)
+            g.nnz_d = int((d_idx >= 0).sum()) if d_idx is not None else 0
             assert g.K % 4 == 0, (name, g.K)
             g.w = self._n_fwd
             self._pack_parts.append(w_idx.reshape(-1))
@@ -786,3 +788,96 @@ class Plan:
         """Runs the backward launch list; `self.gscale` must hold d total / d loss_k."""
         for f in self.Bw:
             f()
+
+
+class TrainStep:
+    """One whole training step — forward, losses, backward, grad-norm clip, optimizer — as a single
+    launch sequence over a plan's static buffers, optionally replayed from a CUDA graph.  Same kernels
+    and order as the public-API path (train/trainer.py: predict_batch -> get_batch_loss -> backward ->
+    clip_grad_norm_ -> optimizer.step), minus the Python between them.
+
+    `comm` (optional): callable(engine, phase) hook used by data parallelism (parallel.py) to launch the
+    gradient all-reduce; phase is "post_backward"."""
+
+    def __init__(self, model, optimizer, loss_scale, B, max_norm=1e6, use_graph=True, comm=None):
+        self.model, self.opt = model, optimizer
+        self.eng = model.engine
+        self.plan = self.eng.plan(B)
+        self.max_norm = float(max_norm)
+        self.comm = comm
+        self.plan.set_loss_scale(loss_scale)
+        self.opt._bind()
+        if not hasattr(self.eng, "sumsq"):
+            self.eng.sumsq = torch.zeros(1, dtype=torch.double, device=self.eng.device)
+        self.graph = None
+        self.use_graph = use_graph and self.eng.device.type == "cuda"
+        self.n_launch = None
+
+    def _sequence(self):
+        plan, eng, opt = self.plan, self.eng, self.opt
+        m = self.model
+        plan._training = True
+        if m._noise is not None:
+            plan.eps.copy_(m._noise)
+        else:
+            plan.eps.normal_()
+        plan.stats.zero_()
+        eng.nbt.add_(1)
+        eng.repack()
+        for f in plan.F:
+            f()
+        for f in plan.Lk:
+            f()
+        plan.gscale.copy_(plan.loss_scale)
+        for f in plan.Bw:
+            f()
+        if self.comm is not None:
+            self.comm(eng, "post_backward")
+        eng.sumsq.zero_()
+        eng.ops.sumsq(eng.gflat, eng.n_flat, eng.sumsq)
+        grp = opt.param_groups[0]
+        from .train.optim import KIND
+        b1 = grp["momentum"] if opt.kind == "sgd" else grp["betas"][0]
+        eng.ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, eng.n_flat, eng.sumsq, self.max_norm, opt.grad_scale,
+                           float(grp["lr"]), b1, grp["betas"][1], grp["eps"], grp["weight_decay"], 1, KIND[opt.kind],
+                           hyper=opt.hyper)
+
+    def run(self, data=None):
+        """Returns the static loss vector [jpe, root, prior, <gr>..., total] (device, overwritten each step)."""
+        plan, opt = self.plan, self.opt
+        if data is not None:
+            plan.load_inputs(data, need_loss_inputs=True)
+            plan.load_targets(data)
+        opt._steps += 1
+        opt.hyper_host[0] = float(opt.param_groups[0]["lr"])
+        opt.hyper_host[1] = float(opt._steps)
+        opt.hyper.copy_(opt.hyper_host, non_blocking=True)
+        if not self.use_graph:
+            n0 = self.eng.ops.launch_count()
+            self._sequence()
+            self.n_launch = self.eng.ops.launch_count() - n0
+        elif self.graph is None:
+            # warm-up once eagerly on a side stream (allocations, lazy init), then capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                n0 = self.eng.ops.launch_count()
+                self._sequence()
+                self.n_launch = self.eng.ops.launch_count() - n0
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            # the eager warm-up WAS this step; capture for the following ones
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._sequence()
+            self.graph = g
+        else:
+            self.graph.replay()
+        return plan.loss_out
+
+    def losses(self):
+        """dict view of the last step's losses (0-d device tensors)."""
+        v = self.plan.loss_out
+        d = {n: v[i] for i, n in enumerate(self.plan.loss_names)}
+        d["total"] = v[len(self.plan.loss_names)]
+        return d

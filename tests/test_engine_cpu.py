@@ -115,3 +115,39 @@ def test_eval_mode_and_encode_decode_match_oracle():
         zc = torch.cat([zz, data["heading"]], -1)
         xh = orc.decoder(sd1, zc, cfg, False, None).moveaxis(-1, 1)
         assert _rel(dec["x6d"].reshape(B, 51, -1), xh[..., :-3]) < 1e-5
+
+
+def test_trainstep_sequence_equals_api_path(golden_dir):
+    """The fused TrainStep launch sequence gives the same post-step weights as the public-API path."""
+    from scrubvae_b200.engine import TrainStep
+    z = np.load(os.path.join(golden_dir, "step_small_heading.npz"))
+    g = {k: z[k] for k in z.files}
+    ch, zd, B = [int(c) for c in g["meta_ch"]], int(g["meta_z"]), int(g["meta_B"])
+    sd = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd0.")}
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "heading_gr": 1.0}
+    data = orc.synth_batch(B, seed=0)
+    res = []
+    for fused in (False, True):
+        m, dcfg = build_model(ch, zd, ["heading"], ["heading"])
+        m.load_state_dict(sd)
+        m._engine = Engine(m, ops=EmuOps())
+        m.train()
+        m._noise = orc.synth_eps(B, zd, seed=2)
+        opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-4, "lr_schedule": None})
+        for _ in range(2):
+            if fused:
+                step = TrainStep(m, opt, scale, B, use_graph=False) if _ == 0 else step
+                lv = step.run(data).clone()
+            else:
+                data_o = sv.train.predict_batch(m, data, m.disentangle_keys)
+                losses = sv.train.get_batch_loss(m, data, data_o, scale, dcfg)
+                for p in m.parameters():
+                    p.grad = None
+                losses["total"].backward()
+                sv.train.clip_grad_norm_(m, max_norm=1e6)
+                opt.step()
+                lv = losses["total"].detach().clone()
+        res.append(({k: v.clone() for k, v in m.state_dict().items()}, lv.reshape(-1)[-1]))
+    assert abs(res[0][1].item() - res[1][1].item()) <= 1e-6 * abs(res[0][1].item())
+    for k in res[0][0]:
+        assert torch.equal(res[0][0][k], res[1][0][k]), k

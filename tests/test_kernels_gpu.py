@@ -1,0 +1,225 @@
+"""Every CUDA entry point of libscv.so (called through the C ABI via ctypes) against the torch-on-CPU
+statement of its semantics (tests/emu_ops.py) on the same seeded inputs."""
+import math
+
+import pytest
+import torch
+
+from emu_ops import EmuOps
+from scrubvae_b200._ops import Ref, BN, PRELU, TRAIN, ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELUMASK
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from scrubvae_b200._ops import get_ops
+    return get_ops()
+
+
+def run_both(ops, tensors, call, tol=1e-5, check=None):
+    """tensors: name -> CPU tensor.  call(ops, T) launches with T[name] on the right device."""
+    cpu = {k: v.clone() for k, v in tensors.items()}
+    gpu = {k: v.clone().cuda() for k, v in tensors.items()}
+    call(EmuOps(), cpu)
+    call(ops, gpu)
+    torch.cuda.synchronize()
+    for k in (check or tensors.keys()):
+        a, b = gpu[k].cpu().double(), cpu[k].double()
+        err = (a - b).norm().item() / (b.norm().item() + 1e-20)
+        assert err < tol or (a - b).abs().max().item() < tol * 1e-2, (k, err, (a - b).abs().max().item())
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+GEMM_CASES = [
+    # B, Lo, rows(per batch), C(=a_ls/stride), stride, taps, N, n_last, act, resid, stats
+    (3, 26, 56, 8, 2, 5, 16, None, ACT_NONE, False, True),
+    (5, 7, 9, 64, 1, 3, 128, 64, ACT_NONE, True, True),
+    (4, 51, 57, 112, 1, 7, 64, None, ACT_NONE, False, False),
+    (6, 1, 1, 512, 1, 1, 44, None, ACT_RELU, False, False),
+    (2, 51, 59, 8, 1, 9, 112, None, ACT_TANH, False, False),
+    (7, 1, 1, 64, 1, 1, 4, None, ACT_RELUMASK, True, False),
+    (130, 4, 8, 128, 1, 5, 256, None, ACT_NONE, True, True),
+]
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("case", GEMM_CASES)
+def test_gemm(ops, case, prec):
+    B, Lo, rows, C, s, taps, N, n_last, act, resid, stats = case
+    K = taps * C
+    a_bs, a_ls = rows * C, s * C
+    T = {
+        "A": torch.randn(B * rows * C + K, generator=g(1)),
+        "W": torch.randn(N * K, generator=g(2)) / math.sqrt(K),
+        "bias": torch.randn(N, generator=g(3)),
+        "Y": torch.zeros(B * Lo * N),
+        "R": torch.randn(B * Lo * N, generator=g(4)),
+        "stats": torch.zeros(2 * N, dtype=torch.double),
+    }
+    if n_last is not None:
+        bias_mod = N // 2
+    else:
+        bias_mod = N
+
+    def call(o, t):
+        o.gemm(t["A"], a_bs, a_ls, B, Lo, K, N, t["W"], t["Y"], Lo * N, N, bias=t["bias"], bias_mod=bias_mod,
+               bias_n=N, n_last=n_last, R=t["R"] if resid else None, r_bs=Lo * N, r_ls=N, act=act, out_scale=0.5,
+               stats=t["stats"] if stats else None, precision=prec)
+    run_both(ops, T, call, tol=1e-5 if prec == 0 else 2e-3, check=["Y", "stats"])
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("case", GEMM_CASES[:5] + [GEMM_CASES[6]])
+def test_wgrad(ops, case, prec):
+    B, Lo, rows, C, s, taps, N, n_last, act, resid, stats = case
+    K = taps * C
+    a_bs, a_ls = rows * C, s * C
+    T = {
+        "A": torch.randn(B * rows * C + K, generator=g(1)),
+        "dY": torch.randn(B * Lo * N, generator=g(2)),
+        "dW": torch.zeros(N * K),
+        "db": torch.zeros(N),
+    }
+    bias_mod = N // 2 if n_last is not None else N
+
+    def call(o, t):
+        o.wgrad(t["A"], a_bs, a_ls, B, Lo, K, N, t["dY"], Lo * N, N, t["dW"], dbias=t["db"], bias_mod=bias_mod,
+                bias_n=N, precision=prec)
+    run_both(ops, T, call, tol=2e-5 if prec == 0 else 2e-3, check=["dW", "db"])
+
+
+def test_pack_input(ops):
+    B, W, J = 5, 51, 18
+    nx, C, halo = J * 6, 112, 3
+    T = {"x": torch.randn(B, W, nx, generator=g(1)), "r": torch.rand(B, W, 3, generator=g(2)) * 50,
+         "arena": torch.tensor([[-100.0, -100, 0], [100, 100, 50]]), "out": torch.zeros(B * (W + 2 * halo) * C)}
+    run_both(ops, T, lambda o, t: o.pack_input(t["x"], t["r"], t["arena"], t["out"], B, W, nx, C, halo))
+
+
+@pytest.mark.parametrize("B,L,C,fold,up", [(4, 13, 64, 1, True), (3, 7, 16, 2, False), (9, 51, 8, 1, True),
+                                           (2, 4, 1024, 1, True)])
+@pytest.mark.parametrize("mode", [BN | PRELU | TRAIN, BN | PRELU, PRELU, 0])
+def test_bnact_fwd_bwd(ops, B, L, C, fold, up, mode):
+    x = torch.randn(B * L * C, generator=g(1)) * 2 + 0.3
+    xv = x.view(B * L, C).double()
+    if fold == 2:  # statistics arrive as two column groups (polyphase GEMM): split rows in two halves
+        h = (B * L) // 2
+        st = torch.cat([xv[:h].sum(0), xv[h:].sum(0), (xv[:h] ** 2).sum(0), (xv[h:] ** 2).sum(0)])
+    else:
+        st = torch.cat([xv.sum(0), (xv ** 2).sum(0)])
+    T = {
+        "X": x, "stats": st, "gamma": 1 + 0.1 * torch.randn(C, generator=g(2)), "beta": 0.1 * torch.randn(C, generator=g(3)),
+        "rm": torch.randn(C, generator=g(4)), "rv": torch.rand(C, generator=g(5)) + 0.5,
+        "slope": torch.tensor([0.25]), "H": torch.zeros(B * L * C), "U": torch.zeros(B * 2 * L * C),
+        "dO": torch.randn(B * L * C, generator=g(6)), "dU": torch.randn(B * 2 * L * C, generator=g(7)),
+        "sums": torch.zeros(2 * C + 1, dtype=torch.double), "dX": torch.zeros(B * L * C),
+        "dgamma": torch.zeros(C), "dbeta": torch.zeros(C), "dslope": torch.zeros(1),
+    }
+    cnt = float(B * L)
+
+    def fwd(o, t):
+        o.bnact_fwd(t["X"], L * C, C, B, L, C, mode, stats=t["stats"], fold=fold, count=cnt, eps=1e-4, momentum=0.1,
+                    gamma=t["gamma"], beta=t["beta"], running_mean=t["rm"], running_var=t["rv"], slope=t["slope"],
+                    H=t["H"], h_bs=L * C, h_ls=C, U=t["U"] if up else None, u_bs=2 * L * C, u_ls=C)
+    run_both(ops, T, fwd, check=["H", "U", "rm", "rv"])
+    if not (mode & BN) or (mode & TRAIN):
+        def bwd(o, t):
+            kw = dict(stats=t["stats"], fold=fold, count=cnt, eps=1e-4, gamma=t["gamma"], beta=t["beta"],
+                      slope=t["slope"], dO=t["dO"], o_bs=L * C, o_ls=C, dU=t["dU"] if up else None, u_bs=2 * L * C,
+                      u_ls=C)
+            if mode & 3:
+                o.bnact_bwd_reduce(t["X"], L * C, C, B, L, C, mode, t["sums"], **kw)
+            o.bnact_bwd_apply(t["X"], L * C, C, B, L, C, mode, sums=t["sums"] if mode & 3 else None, dX=t["dX"],
+                              d_bs=L * C, d_ls=C, dgamma=t["dgamma"], dbeta=t["dbeta"], dslope=t["dslope"], **kw)
+        run_both(ops, T, bwd, tol=2e-5, check=["sums", "dX", "dgamma", "dbeta", "dslope"])
+
+
+@pytest.mark.parametrize("z,nvar,with_eps", [(64, 2, True), (8, 9, True), (16, 0, False)])
+def test_reparam_kl(ops, z, nvar, with_eps):
+    B = 7
+    nsig = z * (z + 1) // 2
+    ms_ld, zc_ld = (z + nsig + 15) // 16 * 16, (z + nvar + 3) // 4 * 4
+    T = {"ms": torch.randn(B, ms_ld, generator=g(1)), "eps": torch.randn(B, z, generator=g(2)),
+         "var": torch.randn(B, max(nvar, 1), generator=g(3)), "mu": torch.zeros(B, z), "L": torch.zeros(B, z, z),
+         "zc": torch.zeros(B, zc_ld), "loss": torch.zeros(1, dtype=torch.double), "gs": torch.tensor([0.37]),
+         "dmu": torch.zeros(B, z), "dL": torch.zeros(B, z, z), "dmu2": torch.randn(B, z, generator=g(4)),
+         "dz": torch.randn(B, zc_ld, generator=g(5)), "dms": torch.zeros(B, ms_ld)}
+    T["ms"][:, z + 5] = 25.0  # softplus linear branch
+
+    def call(o, t):
+        e = t["eps"] if with_eps else None
+        o.reparam_fwd(t["ms"], ms_ld, e, t["var"] if nvar else None, nvar, t["mu"], t["L"], t["zc"], zc_ld, B, z)
+        o.kl(t["mu"], t["L"], t["loss"], None, None, None, B, z)
+        o.kl(t["mu"], t["L"], None, t["gs"], t["dmu"], t["dL"], B, z)
+        o.reparam_bwd(t["ms"], ms_ld, e, t["dmu"], t["dmu2"], -1.5, t["dz"], zc_ld, t["dL"], t["dms"], ms_ld, B, z)
+    run_both(ops, T, call, tol=2e-5, check=["mu", "L", "zc", "loss", "dmu", "dL", "dms"])
+
+
+def test_recon_loss_and_out_bwd(ops):
+    from oracle import scvae_oracle as orc
+    B, W, J, C = 3, 51, 18, 112
+    F = B * W
+    d = orc.synth_batch(B, seed=3)
+    tr = [len(orc.KINEMATIC_TREE)]
+    for c in orc.KINEMATIC_TREE:
+        tr += [len(c)] + list(c)
+    T = {"xh": torch.tanh(torch.randn(F, C, generator=g(1))), "off": d["offsets"].reshape(F, J, 3).contiguous(),
+         "tgt": d["target_pose"].reshape(F, J, 3).contiguous(), "root": d["root"].reshape(F, 3).contiguous(),
+         "arena": torch.tensor(orc.ARENA), "tree": torch.tensor(tr, dtype=torch.int32),
+         "loss": torch.zeros(2, dtype=torch.double), "rh": torch.zeros(F, 3), "rh2": torch.zeros(F, 3),
+         "dxh": torch.zeros(F, C), "gj": torch.tensor([0.7]), "gr": torch.tensor([1.3]),
+         "draw": torch.zeros(B * (W + 6) * C)}
+
+    def call(o, t):
+        o.recon_loss(t["xh"], C, t["off"], t["tgt"], t["root"], t["arena"], t["tree"], len(tr), t["loss"], t["rh"],
+                     t["dxh"], F, B, J)
+        o.unpack_root(t["xh"], C, J * 6, t["arena"], t["rh2"], F)
+        o.out_bwd(t["xh"], t["dxh"], C, t["gj"], t["gr"], J * 6, Ref(t["draw"], 3 * C), (W + 6) * C, C, B, W)
+    run_both(ops, T, call, tol=3e-5, check=["loss", "rh", "rh2", "dxh", "draw"])
+
+
+@pytest.mark.parametrize("d,ce", [(2, False), (3, False), (4, True)])
+def test_gr_loss(ops, d, ce):
+    B, ld, n = 37, 4, 4
+    T = {f"p{i}": torch.randn(B, ld, generator=g(i)) for i in range(n)}
+    T.update({f"d{i}": torch.zeros(B, ld) for i in range(n)})
+    T.update({"tgt": torch.randn(B, d, generator=g(9)), "lab": torch.randint(0, d, (B,), generator=g(10)),
+              "loss": torch.zeros(1, dtype=torch.double), "gs": torch.tensor([0.9])})
+
+    def call(o, t):
+        preds = [Ref(t[f"p{i}"]) for i in range(n)]
+        dps = [Ref(t[f"d{i}"]) for i in range(n)]
+        o.gr_loss(preds, None, ld, None if ce else t["tgt"], t["lab"] if ce else None, B, d, 3, t["loss"], None)
+        o.gr_loss(preds, dps, ld, None if ce else t["tgt"], t["lab"] if ce else None, B, d, 3, None, t["gs"])
+    run_both(ops, T, call, tol=2e-5, check=["loss"] + [f"d{i}" for i in range(n)])
+
+
+def test_gather_sumsq_optim_finalize(ops):
+    n = 100003
+    idx = torch.randint(-1, n, (n + 5,), generator=g(1)).to(torch.int32)
+    T = {"src": torch.randn(n, generator=g(2)), "idx": idx, "dst": torch.ones(n + 5), "dst2": torch.ones(n + 5),
+         "ss": torch.zeros(1, dtype=torch.double), "p": torch.randn(n, generator=g(3)),
+         "m": torch.randn(n, generator=g(4)) * 0.01, "v": torch.rand(n, generator=g(5)) * 1e-4,
+         "hyper": torch.tensor([3e-4, 7.0], dtype=torch.double),
+         "acc": torch.rand(5, dtype=torch.double, generator=g(6)), "sc": torch.tensor([1.0, 0.0, 1e-4, 2.0, 1.0]),
+         "lout": torch.zeros(6)}
+    for kind in (0, 1, 2):
+        def call(o, t, kind=kind):
+            o.gather(t["src"], t["idx"], t["dst"], n + 5, False)
+            o.gather(t["src"], t["idx"], t["dst2"], n + 5, True)
+            t["ss"].zero_()
+            o.sumsq(t["src"], n, t["ss"])
+            o.optim_step(t["p"], t["src"], t["m"], t["v"], n, t["ss"], 10.0, 0.5, 1e-3, 0.9, 0.999, 1e-8, 0.01, 3,
+                         kind, hyper=t["hyper"] if kind == 1 else None)
+            o.loss_finalize(t["acc"], t["sc"], t["lout"], 5)
+        run_both(ops, T, call, tol=1e-5, check=["dst", "dst2", "ss", "p", "m", "v", "lout"])
+
+
+def test_library_fails_loudly_when_missing(tmp_path):
+    from scrubvae_b200 import _ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _ops.load_library(str(tmp_path / "nope.so"))
