@@ -102,7 +102,7 @@ def test_default_arch_step_vs_oracle(precision, B):
         assert abs(got1[k] - l1[k].item()) <= ltol * abs(l1[k].item()) + 1e-6, (k, got1[k], l1[k].item())
         # the second step sees the Adam-updated weights: looser (Adam amplifies rounding of tiny gradients)
         assert abs(got2[k] - l2[k].item()) <= 20 * ltol * abs(l2[k].item()) + 1e-5, (k, got2[k], l2[k].item())
-    assert step.graph is not None and step.n_launch > 200
+    assert step.graph is not None and step.n_launch > 100
 
 
 def test_eval_mode_matches_oracle():
