@@ -1,7 +1,630 @@
-// tcgen05 / TMA overlapping-row GEMM (placeholder until the tensor-core kernels land):
-// returning 1 tells the dispatcher that the shape is not taken by the tensor-core path.
-#include "scv_common.cuh"
+// tcgen05 / TMA overlapping-row GEMM and weight-gradient kernels (sm_100a), kind::tf32:
+// fp32 operands as stored (the tensor core reads the TF32 part), fp32 accumulation in TMEM.
+//
+// Forward / dgrad (gemm_tc_kernel), one persistent CTA per SM, warp-specialised:
+//   warp 0   TMA producer: A tile = 3-D box (32 k, bl rows of l, nb windows) of the halo-padded
+//            channels-last activation viewed as (K, Lo, B) with OVERLAPPING strides (1, a_ls, a_bs) — the
+//            implicit-GEMM im2col is done by the tensor map; W tile = 2-D box (32 k, bn) of the packed
+//            [N][K] weights.  128-byte swizzle, out-of-bounds -> 0 (K tail, ragged l / b / n edges).
+//   warp 1   one elected thread issues tcgen05.mma (M=128, N=bn<=256, K=8 per instruction), both operands
+//            K-major from shared memory, accumulators double-buffered in TMEM (2 x 256 columns).
+//   warp 2   TMEM allocation.
+//   warps 4-7 epilogue: tcgen05.ld -> per-warp transpose through shared memory -> out_scale, bias,
+//            residual, BatchNorm column sums (sum / sum of squares), activation, coalesced row stores.
+// Weight gradient (wgrad_tc_kernel): D[n][k] = sum_m dY[m][n] A[m][k]; both operands are MN-major in
+// shared memory (dY rows are n-contiguous, A rows k-contiguous; 128B swizzle with 32-byte atoms, the only
+// layout tcgen05 takes for MN-major tf32), the reduction runs over the rows of
+// the same (32, bl, nb) boxes; work items (n tile, k tile, row split) are spread over the SMs and the
+// epilogue adds into dW with coalesced fp32 reductions.
+#include "scv_tc.cuh"
+
 namespace scv {
-int gemm_tc(const scv_gemm_t*, cudaStream_t) { return 1; }
-int wgrad_tc(const scv_wgrad_t*, cudaStream_t) { return 1; }
+namespace tc {
+
+encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (encode_tiled_fn)p;
+  }
+  return fn;
+}
+
+int make_tmap(CUtensorMap* tm, const float* base, int rank, const int64_t* dims, const int64_t* strides_elems,
+              const int* box, const char* what, bool atom32) {
+  encode_tiled_fn fn = get_encode_tiled();
+  if (!fn) {
+    set_error("%s: cuTensorMapEncodeTiled is not available from the driver", what);
+    return -2;
+  }
+  cuuint64_t gd[5];
+  cuuint64_t gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    es[i] = 1;
+    if (i > 0) gs[i - 1] = (cuuint64_t)strides_elems[i] * sizeof(float);
+  }
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d; dims %lld,%lld,%lld strides %lld,%lld box %d,%d,%d)",
+              what, (int)r, (long long)dims[0], (long long)(rank > 1 ? dims[1] : 0), (long long)(rank > 2 ? dims[2] : 0),
+              (long long)(rank > 1 ? strides_elems[1] : 0), (long long)(rank > 2 ? strides_elems[2] : 0), box[0],
+              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
+    return -3;
+  }
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace scv
+
+namespace {
+
+using namespace scv::tc;
+
+constexpr int kThreads = 256;       // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue
+constexpr int kBM = 128;            // UMMA M (TMEM lanes)
+constexpr int kBK = 32;             // k floats per stage row = one 128-byte swizzle span
+constexpr int kMaxBN = 256;         // UMMA N limit (cta_group::1)
+constexpr int kTmemCols = 512;      // two accumulator buffers of 256 columns
+constexpr int kStagePitch = 33;     // floats; epilogue transpose tile 32 x 33 per warp
+constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
+constexpr int kMaxStages = 8;
+
+struct GemmTcParams {
+  int64_t B, Lo;
+  int K, N;
+  int bl, nb, lt, bt;  // A box rows = bl (l) x nb (windows); lt x bt row tiles
+  int bn, n_tiles, m_tiles, k_chunks, stages;
+  const float* bias;
+  int bias_mod, bias_n;
+  float* Y;
+  int64_t y_bs, y_ls;
+  int n_last;
+  const float* R;
+  int64_t r_bs, r_ls;
+  int act;
+  float out_scale;
+  double* stats;
+};
+
+struct SmemCtl {  // lives after the operand stages
+  uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  long long yoff[kBM];  // element offset of each tile row in Y (-1: row not stored)
+  long long roff[kBM];
+  int ncap[kBM];
+};
+
+__device__ __forceinline__ float act_apply(float v, int act, float r) {
+  if (act == SCV_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == SCV_ACT_TANH) return tanhf(v);
+  if (act == SCV_ACT_RELUMASK) return r > 0.f ? v : 0.f;
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = kBM * kBK * 4;             // 16 KB
+  const uint32_t w_bytes = (uint32_t)p.bn * kBK * 4;  // bn rows of 128 B (bn % 16 == 0 -> 2 KB multiple)
+  const uint32_t stage_bytes = a_bytes + w_bytes;
+  uint8_t* ctl_raw = smem + (size_t)p.stages * stage_bytes;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(ctl_raw);
+  float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtl) + 15) & ~size_t(15)));  // 4 x 32 x 33 floats
+  const uint32_t tile_tx = (uint32_t)(p.bl * p.nb) * kBK * 4 + w_bytes;
+  const int total = p.n_tiles * p.m_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&ctl->full[s]), 1);
+      mbar_init(smem_u32(&ctl->empty[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&ctl->tfull[i]), 1);
+      mbar_init(smem_u32(&ctl->tempty[i]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
+        const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;
+        const int l0 = lt_i * p.bl, b0 = bt_i * p.nb, n0 = nt * p.bn;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1);
+          const uint32_t fb = smem_u32(&ctl->full[s]);
+          mbar_expect_tx(fb, tile_tx);
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          tma_load_3d(sa, &tmA, fb, kc * kBK, l0, b0);
+          tma_load_2d(sa + a_bytes, &tmW, fb, kc * kBK, n0);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(kBM, p.bn, 0, 0);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(smem_u32(&ctl->tempty[acc]), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(smem_u32(&ctl->full[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sw = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k)
+            umma_tf32(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sw + k * 32, 16, 1024), idesc,
+                      (kc | k) != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&ctl->empty[s]));
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(smem_u32(&ctl->tfull[acc]));
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int ew = warp - 4;  // TMEM lane quarter this warp may read
+    const int row = ew * 32 + lane;
+    float* xp = xpose + ew * (32 * kStagePitch);
+    const int rows_in_box = p.bl * p.nb;
+    const int N = p.N;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
+      const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;
+      const int n0 = nt * p.bn;
+      {
+        const int bi = row / p.bl, li = row - bi * p.bl;
+        const int64_t b = (int64_t)bt_i * p.nb + bi, l = (int64_t)lt_i * p.bl + li;
+        const bool ok = row < rows_in_box && b < p.B && l < p.Lo;
+        ctl->yoff[row] = ok ? (long long)(b * p.y_bs + l * p.y_ls) : -1;
+        ctl->roff[row] = (ok && p.R) ? (long long)(b * p.r_bs + l * p.r_ls) : 0;
+        ctl->ncap[row] = ok ? ((l == p.Lo - 1) ? p.n_last : N) : 0;
+      }
+      __syncwarp();
+      const int acc = it & 1;
+      mbar_wait(smem_u32(&ctl->tfull[acc]), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kMaxBN;
+      const int ncols = min(p.bn, N - n0);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xp[lane * kStagePitch + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int n = n0 + c0 + lane;
+        const float bv = (p.bias && n < p.bias_n) ? __ldg(p.bias + (n % p.bias_mod)) : 0.f;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const long long yo = ctl->yoff[ew * 32 + rr];
+          if (yo < 0) continue;
+          if (n < ctl->ncap[ew * 32 + rr]) {
+            float tv = p.out_scale * xp[rr * kStagePitch + lane] + bv;
+            const float r = p.R ? __ldg(p.R + ctl->roff[ew * 32 + rr] + n) : 0.f;
+            if (p.act != SCV_ACT_RELUMASK) tv += r;
+            s1 += tv;
+            s2 += tv * tv;
+            p.Y[yo + n] = act_apply(tv, p.act, r);
+          }
+        }
+        if (p.stats && n < N) {
+          atomicAdd(p.stats + n, (double)s1);
+          atomicAdd(p.stats + N + n, (double)s2);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ctl->tempty[acc]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient
+// ---------------------------------------------------------------------------------------------
+struct WgradTcParams {
+  int K, N;
+  int bl, nb, lt, bt;   // row boxes as above; R = bl*nb rows (multiple of 8) reduced per stage
+  int bnk;              // k tile width (UMMA N), multiple of 16, <= 256
+  int n_tiles, k_tiles, splits, groups, gps, stages;
+  float* dW;
+};
+
+struct SmemCtlW {
+  uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmA, const WgradTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.bl * p.nb;
+  const uint32_t slab = (uint32_t)R * 128;  // one 32-wide slab of R rows (R % 8 == 0 -> 1 KB multiple)
+  const int a_slabs = (p.bnk + 31) / 32;
+  const uint32_t y_bytes = 4 * slab, a_bytes = (uint32_t)a_slabs * slab;
+  const uint32_t stage_bytes = y_bytes + a_bytes;
+  uint8_t* ctl_raw = smem + (size_t)p.stages * stage_bytes;
+  SmemCtlW* ctl = reinterpret_cast<SmemCtlW*>(ctl_raw);
+  float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtlW) + 15) & ~size_t(15)));
+  const int total = p.n_tiles * p.k_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmY);
+    prefetch_tmap(&tmA);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&ctl->full[s]), 1);
+      mbar_init(smem_u32(&ctl->empty[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&ctl->tfull[i]), 1);
+      mbar_init(smem_u32(&ctl->tempty[i]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  // item -> (split, k tile, n tile): consecutive CTAs share the row range (A / dY slabs hit in L2)
+  auto decode = [&](int t, int& nt, int& kt, int& g0, int& g1) {
+    const int tiles = p.n_tiles * p.k_tiles;
+    const int sp = t / tiles, r = t - sp * tiles;
+    kt = r / p.n_tiles;
+    nt = r - kt * p.n_tiles;
+    g0 = sp * p.gps;
+    g1 = min(p.groups, g0 + p.gps);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int nt, kt, g0, g1;
+        decode(t, nt, kt, g0, g1);
+        for (int g = g0; g < g1; ++g) {
+          const int bt_i = g / p.lt, lt_i = g - bt_i * p.lt;
+          const int l0 = lt_i * p.bl, b0 = bt_i * p.nb;
+          mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1);
+          const uint32_t fb = smem_u32(&ctl->full[s]);
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sy = smem_u32(smem + (size_t)s * stage_bytes);
+          for (int j = 0; j < 4; ++j) tma_load_3d(sy + j * slab, &tmY, fb, nt * kBM + j * 32, l0, b0);
+          for (int j = 0; j < a_slabs; ++j) tma_load_3d(sy + y_bytes + j * slab, &tmA, fb, kt * p.bnk + j * 32, l0, b0);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(kBM, p.bnk, 1, 1);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        int nt, kt, g0, g1;
+        decode(t, nt, kt, g0, g1);
+        const int acc = it & 1;
+        mbar_wait(smem_u32(&ctl->tempty[acc]), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;
+        for (int g = g0; g < g1; ++g) {
+          mbar_wait(smem_u32(&ctl->full[s]), ph);
+          tc_fence_after();
+          const uint32_t sy = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sa = sy + y_bytes;
+          for (int r8 = 0; r8 < R / 8; ++r8)
+            umma_tf32(d_tmem, smem_desc(sy + r8 * 1024, slab, 512, 1), smem_desc(sa + r8 * 1024, slab, 512, 1), idesc,
+                      (g > g0 || r8 > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&ctl->empty[s]));
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(smem_u32(&ctl->tfull[acc]));
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    float* xp = xpose + ew * (32 * kStagePitch);
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      int nt, kt, g0, g1;
+      decode(t, nt, kt, g0, g1);
+      const int acc = it & 1;
+      mbar_wait(smem_u32(&ctl->tfull[acc]), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kMaxBN;
+      const int nbase = nt * kBM + ew * 32;
+      const int kbase = kt * p.bnk;
+      const int kcols = min(p.bnk, p.K - kbase);
+      if (g1 > g0 && nbase < p.N) {
+        for (int c0 = 0; c0 < kcols; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xp[lane * kStagePitch + j] = __uint_as_float(v[j]);
+          __syncwarp();
+          const int k = kbase + c0 + lane;
+          if (k < p.K) {
+            const int nrows = min(32, p.N - nbase);
+            for (int rr = 0; rr < nrows; ++rr)
+              atomicAdd(p.dW + (size_t)(nbase + rr) * p.K + k, xp[rr * kStagePitch + lane]);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ctl->tempty[acc]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// dbias[n % bias_mod] += sum_{b,l} dY[b][l][n]  (n < bias_n).  Block = (256 / cw) rows x cw columns,
+// coalesced along n; grid.y splits the rows.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dY, int64_t y_bs, int64_t y_ls, int64_t B,
+                                                     int64_t Lo, int ncol, int bias_mod, float* dbias, int cw,
+                                                     int64_t rows_per_block) {
+  __shared__ float red[256];
+  const int64_t M = B * Lo;
+  const int tx = threadIdx.x % cw, ty = threadIdx.x / cw, rstep = 256 / cw;
+  const int64_t m0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  const int n = blockIdx.x * cw + tx;
+  float s0 = 0.f, s1 = 0.f;
+  if (n < ncol) {
+    int64_t m = m0 + ty;
+    for (; m + rstep < m1; m += 2 * rstep) {
+      const int64_t ba = m / Lo, la = m - ba * Lo;
+      const int64_t mb = m + rstep, bb = mb / Lo, lb = mb - bb * Lo;
+      s0 += __ldg(dY + ba * y_bs + la * y_ls + n);
+      s1 += __ldg(dY + bb * y_bs + lb * y_ls + n);
+    }
+    if (m < m1) {
+      const int64_t ba = m / Lo, la = m - ba * Lo;
+      s0 += __ldg(dY + ba * y_bs + la * y_ls + n);
+    }
+  }
+  red[threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (ty == 0 && n < ncol) {
+    float s = 0.f;
+    for (int r = 0; r < rstep; ++r) s += red[r * cw + tx];
+    atomicAdd(dbias + (n % bias_mod), s);
+  }
+}
+
+int g_attr_done = 0;
+
+int ensure_attrs() {
+  if (g_attr_done) return 0;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e != cudaSuccess) {
+    scv::set_error("tensor-core GEMM: cannot opt in to %d B of shared memory: %s", kSmemLimit, cudaGetErrorString(e));
+    cudaGetLastError();
+    return (int)e;
+  }
+  g_attr_done = 1;
+  return 0;
+}
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// rows of a (bl x nb) box, at most `rmax`; forward wants the best use of the 128 MMA rows,
+// the weight gradient wants rows % 8 == 0 and as few zero-filled rows as possible
+void choose_box(int64_t Lo, int64_t B, int rmax, bool mult8, int& bl, int& nb) {
+  double best = -1.0;
+  bl = 1;
+  nb = mult8 ? 8 : 1;
+  int lmax = (int)(mult8 ? (Lo + 7) / 8 * 8 : Lo);
+  if (lmax > rmax) lmax = rmax;
+  if (lmax > 256) lmax = 256;
+  for (int l = lmax; l >= 1; --l) {
+    for (int n = 1; n * l <= rmax && n <= 256; ++n) {
+      const int r = l * n;
+      if (mult8 && r % 8) continue;
+      const double covered = (double)(cdiv(Lo, l) * l) * (double)(cdiv(B, n) * n);
+      double eff = (double)Lo * (double)B / covered;
+      eff *= (double)r / rmax;  // forward: unused MMA rows; wgrad: short stages pay more barrier round trips
+      if (eff > best + 1e-9 || (eff > best - 1e-9 && r > bl * nb)) {
+        best = eff;
+        bl = l;
+        nb = n;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+namespace scv {
+
+int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
+  const int64_t M = p->B * p->Lo;
+  // shapes the tensor-core path does not take (tiny scrubber-head layers, unaligned views)
+  if (p->N < 16 || p->K < 32 || M < 64) return 1;
+  if (p->K % 4 || p->a_bs % 4 || p->a_ls % 4 || !aligned16(p->A) || !aligned16(p->W)) return 1;
+  if (p->K > (1 << 30) || p->N > (1 << 30) || p->B >= (1LL << 31) || p->Lo >= (1LL << 31)) return 1;
+  int rc = ensure_attrs();
+  if (rc) return rc;
+
+  GemmTcParams q;
+  q.B = p->B; q.Lo = p->Lo; q.K = (int)p->K; q.N = (int)p->N;
+  choose_box(p->Lo, p->B, kBM, false, q.bl, q.nb);
+  q.lt = (int)cdiv(p->Lo, q.bl);
+  q.bt = (int)cdiv(p->B, q.nb);
+  // N tile: as wide as the MMA allows, balanced over the tiles, multiple of 16
+  const int n16 = (int)cdiv(p->N, 16) * 16;
+  const int nt0 = (int)cdiv(n16, kMaxBN);
+  q.bn = (int)cdiv(cdiv(n16, nt0), 16) * 16;
+  q.n_tiles = (int)cdiv(p->N, q.bn);
+  q.m_tiles = q.lt * q.bt;
+  q.k_chunks = (int)cdiv(p->K, kBK);
+  const size_t stage_bytes = (size_t)kBM * kBK * 4 + (size_t)q.bn * kBK * 4;
+  const size_t fixed = 1024 + ((sizeof(SmemCtl) + 15) & ~size_t(15)) + 4 * 32 * kStagePitch * 4;
+  int stages = (int)((kSmemLimit - fixed) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > q.k_chunks + 1) stages = q.k_chunks + 1;
+  if (stages < 2) stages = 2;
+  q.stages = stages;
+  q.bias = p->bias; q.bias_mod = (int)(p->bias ? p->bias_mod : 1); q.bias_n = (int)(p->bias ? p->bias_n : 0);
+  q.Y = p->Y; q.y_bs = p->y_bs; q.y_ls = p->y_ls; q.n_last = (int)p->n_last;
+  q.R = p->R; q.r_bs = p->r_bs; q.r_ls = p->r_ls;
+  q.act = (int)p->act; q.out_scale = (float)p->out_scale; q.stats = p->stats;
+
+  CUtensorMap tmA, tmW;
+  {
+    const int64_t dims[3] = {p->K, p->Lo, p->B};
+    const int64_t str[3] = {1, p->a_ls ? p->a_ls : p->a_bs, p->a_bs ? p->a_bs : 4};
+    const int box[3] = {kBK, q.bl, q.nb};
+    rc = tc::make_tmap(&tmA, p->A, 3, dims, str, box, "scv_gemm A");
+    if (rc) return rc;
+  }
+  {
+    const int64_t dims[2] = {p->K, p->N};
+    const int64_t str[2] = {1, p->K};
+    const int box[2] = {kBK, q.bn};
+    rc = tc::make_tmap(&tmW, p->W, 2, dims, str, box, "scv_gemm W");
+    if (rc) return rc;
+  }
+  const int total = q.n_tiles * q.m_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  const size_t smem = fixed + (size_t)stages * stage_bytes;
+  gemm_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, q);
+  return check_launch("gemm_tc_kernel");
+}
+
+int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
+  const int64_t M = p->B * p->Lo;
+  if (p->N < 16 || p->K < 32 || M < 256) return 1;
+  if (p->K % 4 || p->N % 4 || p->a_bs % 4 || p->a_ls % 4 || p->y_bs % 4 || p->y_ls % 4 || !aligned16(p->A) ||
+      !aligned16(p->dY))
+    return 1;
+  if (p->K > (1 << 30) || p->N > (1 << 30) || p->B >= (1LL << 31) || p->Lo >= (1LL << 31)) return 1;
+  int rc = ensure_attrs();
+  if (rc) return rc;
+
+  WgradTcParams q;
+  q.K = (int)p->K; q.N = (int)p->N; q.dW = p->dW;
+  choose_box(p->Lo, p->B, 32, true, q.bl, q.nb);
+  q.lt = (int)cdiv(p->Lo, q.bl);
+  q.bt = (int)cdiv(p->B, q.nb);
+  q.groups = q.lt * q.bt;
+  const int k16 = (int)cdiv(p->K, 16) * 16;
+  const int kt0 = (int)cdiv(k16, kMaxBN);
+  q.bnk = (int)cdiv(cdiv(k16, kt0), 16) * 16;
+  q.k_tiles = (int)cdiv(p->K, q.bnk);
+  q.n_tiles = (int)cdiv(p->N, kBM);
+  const int tiles = q.n_tiles * q.k_tiles;
+  // row splits: fill the SMs ~2x over, but keep at least 4 row groups per item
+  int splits = (int)cdiv(2 * sm_count(), tiles);
+  if (splits > q.groups / 4) splits = q.groups / 4;
+  if (splits < 1) splits = 1;
+  q.gps = (int)cdiv(q.groups, splits);
+  q.splits = (int)cdiv(q.groups, q.gps);
+  const int R = q.bl * q.nb;
+  const size_t stage_bytes = (size_t)(4 + (q.bnk + 31) / 32) * R * 128;
+  const size_t fixed = 1024 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + 4 * 32 * kStagePitch * 4;
+  int stages = (int)((kSmemLimit - fixed) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return 1;
+  q.stages = stages;
+
+  CUtensorMap tmY, tmA;
+  {
+    const int64_t dims[3] = {p->N, p->Lo, p->B};
+    const int64_t str[3] = {1, p->y_ls ? p->y_ls : p->y_bs, p->y_bs ? p->y_bs : 4};
+    const int box[3] = {32, q.bl, q.nb};
+    rc = tc::make_tmap(&tmY, p->dY, 3, dims, str, box, "scv_wgrad dY", true);
+    if (rc) return rc;
+  }
+  {
+    const int64_t dims[3] = {p->K, p->Lo, p->B};
+    const int64_t str[3] = {1, p->a_ls ? p->a_ls : p->a_bs, p->a_bs ? p->a_bs : 4};
+    const int box[3] = {32, q.bl, q.nb};
+    rc = tc::make_tmap(&tmA, p->A, 3, dims, str, box, "scv_wgrad A", true);
+    if (rc) return rc;
+  }
+  const int total = tiles * q.splits;
+  const int grid = total < sm_count() ? total : sm_count();
+  const size_t smem = fixed + (size_t)stages * stage_bytes;
+  wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tmY, tmA, q);
+  rc = check_launch("wgrad_tc_kernel");
+  if (rc) return rc;
+  if (p->dbias && p->bias_n > 0) {
+    const int ncol = (int)(p->bias_n < p->N ? p->bias_n : p->N);
+    int cw = 32;
+    while (cw < 256 && cw < ncol) cw *= 2;
+    const int gx = (ncol + cw - 1) / cw;
+    int64_t gy = cdiv(8LL * sm_count(), gx);
+    if (gy > cdiv(M, 4 * (256 / cw))) gy = cdiv(M, 4 * (256 / cw));
+    if (gy < 1) gy = 1;
+    const int64_t rpb = cdiv(M, gy);
+    gy = cdiv(M, rpb);
+    colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(p->dY, p->y_bs, p->y_ls, p->B, p->Lo, ncol, (int)p->bias_mod,
+                                                          p->dbias, cw, rpb);
+    rc = check_launch("colsum_kernel");
+  }
+  return rc;
+}
+
 }  // namespace scv
