@@ -27,6 +27,15 @@ extern "C" {
 #define SCV_ACT_RELU 1
 #define SCV_ACT_TANH 2
 #define SCV_ACT_RELUMASK 3 /* y = (R > 0) ? y : 0 ; R is a mask, not added */
+#define SCV_ACT_ROUND_TF32 16 /* OR-ed into act: round the stored Y to TF32 (it feeds a tensor-core GEMM) */
+
+/* `flags` arguments of the kernels that PRODUCE tensor-core GEMM operands: round what is stored to TF32
+ * (round-to-nearest, ties away: cvt.rna.tf32.f32).  tcgen05 kind::tf32 truncates fp32 operands; rounding at
+ * the producer makes the operand error unbiased.  0 keeps plain fp32 (the SCV_PREC_FP32 path). */
+#define SCV_F_ROUND_TF32 1
+#define SCV_GATHER_SKIP_NEG 1
+#define SCV_GATHER_ROUND_TF32 2
+#define SCV_MODE_ROUND_TF32 8 /* scv_bnact_*: mode bit3 */
 
 #define SCV_PREC_FP32 0 /* FFMA, fp32 exact */
 #define SCV_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
@@ -74,10 +83,11 @@ int scv_wgrad(const scv_wgrad_t* p, void* stream);
 /* ---- input pack: ResVAE.encode model/residual.py:438-451 + normalize_root :428-431 --------
  * out[b][halo+w][0..nx) = x6d[b][w][:], [nx..nx+3) = 2*(root-a0)/(a1-a0)-1, rest 0 (C floats/row) */
 int scv_pack_input(const float* x6d, const float* root, const float* arena, float* out,
-                   int64_t B, int64_t W, int64_t nx, int64_t C, int64_t halo, void* stream);
+                   int64_t B, int64_t W, int64_t nx, int64_t C, int64_t halo, int64_t flags, void* stream);
 
 /* ---- BatchNorm1d(train/eval) + PReLU (+ x2 linear upsample) -------------------------------
  * model/residual.py:88-89,112-113,146-147,160,172-174,199.  X rows (b,l) of C floats.
+ * mode bit3: round H/U (forward) or dX (backward) to TF32.
  * mode bit0: batch-norm present, bit1: PReLU present, bit2: training (batch statistics from
  * `stats` = column sums / sums of squares over `fold` column groups, `count` elements per channel;
  * running stats updated with `momentum`), else running statistics are used.
@@ -116,12 +126,13 @@ int scv_bnact_bwd_apply(const scv_bnact_bwd_t* p, void* stream);
  * ms rows: [mu (z) | sigma raw (z(z+1)/2)] with row stride ms_ld.  Writes mu (B,z), dense L (B,z,z),
  * zc rows [z | var | 0-pad] (row stride zc_ld; var = B x nvar, may be NULL).  eps NULL => z = mu. */
 int scv_reparam_fwd(const float* ms, int64_t ms_ld, const float* eps, const float* var, int64_t nvar,
-                    float* mu, float* L, float* zc, int64_t zc_ld, int64_t B, int64_t z, void* stream);
+                    float* mu, float* L, float* zc, int64_t zc_ld, int64_t B, int64_t z, int64_t flags,
+                    void* stream); /* flags: zc is rounded */
 /* dms = backward of the above given dmu (B,z), dz rows (stride dz_ld), dL dense (each may be NULL);
  * dmu2 (optional, B x z) is added to dmu scaled by dmu2_scale (gradient reversal: -alpha). */
 int scv_reparam_bwd(const float* ms, int64_t ms_ld, const float* eps, const float* dmu, const float* dmu2,
                     double dmu2_scale, const float* dz, int64_t dz_ld, const float* dL, float* dms,
-                    int64_t dms_ld, int64_t B, int64_t z, void* stream);
+                    int64_t dms_ld, int64_t B, int64_t z, int64_t flags, void* stream); /* flags: dms is rounded */
 
 /* ---- prior_loss train/losses.py:138-146: loss[0] += KL/B (double, if loss != NULL);
  * if dmu/dL != NULL they get gscale[0] * dKL/dmu, dKL/dL (gscale: device scalar, NULL = 1) ------*/
@@ -144,7 +155,8 @@ int scv_recon_loss(const float* xh, int64_t ld, const float* offsets, const floa
 /* draw[b][halo+w][c] = (g_jpe*dxh[c<nx] | g_root*dxh[nx<=c<nx+3]) * (1 - xh^2); g_* are device
  * scalars (NULL = 0).  Backward of tanh at model/residual.py:291 fused with the loss scales. */
 int scv_out_bwd(const float* xh, const float* dxh, int64_t ld, const float* g_jpe, const float* g_root,
-                int64_t nx, float* draw, int64_t d_bs, int64_t d_ls, int64_t B, int64_t W, void* stream);
+                int64_t nx, float* draw, int64_t d_bs, int64_t d_ls, int64_t B, int64_t W, int64_t flags,
+                void* stream);
 
 /* ---- gradient-reversal head loss train/losses.py:267-284 (nested normalisation, quirk i) ------
  * pred[e] (B x d, row stride ld) for e < n_ens; target (B x d float) or labels (B int64, CE).
@@ -155,8 +167,8 @@ int scv_gr_loss(const float* const* pred, float* const* dpred, int64_t ld, int64
                 double* loss, const float* gscale, void* stream);
 
 /* ---- gather  dst[i] = idx[i] >= 0 ? src[idx[i]] : 0  (weight repack / gradient unpack;
- * skip_neg != 0 leaves dst[i] untouched where idx[i] < 0) */
-int scv_gather(const float* src, const int32_t* idx, float* dst, int64_t n, int64_t skip_neg, void* stream);
+ * flags & SCV_GATHER_SKIP_NEG leaves dst[i] untouched where idx[i] < 0, & SCV_GATHER_ROUND_TF32 rounds) */
+int scv_gather(const float* src, const int32_t* idx, float* dst, int64_t n, int64_t flags, void* stream);
 
 /* ---- step tail train/trainer.py:160-165: clip_grad_norm_(max_norm) + Adam/AdamW/SGD ----------
  * sumsq[0] += sum g^2 (double).  The update kernel derives the clip coefficient

@@ -17,8 +17,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libscv.so")
 
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELUMASK = 0, 1, 2, 3
+ACT_ROUND_TF32 = 16  # OR-ed into act: the stored output is rounded to TF32 (it feeds a tensor-core GEMM)
 PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
-BN, PRELU, TRAIN = 1, 2, 4  # bnact mode bits
+BN, PRELU, TRAIN, ROUND_TF32 = 1, 2, 4, 8  # bnact mode bits
 
 
 class Ref:
@@ -80,15 +81,15 @@ _SIGS = {
     "scv_launch_count": (_i64, []),
     "scv_gemm": (C.c_int, [C.POINTER(GemmT), _vp]),
     "scv_wgrad": (C.c_int, [C.POINTER(WgradT), _vp]),
-    "scv_pack_input": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "scv_pack_input": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp]),
     "scv_bnact_fwd": (C.c_int, [C.POINTER(BnactT), _vp]),
     "scv_bnact_bwd_reduce": (C.c_int, [C.POINTER(BnactBwdT), _vp]),
     "scv_bnact_bwd_apply": (C.c_int, [C.POINTER(BnactBwdT), _vp]),
-    "scv_reparam_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
-    "scv_reparam_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _f64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "scv_reparam_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "scv_reparam_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _f64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "scv_kl": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "scv_recon_loss": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
-    "scv_out_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "scv_out_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "scv_gr_loss": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "scv_gather": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "scv_sumsq": (C.c_int, [_vp, _i64, _vp, _vp]),
@@ -144,9 +145,9 @@ class CudaOps:
                    precision)
         self._check(self.lib.scv_wgrad(C.byref(p), self._stream()), "scv_wgrad")
 
-    def pack_input(self, x6d, root, arena, out, B, W, nx, Cc, halo):
+    def pack_input(self, x6d, root, arena, out, B, W, nx, Cc, halo, round_tf32=False):
         self._check(self.lib.scv_pack_input(_ptr(x6d), _ptr(root), _ptr(arena), _ptr(out), B, W, nx, Cc, halo,
-                                            self._stream()), "scv_pack_input")
+                                            int(round_tf32), self._stream()), "scv_pack_input")
 
     def bnact_fwd(self, X, x_bs, x_ls, B, L, Cc, mode, stats=None, fold=1, count=1.0, eps=1e-4, momentum=0.1,
                   gamma=None, beta=None, running_mean=None, running_var=None, slope=None,
@@ -174,13 +175,14 @@ class CudaOps:
                              o_ls, dU, u_bs, u_ls, sums, dX, d_bs, d_ls, dgamma, dbeta, dslope)
         self._check(self.lib.scv_bnact_bwd_apply(C.byref(p), self._stream()), "scv_bnact_bwd_apply")
 
-    def reparam_fwd(self, ms, ms_ld, eps, var, nvar, mu, L, zc, zc_ld, B, z):
+    def reparam_fwd(self, ms, ms_ld, eps, var, nvar, mu, L, zc, zc_ld, B, z, round_tf32=False):
         self._check(self.lib.scv_reparam_fwd(_ptr(ms), ms_ld, _ptr(eps), _ptr(var), nvar, _ptr(mu), _ptr(L), _ptr(zc),
-                                             zc_ld, B, z, self._stream()), "scv_reparam_fwd")
+                                             zc_ld, B, z, int(round_tf32), self._stream()), "scv_reparam_fwd")
 
-    def reparam_bwd(self, ms, ms_ld, eps, dmu, dmu2, dmu2_scale, dz, dz_ld, dL, dms, dms_ld, B, z):
+    def reparam_bwd(self, ms, ms_ld, eps, dmu, dmu2, dmu2_scale, dz, dz_ld, dL, dms, dms_ld, B, z, round_tf32=False):
         self._check(self.lib.scv_reparam_bwd(_ptr(ms), ms_ld, _ptr(eps), _ptr(dmu), _ptr(dmu2), float(dmu2_scale),
-                                             _ptr(dz), dz_ld, _ptr(dL), _ptr(dms), dms_ld, B, z, self._stream()),
+                                             _ptr(dz), dz_ld, _ptr(dL), _ptr(dms), dms_ld, B, z, int(round_tf32),
+                                             self._stream()),
                     "scv_reparam_bwd")
 
     def kl(self, mu, L, loss, gscale, dmu, dL, B, z):
@@ -192,9 +194,9 @@ class CudaOps:
                                             _ptr(tree), n_tree, _ptr(loss), _ptr(root_hat), _ptr(dxh), F, B, J,
                                             self._stream()), "scv_recon_loss")
 
-    def out_bwd(self, xh, dxh, ld, g_jpe, g_root, nx, draw, d_bs, d_ls, B, W):
+    def out_bwd(self, xh, dxh, ld, g_jpe, g_root, nx, draw, d_bs, d_ls, B, W, round_tf32=False):
         self._check(self.lib.scv_out_bwd(_ptr(xh), _ptr(dxh), ld, _ptr(g_jpe), _ptr(g_root), nx, _ptr(draw), d_bs,
-                                         d_ls, B, W, self._stream()), "scv_out_bwd")
+                                         d_ls, B, W, int(round_tf32), self._stream()), "scv_out_bwd")
 
     def gr_loss(self, preds: Sequence[Ref], dpreds: Optional[Sequence[Ref]], ld, target, labels, B, d, num_keys,
                 loss, gscale):
@@ -204,8 +206,9 @@ class CudaOps:
         self._check(self.lib.scv_gr_loss(pa, da, ld, n, _ptr(target), _ptr(labels), B, d, num_keys, _ptr(loss),
                                          _ptr(gscale), self._stream()), "scv_gr_loss")
 
-    def gather(self, src, idx, dst, n, skip_neg=False):
-        self._check(self.lib.scv_gather(_ptr(src), _ptr(idx), _ptr(dst), n, int(skip_neg), self._stream()),
+    def gather(self, src, idx, dst, n, skip_neg=False, round_tf32=False):
+        self._check(self.lib.scv_gather(_ptr(src), _ptr(idx), _ptr(dst), n, int(bool(skip_neg)) | (2 if round_tf32 else 0),
+                                        self._stream()),
                     "scv_gather")
 
     def sumsq(self, g, n, out):

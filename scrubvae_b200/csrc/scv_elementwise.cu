@@ -127,11 +127,12 @@ __global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, cons
     }
   }
   const int64_t L = p.L;
+  const bool rnd = mode & SCV_MODE_ROUND_TF32;
   for (int64_t r = t.r0; r < t.rend; r += t.rstep) {
     int64_t b = r / L, l = r - b * L;
     const float* xr = p.X + b * p.x_bs + l * p.x_ls + t.c * 4;
     float4 a = bn_prelu(ld4(xr), cb, has_act, slope);
-    if (p.H) st4(p.H + b * p.h_bs + l * p.h_ls + t.c * 4, a);
+    if (p.H) st4(p.H + b * p.h_bs + l * p.h_ls + t.c * 4, rnd ? scv::round_tf32(a) : a);
     if (p.U) {
       float4 am = l > 0 ? bn_prelu(ld4(xr - p.x_ls), cb, has_act, slope) : a;
       float4 ap = l < L - 1 ? bn_prelu(ld4(xr + p.x_ls), cb, has_act, slope) : a;
@@ -141,8 +142,8 @@ __global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, cons
       o.x = 0.75f * a.x + 0.25f * ap.x; o.y = 0.75f * a.y + 0.25f * ap.y;
       o.z = 0.75f * a.z + 0.25f * ap.z; o.w = 0.75f * a.w + 0.25f * ap.w;
       float* ur = p.U + b * p.u_bs + (2 * l) * p.u_ls + t.c * 4;
-      st4(ur, e);
-      st4(ur + p.u_ls, o);
+      st4(ur, rnd ? scv::round_tf32(e) : e);
+      st4(ur + p.u_ls, rnd ? scv::round_tf32(o) : o);
     }
   }
 }
@@ -269,13 +270,14 @@ __global__ void __launch_bounds__(NT) bnact_bwd_apply_kernel(const scv_bnact_bwd
         d[q] = gg;
       }
     }
-    st4(p.dX + b * p.d_bs + l * p.d_ls + t.c * 4, make_float4(d[0], d[1], d[2], d[3]));
+    float4 dv = make_float4(d[0], d[1], d[2], d[3]);
+    st4(p.dX + b * p.d_bs + l * p.d_ls + t.c * 4, (mode & SCV_MODE_ROUND_TF32) ? scv::round_tf32(dv) : dv);
   }
 }
 
 __global__ void __launch_bounds__(NT) pack_input_kernel(const float* __restrict__ x6d, const float* __restrict__ root,
                                                         const float* __restrict__ arena, float* __restrict__ out,
-                                                        int64_t rows, int W, int nx, int C, int halo) {
+                                                        int64_t rows, int W, int nx, int C, int halo, int rnd) {
   const int64_t total = rows * C;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
     int64_t r = i / C;
@@ -290,16 +292,17 @@ __global__ void __launch_bounds__(NT) pack_input_kernel(const float* __restrict_
       float a0 = arena[d], a1 = arena[3 + d];
       v = 2.f * (root[r * 3 + d] - a0) / (a1 - a0) - 1.f;
     }
-    out[(b * (W + 2 * halo) + halo + w) * C + c] = v;
+    out[(b * (W + 2 * halo) + halo + w) * C + c] = rnd ? scv::round_tf32(v) : v;
   }
 }
 
 __global__ void __launch_bounds__(NT) gather_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
-                                                    float* __restrict__ dst, int64_t n, int skip_neg) {
+                                                    float* __restrict__ dst, int64_t n, int flags) {
+  const bool rnd = flags & SCV_GATHER_ROUND_TF32;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * NT) {
     int32_t j = idx[i];
-    if (j >= 0) dst[i] = __ldg(src + j);
-    else if (!skip_neg) dst[i] = 0.f;
+    if (j >= 0) { float v = __ldg(src + j); dst[i] = rnd ? scv::round_tf32(v) : v; }
+    else if (!(flags & SCV_GATHER_SKIP_NEG)) dst[i] = 0.f;
   }
 }
 
@@ -395,10 +398,11 @@ int grid1d(int64_t n, int per_sm) {
 extern "C" {
 
 int scv_pack_input(const float* x6d, const float* root, const float* arena, float* out, int64_t B, int64_t W,
-                   int64_t nx, int64_t C, int64_t halo, void* stream) {
+                   int64_t nx, int64_t C, int64_t halo, int64_t flags, void* stream) {
   SCV_REQUIRE(nx + 3 <= C, "scv_pack_input: C too small");
   pack_input_kernel<<<grid1d(B * W * C, 8), NT, 0, (cudaStream_t)stream>>>(x6d, root, arena, out, B * W, (int)W,
-                                                                          (int)nx, (int)C, (int)halo);
+                                                                          (int)nx, (int)C, (int)halo,
+                                                                          (int)(flags & SCV_F_ROUND_TF32));
   return scv::check_launch("pack_input_kernel");
 }
 
@@ -440,9 +444,9 @@ int scv_bnact_bwd_apply(const scv_bnact_bwd_t* p, void* stream) {
   return scv::check_launch("bnact_bwd_apply_kernel");
 }
 
-int scv_gather(const float* src, const int32_t* idx, float* dst, int64_t n, int64_t skip_neg, void* stream) {
+int scv_gather(const float* src, const int32_t* idx, float* dst, int64_t n, int64_t flags, void* stream) {
   if (n <= 0) return 0;
-  gather_kernel<<<grid1d(n, 16), NT, 0, (cudaStream_t)stream>>>(src, idx, dst, n, (int)skip_neg);
+  gather_kernel<<<grid1d(n, 16), NT, 0, (cudaStream_t)stream>>>(src, idx, dst, n, (int)flags);
   return scv::check_launch("gather_kernel");
 }
 

@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(NT, 2) gemm_ffma_kernel(const scv_gemm_t p, co
 
   // ---- epilogue
   const float osc = (float)p.out_scale;
-  const int act = (int)p.act;
+  const int act = (int)(p.act & 15);
+  const bool rnd = p.act & SCV_ACT_ROUND_TF32;
   float csum[8], csq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) csum[j] = csq[j] = 0.f;
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_ffma_kernel(const scv_gemm_t p, co
         if (act != SCV_ACT_RELUMASK) t += r[q];
         if (nb + q < ncap) { csum[h * 4 + q] += t; csq[h * 4 + q] += t * t; }
         v[q] = apply_act(t, act, r[q]);
+        if (rnd) v[q] = scv::round_tf32(v[q]);
       }
       if (vec) {
         *reinterpret_cast<float4*>(yrow + nb) = make_float4(v[0], v[1], v[2], v[3]);

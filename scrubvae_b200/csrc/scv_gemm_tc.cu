@@ -93,7 +93,7 @@ struct GemmTcParams {
   int n_last;
   const float* R;
   int64_t r_bs, r_ls;
-  int act;
+  int act, round_out;
   float out_scale;
   double* stats;
 };
@@ -229,22 +229,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 32; ++j) xp[lane * kStagePitch + j] = __uint_as_float(v[j]);
         __syncwarp();
         const int n = n0 + c0 + lane;
+        const bool col_ok = c0 + lane < ncols;  // bn need not be a multiple of 32: the rest is the next tile's
         const float bv = (p.bias && n < p.bias_n) ? __ldg(p.bias + (n % p.bias_mod)) : 0.f;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
           const long long yo = ctl->yoff[ew * 32 + rr];
           if (yo < 0) continue;
-          if (n < ctl->ncap[ew * 32 + rr]) {
+          if (col_ok && n < ctl->ncap[ew * 32 + rr]) {
             float tv = p.out_scale * xp[rr * kStagePitch + lane] + bv;
             const float r = p.R ? __ldg(p.R + ctl->roff[ew * 32 + rr] + n) : 0.f;
             if (p.act != SCV_ACT_RELUMASK) tv += r;
             s1 += tv;
             s2 += tv * tv;
-            p.Y[yo + n] = act_apply(tv, p.act, r);
+            const float yv = act_apply(tv, p.act, r);
+            p.Y[yo + n] = p.round_out ? scv::round_tf32(yv) : yv;
           }
         }
-        if (p.stats && n < N) {
+        if (p.stats && col_ok) {
           atomicAdd(p.stats + n, (double)s1);
           atomicAdd(p.stats + N + n, (double)s2);
         }
@@ -397,7 +399,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           for (int j = 0; j < 32; ++j) xp[lane * kStagePitch + j] = __uint_as_float(v[j]);
           __syncwarp();
           const int k = kbase + c0 + lane;
-          if (k < p.K) {
+          if (c0 + lane < kcols) {
             const int nrows = min(32, p.N - nbase);
             for (int rr = 0; rr < nrows; ++rr)
               atomicAdd(p.dW + (size_t)(nbase + rr) * p.K + k, xp[rr * kStagePitch + lane]);
@@ -529,7 +531,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   q.bias = p->bias; q.bias_mod = (int)(p->bias ? p->bias_mod : 1); q.bias_n = (int)(p->bias ? p->bias_n : 0);
   q.Y = p->Y; q.y_bs = p->y_bs; q.y_ls = p->y_ls; q.n_last = (int)p->n_last;
   q.R = p->R; q.r_bs = p->r_bs; q.r_ls = p->r_ls;
-  q.act = (int)p->act; q.out_scale = (float)p->out_scale; q.stats = p->stats;
+  q.act = (int)(p->act & 15); q.round_out = (p->act & SCV_ACT_ROUND_TF32) ? 1 : 0; q.out_scale = (float)p->out_scale; q.stats = p->stats;
 
   CUtensorMap tmA, tmW;
   {

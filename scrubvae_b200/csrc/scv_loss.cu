@@ -13,7 +13,7 @@ __device__ __forceinline__ float softplus_grad(float x) { return x > 20.f ? 1.f 
 __global__ void __launch_bounds__(256) reparam_fwd_kernel(const float* __restrict__ ms, int64_t ms_ld,
                                                           const float* __restrict__ eps, const float* __restrict__ var,
                                                           int nvar, float* __restrict__ mu, float* __restrict__ L,
-                                                          float* __restrict__ zc, int64_t zc_ld, int z) {
+                                                          float* __restrict__ zc, int64_t zc_ld, int z, int rnd) {
   extern __shared__ float sh[];
   const int nsig = z * (z + 1) / 2;
   float* sig = sh;          // nsig
@@ -29,11 +29,11 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(const float* __restric
     for (int j = 0; j < i; ++j) acc = fmaf(sig[tri + j], e[j], acc);
     acc = fmaf(softplus_f(sig[tri + i]), e[i], acc);
     if (mu) mu[b * z + i] = m;
-    if (zc) zc[b * zc_ld + i] = eps ? acc : m;
+    if (zc) { float zv = eps ? acc : m; zc[b * zc_ld + i] = rnd ? scv::round_tf32(zv) : zv; }
   }
   if (zc) {
     for (int t = threadIdx.x; t < (int)zc_ld - z; t += blockDim.x)
-      zc[b * zc_ld + z + t] = t < nvar ? var[b * nvar + t] : 0.f;
+      { float vv = t < nvar ? var[b * nvar + t] : 0.f; zc[b * zc_ld + z + t] = rnd ? scv::round_tf32(vv) : vv; }
   }
   if (L) {
     float* Lb = L + b * (int64_t)z * z;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) reparam_bwd_kernel(const float* __restric
                                                           const float* __restrict__ dmu2, float s2,
                                                           const float* __restrict__ dz, int64_t dz_ld,
                                                           const float* __restrict__ dL, float* __restrict__ dms,
-                                                          int64_t dms_ld, int z) {
+                                                          int64_t dms_ld, int z, int rnd) {
   extern __shared__ float sh[];
   float* e = sh;       // z
   float* gz = sh + z;  // z
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) reparam_bwd_kernel(const float* __restric
     if (dmu) g += dmu[b * z + i];
     if (dmu2) g += s2 * dmu2[b * z + i];
     if (dz) g += dz[b * dz_ld + i];
-    dms[b * dms_ld + i] = g;
+    dms[b * dms_ld + i] = rnd ? scv::round_tf32(g) : g;
   }
   __syncthreads();
   const float* sraw = ms + b * ms_ld + z;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) reparam_bwd_kernel(const float* __restric
     if (dLb) g += dLb[idx];
     const int t = i * (i + 1) / 2 + j;
     if (j == i) g *= softplus_grad(sraw[t]);
-    drow[t] = g;
+    drow[t] = rnd ? scv::round_tf32(g) : g;
   }
   for (int t = z + nsig + threadIdx.x; t < dms_ld; t += blockDim.x) dms[b * dms_ld + t] = 0.f;
 }
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(FK_THREADS) recon_loss_kernel(const float* __r
 __global__ void __launch_bounds__(256) out_bwd_kernel(const float* __restrict__ xh, const float* __restrict__ dxh,
                                                       int ld, const float* g_jpe, const float* g_root, int nx,
                                                       float* __restrict__ draw, int64_t d_bs, int64_t d_ls,
-                                                      int64_t rows, int W) {
+                                                      int64_t rows, int W, int rnd) {
   const float gj = g_jpe ? *g_jpe : 0.f, gr = g_root ? *g_root : 0.f;
   const int64_t total = rows * ld;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(256) out_bwd_kernel(const float* __restrict__ 
     int w = (int)(r - b * W);
     float y = xh[i];
     float g = dxh[i] * (c < nx ? gj : (c < nx + 3 ? gr : 0.f));
-    draw[b * d_bs + w * d_ls + c] = g * (1.f - y * y);
+    const float dv = g * (1.f - y * y);
+    draw[b * d_bs + w * d_ls + c] = rnd ? scv::round_tf32(dv) : dv;
   }
 }
 
@@ -223,22 +224,22 @@ __global__ void __launch_bounds__(256) gr_loss_kernel(const GrPtrs P, int ld, in
 extern "C" {
 
 int scv_reparam_fwd(const float* ms, int64_t ms_ld, const float* eps, const float* var, int64_t nvar, float* mu,
-                    float* L, float* zc, int64_t zc_ld, int64_t B, int64_t z, void* stream) {
+                    float* L, float* zc, int64_t zc_ld, int64_t B, int64_t z, int64_t flags, void* stream) {
   size_t sh = (size_t)(z * (z + 1) / 2 + z) * sizeof(float);
   SCV_REQUIRE(sh <= 48 * 1024, "scv_reparam_fwd: z_dim %lld too large", (long long)z);
   SCV_REQUIRE(!zc || zc_ld >= z + nvar, "scv_reparam_fwd: zc_ld too small");
   if (B <= 0) return 0;
   reparam_fwd_kernel<<<(unsigned)B, 256, sh, (cudaStream_t)stream>>>(ms, ms_ld, eps, var, (int)nvar, mu, L, zc, zc_ld,
-                                                                    (int)z);
+                                                                    (int)z, (int)(flags & SCV_F_ROUND_TF32));
   return scv::check_launch("reparam_fwd_kernel");
 }
 
 int scv_reparam_bwd(const float* ms, int64_t ms_ld, const float* eps, const float* dmu, const float* dmu2,
                     double dmu2_scale, const float* dz, int64_t dz_ld, const float* dL, float* dms, int64_t dms_ld,
-                    int64_t B, int64_t z, void* stream) {
+                    int64_t B, int64_t z, int64_t flags, void* stream) {
   if (B <= 0) return 0;
   reparam_bwd_kernel<<<(unsigned)B, 256, (size_t)(2 * z) * sizeof(float), (cudaStream_t)stream>>>(
-      ms, ms_ld, eps, dmu, dmu2, (float)dmu2_scale, dz, dz_ld, dL, dms, dms_ld, (int)z);
+      ms, ms_ld, eps, dmu, dmu2, (float)dmu2_scale, dz, dz_ld, dL, dms, dms_ld, (int)z, (int)(flags & SCV_F_ROUND_TF32));
   return scv::check_launch("reparam_bwd_kernel");
 }
 
@@ -260,14 +261,15 @@ int scv_recon_loss(const float* xh, int64_t ld, const float* offsets, const floa
 }
 
 int scv_out_bwd(const float* xh, const float* dxh, int64_t ld, const float* g_jpe, const float* g_root, int64_t nx,
-                float* draw, int64_t d_bs, int64_t d_ls, int64_t B, int64_t W, void* stream) {
+                float* draw, int64_t d_bs, int64_t d_ls, int64_t B, int64_t W, int64_t flags, void* stream) {
   int64_t total = B * W * ld;
   int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)scv::sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) return 0;
   out_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(xh, dxh, (int)ld, g_jpe, g_root, (int)nx, draw,
-                                                                    d_bs, d_ls, B * W, (int)W);
+                                                                    d_bs, d_ls, B * W, (int)W,
+                                                                    (int)(flags & SCV_F_ROUND_TF32));
   return scv::check_launch("out_bwd_kernel");
 }
 

@@ -27,7 +27,7 @@ import torch
 import torch.nn as nn
 
 from . import layout as lay
-from ._ops import ACT_NONE, ACT_RELU, ACT_RELUMASK, ACT_TANH, BN, PREC, PRELU, TRAIN, Ref
+from ._ops import ACT_NONE, ACT_RELU, ACT_RELUMASK, ACT_ROUND_TF32, ACT_TANH, BN, PREC, PRELU, ROUND_TF32, TRAIN, Ref
 
 FEAT_FLOAT = ("avg_speed", "part_speed", "frame_speed", "avg_speed_3d", "heading", "heading_change", "fluorescence")
 
@@ -71,6 +71,9 @@ class Engine:
         self.ops = ops
         self.m = model
         self.precision = PREC[getattr(model, "precision", "tf32")]
+        # tensor-core path: every kernel that PRODUCES a GEMM operand rounds it to TF32 (round-to-nearest); the
+        # MMA itself would truncate, which biases sums that cancel (BatchNorm backward subtracts batch means)
+        self.rnd = self.precision != 0
         self.device = next(model.parameters()).device
         if ops.name == "cuda" and self.device.type != "cuda":
             raise RuntimeError("scrubvae_b200: the model must live on a CUDA device (there is no CPU path); "
@@ -265,7 +268,7 @@ class Engine:
         return None if g.b is None else Ref(self.gpacked, g.b)
 
     def repack(self):
-        self.ops.gather(self.flat, self.pack_idx, self.packed, self.packed.numel(), False)
+        self.ops.gather(self.flat, self.pack_idx, self.packed, self.packed.numel(), False, round_tf32=self.rnd)
 
     # ------------------------------------------------------------------ API
     def plan(self, B: int) -> "Plan":
@@ -299,6 +302,8 @@ class Plan:
         self.nx = self.J * 6
         C0 = eng.C0
         prec = eng.precision
+        rnd = eng.rnd
+        rmode = ROUND_TF32 if rnd else 0
         slack = eng.max_k + 64
         p2 = k // 2
         f32 = dict(device=dev, dtype=torch.float32)
@@ -366,7 +371,7 @@ class Plan:
         self._training = True
 
         def bn_mode(has_bn=True, has_act=True):
-            return (BN if has_bn else 0) | (PRELU if has_act else 0)
+            return (BN if has_bn else 0) | (PRELU if has_act else 0) | rmode
 
         def gemm(**kw):
             kw.setdefault("precision", prec)
@@ -433,7 +438,8 @@ class Plan:
         # =============================================================== encoder
         X0 = A(W, C0, 3, 3)
         self.X0 = X0
-        F.append(lambda: ops.pack_input(self.inp["x6d"], self.inp["root"], arena, X0.t, B, W, self.nx, C0, 3))
+        F.append(lambda: ops.pack_input(self.inp["x6d"], self.inp["root"], arena, X0.t, B, W, self.nx, C0, 3,
+                                        round_tf32=rnd))
         Y0 = A(W, ch[0])
         g = WG["enc.conv_in"]
         gemm(A=X0.at(-3), a_bs=X0.bs, a_ls=C0, B=B, Lo=W, K=g.K, N=g.N, W=eng.wref(g), bias=eng.bref(g),
@@ -480,7 +486,7 @@ class Plan:
         def reparam():
             ops.reparam_fwd(self.ms, eng.ms_ld, self.eps if self._training else None,
                             self.var if eng.cond_dim > 0 else None, eng.cond_dim, self.mu, self.Lmat, self.zc,
-                            eng.zc_ld, B, z)
+                            eng.zc_ld, B, z, round_tf32=rnd)
         F.append(reparam)
         self._n_enc = len(F)
 
@@ -489,7 +495,8 @@ class Plan:
         gin = WG["dec.fc_in"]
         H = A(Ll, Cl, p2, p2)
         gemm(A=self.zc, a_bs=eng.zc_ld, a_ls=0, B=B, Lo=1, K=gin.K, N=gin.N, W=eng.wref(gin), bias=eng.bref(gin),
-             bias_mod=gin.bias_mod, bias_n=gin.N, Y=H.at(0), y_bs=H.bs, y_ls=0)
+             bias_mod=gin.bias_mod, bias_n=gin.N, Y=H.at(0), y_bs=H.bs, y_ls=0,
+             act=ACT_ROUND_TF32 if rnd else ACT_NONE)  # fc_in output feeds the next GEMM directly
         U = A(2 * Ll, Cl, p2, p2)
         bnact_fwd(None, None, H, Ll, Cl, None, 1, U=U)
         dec_in = dict(H=H, U=U, g=gin)
@@ -594,7 +601,7 @@ class Plan:
         # conv_out + tanh
         dOut = A(W, C0, 3, 3)
         Bw.append(lambda: ops.out_bwd(self.xh, self.dxh, C0, Ref(self.gscale, 0), Ref(self.gscale, 1), self.nx,
-                                      dOut.at(0), dOut.bs, dOut.ls, B, W))
+                                      dOut.at(0), dOut.bs, dOut.ls, B, W, round_tf32=rnd))
         Bw.append(wgrad(gout, Hlast.at(-ho), Hlast.bs, ch[0], W, dOut.at(0), dOut.bs, dOut.ls))
         dH = A(eng.l_dec, ch[0])
         Bw.append(dgemm(gout, dOut.at(-3), dOut.bs, C0, eng.l_dec, dH.at(0), dH.bs, dH.ls))
@@ -660,7 +667,7 @@ class Plan:
         self.dms = torch.zeros(B, eng.ms_ld, **f32)
         Bw.append(lambda: ops.kl(self.mu, self.Lmat, None, Ref(self.gscale, 2), self.dmu_kl, self.dL_kl, B, z))
         Bw.append(lambda: ops.reparam_bwd(self.ms, eng.ms_ld, self.eps, self.dmu_kl, self.dmu_gr, 1.0, self.dzc,
-                                          eng.zc_ld, self.dL_kl, self.dms, eng.ms_ld, B, z))
+                                          eng.zc_ld, self.dL_kl, self.dms, eng.ms_ld, B, z, round_tf32=rnd))
         Bw.append(wgrad(gfc, Hflat.at(0), Hflat.bs, 0, 1, self.dms, eng.ms_ld, 0))
         dH = A(Ll, Cl)
         Bw.append(dgemm(gfc, self.dms, eng.ms_ld, 0, 1, dH.at(0), dH.bs, 0))

@@ -11,7 +11,14 @@ import math
 import torch
 
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELUMASK = 0, 1, 2, 3
-BN, PRELU, TRAIN = 1, 2, 4
+ACT_ROUND_TF32 = 16
+BN, PRELU, TRAIN, ROUND_TF32 = 1, 2, 4, 8
+
+
+def rtf32(x):
+    """cvt.rna.tf32.f32: round to nearest (ties away from zero) to a 10-bit mantissa"""
+    b = x.contiguous().view(torch.int32)
+    return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
 def _v(ref, shape, strides):
@@ -33,9 +40,12 @@ class EmuOps:
     def gemm(self, A, a_bs, a_ls, B, Lo, K, N, W, Y, y_bs, y_ls, bias=None, bias_mod=1, bias_n=0, n_last=None,
              R=None, r_bs=0, r_ls=0, act=ACT_NONE, out_scale=1.0, stats=None, precision=0):
         self.n += 1
+        rnd, act = bool(act & ACT_ROUND_TF32), act & 15
         n_last = N if n_last is None else n_last
         a = _v(A, (B, Lo, K), (a_bs, a_ls, 1))
         w = _v(W, (N, K), (K, 1))
+        if precision != 0:  # TF32 tensor-core arithmetic: operands carry 10 mantissa bits, fp32 accumulation
+            a, w = rtf32(a), rtf32(w)
         y = out_scale * (a.reshape(B * Lo, K) @ w.t()).reshape(B, Lo, N)
         if bias is not None:
             bb = _v(bias, (bias_mod,), (1,))
@@ -57,6 +67,8 @@ class EmuOps:
             y = torch.tanh(y)
         elif act == ACT_RELUMASK:
             y = torch.where(torch.where(valid, r, torch.zeros(())) > 0, y, torch.zeros(()))
+        if rnd:
+            y = rtf32(y)
         out = _v(Y, (B, Lo, N), (y_bs, y_ls, 1))
         if n_last == N:
             out.copy_(y)
@@ -68,14 +80,18 @@ class EmuOps:
         self.n += 1
         a = _v(A, (B, Lo, K), (a_bs, a_ls, 1)).reshape(B * Lo, K)
         g = _v(dY, (B, Lo, N), (y_bs, y_ls, 1)).reshape(B * Lo, N)
-        _v(dW, (N, K), (K, 1)).add_(g.t() @ a)
+        if precision != 0:
+            a, gm = rtf32(a), rtf32(g)
+        else:
+            gm = g
+        _v(dW, (N, K), (K, 1)).add_(gm.t() @ a)
         if dbias is not None:
             db = _v(dbias, (bias_mod,), (1,))
             s = g.sum(0)
             for n in range(min(N, bias_n)):
                 db[n % bias_mod] += s[n]
 
-    def pack_input(self, x6d, root, arena, out, B, W, nx, Cc, halo):
+    def pack_input(self, x6d, root, arena, out, B, W, nx, Cc, halo, round_tf32=False):
         self.n += 1
         x = _v(x6d, (B, W, nx), (W * nx, nx, 1))
         r = _v(root, (B, W, 3), (W * 3, 3, 1))
@@ -88,6 +104,8 @@ class EmuOps:
         o.zero_()
         o[..., :nx] = x
         o[..., nx:nx + 3] = 2 * (r - a[0]) / (a[1] - a[0]) - 1
+        if round_tf32:
+            o.copy_(rtf32(o.clone()))
 
     # ---- BN + PReLU
     def _chan(self, Cc, mode, stats, fold, count, eps, gamma, beta, rm, rv):
@@ -125,14 +143,15 @@ class EmuOps:
         if mode & PRELU:
             s = _v(slope, (1,), (1,))
             a = torch.where(a < 0, s * a, a)
+        rnd = (lambda t: rtf32(t)) if (mode & ROUND_TF32) else (lambda t: t)
         if H is not None:
-            _v(H, (B, L, Cc), (h_bs, h_ls, 1)).copy_(a)
+            _v(H, (B, L, Cc), (h_bs, h_ls, 1)).copy_(rnd(a))
         if U is not None:
             am = torch.cat([a[:, :1], a[:, :-1]], 1)
             ap = torch.cat([a[:, 1:], a[:, -1:]], 1)
             u = _v(U, (B, L, 2, Cc), (u_bs, 2 * u_ls, u_ls, 1))
-            u[:, :, 0] = 0.25 * am + 0.75 * a
-            u[:, :, 1] = 0.75 * a + 0.25 * ap
+            u[:, :, 0] = rnd(0.25 * am + 0.75 * a)
+            u[:, :, 1] = rnd(0.75 * a + 0.25 * ap)
 
     def _dout(self, B, L, Cc, dO, o_bs, o_ls, dU, u_bs, u_ls):
         g = torch.zeros(B, L, Cc)
@@ -193,10 +212,10 @@ class EmuOps:
             else:
                 d = scale * g
         if dX is not None:
-            _v(dX, (B, L, Cc), (d_bs, d_ls, 1)).copy_(d)
+            _v(dX, (B, L, Cc), (d_bs, d_ls, 1)).copy_(rtf32(d) if (mode & ROUND_TF32) else d)
 
     # ---- latent
-    def reparam_fwd(self, ms, ms_ld, eps, var, nvar, mu, L, zc, zc_ld, B, z):
+    def reparam_fwd(self, ms, ms_ld, eps, var, nvar, mu, L, zc, zc_ld, B, z, round_tf32=False):
         self.n += 1
         nsig = z * (z + 1) // 2
         row = _v(ms, (B, z + nsig), (ms_ld, 1))
@@ -220,8 +239,10 @@ class EmuOps:
                 o[:, :z] = m
             if nvar > 0:
                 o[:, z:z + nvar] = _v(var, (B, nvar), (nvar, 1))
+            if round_tf32:
+                o.copy_(rtf32(o.clone()))
 
-    def reparam_bwd(self, ms, ms_ld, eps, dmu, dmu2, dmu2_scale, dz, dz_ld, dL, dms, dms_ld, B, z):
+    def reparam_bwd(self, ms, ms_ld, eps, dmu, dmu2, dmu2_scale, dz, dz_ld, dL, dms, dms_ld, B, z, round_tf32=False):
         self.n += 1
         nsig = z * (z + 1) // 2
         sig = _v(ms, (B, z + nsig), (ms_ld, 1))[:, z:]
@@ -249,6 +270,8 @@ class EmuOps:
         sp = torch.where(sig > 20, torch.ones(()), torch.sigmoid(sig))
         gs = torch.where(isd[None, :], gs * sp, gs)
         out[:, z:z + nsig] = gs
+        if round_tf32:
+            out.copy_(rtf32(out.clone()))
 
     def kl(self, mu, L, loss, gscale, dmu, dL, B, z):
         self.n += 1
@@ -300,7 +323,7 @@ class EmuOps:
         d[:, :nx] = gx.reshape(F, nx)
         d[:, nx:nx + 3] = gr
 
-    def out_bwd(self, xh, dxh, ld, g_jpe, g_root, nx, draw, d_bs, d_ls, B, W):
+    def out_bwd(self, xh, dxh, ld, g_jpe, g_root, nx, draw, d_bs, d_ls, B, W, round_tf32=False):
         self.n += 1
         y = _v(xh, (B, W, ld), (W * ld, ld, 1))
         d = _v(dxh, (B, W, ld), (W * ld, ld, 1))
@@ -309,7 +332,8 @@ class EmuOps:
         sc = torch.zeros(ld)
         sc[:nx] = gj
         sc[nx:nx + 3] = gr
-        _v(draw, (B, W, ld), (d_bs, d_ls, 1)).copy_(d * sc * (1 - y * y))
+        dv = d * sc * (1 - y * y)
+        _v(draw, (B, W, ld), (d_bs, d_ls, 1)).copy_(rtf32(dv) if round_tf32 else dv)
 
     @torch.enable_grad()
     def gr_loss(self, preds, dpreds, ld, target, labels, B, d, num_keys, loss, gscale):
@@ -334,13 +358,15 @@ class EmuOps:
         if loss is not None:
             _v(loss, (1,), (1,)).add_(tot)
 
-    def gather(self, src, idx, dst, n, skip_neg=False):
+    def gather(self, src, idx, dst, n, skip_neg=False, round_tf32=False):
         self.n += 1
         i = _v(idx, (n,), (1,)).long()
         s = src if isinstance(src, torch.Tensor) else src.t[src.off:]
         o = _v(dst, (n,), (1,))
         ok = i >= 0
         vals = s[i.clamp_min(0)]
+        if round_tf32:
+            vals = rtf32(vals)
         if skip_neg:
             o[ok] = vals[ok]
         else:

@@ -28,6 +28,7 @@ def build_model(ch, z, cond, gr, dc=None, window=51, device="cpu"):
                 features=sorted(set(cond) | set(gr)), alpha=1.0)
     m = sv.get.model(mc, None, None, dcfg, 18, "midfwd", arena_size=torch.tensor(orc.ARENA),
                      kinematic_tree=orc.KINEMATIC_TREE, discrete_classes=dc or {}, device=device, verbose=0)
+    m.precision = "fp32"  # exact path; the GPU tests that exercise the TF32 tensor-core path set it explicitly
     return m, dcfg
 
 

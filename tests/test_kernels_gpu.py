@@ -43,6 +43,12 @@ GEMM_CASES = [
     (2, 51, 59, 8, 1, 9, 112, None, ACT_TANH, False, False),
     (7, 1, 1, 64, 1, 1, 4, None, ACT_RELUMASK, True, False),
     (130, 4, 8, 128, 1, 5, 256, None, ACT_NONE, True, True),
+    # tensor-core tiling edges: several N tiles whose width is not a multiple of 32; K tiles of 208; ragged rows
+    (40, 4, 8, 32, 1, 5, 720, None, ACT_RELU, True, True),
+    (8, 51, 57, 112, 1, 7, 64, None, ACT_NONE, False, True),
+    (300, 1, 1, 96, 1, 1, 272, None, ACT_NONE, False, False),
+    (37, 13, 18, 64, 1, 6, 48, None, ACT_NONE, True, True),
+    (33, 7, 16, 64, 2, 5, 160, 80, ACT_NONE, True, True),
 ]
 
 
@@ -73,7 +79,7 @@ def test_gemm(ops, case, prec):
 
 
 @pytest.mark.parametrize("prec", [0, 1])
-@pytest.mark.parametrize("case", GEMM_CASES[:5] + [GEMM_CASES[6]])
+@pytest.mark.parametrize("case", GEMM_CASES[:5] + GEMM_CASES[6:])
 def test_wgrad(ops, case, prec):
     B, Lo, rows, C, s, taps, N, n_last, act, resid, stats = case
     K = taps * C

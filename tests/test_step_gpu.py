@@ -1,8 +1,15 @@
 """Parity of the CUDA training step (through the public module/loss/optimizer API, all compute in
 libscv.so) with the reference-generated golden fixtures and with the CPU oracle.
-Tolerances: fp32 path 3e-4 relative per gradient tensor / 2e-5 on losses; TF32 tensor-core path
-1e-3 on losses and 2e-2 relative per gradient tensor norm (north star: 1e-3 relative on per-step
-losses and gradients in fp32/TF32; TF32 per-tensor noise is bounded relative to the tensor norm)."""
+
+Tolerances
+  fp32 path (FFMA kernels):  losses 2e-5, every gradient tensor 3e-4 relative — inside the north star's 1e-3.
+  TF32 path (tcgen05 kernels): losses 1e-3 and forward outputs 7e-3 against the fp32 golden.  Gradients are
+    compared with IDEAL TF32 ARITHMETIC — the same step on CPU with every GEMM operand rounded to the nearest
+    TF32 value and exact fp32 accumulation (tests/emu_ops.py, precision=tf32) — at 5e-3 per tensor.  Against the
+    fp32 golden the gradients of this randomly initialised, batch-normalised network at B=6..16 move by ~1e-1
+    under ANY TF32 arithmetic (tools/tf32_sensitivity.py: ideal TF32 gives 1.3e-1 on conv_in.weight): BatchNorm
+    backward subtracts batch means from gradients dominated by a common mode, which amplifies the 1e-3
+    operand rounding ~100x.  The CUDA path must sit on that floor, not above it."""
 import os
 import re
 
@@ -22,6 +29,35 @@ def _to_cuda(d):
     return {k: v.cuda() for k, v in d.items()}
 
 
+def _emulated_tf32_grads(ch, zd, cond, gr, dc, sd, data, eps, scale):
+    """losses + gradients of the step under ideal TF32 arithmetic (CPU, torch emulation of the C ABI)."""
+    from scrubvae_b200.engine import Engine
+    from emu_ops import EmuOps
+    m, dcfg = build_model(ch, zd, cond, gr, dc, device="cpu")
+    m.precision = "tf32"
+    m.load_state_dict(sd)
+    m._engine = Engine(m, ops=EmuOps())
+    m.train()
+    m._noise = eps
+    data_o = sv.train.predict_batch(m, data, m.disentangle_keys)
+    losses = sv.train.get_batch_loss(m, data, data_o, scale, dcfg)
+    for p in m.parameters():
+        p.grad = None
+    losses["total"].backward()
+    return {k: v.item() for k, v in losses.items()}, {n: p.grad.clone() for n, p in m.named_parameters()}
+
+
+def _check_grads(named_grads, ref, tol, what):
+    gnorm = np.sqrt(sum(float((torch.as_tensor(v).double() ** 2).sum()) for v in ref.values()))
+    tot = 0.0
+    for n, gv in named_grads:
+        r = torch.as_tensor(ref[n])
+        err = (gv.cpu().double() - r.double()).norm().item()
+        tot += err * err
+        assert _rel(gv.cpu(), r) < tol or err < tol * 1e-2 * gnorm, (what, n, _rel(gv.cpu(), r), err)
+    return np.sqrt(tot) / gnorm
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
 @pytest.mark.parametrize("name,cond,gr,dc", [
     ("step_small_heading.npz", ["heading"], ["heading"], None),
@@ -37,14 +73,14 @@ def test_step_matches_reference_golden(golden_dir, name, cond, gr, dc, precision
     m.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd0.")})
     m = m.to("cuda")
     m.train()
-    ltol, gtol = (2e-5, 3e-4) if precision == "fp32" else (1e-3, 2e-2)
+    ltol, gtol = (2e-5, 3e-4) if precision == "fp32" else (1e-3, 5e-3)
     data = _to_cuda(orc.synth_batch(B, seed=0))
     m._noise = orc.synth_eps(B, zd, seed=2).cuda()
     scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, **{k + "_gr": 1.0 for k in gr}}
     n0 = m.engine.ops.launch_count()
     data_o = sv.train.predict_batch(m, data, m.disentangle_keys)
     for k in ("mu", "L", "z", "root", "x6d"):
-        assert _rel(data_o[k].cpu(), g["out." + k]) < gtol / 3, k
+        assert _rel(data_o[k].cpu(), g["out." + k]) < (1e-4 if precision == "fp32" else 7e-3), k
     losses = sv.train.get_batch_loss(m, data, data_o, scale, dcfg)
     for k in list(scale) + ["total"]:
         assert abs(losses[k].item() - float(g["loss." + k])) <= ltol * abs(float(g["loss." + k])) + 1e-6, k
@@ -52,11 +88,16 @@ def test_step_matches_reference_golden(golden_dir, name, cond, gr, dc, precision
         p.grad = None
     losses["total"].backward()
     assert m.engine.ops.launch_count() - n0 > 100  # the CUDA library did the work
-    gnorm = np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for k, v in g.items() if k.startswith("grad.")))
-    for n, p in m.named_parameters():
-        ref = torch.from_numpy(g["grad." + n])
-        err = (p.grad.cpu().double() - ref.double()).norm().item()
-        assert _rel(p.grad.cpu(), ref) < gtol or err < gtol * 1e-2 * gnorm, (n, _rel(p.grad.cpu(), ref), err)
+    grads = [(n, p.grad) for n, p in m.named_parameters()]
+    if precision == "fp32":
+        _check_grads(grads, {k[5:]: v for k, v in g.items() if k.startswith("grad.")}, gtol, "vs fp32 golden")
+    else:
+        sd0 = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd0.")}
+        el, eg = _emulated_tf32_grads(ch, zd, cond, gr, dc, sd0, orc.synth_batch(B, seed=0),
+                                      orc.synth_eps(B, zd, seed=2), scale)
+        _check_grads(grads, eg, gtol, "vs ideal TF32 arithmetic")
+        for k in list(scale) + ["total"]:
+            assert abs(losses[k].item() - el[k]) <= 2e-4 * abs(el[k]) + 1e-6, (k, losses[k].item(), el[k])
     opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-4, "lr_schedule": None})
     sv.train.clip_grad_norm_(m, max_norm=1e6)
     opt.step()
@@ -88,14 +129,15 @@ def test_default_arch_step_vs_oracle(precision, B):
     m._noise = eps.cuda()
     opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-4, "lr_schedule": None})
     step = TrainStep(m, opt, scale, B, use_graph=True)
-    ltol, gtol = (5e-5, 1e-3) if precision == "fp32" else (1e-3, 3e-2)
+    ltol, gtol = (5e-5, 1e-3) if precision == "fp32" else (1e-3, 5e-3)
     step.run(_to_cuda(data))
     got1 = {k: v.item() for k, v in step.losses().items()}
-    gnorm = np.sqrt(sum(float((v.double() ** 2).sum()) for v in g1.values()))
-    for (n, p), gv in zip(m.named_parameters(), m.engine.gviews):
-        ref = g1[n]
-        err = (gv.cpu().double() - ref.double()).norm().item()
-        assert _rel(gv.cpu(), ref) < gtol or err < gtol * 1e-2 * gnorm, (n, _rel(gv.cpu(), ref), err)
+    grads = [(n, gv) for (n, p), gv in zip(m.named_parameters(), m.engine.gviews)]
+    if precision == "fp32":
+        _check_grads(grads, g1, gtol, "vs fp32 oracle")
+    else:  # see the module docstring: gradients are held to ideal TF32 arithmetic
+        _, eg = _emulated_tf32_grads([64, 128, 256, 512, 1024], 64, ["heading"], ["heading"], None, sd, data, eps, scale)
+        _check_grads(grads, eg, gtol, "vs ideal TF32 arithmetic")
     step.run()  # replayed from the CUDA graph
     got2 = {k: v.item() for k, v in step.losses().items()}
     for k in l1:
