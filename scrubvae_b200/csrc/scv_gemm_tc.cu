@@ -77,7 +77,7 @@ constexpr int kBM = 128;            // UMMA M (TMEM lanes)
 constexpr int kBK = 32;             // k floats per stage row = one 128-byte swizzle span
 constexpr int kMaxBN = 256;         // UMMA N limit (cta_group::1)
 constexpr int kTmemCols = 512;      // two accumulator buffers of 256 columns
-constexpr int kStagePitch = 33;     // floats; epilogue transpose tile 32 x 33 per warp
+constexpr int kXposeFloats = 32 * 32;  // per-warp epilogue transpose tile: 32 rows x 32 floats, 16-byte chunks XOR-swizzled
 constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
 constexpr int kMaxStages = 8;
 
@@ -102,10 +102,14 @@ struct SmemCtl {  // lives after the operand stages
   uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
   uint32_t tmem_base;
   uint32_t pad;
-  long long yoff[kBM];  // element offset of each tile row in Y (-1: row not stored)
-  long long roff[kBM];
-  int ncap[kBM];
+  float sacc[2][kMaxBN];  // BatchNorm column sums / sums of squares of this CTA's tiles (flushed when the n tile changes)
 };
+
+// epilogue warps only (threads 128..255): named barrier 1
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 __device__ __forceinline__ float act_apply(float v, int act, float r) {
   if (act == SCV_ACT_RELU) return v > 0.f ? v : 0.f;
@@ -125,7 +129,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage_bytes = a_bytes + w_bytes;
   uint8_t* ctl_raw = smem + (size_t)p.stages * stage_bytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(ctl_raw);
-  float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtl) + 15) & ~size_t(15)));  // 4 x 32 x 33 floats
+  float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtl) + 15) & ~size_t(15)));  // 4 warps x 32 x 32 floats
   const uint32_t tile_tx = (uint32_t)(p.bl * p.nb) * kBK * 4 + w_bytes;
   const int total = p.n_tiles * p.m_tiles;
 
@@ -197,64 +201,123 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int ew = warp - 4;  // TMEM lane quarter this warp may read
-    const int row = ew * 32 + lane;
-    float* xp = xpose + ew * (32 * kStagePitch);
+    // Epilogue.  Warp ew owns TMEM lanes [32 ew, 32 ew + 32) = tile rows.  Per 32-column chunk: tcgen05.ld (thread =
+    // row) -> swizzled float4 transpose through shared memory -> lane (rq, cq) holds 4 consecutive columns of rows
+    // 4 i + rq (i < 8): 128-byte contiguous row segments per 8 lanes for the residual loads and the stores.
+    const int ew = warp - 4;
+    const int rq = lane >> 3, cq = lane & 7;
+    float4* xp4 = reinterpret_cast<float4*>(xpose + ew * kXposeFloats);
     const int rows_in_box = p.bl * p.nb;
     const int N = p.N;
-    int it = 0;
+    const int et = threadIdx.x - 128;
+    const bool has_stats = p.stats != nullptr;
+    if (has_stats) {
+      for (int c = et; c < 2 * kMaxBN; c += 128) (&ctl->sacc[0][0])[c] = 0.f;
+      epi_bar();
+    }
+    int it = 0, cur_nt = -1;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
       const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;
       const int n0 = nt * p.bn;
-      {
+      const int ncols = min(p.bn, N - n0);
+      if (has_stats && nt != cur_nt) {
+        if (cur_nt >= 0) {  // flush the finished n tile's column sums
+          epi_bar();
+          const int pn0 = cur_nt * p.bn, pc = min(p.bn, N - pn0);
+          for (int c = et; c < pc; c += 128) {
+            atomicAdd(p.stats + pn0 + c, (double)ctl->sacc[0][c]);
+            atomicAdd(p.stats + N + pn0 + c, (double)ctl->sacc[1][c]);
+            ctl->sacc[0][c] = 0.f;
+            ctl->sacc[1][c] = 0.f;
+          }
+          epi_bar();
+        }
+        cur_nt = nt;
+      }
+      long long yoff[8], roff[8];
+      int ncap[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = ew * 32 + i * 4 + rq;
         const int bi = row / p.bl, li = row - bi * p.bl;
         const int64_t b = (int64_t)bt_i * p.nb + bi, l = (int64_t)lt_i * p.bl + li;
         const bool ok = row < rows_in_box && b < p.B && l < p.Lo;
-        ctl->yoff[row] = ok ? (long long)(b * p.y_bs + l * p.y_ls) : -1;
-        ctl->roff[row] = (ok && p.R) ? (long long)(b * p.r_bs + l * p.r_ls) : 0;
-        ctl->ncap[row] = ok ? ((l == p.Lo - 1) ? p.n_last : N) : 0;
+        yoff[i] = (long long)(b * p.y_bs + l * p.y_ls);
+        roff[i] = (long long)(b * p.r_bs + l * p.r_ls);
+        ncap[i] = ok ? ((l == p.Lo - 1) ? p.n_last : N) : 0;
       }
-      __syncwarp();
       const int acc = it & 1;
       mbar_wait(smem_u32(&ctl->tfull[acc]), (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kMaxBN;
-      const int ncols = min(p.bn, N - n0);
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
+        if (c0 + 32 >= ncols) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&ctl->tempty[acc]));
+        }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) xp[lane * kStagePitch + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 8; ++j)
+          xp4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         __syncwarp();
-        const int n = n0 + c0 + lane;
-        const bool col_ok = c0 + lane < ncols;  // bn need not be a multiple of 32: the rest is the next tile's
-        const float bv = (p.bias && n < p.bias_n) ? __ldg(p.bias + (n % p.bias_mod)) : 0.f;
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const long long yo = ctl->yoff[ew * 32 + rr];
-          if (yo < 0) continue;
-          if (col_ok && n < ctl->ncap[ew * 32 + rr]) {
-            float tv = p.out_scale * xp[rr * kStagePitch + lane] + bv;
-            const float r = p.R ? __ldg(p.R + ctl->roff[ew * 32 + rr] + n) : 0.f;
-            if (p.act != SCV_ACT_RELUMASK) tv += r;
-            s1 += tv;
-            s2 += tv * tv;
-            const float yv = act_apply(tv, p.act, r);
-            p.Y[yo + n] = p.round_out ? scv::round_tf32(yv) : yv;
+        const int cc = c0 + cq * 4;
+        const int n = n0 + cc;
+        const bool col_ok = cc < ncols;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok && n < p.bias_n) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (n % p.bias_mod)));
+        float4 rv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.R && col_ok && n < ncap[i]) rv[i] = __ldg(reinterpret_cast<const float4*>(p.R + roff[i] + n));
+        }
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + rq;
+          float4 a = xp4[r * 8 + (cq ^ (r & 7))];
+          if (col_ok && n < ncap[i]) {
+            float4 tv = make_float4(p.out_scale * a.x + bv.x, p.out_scale * a.y + bv.y, p.out_scale * a.z + bv.z,
+                                    p.out_scale * a.w + bv.w);
+            if (p.act != SCV_ACT_RELUMASK) { tv.x += rv[i].x; tv.y += rv[i].y; tv.z += rv[i].z; tv.w += rv[i].w; }
+            s1.x += tv.x; s1.y += tv.y; s1.z += tv.z; s1.w += tv.w;
+            s2.x += tv.x * tv.x; s2.y += tv.y * tv.y; s2.z += tv.z * tv.z; s2.w += tv.w * tv.w;
+            float4 yv = make_float4(act_apply(tv.x, p.act, rv[i].x), act_apply(tv.y, p.act, rv[i].y),
+                                    act_apply(tv.z, p.act, rv[i].z), act_apply(tv.w, p.act, rv[i].w));
+            if (p.round_out) yv = scv::round_tf32(yv);
+            *reinterpret_cast<float4*>(p.Y + yoff[i] + n) = yv;
           }
         }
-        if (p.stats && col_ok) {
-          atomicAdd(p.stats + n, (double)s1);
-          atomicAdd(p.stats + N + n, (double)s2);
+        if (has_stats) {
+#pragma unroll
+          for (int off = 8; off <= 16; off <<= 1) {
+            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
+            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, off); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, off);
+            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
+            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+          }
+          if (rq == 0 && col_ok) {
+            atomicAdd(&ctl->sacc[0][cc], s1.x); atomicAdd(&ctl->sacc[0][cc + 1], s1.y);
+            atomicAdd(&ctl->sacc[0][cc + 2], s1.z); atomicAdd(&ctl->sacc[0][cc + 3], s1.w);
+            atomicAdd(&ctl->sacc[1][cc], s2.x); atomicAdd(&ctl->sacc[1][cc + 1], s2.y);
+            atomicAdd(&ctl->sacc[1][cc + 2], s2.z); atomicAdd(&ctl->sacc[1][cc + 3], s2.w);
+          }
         }
         __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&ctl->tempty[acc]));
+    }
+    if (has_stats && cur_nt >= 0) {
+      epi_bar();
+      const int pn0 = cur_nt * p.bn, pc = min(p.bn, N - pn0);
+      for (int c = et; c < pc; c += 128) {
+        atomicAdd(p.stats + pn0 + c, (double)ctl->sacc[0][c]);
+        atomicAdd(p.stats + N + pn0 + c, (double)ctl->sacc[1][c]);
+      }
     }
   }
   tc_fence_before();
@@ -378,7 +441,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     __syncwarp();
   } else if (warp >= 4) {
     const int ew = warp - 4;
-    float* xp = xpose + ew * (32 * kStagePitch);
+    const int rq = lane >> 3, cq = lane & 7;
+    float4* xp4 = reinterpret_cast<float4*>(xpose + ew * kXposeFloats);
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       int nt, kt, g0, g1;
@@ -391,18 +455,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       const int kbase = kt * p.bnk;
       const int kcols = min(p.bnk, p.K - kbase);
       if (g1 > g0 && nbase < p.N) {
+        const int nrows = min(32, p.N - nbase);
         for (int c0 = 0; c0 < kcols; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) xp[lane * kStagePitch + j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 8; ++j)
+            xp4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
           __syncwarp();
-          const int k = kbase + c0 + lane;
-          if (c0 + lane < kcols) {
-            const int nrows = min(32, p.N - nbase);
-            for (int rr = 0; rr < nrows; ++rr)
-              atomicAdd(p.dW + (size_t)(nbase + rr) * p.K + k, xp[rr * kStagePitch + lane]);
+          const int cc = c0 + cq * 4;
+          if (cc < kcols) {  // K % 4 == 0: whole float4s
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + rq;
+              if (r < nrows) red_add_v4(p.dW + (size_t)(nbase + r) * p.K + kbase + cc, xp4[r * 8 + (cq ^ (r & 7))]);
+            }
           }
           __syncwarp();
         }
@@ -506,6 +575,10 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   if (p->N < 16 || p->K < 32 || M < 64) return 1;
   if (p->K % 4 || p->a_bs % 4 || p->a_ls % 4 || !aligned16(p->A) || !aligned16(p->W)) return 1;
   if (p->K > (1 << 30) || p->N > (1 << 30) || p->B >= (1LL << 31) || p->Lo >= (1LL << 31)) return 1;
+  // the epilogue moves float4s: rows of Y / R / bias must be 16-byte aligned at every 4-column group
+  if (p->N % 4 || p->n_last % 4 || p->y_bs % 4 || p->y_ls % 4 || !aligned16(p->Y)) return 1;
+  if (p->R && (p->r_bs % 4 || p->r_ls % 4 || !aligned16(p->R))) return 1;
+  if (p->bias && (p->bias_mod % 4 || p->bias_n % 4 || !aligned16(p->bias))) return 1;
   int rc = ensure_attrs();
   if (rc) return rc;
 
@@ -522,7 +595,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   q.m_tiles = q.lt * q.bt;
   q.k_chunks = (int)cdiv(p->K, kBK);
   const size_t stage_bytes = (size_t)kBM * kBK * 4 + (size_t)q.bn * kBK * 4;
-  const size_t fixed = 1024 + ((sizeof(SmemCtl) + 15) & ~size_t(15)) + 4 * 32 * kStagePitch * 4;
+  const size_t fixed = 1024 + ((sizeof(SmemCtl) + 15) & ~size_t(15)) + 4 * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > q.k_chunks + 1) stages = q.k_chunks + 1;
@@ -559,7 +632,7 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   const int64_t M = p->B * p->Lo;
   if (p->N < 16 || p->K < 32 || M < 256) return 1;
   if (p->K % 4 || p->N % 4 || p->a_bs % 4 || p->a_ls % 4 || p->y_bs % 4 || p->y_ls % 4 || !aligned16(p->A) ||
-      !aligned16(p->dY))
+      !aligned16(p->dY) || !aligned16(p->dW))
     return 1;
   if (p->K > (1 << 30) || p->N > (1 << 30) || p->B >= (1LL << 31) || p->Lo >= (1LL << 31)) return 1;
   int rc = ensure_attrs();
@@ -585,7 +658,7 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.splits = (int)cdiv(q.groups, q.gps);
   const int R = q.bl * q.nb;
   const size_t stage_bytes = (size_t)(4 + (q.bnk + 31) / 32) * R * 128;
-  const size_t fixed = 1024 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + 4 * 32 * kStagePitch * 4;
+  const size_t fixed = 1024 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + 4 * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return 1;

