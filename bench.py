@@ -38,47 +38,47 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled through NVML every 5 ms from a thread while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
     def __init__(self, idx):
-        self.idx, self.rows, self.proc = idx, [], None
+        self.idx, self.sm, self.mask, self.mx, self.err = idx, [], 0, None, None
+        self._stop = threading.Event()
+        self._thr = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx),
-                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as ex:
+            self.err = repr(ex)[:120]
+            return
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception as ex:
+                    self.err = repr(ex)[:120]
+                    return
+                time.sleep(0.005)
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["nvml unavailable: %s" % self.err], "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.mx, "sm_min_mhz": sm[0],
+                "reasons": sorted(n for b, n in self.REASONS.items() if self.mask & b), "samples": len(sm)}
 
 
 def cpu_step_throughput(B, steps, warmup, threads=None):
@@ -209,7 +209,9 @@ def run_ours(args, rank, world, local_rank):
         from scrubvae_b200.parallel import GradAllReduce, broadcast_parameters
         broadcast_parameters(m)
         comm = GradAllReduce(m.engine, world)
+        m.engine.comm = comm  # public-API path: total.backward() runs the same bucketed all-reduce
         opt.grad_scale = 1.0 / world
+        torch.cuda.manual_seed(1234 + rank)  # rank-distinct reparameterisation noise
     host = synth_host_batch(B, seed=1000 * rank)
     data = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     step = TrainStep(m, opt, LOSS_SCALE, B, use_graph=not args.no_graph, comm=comm)
@@ -255,8 +257,6 @@ def run_ours(args, rank, world, local_rank):
         for p in m.parameters():
             p.grad = None
         bl["total"].backward()
-        if comm is not None:
-            comm(m.engine, "post_backward")
         sv.train.clip_grad_norm_(m, max_norm=1e6)
         opt.step()
         loss_host.copy_(bl["total"].detach().reshape(1), non_blocking=True)

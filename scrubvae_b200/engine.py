@@ -82,6 +82,7 @@ class Engine:
         self._flatten_params()
         self._build_weights()
         self.step_count = 0
+        self.comm = None  # data-parallel gradient all-reduce hook (parallel.GradAllReduce) for the public-API path
 
     # ------------------------------------------------------------------ parameters
     def invalidate(self):
@@ -90,12 +91,22 @@ class Engine:
     def _flatten_params(self):
         dev = self.device
         names, params = zip(*list(self.m.named_parameters()))
-        offs, tot = [], 0
-        for p in params:
-            if p.dtype != torch.float32:
-                raise RuntimeError("scrubvae_b200: parameters must be float32")
-            offs.append(tot)
-            tot += pad4(p.numel())
+        # flat layout: the parameters whose gradients the elementwise kernels write straight into gflat
+        # (BatchNorm gamma/beta, PReLU slopes) come first, [0, n_direct); the GEMM weights/biases, whose
+        # gradients arrive through gpacked + the final gather, follow.  Data parallelism all-reduces
+        # gflat[:n_direct] and gpacked, never both copies of a weight gradient (parallel.py).
+        direct_mods = {id(q) for mod in self.m.modules() if isinstance(mod, (nn.BatchNorm1d, nn.PReLU))
+                       for q in mod.parameters(recurse=False)}
+        offs, tot = [0] * len(params), 0
+        for want_direct in (True, False):
+            for i, p in enumerate(params):
+                if p.dtype != torch.float32:
+                    raise RuntimeError("scrubvae_b200: parameters must be float32")
+                if (id(p) in direct_mods) == want_direct:
+                    offs[i] = tot
+                    tot += pad4(p.numel())
+            if want_direct:
+                self.n_direct = tot
         self.n_flat = tot
         self.flat = torch.zeros(tot, device=dev)
         self.gflat = torch.zeros(tot, device=dev)
@@ -251,6 +262,8 @@ class Engine:
         self.inv_idx = lay.inverse_map(fwd_idx, self.n_flat).to(torch.int32).to(dev)
         del self._pack_parts, self._pack_parts_d
         self.max_k = max(max(g.K, g.dK if g.wd is not None else 0) for g in self.W.values())
+        # gpacked = [encoder layers | decoder layers + scrubber heads]; backward finishes the second part first
+        self.gp_split = self.W["dec.fc_in"].w
 
     def wref(self, g: GemmW) -> Ref:
         return Ref(self.packed, g.w)
@@ -661,6 +674,7 @@ class Plan:
                                    Y=self.dmu_gr, y_bs=z, y_ls=0, R=None if first else self.dmu_gr, r_bs=z, r_ls=0,
                                    out_scale=-eng.gr_alpha[key], precision=0)
                     Bw.append(lambda kw2=kw2: ops.gemm(**kw2))
+        self._bw_dec_end = len(Bw)  # decoder + scrubber-head weight gradients are final from here on
         # latent
         self.dmu_kl = torch.zeros(B, z, **f32)
         self.dL_kl = torch.zeros(B, z, z, **f32)
@@ -791,9 +805,18 @@ class Plan:
             f()
         return self.loss_out
 
-    def backward(self):
-        """Runs the backward launch list; `self.gscale` must hold d total / d loss_k."""
-        for f in self.Bw:
+    def backward(self, comm=None):
+        """Runs the backward launch list; `self.gscale` must hold d total / d loss_k.
+        `comm(engine, phase)` (data parallelism, parallel.py) is called when the decoder + scrubber-head weight
+        gradients are final ("decoder_done": their all-reduce overlaps the encoder backward) and again before
+        the final gather of the packed gradients ("encoder_done")."""
+        last = len(self.Bw) - 1
+        for i, f in enumerate(self.Bw):
+            if comm is not None:
+                if i == self._bw_dec_end:
+                    comm(self.eng, "decoder_done")
+                if i == last:
+                    comm(self.eng, "encoder_done")
             f()
 
 
@@ -804,7 +827,7 @@ class TrainStep:
     clip_grad_norm_ -> optimizer.step), minus the Python between them.
 
     `comm` (optional): callable(engine, phase) hook used by data parallelism (parallel.py) to launch the
-    gradient all-reduce; phase is "post_backward"."""
+    bucketed gradient all-reduce from inside the backward launch list (Plan.backward)."""
 
     def __init__(self, model, optimizer, loss_scale, B, max_norm=1e6, use_graph=True, comm=None):
         self.model, self.opt = model, optimizer
@@ -836,10 +859,7 @@ class TrainStep:
         for f in plan.Lk:
             f()
         plan.gscale.copy_(plan.loss_scale)
-        for f in plan.Bw:
-            f()
-        if self.comm is not None:
-            self.comm(eng, "post_backward")
+        plan.backward(self.comm)
         eng.sumsq.zero_()
         eng.ops.sumsq(eng.gflat, eng.n_flat, eng.sumsq)
         grp = opt.param_groups[0]

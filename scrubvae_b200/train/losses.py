@@ -26,8 +26,8 @@ class _StepLoss(torch.autograd.Function):
         n = plan.gscale.numel()
         # d total / d loss_k = g_total * scale_k + g_k   (device-side, no host sync)
         torch.addcmul(g[:n], plan.loss_scale, g[n], out=plan.gscale)
-        plan.backward()
         eng = plan.eng
+        plan.backward(getattr(eng, "comm", None))  # eng.comm: data-parallel gradient all-reduce (parallel.py)
         for p, gv in zip(eng.params, eng.gviews):
             if p.grad is None or p.grad is gv:
                 p.grad = gv

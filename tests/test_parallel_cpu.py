@@ -1,0 +1,104 @@
+"""Data-parallel step on 2 ranks (gloo, CPU): the engine's bucketed gradient all-reduce (parallel.py) over the
+torch-on-CPU emulation of the C ABI, against "the oracle run on each shard, gradients averaged" (SURVEY.md §8e:
+per-replica BatchNorm statistics, local-B loss normalisation), through one AdamW update."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CH, Z, BL = [8, 16, 32, 64, 128], 8, 5
+SCALE = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "heading_gr": 1.0}
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import scrubvae_b200 as sv
+    from scrubvae_b200.engine import Engine, TrainStep
+    from scrubvae_b200.parallel import GradAllReduce, broadcast_parameters
+    from oracle import scvae_oracle as orc
+    from emu_ops import EmuOps
+    from test_engine_cpu import build_model, _rel
+    torch.manual_seed(10 + rank)  # replicas start DIFFERENT: broadcast_parameters must make them equal
+    m, dcfg = build_model(CH, Z, ["heading"], ["heading"])
+    m._engine = Engine(m, ops=EmuOps())
+    broadcast_parameters(m)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    m.train()
+    opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
+    opt.grad_scale = 1.0 / world
+    comm = GradAllReduce(m.engine, world)
+    data = orc.synth_batch(BL, seed=100 + rank)
+    eps = orc.synth_eps(BL, Z, seed=200 + rank)
+    m._noise = eps
+    step = TrainStep(m, opt, SCALE, BL, use_graph=False, comm=comm)
+    step.run(data)
+    losses = {k: v.item() for k, v in step.losses().items()}
+    # oracle: every shard on this rank (so that each rank can check alone), gradients averaged, one AdamW step
+    cfg = orc.Cfg(ch=CH, z_dim=Z)
+    gsum, lref = None, None
+    for r in range(world):
+        l, g, _, _, _ = orc.train_step(sd0, orc.synth_batch(BL, seed=100 + r), cfg, SCALE, orc.synth_eps(BL, Z, seed=200 + r))
+        gsum = g if gsum is None else {k: gsum[k] + g[k] for k in g}
+        if r == rank:
+            lref = {k: v.item() for k, v in l.items()}
+    gavg = {k: v / world for k, v in gsum.items()}
+    errs = {}
+    gn = sum(float((v.double() ** 2).sum()) for v in gavg.values()) ** 0.5
+    for (n, p), gv in zip(m.named_parameters(), m.engine.gviews):
+        e = ((gv / world).double() - gavg[n].double()).norm().item()
+        errs[n] = (_rel(gv / world, gavg[n]), e / gn)
+    new = {n: p.detach().clone() for n, p in m.named_parameters()}
+    ref_new = {}
+    for n in gavg:
+        p1, _, _ = orc.adam_update(sd0[n].clone(), gavg[n], torch.zeros_like(gavg[n]), torch.zeros_like(gavg[n]), 1, 1e-3,
+                                   kind="adamw")
+        ref_new[n] = p1
+    perr = {n: _rel(new[n], ref_new[n]) for n in new}
+    flat = torch.cat([p.reshape(-1) for p in new.values()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    same = all(torch.equal(gathered[0], t) for t in gathered)
+    q.put((rank, losses, lref, errs, perr, same, comm.bytes_per_step))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_matches_sharded_oracle():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, losses, lref, errs, perr, same, nbytes in res:
+        for k, v in lref.items():  # local losses = oracle on the local shard
+            assert abs(losses[k] - v) <= 2e-5 * abs(v) + 1e-6, (rank, k, losses[k], v)
+        for n, (rel, glob) in errs.items():  # reduced gradient = mean of the shard gradients
+            assert rel < 3e-4 or glob < 2e-6, (rank, n, rel, glob)
+        # one AdamW step with the averaged gradient.  The first Adam step moves every element by lr * sign(g): the few
+        # elements whose gradient is rounding noise flip sign (2e-3 of |p| each), hence 5e-3 and not 1e-5
+        from test_engine_cpu import ZERO_GRAD_BIAS  # biases in front of a BatchNorm: their true gradient is 0
+        for n, e in perr.items():
+            assert e < 5e-3 or ZERO_GRAD_BIAS.search(n), (rank, n, e)
+        assert same, "replicas diverged after the update"
+        assert nbytes > 0
