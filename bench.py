@@ -177,6 +177,7 @@ def gemm_profile(step, B):
         timed(lambda: orig_wgrad(**kw), 2.0 * kw["B"] * kw["Lo"] * nnz)
 
     ops.gemm, ops.wgrad = gemm, wgrad
+    saved_comm, step.comm = step.comm, None  # rank 0 alone runs this instrumented step: no collective inside
     try:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -186,6 +187,7 @@ def gemm_profile(step, B):
         torch.cuda.synchronize()
     finally:
         del ops.gemm, ops.wgrad
+        step.comm = saved_comm
     t_gemm = sum(a.elapsed_time(b) for a, b, _ in recs) * 1e-3
     fl = sum(f for _, _, f in recs)
     return {"launches": len(recs), "seconds": t_gemm, "flops": fl, "eager_step_seconds": e0.elapsed_time(e1) * 1e-3}
