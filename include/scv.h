@@ -194,6 +194,27 @@ int scv_loss_finalize(const double* acc, const float* scale, float* out, int64_t
 int scv_unpack_root(const float* xh, int64_t ld, int64_t nx, const float* arena, float* root_hat, int64_t F,
                     void* stream);
 
+/* ---- pose-window preprocessing: preprocess_save_data data/dataset.py:313-454 ----------------------
+ * The raw keypoint frames `pose` (N x J x 3 float64) stay resident in HBM; a window is W consecutive frames
+ * starting at starts[w] (run boundaries at animal-id changes are host metadata, get_window_indices :198-233).
+ * scv_window_indices : winds[w][t] = starts[w] + t (int64; bit-exact with the reference index matrix)
+ * scv_window_features: per window, in float64 like numpy: speed[w] = mean keypoint speed (get_speed_outliers
+ *   :299-309; the caller drops windows with speed > threshold), avg_speed_3d[w] = [root, parts[0], mean of the
+ *   other parts] (get_speed_parts :134-163 + :362-374; parts = [n, len, j.., len, j..], the first joint of each part
+ *   is its reference), yaw[w] of the mid frame's joint0->joint1 direction (:236-243), heading = (sin, cos) (:260-267)
+ * scv_preprocess_windows: for the kept windows keep[i] (NULL = all): root centring + mid-forward rotation
+ *   (:383-413), inv_kin (:11-46) -> local quaternions -> 6-D (quaternion.py:325-334), integer-truncated segment
+ *   offsets (:279-296), target_pose = FK with zero root (:438-449).  mode 0 none, 1 midfwd, 2 x360 (centre only).
+ *   tree = [n_chains, len, j.., ...]; offset = J x 3 int32 unit offsets (configs/mouse_skeleton.yaml:95-112).
+ *   Outputs are (n_keep, W, J, 6|3) / (n_keep, W, 3) float32, contiguous. */
+int scv_window_indices(const int64_t* starts, int64_t n_w, int64_t window, int64_t* winds, void* stream);
+int scv_window_features(const double* pose, const int64_t* starts, int64_t n_w, int64_t window, int64_t J,
+                        const int32_t* parts, double* speed, float* avg_speed_3d, float* heading, double* yaw,
+                        void* stream);
+int scv_preprocess_windows(const double* pose, const int64_t* starts, const int64_t* keep, int64_t n_keep,
+                           int64_t window, int64_t J, const int32_t* tree, const int32_t* offset, const double* yaw,
+                           int64_t mode, float* x6d, float* root, float* offsets, float* target_pose, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

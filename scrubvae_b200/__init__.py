@@ -2,3 +2,4 @@
 from . import model
 from . import get
 from . import train
+from . import data

@@ -97,6 +97,9 @@ _SIGS = {
     "scv_d2f": (C.c_int, [_vp, _vp, _i64, _vp]),
     "scv_loss_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "scv_unpack_root": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _i64, _vp]),
+    "scv_window_indices": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    "scv_window_features": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "scv_preprocess_windows": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
 }
 
 EXPORTS = tuple(_SIGS)
@@ -227,6 +230,21 @@ class CudaOps:
     def unpack_root(self, xh, ld, nx, arena, root_hat, F):
         self._check(self.lib.scv_unpack_root(_ptr(xh), ld, nx, _ptr(arena), _ptr(root_hat), F, self._stream()),
                     "scv_unpack_root")
+
+    def window_indices(self, starts, n_w, window, winds):
+        self._check(self.lib.scv_window_indices(_ptr(starts), n_w, window, _ptr(winds), self._stream()),
+                    "scv_window_indices")
+
+    def window_features(self, pose, starts, n_w, window, J, parts, speed, avg3, heading, yaw):
+        self._check(self.lib.scv_window_features(_ptr(pose), _ptr(starts), n_w, window, J, _ptr(parts), _ptr(speed),
+                                                 _ptr(avg3), _ptr(heading), _ptr(yaw), self._stream()),
+                    "scv_window_features")
+
+    def preprocess_windows(self, pose, starts, keep, n_keep, window, J, tree, offset, yaw, mode, x6d, root, offsets,
+                           target_pose):
+        self._check(self.lib.scv_preprocess_windows(_ptr(pose), _ptr(starts), _ptr(keep), n_keep, window, J, _ptr(tree),
+                                                    _ptr(offset), _ptr(yaw), mode, _ptr(x6d), _ptr(root), _ptr(offsets),
+                                                    _ptr(target_pose), self._stream()), "scv_preprocess_windows")
 
     def d2f(self, src, dst, n):
         self._check(self.lib.scv_d2f(_ptr(src), _ptr(dst), n, self._stream()), "scv_d2f")

@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libscv.so")
-SOURCES = ["scv_api.cu", "scv_gemm_ffma.cu", "scv_gemm_tc.cu", "scv_elementwise.cu", "scv_loss.cu"]
+SOURCES = ["scv_api.cu", "scv_gemm_ffma.cu", "scv_gemm_tc.cu", "scv_elementwise.cu", "scv_loss.cu", "scv_preprocess.cu"]
+EXTRA_FLAGS = {"scv_preprocess.cu": ["-fmad=false"]}  # fp32 products and sums round separately, like the reference's torch ops
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -47,7 +48,7 @@ def build(force=False, verbose=False):
 
     def one(src):
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
