@@ -15,7 +15,8 @@
 // shared memory (dY rows are n-contiguous, A rows k-contiguous; 128B swizzle with 32-byte atoms, the only
 // layout tcgen05 takes for MN-major tf32), the reduction runs over the rows of
 // the same (32, bl, nb) boxes; work items (n tile, k tile, row split) are spread over the SMs and the
-// epilogue adds into dW with coalesced fp32 reductions.
+// epilogue adds into dW with coalesced red.global.add.v4.f32.  The bias gradient (column sums of dY) rides
+// along as one extra N=16 MMA per 8 rows against a shared-memory tile of ones (k tile 0 items only).
 #include "scv_tc.cuh"
 
 namespace scv {
@@ -337,7 +338,12 @@ struct WgradTcParams {
   int bnk;              // k tile width (UMMA N), multiple of 16, <= 256
   int n_tiles, k_tiles, splits, groups, gps, stages;
   float* dW;
+  float* dbias;  // bias gradient = column sums of dY: one extra N=16 MMA per 8 rows against a tile of ones (k tile 0 only)
+  int bias_mod, bias_n;
 };
+
+constexpr int kWgradMaxBNK = 240;  // k-tile width limit: 2 x (240 + 16 bias columns) = 512 TMEM columns
+constexpr int kBiasCol = 240;      // TMEM column of the bias accumulator inside each 256-column buffer
 
 struct SmemCtlW {
   uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
@@ -355,6 +361,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const int a_slabs = (p.bnk + 31) / 32;
   const uint32_t y_bytes = 4 * slab, a_bytes = (uint32_t)a_slabs * slab;
   const uint32_t stage_bytes = y_bytes + a_bytes;
+  float* ones = reinterpret_cast<float*>(smem);  // 1 KB = 8 k-rows x 128 B of 1.0f (B operand of the bias MMA)
+  smem += 1024;
   uint8_t* ctl_raw = smem + (size_t)p.stages * stage_bytes;
   SmemCtlW* ctl = reinterpret_cast<SmemCtlW*>(ctl_raw);
   float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtlW) + 15) & ~size_t(15)));
@@ -376,6 +384,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
+  if (warp == 3) {
+    for (int i = lane; i < 256; i += 32) ones[i] = 1.0f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -415,11 +427,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(kBM, p.bnk, 1, 1);
+      const uint32_t idesc_b = idesc_tf32(kBM, 16, 1, 1);
+      const uint64_t ones_desc = smem_desc(smem_u32(ones), 1024, 512, 1);
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         int nt, kt, g0, g1;
         decode(t, nt, kt, g0, g1);
+        const bool do_bias = p.dbias != nullptr && kt == 0;
         const int acc = it & 1;
         mbar_wait(smem_u32(&ctl->tempty[acc]), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -429,9 +444,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           tc_fence_after();
           const uint32_t sy = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sa = sy + y_bytes;
-          for (int r8 = 0; r8 < R / 8; ++r8)
-            umma_tf32(d_tmem, smem_desc(sy + r8 * 1024, slab, 512, 1), smem_desc(sa + r8 * 1024, slab, 512, 1), idesc,
-                      (g > g0 || r8 > 0) ? 1u : 0u);
+          for (int r8 = 0; r8 < R / 8; ++r8) {
+            const uint64_t dy = smem_desc(sy + r8 * 1024, slab, 512, 1);
+            umma_tf32(d_tmem, dy, smem_desc(sa + r8 * 1024, slab, 512, 1), idesc, (g > g0 || r8 > 0) ? 1u : 0u);
+            if (do_bias) umma_tf32(d_tmem + kBiasCol, dy, ones_desc, idesc_b, (g > g0 || r8 > 0) ? 1u : 0u);
+          }
           umma_commit(smem_u32(&ctl->empty[s]));
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -475,6 +492,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           }
           __syncwarp();
         }
+        if (p.dbias != nullptr && kt == 0) {  // every one of the 16 bias columns holds sum_rows dY[row][n] for n = TMEM lane
+          uint32_t bv[16];
+          tmem_ld16(taddr + kBiasCol, bv);
+          tmem_ld_wait();
+          const int n = nbase + lane;
+          if (n < p.N && n < p.bias_n) atomicAdd(p.dbias + (n % p.bias_mod), __uint_as_float(bv[0]));
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -486,40 +510,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
-// dbias[n % bias_mod] += sum_{b,l} dY[b][l][n]  (n < bias_n).  Block = (256 / cw) rows x cw columns,
-// coalesced along n; grid.y splits the rows.
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dY, int64_t y_bs, int64_t y_ls, int64_t B,
-                                                     int64_t Lo, int ncol, int bias_mod, float* dbias, int cw,
-                                                     int64_t rows_per_block) {
-  __shared__ float red[256];
-  const int64_t M = B * Lo;
-  const int tx = threadIdx.x % cw, ty = threadIdx.x / cw, rstep = 256 / cw;
-  const int64_t m0 = (int64_t)blockIdx.y * rows_per_block;
-  const int64_t m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
-  const int n = blockIdx.x * cw + tx;
-  float s0 = 0.f, s1 = 0.f;
-  if (n < ncol) {
-    int64_t m = m0 + ty;
-    for (; m + rstep < m1; m += 2 * rstep) {
-      const int64_t ba = m / Lo, la = m - ba * Lo;
-      const int64_t mb = m + rstep, bb = mb / Lo, lb = mb - bb * Lo;
-      s0 += __ldg(dY + ba * y_bs + la * y_ls + n);
-      s1 += __ldg(dY + bb * y_bs + lb * y_ls + n);
-    }
-    if (m < m1) {
-      const int64_t ba = m / Lo, la = m - ba * Lo;
-      s0 += __ldg(dY + ba * y_bs + la * y_ls + n);
-    }
-  }
-  red[threadIdx.x] = s0 + s1;
-  __syncthreads();
-  if (ty == 0 && n < ncol) {
-    float s = 0.f;
-    for (int r = 0; r < rstep; ++r) s += red[r * cw + tx];
-    atomicAdd(dbias + (n % bias_mod), s);
   }
 }
 
@@ -640,12 +630,16 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
 
   WgradTcParams q;
   q.K = (int)p->K; q.N = (int)p->N; q.dW = p->dW;
+  const bool want_bias = p->dbias && p->bias_n > 0;
+  q.dbias = want_bias ? p->dbias : nullptr;
+  q.bias_mod = (int)(want_bias ? p->bias_mod : 1);
+  q.bias_n = (int)(want_bias ? p->bias_n : 0);
   choose_box(p->Lo, p->B, 32, true, q.bl, q.nb);
   q.lt = (int)cdiv(p->Lo, q.bl);
   q.bt = (int)cdiv(p->B, q.nb);
   q.groups = q.lt * q.bt;
   const int k16 = (int)cdiv(p->K, 16) * 16;
-  const int kt0 = (int)cdiv(k16, kMaxBN);
+  const int kt0 = (int)cdiv(k16, kWgradMaxBNK);
   q.bnk = (int)cdiv(cdiv(k16, kt0), 16) * 16;
   q.k_tiles = (int)cdiv(p->K, q.bnk);
   q.n_tiles = (int)cdiv(p->N, kBM);
@@ -658,7 +652,7 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.splits = (int)cdiv(q.groups, q.gps);
   const int R = q.bl * q.nb;
   const size_t stage_bytes = (size_t)(4 + (q.bnk + 31) / 32) * R * 128;
-  const size_t fixed = 1024 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + 4 * kXposeFloats * 4;
+  const size_t fixed = 1024 + 1024 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + 4 * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return 1;
@@ -685,20 +679,6 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tmY, tmA, q);
   rc = check_launch("wgrad_tc_kernel");
   if (rc) return rc;
-  if (p->dbias && p->bias_n > 0) {
-    const int ncol = (int)(p->bias_n < p->N ? p->bias_n : p->N);
-    int cw = 32;
-    while (cw < 256 && cw < ncol) cw *= 2;
-    const int gx = (ncol + cw - 1) / cw;
-    int64_t gy = cdiv(8LL * sm_count(), gx);
-    if (gy > cdiv(M, 4 * (256 / cw))) gy = cdiv(M, 4 * (256 / cw));
-    if (gy < 1) gy = 1;
-    const int64_t rpb = cdiv(M, gy);
-    gy = cdiv(M, rpb);
-    colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(p->dY, p->y_bs, p->y_ls, p->B, p->Lo, ncol, (int)p->bias_mod,
-                                                          p->dbias, cw, rpb);
-    rc = check_launch("colsum_kernel");
-  }
   return rc;
 }
 
