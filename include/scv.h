@@ -80,6 +80,12 @@ typedef struct {
 } scv_wgrad_t;
 int scv_wgrad(const scv_wgrad_t* p, void* stream);
 
+/* Up to 6 small INDEPENDENT problems (no output of one is an input of another) in ONE launch on the fp32 FFMA
+ * path; `precision` is ignored.  Used for the four MLPs of a scrubber-head ensemble (model/disentangle.py:583-632):
+ * their same-depth layers run side by side instead of as 11 + 22 serial launches. */
+int scv_gemm_group(const scv_gemm_t* p, int64_t n, void* stream);
+int scv_wgrad_group(const scv_wgrad_t* p, int64_t n, void* stream);
+
 /* ---- input pack: ResVAE.encode model/residual.py:438-451 + normalize_root :428-431 --------
  * out[b][halo+w][0..nx) = x6d[b][w][:], [nx..nx+3) = 2*(root-a0)/(a1-a0)-1, rest 0 (C floats/row) */
 int scv_pack_input(const float* x6d, const float* root, const float* arena, float* out,

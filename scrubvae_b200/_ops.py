@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libscv.so")
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELUMASK = 0, 1, 2, 3
 ACT_ROUND_TF32 = 16  # OR-ed into act: the stored output is rounded to TF32 (it feeds a tensor-core GEMM)
 PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
+MAX_GROUP = 6  # problems per scv_gemm_group / scv_wgrad_group launch
 BN, PRELU, TRAIN, ROUND_TF32 = 1, 2, 4, 8  # bnact mode bits
 
 
@@ -81,6 +82,8 @@ _SIGS = {
     "scv_launch_count": (_i64, []),
     "scv_gemm": (C.c_int, [C.POINTER(GemmT), _vp]),
     "scv_wgrad": (C.c_int, [C.POINTER(WgradT), _vp]),
+    "scv_gemm_group": (C.c_int, [C.POINTER(GemmT), _i64, _vp]),
+    "scv_wgrad_group": (C.c_int, [C.POINTER(WgradT), _i64, _vp]),
     "scv_pack_input": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp]),
     "scv_bnact_fwd": (C.c_int, [C.POINTER(BnactT), _vp]),
     "scv_bnact_bwd_reduce": (C.c_int, [C.POINTER(BnactBwdT), _vp]),
@@ -137,16 +140,33 @@ class CudaOps:
         return int(self.lib.scv_launch_count())
 
     # -- kernels
-    def gemm(self, A, a_bs, a_ls, B, Lo, K, N, W, Y, y_bs, y_ls, bias=None, bias_mod=1, bias_n=0, n_last=None,
-             R=None, r_bs=0, r_ls=0, act=ACT_NONE, out_scale=1.0, stats=None, precision=0):
-        p = GemmT(_ptr(A), a_bs, a_ls, B, Lo, K, N, _ptr(W), _ptr(bias), bias_mod, bias_n, _ptr(Y), y_bs, y_ls,
-                  N if n_last is None else n_last, _ptr(R), r_bs, r_ls, act, out_scale, _ptr(stats), precision)
+    @staticmethod
+    def _gemm_struct(A, a_bs, a_ls, B, Lo, K, N, W, Y, y_bs, y_ls, bias=None, bias_mod=1, bias_n=0, n_last=None,
+                     R=None, r_bs=0, r_ls=0, act=ACT_NONE, out_scale=1.0, stats=None, precision=0):
+        return GemmT(_ptr(A), a_bs, a_ls, B, Lo, K, N, _ptr(W), _ptr(bias), bias_mod, bias_n, _ptr(Y), y_bs, y_ls,
+                     N if n_last is None else n_last, _ptr(R), r_bs, r_ls, act, out_scale, _ptr(stats), precision)
+
+    @staticmethod
+    def _wgrad_struct(A, a_bs, a_ls, B, Lo, K, N, dY, y_bs, y_ls, dW, dbias=None, bias_mod=1, bias_n=0, precision=0):
+        return WgradT(_ptr(A), a_bs, a_ls, B, Lo, K, N, _ptr(dY), y_bs, y_ls, _ptr(dW), _ptr(dbias), bias_mod, bias_n,
+                      precision)
+
+    def gemm(self, *a, **kw):
+        p = self._gemm_struct(*a, **kw)
         self._check(self.lib.scv_gemm(C.byref(p), self._stream()), "scv_gemm")
 
-    def wgrad(self, A, a_bs, a_ls, B, Lo, K, N, dY, y_bs, y_ls, dW, dbias=None, bias_mod=1, bias_n=0, precision=0):
-        p = WgradT(_ptr(A), a_bs, a_ls, B, Lo, K, N, _ptr(dY), y_bs, y_ls, _ptr(dW), _ptr(dbias), bias_mod, bias_n,
-                   precision)
+    def wgrad(self, *a, **kw):
+        p = self._wgrad_struct(*a, **kw)
         self._check(self.lib.scv_wgrad(C.byref(p), self._stream()), "scv_wgrad")
+
+    def gemm_group(self, problems: Sequence[dict]):
+        """Up to MAX_GROUP independent small problems (keyword dicts of `gemm`) in one fp32 launch."""
+        arr = (GemmT * len(problems))(*[self._gemm_struct(**kw) for kw in problems])
+        self._check(self.lib.scv_gemm_group(arr, len(problems), self._stream()), "scv_gemm_group")
+
+    def wgrad_group(self, problems: Sequence[dict]):
+        arr = (WgradT * len(problems))(*[self._wgrad_struct(**kw) for kw in problems])
+        self._check(self.lib.scv_wgrad_group(arr, len(problems), self._stream()), "scv_wgrad_group")
 
     def pack_input(self, x6d, root, arena, out, B, W, nx, Cc, halo, round_tf32=False):
         self._check(self.lib.scv_pack_input(_ptr(x6d), _ptr(root), _ptr(arena), _ptr(out), B, W, nx, Cc, halo,

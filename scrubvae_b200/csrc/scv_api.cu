@@ -27,6 +27,8 @@ int sm_count() {
 
 int gemm_ffma(const scv_gemm_t* p, cudaStream_t st);
 int wgrad_ffma(const scv_wgrad_t* p, cudaStream_t st);
+int gemm_ffma_group(const scv_gemm_t* p, int n, cudaStream_t st);
+int wgrad_ffma_group(const scv_wgrad_t* p, int n, cudaStream_t st);
 int gemm_tc(const scv_gemm_t* p, cudaStream_t st);    // returns 1 if the shape is not taken
 int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st);  // returns 1 if the shape is not taken
 
@@ -48,6 +50,27 @@ int scv_gemm(const scv_gemm_t* p, void* stream) {
     if (r != 1) return r;
   }
   return scv::gemm_ffma(p, (cudaStream_t)stream);
+}
+
+int scv_gemm_group(const scv_gemm_t* p, int64_t n, void* stream) {
+  SCV_REQUIRE(p && n >= 1, "scv_gemm_group: no problems");
+  for (int64_t i = 0; i < n; ++i) {
+    SCV_REQUIRE(p[i].A && p[i].W && p[i].Y, "scv_gemm_group: null pointer (problem %lld)", (long long)i);
+    SCV_REQUIRE(p[i].B > 0 && p[i].Lo > 0 && p[i].K > 0 && p[i].N > 0, "scv_gemm_group: empty problem");
+    SCV_REQUIRE(p[i].n_last >= 0 && p[i].n_last <= p[i].N, "scv_gemm_group: n_last out of range");
+    SCV_REQUIRE(!p[i].bias || (p[i].bias_mod > 0 && p[i].bias_n <= p[i].N), "scv_gemm_group: bad bias_mod/bias_n");
+  }
+  return scv::gemm_ffma_group(p, (int)n, (cudaStream_t)stream);
+}
+
+int scv_wgrad_group(const scv_wgrad_t* p, int64_t n, void* stream) {
+  SCV_REQUIRE(p && n >= 1, "scv_wgrad_group: no problems");
+  for (int64_t i = 0; i < n; ++i) {
+    SCV_REQUIRE(p[i].A && p[i].dY && p[i].dW, "scv_wgrad_group: null pointer (problem %lld)", (long long)i);
+    SCV_REQUIRE(p[i].B > 0 && p[i].Lo > 0 && p[i].K > 0 && p[i].N > 0, "scv_wgrad_group: empty problem");
+    SCV_REQUIRE(!p[i].dbias || (p[i].bias_mod > 0 && p[i].bias_n <= p[i].N), "scv_wgrad_group: bad bias_mod/bias_n");
+  }
+  return scv::wgrad_ffma_group(p, (int)n, (cudaStream_t)stream);
 }
 
 int scv_wgrad(const scv_wgrad_t* p, void* stream) {

@@ -17,7 +17,11 @@ __device__ __forceinline__ float apply_act(float v, int act, float r) {
   return v;
 }
 
-__global__ void __launch_bounds__(NT, 2) gemm_ffma_kernel(const scv_gemm_t p, const int vec) {
+constexpr int kMaxGroup = 6;  // independent problems per grouped launch (scv_gemm_group / scv_wgrad_group)
+struct GemmGroupArgs { scv_gemm_t p[kMaxGroup]; int vec[kMaxGroup]; };
+struct WgradGroupArgs { scv_wgrad_t p[kMaxGroup]; int64_t rps[kMaxGroup]; int vecy[kMaxGroup]; int zbeg[kMaxGroup + 1]; };
+
+__device__ __forceinline__ void gemm_ffma_body(const scv_gemm_t& p, const int vec) {
   __shared__ __align__(16) float As[2][BK][LDS];
   __shared__ __align__(16) float Bs[2][BK][LDS];
   const int tid = threadIdx.x;
@@ -167,9 +171,18 @@ __global__ void __launch_bounds__(NT, 2) gemm_ffma_kernel(const scv_gemm_t p, co
   }
 }
 
+__global__ void __launch_bounds__(NT, 2) gemm_ffma_kernel(const scv_gemm_t p, const int vec) { gemm_ffma_body(p, vec); }
+
+// several small independent problems in one launch: blockIdx.z picks the problem
+__global__ void __launch_bounds__(NT, 2) gemm_ffma_group_kernel(const __grid_constant__ GemmGroupArgs g) {
+  const scv_gemm_t& p = g.p[blockIdx.z];
+  if ((int64_t)blockIdx.x * BM >= p.B * p.Lo || (int64_t)blockIdx.y * BN >= p.N) return;
+  gemm_ffma_body(p, g.vec[blockIdx.z]);
+}
+
 // dW[n][k] += sum_m dY[m][n] * A[m][k] over this block's m-range (split-M, fp32 atomics)
-__global__ void __launch_bounds__(NT, 2) wgrad_ffma_kernel(const scv_wgrad_t p, const int64_t rows_per_split,
-                                                        const int vecy) {
+__device__ __forceinline__ void wgrad_ffma_body(const scv_wgrad_t& p, const int64_t rows_per_split, const int vecy,
+                                                const int split) {
   __shared__ __align__(16) float Ys[2][BK][LDS];
   __shared__ __align__(16) float As[2][BK][LDS];
   const int tid = threadIdx.x;
@@ -177,7 +190,7 @@ __global__ void __launch_bounds__(NT, 2) wgrad_ffma_kernel(const scv_wgrad_t p, 
   const int64_t M = p.B * p.Lo;
   const int k0 = blockIdx.x * BM;  // K tile
   const int n0 = blockIdx.y * BN;  // N tile
-  const int64_t mbeg = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t mbeg = (int64_t)split * rows_per_split;
   const int64_t mend = mbeg + rows_per_split < M ? mbeg + rows_per_split : M;
   const int K = (int)p.K, N = (int)p.N;
   const int c4 = (tid & 31) * 4;
@@ -264,21 +277,97 @@ __global__ void __launch_bounds__(NT, 2) wgrad_ffma_kernel(const scv_wgrad_t p, 
   }
 }
 
+__global__ void __launch_bounds__(NT, 2) wgrad_ffma_kernel(const scv_wgrad_t p, const int64_t rows_per_split,
+                                                        const int vecy) {
+  wgrad_ffma_body(p, rows_per_split, vecy, blockIdx.z);
+}
+
+__global__ void __launch_bounds__(NT, 2) wgrad_ffma_group_kernel(const __grid_constant__ WgradGroupArgs g) {
+  int i = 0;
+  while (i + 1 < kMaxGroup && (int)blockIdx.z >= g.zbeg[i + 1]) ++i;
+  const scv_wgrad_t& p = g.p[i];
+  if ((int64_t)blockIdx.x * BM >= p.K || (int64_t)blockIdx.y * BN >= p.N) return;
+  wgrad_ffma_body(p, g.rps[i], g.vecy[i], (int)blockIdx.z - g.zbeg[i]);
+}
+
 }  // namespace
 
 namespace scv {
+
+static int gemm_vec(const scv_gemm_t* p) {
+  int vec = p->N % 4 == 0 && p->n_last % 4 == 0 && p->y_bs % 4 == 0 && p->y_ls % 4 == 0 && aligned16(p->Y);
+  if (p->R) vec = vec && p->r_bs % 4 == 0 && p->r_ls % 4 == 0 && aligned16(p->R);
+  return vec;
+}
+
+int gemm_ffma_group(const scv_gemm_t* p, int n, cudaStream_t st) {
+  SCV_REQUIRE(n >= 1 && n <= kMaxGroup, "scv_gemm_group: 1..%d problems per launch", kMaxGroup);
+  GemmGroupArgs g;
+  unsigned gx = 1, gy = 1;
+  for (int i = 0; i < n; ++i) {
+    SCV_REQUIRE(p[i].K % 4 == 0 && p[i].a_bs % 4 == 0 && p[i].a_ls % 4 == 0 && aligned16(p[i].A) && aligned16(p[i].W),
+                "scv_gemm_group: A/W rows must be 16-byte aligned (problem %d)", i);
+    g.p[i] = p[i];
+    g.vec[i] = gemm_vec(p + i);
+    const unsigned x = (unsigned)((p[i].B * p[i].Lo + BM - 1) / BM), y = (unsigned)((p[i].N + BN - 1) / BN);
+    gx = x > gx ? x : gx;
+    gy = y > gy ? y : gy;
+  }
+  SCV_REQUIRE(gy <= 65535, "scv_gemm_group: N too large");
+  gemm_ffma_group_kernel<<<dim3(gx, gy, (unsigned)n), NT, 0, st>>>(g);
+  return check_launch("gemm_ffma_group_kernel");
+}
 
 int gemm_ffma(const scv_gemm_t* p, cudaStream_t st) {
   const int64_t M = p->B * p->Lo;
   SCV_REQUIRE(p->K % 4 == 0 && p->a_bs % 4 == 0 && p->a_ls % 4 == 0 && aligned16(p->A) && aligned16(p->W),
               "scv_gemm: A/W rows must be 16-byte aligned (K=%lld a_bs=%lld a_ls=%lld)", (long long)p->K,
               (long long)p->a_bs, (long long)p->a_ls);
-  int vec = p->N % 4 == 0 && p->n_last % 4 == 0 && p->y_bs % 4 == 0 && p->y_ls % 4 == 0 && aligned16(p->Y);
-  if (p->R) vec = vec && p->r_bs % 4 == 0 && p->r_ls % 4 == 0 && aligned16(p->R);
+  const int vec = gemm_vec(p);
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((p->N + BN - 1) / BN));
   SCV_REQUIRE(grid.y <= 65535, "scv_gemm: N too large");
   gemm_ffma_kernel<<<grid, NT, 0, st>>>(*p, vec);
   return check_launch("gemm_ffma_kernel");
+}
+
+// row splits of one weight-gradient problem: ~`ctas` CTAs in flight over its tiles, at least 8 k-steps per split
+static void wgrad_splits(const scv_wgrad_t* p, int64_t ctas, int64_t& S, int64_t& rps) {
+  const int64_t M = p->B * p->Lo;
+  int64_t tiles = ((p->K + BM - 1) / BM) * ((p->N + BN - 1) / BN);
+  int64_t want = (ctas + tiles - 1) / tiles;
+  int64_t maxs = (M + 8 * BK - 1) / (8 * BK);
+  S = want < 1 ? 1 : want;
+  if (S > maxs) S = maxs;
+  if (S > 65535) S = 65535;
+  if (S < 1) S = 1;
+  rps = (M + S - 1) / S;
+  rps = (rps + BK - 1) / BK * BK;
+  S = (M + rps - 1) / rps;
+}
+
+int wgrad_ffma_group(const scv_wgrad_t* p, int n, cudaStream_t st) {
+  SCV_REQUIRE(n >= 1 && n <= kMaxGroup, "scv_wgrad_group: 1..%d problems per launch", kMaxGroup);
+  WgradGroupArgs g;
+  unsigned gx = 1, gy = 1;
+  int z = 0;
+  for (int i = 0; i < kMaxGroup + 1; ++i) g.zbeg[i] = 0x7fffffff;
+  for (int i = 0; i < n; ++i) {
+    SCV_REQUIRE(p[i].K % 4 == 0 && p[i].a_bs % 4 == 0 && p[i].a_ls % 4 == 0 && aligned16(p[i].A),
+                "scv_wgrad_group: A rows must be 16-byte aligned (problem %d)", i);
+    g.p[i] = p[i];
+    g.vecy[i] = p[i].N % 4 == 0 && p[i].y_bs % 4 == 0 && p[i].y_ls % 4 == 0 && aligned16(p[i].dY);
+    int64_t S, rps;
+    wgrad_splits(p + i, 4LL * sm_count() / n, S, rps);
+    g.rps[i] = rps;
+    g.zbeg[i] = z;
+    z += (int)S;
+    const unsigned x = (unsigned)((p[i].K + BM - 1) / BM), y = (unsigned)((p[i].N + BN - 1) / BN);
+    gx = x > gx ? x : gx;
+    gy = y > gy ? y : gy;
+  }
+  SCV_REQUIRE(gy <= 65535 && z <= 65535, "scv_wgrad_group: problem too large");
+  wgrad_ffma_group_kernel<<<dim3(gx, gy, (unsigned)z), NT, 0, st>>>(g);
+  return check_launch("wgrad_ffma_group_kernel");
 }
 
 int wgrad_ffma(const scv_wgrad_t* p, cudaStream_t st) {
@@ -286,16 +375,9 @@ int wgrad_ffma(const scv_wgrad_t* p, cudaStream_t st) {
   SCV_REQUIRE(p->K % 4 == 0 && p->a_bs % 4 == 0 && p->a_ls % 4 == 0 && aligned16(p->A),
               "scv_wgrad: A rows must be 16-byte aligned");
   int vecy = p->N % 4 == 0 && p->y_bs % 4 == 0 && p->y_ls % 4 == 0 && aligned16(p->dY);
-  int64_t tiles = ((p->K + BM - 1) / BM) * ((p->N + BN - 1) / BN);
-  int64_t want = (4LL * sm_count() + tiles - 1) / tiles;  // ~4 CTAs per SM in flight
-  int64_t maxs = (M + 8 * BK - 1) / (8 * BK);
-  int64_t S = want < 1 ? 1 : want;
-  if (S > maxs) S = maxs;
-  if (S > 65535) S = 65535;
-  if (S < 1) S = 1;
-  int64_t rps = (M + S - 1) / S;
-  rps = (rps + BK - 1) / BK * BK;
-  S = (M + rps - 1) / rps;
+  int64_t S, rps;
+  wgrad_splits(p, 4LL * sm_count(), S, rps);
+  (void)M;
   dim3 grid((unsigned)((p->K + BM - 1) / BM), (unsigned)((p->N + BN - 1) / BN), (unsigned)S);
   SCV_REQUIRE(grid.y <= 65535, "scv_wgrad: N too large");
   wgrad_ffma_kernel<<<grid, NT, 0, st>>>(*p, rps, vecy);

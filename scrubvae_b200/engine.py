@@ -251,6 +251,20 @@ class Engine:
                         layers.append(g)
                     mlps.append(layers)
                 self.gr_layers[key] = mlps
+                # gradient reversal into mu: ONE GEMM over the concatenated first-layer output gradients of all
+                # ensemble members, W_cat[z][sum N_m] = [W_0^T | W_1^T | ...]
+                cat = torch.cat([lay.pad_rows(I(f"{pre}mlp{mi + 1}.0.weight"), mlps[mi][0].N).t() for mi in range(len(mlps))],
+                                dim=1).contiguous()
+                gc = GemmW()
+                gc.name, gc.dN, gc.dK = f"gr.{key}.cat0", cat.shape[0], cat.shape[1]
+                gc.nnz_d = int((cat >= 0).sum())
+                gc.wd = self._n_d
+                self._pack_parts_d.append(cat.reshape(-1))
+                self._n_d += pad4(cat.numel())
+                if cat.numel() % 4:
+                    self._pack_parts_d.append(torch.full((pad4(cat.numel()) - cat.numel(),), -1, dtype=torch.long))
+                self.gr_cat = getattr(self, "gr_cat", {})
+                self.gr_cat[key] = gc
 
         dev = self.device
         fwd_idx = torch.cat(self._pack_parts)
@@ -262,6 +276,8 @@ class Engine:
         self.inv_idx = lay.inverse_map(fwd_idx, self.n_flat).to(torch.int32).to(dev)
         del self._pack_parts, self._pack_parts_d
         self.max_k = max(max(g.K, g.dK if g.wd is not None else 0) for g in self.W.values())
+        for gc in getattr(self, "gr_cat", {}).values():
+            self.max_k = max(self.max_k, gc.dK)
         # gpacked = [encoder layers | decoder layers + scrubber heads]; backward finishes the second part first
         self.gp_split = self.W["dec.fc_in"].w
 
@@ -558,26 +574,53 @@ class Plan:
         Hlast = H
 
         # =============================================================== scrubber heads (forward)
+        # The MLPs of an ensemble are independent: their same-depth layers run as ONE grouped fp32 launch.  The
+        # first-layer outputs (and their gradients) of all members share one [B x sum N] buffer so that the
+        # gradient into mu is a single GEMM over the concatenation.
+        from ._ops import MAX_GROUP
         self.dmu_gr = torch.zeros(B, z, **f32) if eng.gr_keys else None
-        self.gr_act: Dict[str, List[List[torch.Tensor]]] = {}
-        self.gr_dact: Dict[str, List[List[torch.Tensor]]] = {}
+        self.gr_act: Dict[str, List[List]] = {}
+        self.gr_dact: Dict[str, List[List]] = {}
+        self.gr_cat_ld: Dict[str, int] = {}
+        self.gr_dact0: Dict[str, torch.Tensor] = {}
+
+        def chunks(lst):
+            return [lst[i:i + MAX_GROUP] for i in range(0, len(lst), MAX_GROUP)]
+
+        fwd_levels: Dict[int, List[dict]] = {}
         for key in eng.gr_keys:
+            mlps = eng.gr_layers[key]
+            ld0 = sum(layers[0].N for layers in mlps)
+            self.gr_cat_ld[key] = ld0
+            act0 = torch.zeros(B, ld0, **f32)
+            dact0 = torch.zeros(B, ld0, **f32)
+            self.gr_dact0[key] = dact0
             acts_k, dacts_k = [], []
-            for layers in eng.gr_layers[key]:
-                acts, dacts = [], []
-                hin, kin = self.mu, z
+            col = 0
+            for layers in mlps:
+                acts, dacts = [], []   # entries: (Ref, row stride)
+                hin, h_ld = Ref(self.mu), z
                 for li, gl in enumerate(layers):
-                    out = torch.zeros(B, gl.N, **f32)
+                    if li == 0:
+                        out, dout, o_ld = Ref(act0, col), Ref(dact0, col), ld0
+                        col += gl.N
+                    else:
+                        out, dout, o_ld = Ref(torch.zeros(B, gl.N, **f32)), Ref(torch.zeros(B, gl.N, **f32)), gl.N
                     lastl = li == len(layers) - 1
-                    gemm(A=hin, a_bs=kin, a_ls=0, B=B, Lo=1, K=gl.K, N=gl.N, W=eng.wref(gl), bias=eng.bref(gl),
-                         bias_mod=gl.bias_mod, bias_n=gl.N, Y=out, y_bs=gl.N, y_ls=0,
-                         act=ACT_NONE if lastl else ACT_RELU, precision=0)
-                    acts.append(out)
-                    dacts.append(torch.zeros(B, gl.N, **f32))
-                    hin, kin = out, gl.N
+                    fwd_levels.setdefault(li, []).append(dict(
+                        A=hin, a_bs=h_ld, a_ls=0, B=B, Lo=1, K=gl.K, N=gl.N, W=eng.wref(gl), bias=eng.bref(gl),
+                        bias_mod=gl.bias_mod, bias_n=gl.N, Y=out, y_bs=o_ld, y_ls=0,
+                        act=ACT_NONE if lastl else ACT_RELU, precision=0))
+                    acts.append((out, o_ld))
+                    dacts.append((dout, o_ld))
+                    hin, h_ld = out, o_ld
                 acts_k.append(acts)
                 dacts_k.append(dacts)
             self.gr_act[key], self.gr_dact[key] = acts_k, dacts_k
+        for li in sorted(fwd_levels):
+            for grp in chunks(fwd_levels[li]):
+                F.append(lambda grp=grp: ops.gemm_group(grp))
+        self._n_head_launches = sum(len(chunks(v)) for v in fwd_levels.values())
 
         self.F = F
 
@@ -595,8 +638,8 @@ class Plan:
         Lk.append(recon)
         Lk.append(lambda: ops.kl(self.mu, self.Lmat, Ref(self.loss_acc, 2), None, None, None, B, z))
         for ki, key in enumerate(eng.gr_keys):
-            preds = [Ref(a[-1]) for a in self.gr_act[key]]
-            ld = self.gr_act[key][0][-1].shape[1]
+            preds = [a[-1][0] for a in self.gr_act[key]]
+            ld = self.gr_act[key][0][-1][1]
             Lk.append(lambda preds=preds, ld=ld, key=key, ki=ki: ops.gr_loss(
                 preds, None, ld, self.gr_target.get(key), self.gr_labels.get(key), B, self.gr_dim[key],
                 len(eng.gr_keys), Ref(self.loss_acc, 3 + ki), None))
@@ -648,32 +691,44 @@ class Plan:
         Bw.append(wgrad(gin, self.zc, eng.zc_ld, 0, 1, dX0.at(0), dX0.bs, 0))
         self.dzc = torch.zeros(B, eng.zc_ld, **f32)
         Bw.append(dgemm(gin, dX0.at(0), dX0.bs, 0, 1, self.dzc, eng.zc_ld, 0))
-        # scrubber heads
+        # scrubber heads: dpred from the loss, then level by level from the output side — the weight gradients and
+        # the data gradients of all ensemble members at the same distance from the output are one grouped launch
+        # each; the gradient-reversed gradient into mu is one GEMM per key over the concatenated first layers
         for ki, key in enumerate(eng.gr_keys):
-            preds = [Ref(a[-1]) for a in self.gr_act[key]]
-            dpreds = [Ref(d[-1]) for d in self.gr_dact[key]]
-            ld = self.gr_act[key][0][-1].shape[1]
+            preds = [a[-1][0] for a in self.gr_act[key]]
+            dpreds = [d[-1][0] for d in self.gr_dact[key]]
+            ld = self.gr_act[key][0][-1][1]
             Bw.append(lambda preds=preds, dpreds=dpreds, ld=ld, key=key, ki=ki: ops.gr_loss(
                 preds, dpreds, ld, self.gr_target.get(key), self.gr_labels.get(key), B, self.gr_dim[key],
                 len(eng.gr_keys), None, Ref(self.gscale, 3 + ki)))
-            for mi, layers in enumerate(eng.gr_layers[key]):
-                acts, dacts = self.gr_act[key][mi], self.gr_dact[key][mi]
-                for li in range(len(layers) - 1, -1, -1):
+        depth = max((len(l) for kk in eng.gr_keys for l in eng.gr_layers[kk]), default=0)
+        for t in range(depth):  # t = distance from the output layer
+            wg, dg = [], []
+            for key in eng.gr_keys:
+                for mi, layers in enumerate(eng.gr_layers[key]):
+                    li = len(layers) - 1 - t
+                    if li < 0:
+                        continue
                     gl = layers[li]
-                    hin, kin = (acts[li - 1], layers[li - 1].N) if li > 0 else (self.mu, z)
-                    kw = dict(A=hin, a_bs=kin, a_ls=0, B=B, Lo=1, K=gl.K, N=gl.N, dY=dacts[li], y_bs=gl.N, y_ls=0,
-                              dW=eng.gwref(gl), dbias=eng.gbref(gl), bias_mod=gl.bias_mod, bias_n=gl.N, precision=0)
-                    Bw.append(lambda kw=kw: ops.wgrad(**kw))
+                    acts, dacts = self.gr_act[key][mi], self.gr_dact[key][mi]
+                    hin, h_ld = acts[li - 1] if li > 0 else (Ref(self.mu), z)
+                    dy, dy_ld = dacts[li]
+                    wg.append(dict(A=hin, a_bs=h_ld, a_ls=0, B=B, Lo=1, K=gl.K, N=gl.N, dY=dy, y_bs=dy_ld, y_ls=0,
+                                   dW=eng.gwref(gl), dbias=eng.gbref(gl), bias_mod=gl.bias_mod, bias_n=gl.N, precision=0))
                     if li > 0:
-                        kw2 = dict(A=dacts[li], a_bs=gl.N, a_ls=0, B=B, Lo=1, K=gl.dK, N=gl.dN, W=eng.wdref(gl),
-                                   Y=dacts[li - 1], y_bs=gl.dN, y_ls=0, R=acts[li - 1], r_bs=gl.dN, r_ls=0,
-                                   act=ACT_RELUMASK, precision=0)
-                    else:  # gradient reversal: -alpha * g accumulated over ensemble members and keys
-                        first = ki == 0 and mi == 0
-                        kw2 = dict(A=dacts[li], a_bs=gl.N, a_ls=0, B=B, Lo=1, K=gl.dK, N=gl.dN, W=eng.wdref(gl),
-                                   Y=self.dmu_gr, y_bs=z, y_ls=0, R=None if first else self.dmu_gr, r_bs=z, r_ls=0,
-                                   out_scale=-eng.gr_alpha[key], precision=0)
-                    Bw.append(lambda kw2=kw2: ops.gemm(**kw2))
+                        dprev, dp_ld = dacts[li - 1]
+                        dg.append(dict(A=dy, a_bs=dy_ld, a_ls=0, B=B, Lo=1, K=gl.dK, N=gl.dN, W=eng.wdref(gl), Y=dprev,
+                                       y_bs=dp_ld, y_ls=0, R=hin, r_bs=h_ld, r_ls=0, act=ACT_RELUMASK, precision=0))
+            for grp in chunks(wg):
+                Bw.append(lambda grp=grp: ops.wgrad_group(grp))
+            for grp in chunks(dg):
+                Bw.append(lambda grp=grp: ops.gemm_group(grp))
+        for ki, key in enumerate(eng.gr_keys):  # gradient reversal: dmu_gr (+)= -alpha * dact0_cat . W_cat^T
+            gc = eng.gr_cat[key]
+            kw2 = dict(A=self.gr_dact0[key], a_bs=self.gr_cat_ld[key], a_ls=0, B=B, Lo=1, K=gc.dK, N=gc.dN,
+                       W=eng.wdref(gc), Y=self.dmu_gr, y_bs=z, y_ls=0, R=None if ki == 0 else self.dmu_gr, r_bs=z, r_ls=0,
+                       out_scale=-eng.gr_alpha[key], precision=0)
+            Bw.append(lambda kw2=kw2: ops.gemm(**kw2))
         self._bw_dec_end = len(Bw)  # decoder + scrubber-head weight gradients are final from here on
         # latent
         self.dmu_kl = torch.zeros(B, z, **f32)
@@ -767,8 +822,7 @@ class Plan:
             self.zc[:, :m.z_dim].copy_(z_given)
             if eng.cond_dim > 0:
                 self.zc[:, m.z_dim:m.z_dim + eng.cond_dim].copy_(self.var)
-            nheads = sum(len(l) for kk in eng.gr_keys for l in eng.gr_layers[kk])
-            for f in self.F[self._n_enc:len(self.F) - nheads]:
+            for f in self.F[self._n_enc:len(self.F) - self._n_head_launches]:
                 f()
         out = {}
         if z_given is None:
@@ -785,7 +839,7 @@ class Plan:
             out["disentangle"] = {}
             if eng.gr_keys:
                 out["disentangle"]["grad_reversal"] = {
-                    key: [a[-1][:, :self.gr_dim[key]] for a in self.gr_act[key]] for key in eng.gr_keys}
+                    key: [a[-1][0].t[:, :self.gr_dim[key]] for a in self.gr_act[key]] for key in eng.gr_keys}
             out["_plan"] = self
         return out
 

@@ -76,6 +76,14 @@ class EmuOps:
             out[:, :Lo - 1].copy_(y[:, :Lo - 1])
             out[:, Lo - 1, :n_last].copy_(y[:, Lo - 1, :n_last])
 
+    def gemm_group(self, problems):
+        for kw in problems:
+            self.gemm(**{**kw, "precision": 0})
+
+    def wgrad_group(self, problems):
+        for kw in problems:
+            self.wgrad(**{**kw, "precision": 0})
+
     def wgrad(self, A, a_bs, a_ls, B, Lo, K, N, dY, y_bs, y_ls, dW, dbias=None, bias_mod=1, bias_n=0, precision=0):
         self.n += 1
         a = _v(A, (B, Lo, K), (a_bs, a_ls, 1)).reshape(B * Lo, K)
