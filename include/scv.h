@@ -69,6 +69,8 @@ int scv_gemm(const scv_gemm_t* p, void* stream);
 
 /* dW[n][k] += sum_{b,l} dY[b*y_bs + l*y_ls + n] * A[b*a_bs + l*a_ls + k];
  * dbias[n % bias_mod] += sum_{b,l} dY[..n] (n < bias_n).  dY must hold zeros where invalid.
+ * The tensor-core path fetches whole 32-float column slabs: A and dY must be READABLE up to the next multiple of
+ * 32 floats past the end of their last row (what is read there never reaches a stored result).
  * Replaces cuDNN wgrad / cuBLAS for the same layers (autograd of the sites above). */
 typedef struct {
   const float* A; int64_t a_bs, a_ls;

@@ -342,7 +342,7 @@ struct WgradTcParams {
   int bias_mod, bias_n;
 };
 
-constexpr int kWgradMaxBNK = 240;  // k-tile width limit: 2 x (240 + 16 bias columns) = 512 TMEM columns
+constexpr int kWgradMaxBNK = 224;  // k-tile width limit (whole 32-float slabs); 224 + 16 bias columns fit a 256-column TMEM buffer
 constexpr int kBiasCol = 240;      // TMEM column of the bias accumulator inside each 256-column buffer
 
 struct SmemCtlW {
@@ -417,8 +417,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           const uint32_t fb = smem_u32(&ctl->full[s]);
           mbar_expect_tx(fb, stage_bytes);
           const uint32_t sy = smem_u32(smem + (size_t)s * stage_bytes);
-          for (int j = 0; j < 4; ++j) tma_load_3d(sy + j * slab, &tmY, fb, nt * kBM + j * 32, l0, b0);
-          for (int j = 0; j < a_slabs; ++j) tma_load_3d(sy + y_bytes + j * slab, &tmA, fb, kt * p.bnk + j * 32, l0, b0);
+          // one TMA per operand: 4-D boxes (32 floats, bl, nb, slabs) land slab-major, exactly the MN-major layout
+          tma_load_4d(sy, &tmY, fb, 0, l0, b0, nt * (kBM / 32));
+          tma_load_4d(sy + y_bytes, &tmA, fb, 0, l0, b0, kt * (p.bnk / 32));
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -638,9 +639,10 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.lt = (int)cdiv(p->Lo, q.bl);
   q.bt = (int)cdiv(p->B, q.nb);
   q.groups = q.lt * q.bt;
-  const int k16 = (int)cdiv(p->K, 16) * 16;
-  const int kt0 = (int)cdiv(k16, kWgradMaxBNK);
-  q.bnk = (int)cdiv(cdiv(k16, kt0), 16) * 16;
+  // k tile: whole 32-float slabs (the TMA box counts slabs), balanced over the tiles
+  const int k32 = (int)cdiv(p->K, 32) * 32;
+  const int kt0 = (int)cdiv(k32, kWgradMaxBNK);
+  q.bnk = (int)cdiv(cdiv(k32, kt0), 32) * 32;
   q.k_tiles = (int)cdiv(p->K, q.bnk);
   q.n_tiles = (int)cdiv(p->N, kBM);
   const int tiles = q.n_tiles * q.k_tiles;
@@ -659,18 +661,21 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.stages = stages;
 
   CUtensorMap tmY, tmA;
+  // (32 floats, l, b, slab): the 4th dimension walks the 32-float column slabs of a row.  A partial last slab
+  // reads past the row's end (the next row / the buffer's slack): those columns only reach output rows n >= N or
+  // output columns k >= K, which the epilogue does not store.
   {
-    const int64_t dims[3] = {p->N, p->Lo, p->B};
-    const int64_t str[3] = {1, p->y_ls ? p->y_ls : p->y_bs, p->y_bs ? p->y_bs : 4};
-    const int box[3] = {32, q.bl, q.nb};
-    rc = tc::make_tmap(&tmY, p->dY, 3, dims, str, box, "scv_wgrad dY", true);
+    const int64_t dims[4] = {32, p->Lo, p->B, cdiv(p->N, 32)};
+    const int64_t str[4] = {1, p->y_ls ? p->y_ls : p->y_bs, p->y_bs ? p->y_bs : 4, 32};
+    const int box[4] = {32, q.bl, q.nb, 4};
+    rc = tc::make_tmap(&tmY, p->dY, 4, dims, str, box, "scv_wgrad dY", true);
     if (rc) return rc;
   }
   {
-    const int64_t dims[3] = {p->K, p->Lo, p->B};
-    const int64_t str[3] = {1, p->a_ls ? p->a_ls : p->a_bs, p->a_bs ? p->a_bs : 4};
-    const int box[3] = {32, q.bl, q.nb};
-    rc = tc::make_tmap(&tmA, p->A, 3, dims, str, box, "scv_wgrad A", true);
+    const int64_t dims[4] = {32, p->Lo, p->B, cdiv(p->K, 32)};
+    const int64_t str[4] = {1, p->a_ls ? p->a_ls : p->a_bs, p->a_bs ? p->a_bs : 4, 32};
+    const int box[4] = {32, q.bl, q.nb, q.bnk / 32};
+    rc = tc::make_tmap(&tmA, p->A, 4, dims, str, box, "scv_wgrad A", true);
     if (rc) return rc;
   }
   const int total = tiles * q.splits;

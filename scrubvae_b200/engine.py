@@ -510,7 +510,7 @@ class Plan:
              bias_mod=gfc.bias_mod, bias_n=gfc.N, Y=self.ms, y_bs=eng.ms_ld, y_ls=0)
         self.mu = torch.zeros(B, z, **f32)
         self.Lmat = torch.zeros(B, z, z, **f32)
-        self.zc = torch.zeros(B, eng.zc_ld, **f32)
+        self.zc = torch.zeros(B * eng.zc_ld + 64, **f32)[:B * eng.zc_ld].view(B, eng.zc_ld)  # + slab read slack (scv.h)
 
         def reparam():
             ops.reparam_fwd(self.ms, eng.ms_ld, self.eps if self._training else None,
@@ -733,7 +733,7 @@ class Plan:
         # latent
         self.dmu_kl = torch.zeros(B, z, **f32)
         self.dL_kl = torch.zeros(B, z, z, **f32)
-        self.dms = torch.zeros(B, eng.ms_ld, **f32)
+        self.dms = torch.zeros(B * eng.ms_ld + 64, **f32)[:B * eng.ms_ld].view(B, eng.ms_ld)
         Bw.append(lambda: ops.kl(self.mu, self.Lmat, None, Ref(self.gscale, 2), self.dmu_kl, self.dL_kl, B, z))
         Bw.append(lambda: ops.reparam_bwd(self.ms, eng.ms_ld, self.eps, self.dmu_kl, self.dmu_gr, 1.0, self.dzc,
                                           eng.zc_ld, self.dL_kl, self.dms, eng.ms_ld, B, z, round_tf32=rnd))

@@ -16,7 +16,7 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(128, 1) rate_kernel(int kind, int N, int iters, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int kind, int N, int iters, long long* out, int mn) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -29,11 +29,12 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int kind, int N, int iters
   tc_fence_after();
   if (threadIdx.x == 0) {
     const uint32_t sa = smem_u32(smem), sb = sa + 16384;
-    const uint32_t idesc = kind == 0 ? idesc_tf32(128, N, 0, 0) : idesc_bf16(128, N);
+    const uint32_t idesc = kind == 0 ? idesc_tf32(128, N, mn, mn) : idesc_bf16(128, N);
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const uint32_t koff = (i & 3) * 32;
-      if (kind == 0) umma_tf32(tbase, smem_desc(sa + koff, 16, 1024), smem_desc(sb + koff, 16, 1024), idesc, 1u);
+      if (kind == 0 && mn) umma_tf32(tbase, smem_desc(sa + (i & 3) * 1024, 4096, 512, 1), smem_desc(sb + (i & 3) * 1024, 4096, 512, 1), idesc, 1u);
+      else if (kind == 0) umma_tf32(tbase, smem_desc(sa + koff, 16, 1024), smem_desc(sb + koff, 16, 1024), idesc, 1u);
       else umma_f16(tbase, smem_desc(sa + koff, 16, 1024), smem_desc(sb + koff, 16, 1024), idesc, 1u);
     }
     umma_commit(smem_u32(&bar));
@@ -50,11 +51,11 @@ int main() {
   long long* d; cudaMalloc(&d, 148 * 8);
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int iters = 4000;
-  for (int grid : {1, 148}) for (int kind = 0; kind < 2; ++kind) for (int N : {64, 128, 256}) {
-    rate_kernel<<<grid, 128, 64 * 1024>>>(kind, N, iters, d);
+  for (int mn = 0; mn < 2; ++mn) for (int grid : {1, 148}) for (int kind = 0; kind < 2 - mn; ++kind) for (int N : {64, 128, 240, 256}) {
+    rate_kernel<<<grid, 128, 64 * 1024>>>(kind, N, iters, d, mn);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    rate_kernel<<<grid, 128, 64 * 1024>>>(kind, N, iters, d);
+    rate_kernel<<<grid, 128, 64 * 1024>>>(kind, N, iters, d, mn);
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -62,7 +63,7 @@ int main() {
     const int kk = kind == 0 ? 8 : 16;
     double cyc = (double)h[0] / iters;
     double tf = 2.0 * 128 * N * kk * iters * grid / (ms * 1e-3) / 1e12;
-    printf("grid %3d kind %s N %3d: %.1f cycles/MMA (128x%dx%d), %.1f TFLOP/s by events (%s)\n", grid, kind == 0 ? "tf32" : "bf16", N, cyc,
+    printf("%s grid %3d kind %s N %3d: %.1f cycles/MMA (128x%dx%d), %.1f TFLOP/s by events (%s)\n", mn ? "MN-major" : "K-major ", grid, kind == 0 ? "tf32" : "bf16", N, cyc,
            N, kk, tf, cudaGetErrorString(e));
   }
   return 0;

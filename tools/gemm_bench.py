@@ -36,7 +36,7 @@ for g in eng.W.values():
 calls = []
 og, ow = ops.gemm, ops.wgrad
 def rg(**kw):
-    lab, nnz = names[_ptr(kw["W"])]
+    lab, nnz = names.get(_ptr(kw["W"]), ("gr.cat0:dgrad", kw["N"] * kw["K"]))
     calls.append((lab, "gemm", kw, 2.0 * kw["B"] * kw["Lo"] * nnz)); og(**kw)
 def rw(**kw):
     lab, nnz = names[("g", _ptr(kw["dW"]))]

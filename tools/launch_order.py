@@ -47,7 +47,7 @@ out = []
 for k, a, kw in rec.calls:
     d = {"op": k}
     if k == "gemm":
-        lab, nnz = names[_ptr(kw["W"])]
+        lab, nnz = names.get(_ptr(kw["W"]), ("gr.cat0:dgrad", kw["N"] * kw["K"]))
         d.update(label=lab, Lo=kw["Lo"], M=B * kw["Lo"], N=kw["N"], K=kw["K"], flops=2.0 * B * kw["Lo"] * nnz,
                  R=kw.get("R") is not None, stats=kw.get("stats") is not None, prec=kw.get("precision", 0))
     elif k == "wgrad":
