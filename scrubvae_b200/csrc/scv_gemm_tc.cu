@@ -119,20 +119,29 @@ __device__ __forceinline__ float act_apply(float v, int act, float r) {
   return v;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcParams p) {
+// kCtas = 1: one CTA per 128-row tile (cta_group::1).  kCtas = 2: the two CTAs of a cluster share a 256-row tile
+// (cta_group::2): each loads its own 128 A rows and HALF of the W tile, the leader's single thread issues M = 256
+// MMAs that read W from both shared memories — per SM the shared-memory fill and operand-read traffic per FLOP
+// drops by a third, which is what paces the large TF32 layers.
+template <int kCtas>
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmTcParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const int bnw = p.bn / kCtas;                       // W rows held by this CTA
   const uint32_t a_bytes = kBM * kBK * 4;             // 16 KB
-  const uint32_t w_bytes = (uint32_t)p.bn * kBK * 4;  // bn rows of 128 B (bn % 16 == 0 -> 2 KB multiple)
+  const uint32_t w_bytes = (uint32_t)bnw * kBK * 4;   // rows of 128 B (multiple of 2 KB)
   const uint32_t stage_bytes = a_bytes + w_bytes;
   uint8_t* ctl_raw = smem + (size_t)p.stages * stage_bytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(ctl_raw);
   float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtl) + 15) & ~size_t(15)));  // 4 warps x 32 x 32 floats
-  const uint32_t tile_tx = (uint32_t)(p.bl * p.nb) * kBK * 4 + w_bytes;
-  const int total = p.n_tiles * p.m_tiles;
+  const uint32_t tile_tx = ((uint32_t)(p.bl * p.nb) * kBK * 4 + w_bytes) * kCtas;
+  // work items: (n tile, group of kCtas consecutive m tiles); the CTAs of a pair walk the same list
+  const int m_groups = (p.m_tiles + kCtas - 1) / kCtas;
+  const int total = p.n_tiles * m_groups;
+  const int first = (int)blockIdx.x / kCtas, step = (int)gridDim.x / kCtas;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -140,18 +149,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&ctl->full[s]), 1);
+      mbar_init(smem_u32(&ctl->full[s]), kCtas);   // pair: the leader's expect_tx arrive + the peer's arrive
       mbar_init(smem_u32(&ctl->empty[s]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&ctl->tfull[i]), 1);
-      mbar_init(smem_u32(&ctl->tempty[i]), 4);
+      mbar_init(smem_u32(&ctl->tempty[i]), 4 * kCtas);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
+  if (warp == 2) {
+    if (kCtas == 2) tmem_alloc2(smem_u32(&ctl->tmem_base), kTmemCols);
+    else tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
@@ -159,28 +171,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
-        const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;
-        const int l0 = lt_i * p.bl, b0 = bt_i * p.nb, n0 = nt * p.bn;
+      for (int t = first; t < total; t += step) {
+        const int nt = t / m_groups, mt = (t - nt * m_groups) * kCtas + (int)rank;
+        const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;  // mt >= m_tiles (odd tail): box fully out of bounds -> zeros
+        const int l0 = lt_i * p.bl, b0 = bt_i * p.nb, n0 = nt * p.bn + (int)rank * bnw;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1);
-          const uint32_t fb = smem_u32(&ctl->full[s]);
-          mbar_expect_tx(fb, tile_tx);
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          tma_load_3d(sa, &tmA, fb, kc * kBK, l0, b0);
-          tma_load_2d(sa + a_bytes, &tmW, fb, kc * kBK, n0);
+          if (kCtas == 2) {
+            const uint32_t fb = mapa_rank(smem_u32(&ctl->full[s]), 0);  // the leader's barrier counts both CTAs' bytes
+            if (rank == 0) mbar_expect_tx(smem_u32(&ctl->full[s]), tile_tx);
+            else mbar_arrive_cluster(fb);
+            tma2_load_3d(sa, &tmA, fb, kc * kBK, l0, b0);
+            tma2_load_2d(sa + a_bytes, &tmW, fb, kc * kBK, n0);
+          } else {
+            const uint32_t fb = smem_u32(&ctl->full[s]);
+            mbar_expect_tx(fb, tile_tx);
+            tma_load_3d(sa, &tmA, fb, kc * kBK, l0, b0);
+            tma_load_2d(sa + a_bytes, &tmW, fb, kc * kBK, n0);
+          }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(kBM, p.bn, 0, 0);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = idesc_tf32(kBM * kCtas, p.bn, 0, 0);
       int s = 0, it = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      for (int t = first; t < total; t += step, ++it) {
         const int acc = it & 1;
         mbar_wait(smem_u32(&ctl->tempty[acc]), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -191,13 +211,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sw = sa + a_bytes;
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k)
-            umma_tf32(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sw + k * 32, 16, 1024), idesc,
-                      (kc | k) != 0 ? 1u : 0u);
-          umma_commit(smem_u32(&ctl->empty[s]));
+          for (int k = 0; k < kBK / 8; ++k) {
+            if (kCtas == 2)
+              umma2_tf32(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sw + k * 32, 16, 1024), idesc,
+                         (kc | k) != 0 ? 1u : 0u);
+            else
+              umma_tf32(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sw + k * 32, 16, 1024), idesc,
+                        (kc | k) != 0 ? 1u : 0u);
+          }
+          if (kCtas == 2) umma2_commit(smem_u32(&ctl->empty[s])); else umma_commit(smem_u32(&ctl->empty[s]));
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(smem_u32(&ctl->tfull[acc]));
+        if (kCtas == 2) umma2_commit(smem_u32(&ctl->tfull[acc])); else umma_commit(smem_u32(&ctl->tfull[acc]));
       }
     }
     __syncwarp();
@@ -216,9 +241,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = et; c < 2 * kMaxBN; c += 128) (&ctl->sacc[0][0])[c] = 0.f;
       epi_bar();
     }
+    const uint32_t tempty_addr[2] = {kCtas == 2 ? mapa_rank(smem_u32(&ctl->tempty[0]), 0) : smem_u32(&ctl->tempty[0]),
+                                     kCtas == 2 ? mapa_rank(smem_u32(&ctl->tempty[1]), 0) : smem_u32(&ctl->tempty[1])};
     int it = 0, cur_nt = -1;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
+    for (int t = first; t < total; t += step, ++it) {
+      const int nt = t / m_groups, mt = (t - nt * m_groups) * kCtas + (int)rank;
       const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;
       const int n0 = nt * p.bn;
       const int ncols = min(p.bn, N - n0);
@@ -243,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row = ew * 32 + i * 4 + rq;
         const int bi = row / p.bl, li = row - bi * p.bl;
         const int64_t b = (int64_t)bt_i * p.nb + bi, l = (int64_t)lt_i * p.bl + li;
-        const bool ok = row < rows_in_box && b < p.B && l < p.Lo;
+        const bool ok = row < rows_in_box && mt < p.m_tiles && b < p.B && l < p.Lo;
         yoff[i] = (long long)(b * p.y_bs + l * p.y_ls);
         roff[i] = (long long)(b * p.r_bs + l * p.r_ls);
         ncap[i] = ok ? ((l == p.Lo - 1) ? p.n_last : N) : 0;
@@ -259,7 +286,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (c0 + 32 >= ncols) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&ctl->tempty[acc]));
+          if (lane == 0) {
+            if (kCtas == 2) mbar_arrive_cluster(tempty_addr[acc]); else mbar_arrive(tempty_addr[acc]);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -322,11 +351,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();  // pair: no CTA may exit while its peer still signals it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kCtas == 2) tmem_dealloc2(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcParams p) {
+  gemm_tc_body<1>(tmA, tmW, p);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcParams p) {
+  gemm_tc_body<2>(tmA, tmW, p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -515,10 +554,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 }
 
 int g_attr_done = 0;
+int g_pair_capacity = -1;
+
+// number of CTA pairs (clusters of 2) of the 2-CTA GEMM that can be resident at once
+int pair_capacity() { return g_pair_capacity; }
 
 int ensure_attrs() {
   if (g_attr_done) return 0;
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (scv::sm_count() / 2));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemLimit;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel, &cfg) == cudaSuccess) g_pair_capacity = n;
+    else { g_pair_capacity = 0; cudaGetLastError(); }
+  }
   if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e != cudaSuccess) {
     scv::set_error("tensor-core GEMM: cannot opt in to %d B of shared memory: %s", kSmemLimit, cudaGetErrorString(e));
@@ -578,14 +636,22 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   choose_box(p->Lo, p->B, kBM, false, q.bl, q.nb);
   q.lt = (int)cdiv(p->Lo, q.bl);
   q.bt = (int)cdiv(p->B, q.nb);
-  // N tile: as wide as the MMA allows, balanced over the tiles, multiple of 16
-  const int n16 = (int)cdiv(p->N, 16) * 16;
-  const int nt0 = (int)cdiv(n16, kMaxBN);
-  q.bn = (int)cdiv(cdiv(n16, nt0), 16) * 16;
-  q.n_tiles = (int)cdiv(p->N, q.bn);
   q.m_tiles = q.lt * q.bt;
   q.k_chunks = (int)cdiv(p->K, kBK);
-  const size_t stage_bytes = (size_t)kBM * kBK * 4 + (size_t)q.bn * kBK * 4;
+  // CTA pairs (cta_group::2, gemm_tc2_kernel) are correct (kernel tests pass with SCV_TC_PAIR=1) but measured
+  // SLOWER on every layer of the step (profiles/r01_pair_vs_single.md: the M=256 pair MMA issues at the same
+  // 162 cycles as two M=128 MMAs, tools/cu/mma_rate2.cu, and the cross-SM operand fetch costs on top), so the
+  // single-CTA kernel is the default; SCV_TC_PAIR=1 selects the pair kernel for experiments.
+  static const int force_pair = [] { const char* e = getenv("SCV_TC_PAIR"); return e ? atoi(e) : 0; }();
+  int ctas = force_pair ? 2 : 1;
+  if (q.m_tiles < 2 || pair_capacity() < 1) ctas = 1;
+  // N tile: as wide as the MMA allows, balanced over the tiles, multiple of 16 (of 32 for a pair: each CTA holds half)
+  const int ng = 16 * ctas;
+  const int n16 = (int)cdiv(p->N, ng) * ng;
+  const int nt0 = (int)cdiv(n16, kMaxBN);
+  q.bn = (int)cdiv(cdiv(n16, nt0), ng) * ng;
+  q.n_tiles = (int)cdiv(p->N, q.bn);
+  const size_t stage_bytes = (size_t)kBM * kBK * 4 + (size_t)(q.bn / ctas) * kBK * 4;
   const size_t fixed = 1024 + ((sizeof(SmemCtl) + 15) & ~size_t(15)) + 4 * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -608,13 +674,19 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   {
     const int64_t dims[2] = {p->K, p->N};
     const int64_t str[2] = {1, p->K};
-    const int box[2] = {kBK, q.bn};
+    const int box[2] = {kBK, q.bn / ctas};
     rc = tc::make_tmap(&tmW, p->W, 2, dims, str, box, "scv_gemm W");
     if (rc) return rc;
   }
+  const size_t smem = fixed + (size_t)stages * stage_bytes;
+  if (ctas == 2) {
+    const int items = q.n_tiles * (int)cdiv(q.m_tiles, 2);
+    const int pairs = items < pair_capacity() ? items : pair_capacity();
+    gemm_tc2_kernel<<<2 * pairs, kThreads, smem, st>>>(tmA, tmW, q);
+    return check_launch("gemm_tc2_kernel");
+  }
   const int total = q.n_tiles * q.m_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  const size_t smem = fixed + (size_t)stages * stage_bytes;
   gemm_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, q);
   return check_launch("gemm_tc_kernel");
 }
