@@ -97,7 +97,20 @@ struct GemmTcParams {
   int act, round_out;
   float out_scale;
   double* stats;
+  int epi_kind;      // which compiled epilogue variant serves (act, R, stats, round_out); see gemm_tc_body
+  long long* trace;  // debug (SCV_TC_TRACE=<n events>): CTA 0 appends (role, event, tile, clock) records
 };
+
+// debug timeline of CTA 0: role 0 producer / 1 mma / 2 epilogue warp 0; only active when p.trace != nullptr
+__device__ __forceinline__ void tc_trace(const GemmTcParams& p, int role, int ev, int tile) {
+  if (p.trace && blockIdx.x == 0) {
+    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(p.trace), 1ULL);
+    if (i < 4000) {
+      p.trace[1 + 2 * i] = ((long long)role << 40) | ((long long)ev << 32) | (unsigned)tile;
+      p.trace[2 + 2 * i] = clock64();
+    }
+  }
+}
 
 struct SmemCtl {  // lives after the operand stages
   uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
@@ -117,6 +130,48 @@ __device__ __forceinline__ float act_apply(float v, int act, float r) {
   if (act == SCV_ACT_TANH) return tanhf(v);
   if (act == SCV_ACT_RELUMASK) return r > 0.f ? v : 0.f;
   return v;
+}
+
+// Epilogue arithmetic of one 32x32 chunk for lane (rq, cq): rows 4 i + rq (i < 8), columns n .. n + 3.
+// ACT >= 0 / RD / ST / RND are compile-time; ACT = -1 is the generic path (activation, rounding from p at run time).
+template <int ACT, bool RD, bool ST, bool RND>
+__device__ __forceinline__ void epi_rows(const GemmTcParams& p, const float4* xp4, const int rq, const int cq, const bool col_ok,
+                                         const int n, const float4 bv, const long long (&yoff)[8], const long long (&roff)[8],
+                                         const int (&ncap)[8], float4& s1, float4& s2) {
+  const int act = ACT >= 0 ? ACT : p.act;
+  const bool rnd = ACT >= 0 ? RND : (p.round_out != 0);
+  const float osc = p.out_scale;
+  float4 rv[8];
+  if (RD) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok && n < ncap[i]) rv[i] = __ldg(reinterpret_cast<const float4*>(p.R + roff[i] + n));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rq;
+    const float4 a = xp4[r * 8 + (cq ^ (r & 7))];
+    if (col_ok && n < ncap[i]) {
+      float4 tv = make_float4(fmaf(osc, a.x, bv.x), fmaf(osc, a.y, bv.y), fmaf(osc, a.z, bv.z), fmaf(osc, a.w, bv.w));
+      float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (RD) {
+        r4 = rv[i];
+        if (act != SCV_ACT_RELUMASK) { tv.x += r4.x; tv.y += r4.y; tv.z += r4.z; tv.w += r4.w; }
+      }
+      if (ST) {
+        s1.x += tv.x; s1.y += tv.y; s1.z += tv.z; s1.w += tv.w;
+        s2.x = fmaf(tv.x, tv.x, s2.x); s2.y = fmaf(tv.y, tv.y, s2.y); s2.z = fmaf(tv.z, tv.z, s2.z); s2.w = fmaf(tv.w, tv.w, s2.w);
+      }
+      float4 yv = tv;
+      if (act != SCV_ACT_NONE)
+        yv = make_float4(act_apply(tv.x, act, r4.x), act_apply(tv.y, act, r4.y), act_apply(tv.z, act, r4.z),
+                         act_apply(tv.w, act, r4.w));
+      if (rnd) yv = scv::round_tf32(yv);
+      *reinterpret_cast<float4*>(p.Y + yoff[i] + n) = yv;
+    }
+  }
 }
 
 // kCtas = 1: one CTA per 128-row tile (cta_group::1).  kCtas = 2: the two CTAs of a cluster share a 256-row tile
@@ -175,8 +230,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         const int nt = t / m_groups, mt = (t - nt * m_groups) * kCtas + (int)rank;
         const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;  // mt >= m_tiles (odd tail): box fully out of bounds -> zeros
         const int l0 = lt_i * p.bl, b0 = bt_i * p.nb, n0 = nt * p.bn + (int)rank * bnw;
+        tc_trace(p, 0, 0, t);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1);
+          if (kc == 0 || kc == p.k_chunks - 1) tc_trace(p, 0, 1 + (kc != 0), t);
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           if (kCtas == 2) {
             const uint32_t fb = mapa_rank(smem_u32(&ctl->full[s]), 0);  // the leader's barrier counts both CTAs' bytes
@@ -202,12 +259,15 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
       uint32_t ph = 0;
       for (int t = first; t < total; t += step, ++it) {
         const int acc = it & 1;
+        tc_trace(p, 1, 0, t);
         mbar_wait(smem_u32(&ctl->tempty[acc]), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
+        tc_trace(p, 1, 1, t);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(smem_u32(&ctl->full[s]), ph);
           tc_fence_after();
+          if (kc == 0 || kc == p.k_chunks - 1) tc_trace(p, 1, 2 + (kc != 0), t);
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sw = sa + a_bytes;
 #pragma unroll
@@ -276,8 +336,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         ncap[i] = ok ? ((l == p.Lo - 1) ? p.n_last : N) : 0;
       }
       const int acc = it & 1;
+      if (ew == 0 && lane == 0) tc_trace(p, 2, 0, t);
       mbar_wait(smem_u32(&ctl->tfull[acc]), (it >> 1) & 1);
       tc_fence_after();
+      if (ew == 0 && lane == 0) tc_trace(p, 2, 1, t);
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kMaxBN;
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
@@ -300,28 +362,21 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         const bool col_ok = cc < ncols;
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias && col_ok && n < p.bias_n) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (n % p.bias_mod)));
-        float4 rv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.R && col_ok && n < ncap[i]) rv[i] = __ldg(reinterpret_cast<const float4*>(p.R + roff[i] + n));
-        }
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + rq;
-          float4 a = xp4[r * 8 + (cq ^ (r & 7))];
-          if (col_ok && n < ncap[i]) {
-            float4 tv = make_float4(p.out_scale * a.x + bv.x, p.out_scale * a.y + bv.y, p.out_scale * a.z + bv.z,
-                                    p.out_scale * a.w + bv.w);
-            if (p.act != SCV_ACT_RELUMASK) { tv.x += rv[i].x; tv.y += rv[i].y; tv.z += rv[i].z; tv.w += rv[i].w; }
-            s1.x += tv.x; s1.y += tv.y; s1.z += tv.z; s1.w += tv.w;
-            s2.x += tv.x * tv.x; s2.y += tv.y * tv.y; s2.z += tv.z * tv.z; s2.w += tv.w * tv.w;
-            float4 yv = make_float4(act_apply(tv.x, p.act, rv[i].x), act_apply(tv.y, p.act, rv[i].y),
-                                    act_apply(tv.z, p.act, rv[i].z), act_apply(tv.w, p.act, rv[i].w));
-            if (p.round_out) yv = scv::round_tf32(yv);
-            *reinterpret_cast<float4*>(p.Y + yoff[i] + n) = yv;
-          }
+        const bool rd = p.R != nullptr;
+        // one instantiation per (activation, residual, sums, rounding) combination the step uses: the per-element
+        // work is then a handful of instructions instead of a runtime-branching generic path (one epilogue warp
+        // per scheduler: every instruction's latency is exposed)
+        switch (p.epi_kind) {
+          case 0: epi_rows<SCV_ACT_NONE, false, false, false>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
+          case 1: epi_rows<SCV_ACT_NONE, false, true, false>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
+          case 2: epi_rows<SCV_ACT_NONE, true, false, false>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
+          case 3: epi_rows<SCV_ACT_NONE, true, true, false>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
+          case 4: epi_rows<SCV_ACT_NONE, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
+          case 5: epi_rows<SCV_ACT_TANH, false, false, false>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
+          default:
+            if (rd) epi_rows<-1, true, true, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2);
+            else epi_rows<-1, false, true, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2);
         }
         if (has_stats) {
 #pragma unroll
@@ -340,6 +395,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         }
         __syncwarp();
       }
+      if (ew == 0 && lane == 0) tc_trace(p, 2, 2, t);
     }
     if (has_stats && cur_nt >= 0) {
       epi_bar();
@@ -662,6 +718,17 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   q.Y = p->Y; q.y_bs = p->y_bs; q.y_ls = p->y_ls; q.n_last = (int)p->n_last;
   q.R = p->R; q.r_bs = p->r_bs; q.r_ls = p->r_ls;
   q.act = (int)(p->act & 15); q.round_out = (p->act & SCV_ACT_ROUND_TF32) ? 1 : 0; q.out_scale = (float)p->out_scale; q.stats = p->stats;
+  {
+    const bool rd = q.R != nullptr, stt = q.stats != nullptr, rn = q.round_out != 0;
+    if (q.act == SCV_ACT_NONE && !rn) q.epi_kind = (rd ? 2 : 0) + (stt ? 1 : 0);
+    else if (q.act == SCV_ACT_NONE && rn && !rd && !stt) q.epi_kind = 4;
+    else if (q.act == SCV_ACT_TANH && !rn && !rd && !stt) q.epi_kind = 5;
+    else q.epi_kind = 99;  // generic
+  }
+  q.trace = nullptr;
+  if (const char* tr = getenv("SCV_TC_TRACE")) {  // debug: device buffer address (decimal) to receive CTA 0's timeline
+    q.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 10));
+  }
 
   CUtensorMap tmA, tmW;
   {
