@@ -255,6 +255,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       const uint32_t idesc = idesc_tf32(kBM * kCtas, p.bn, 0, 0);
+      // K-major, 128B swizzle: LBO 16 B (unused), SBO 1024 B; the stage base addresses are 1024-byte aligned
+      const uint64_t desc0 = smem_desc(smem_u32(smem), 16, 1024);
+      const uint32_t desc_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
+      const uint32_t stage_units = stage_bytes >> 4;
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int t = first; t < total; t += step, ++it) {
@@ -268,16 +272,19 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
           mbar_wait(smem_u32(&ctl->full[s]), ph);
           tc_fence_after();
           if (kc == 0 || kc == p.k_chunks - 1) tc_trace(p, 1, 2 + (kc != 0), t);
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sw = sa + a_bytes;
-#pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) {
-            if (kCtas == 2)
-              umma2_tf32(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sw + k * 32, 16, 1024), idesc,
-                         (kc | k) != 0 ? 1u : 0u);
-            else
-              umma_tf32(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sw + k * 32, 16, 1024), idesc,
-                        (kc | k) != 0 ? 1u : 0u);
+          // descriptor low words of this stage; each k step of 8 floats advances the start address by 32 B = 2 units
+          const uint32_t a_lo = desc_lo0 + (uint32_t)s * stage_units, b_lo = a_lo + (a_bytes >> 4);
+          const uint32_t acc0 = kc != 0 ? 1u : 0u;
+          if (kCtas == 2) {
+            umma2_tf32_lh(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, acc0);
+            umma2_tf32_lh(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
+            umma2_tf32_lh(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
+            umma2_tf32_lh(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
+          } else {
+            umma_tf32_lh(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, acc0);
+            umma_tf32_lh(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
+            umma_tf32_lh(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
+            umma_tf32_lh(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
           }
           if (kCtas == 2) umma2_commit(smem_u32(&ctl->empty[s])); else umma_commit(smem_u32(&ctl->empty[s]));
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -525,6 +532,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       const uint32_t idesc = idesc_tf32(kBM, p.bnk, 1, 1);
       const uint32_t idesc_b = idesc_tf32(kBM, 16, 1, 1);
       const uint64_t ones_desc = smem_desc(smem_u32(ones), 1024, 512, 1);
+      const uint32_t ones_lo = (uint32_t)ones_desc, ones_hi = (uint32_t)(ones_desc >> 32);
+      // MN-major, 128B swizzle with 32-byte atoms: LBO = slab pitch, SBO = 512 B (4 k-rows)
+      const uint64_t ydesc0 = smem_desc(smem_u32(smem), slab, 512, 1);
+      const uint32_t ydesc_lo0 = (uint32_t)ydesc0, desc_hi = (uint32_t)(ydesc0 >> 32);
+      const uint32_t stage_units = stage_bytes >> 4;
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
@@ -540,10 +552,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           tc_fence_after();
           const uint32_t sy = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sa = sy + y_bytes;
-          for (int r8 = 0; r8 < R / 8; ++r8) {
-            const uint64_t dy = smem_desc(sy + r8 * 1024, slab, 512, 1);
-            umma_tf32(d_tmem, dy, smem_desc(sa + r8 * 1024, slab, 512, 1), idesc, (g > g0 || r8 > 0) ? 1u : 0u);
-            if (do_bias) umma_tf32(d_tmem + kBiasCol, dy, ones_desc, idesc_b, (g > g0 || r8 > 0) ? 1u : 0u);
+          const uint32_t y_lo = ydesc_lo0 + (uint32_t)s * stage_units, a_lo = y_lo + (y_bytes >> 4);
+          uint32_t accf = g > g0 ? 1u : 0u;
+          for (int r8 = 0; r8 < R / 8; ++r8) {  // 8 reduction rows = 1024 B = 64 units per MMA
+            umma_tf32_lh(d_tmem, y_lo + r8 * 64, desc_hi, a_lo + r8 * 64, desc_hi, idesc, accf);
+            if (do_bias) umma_tf32_lh(d_tmem + kBiasCol, y_lo + r8 * 64, desc_hi, ones_lo, ones_hi, idesc_b, accf);
+            accf = 1u;
           }
           umma_commit(smem_u32(&ctl->empty[s]));
           if (++s == p.stages) { s = 0; ph ^= 1; }

@@ -30,12 +30,26 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int kind, int N, int iters
   if (threadIdx.x == 0) {
     const uint32_t sa = smem_u32(smem), sb = sa + 16384;
     const uint32_t idesc = kind == 0 ? idesc_tf32(128, N, mn, mn) : idesc_bf16(128, N);
+    uint64_t da[4], db[4];
+    for (int k = 0; k < 4; ++k) {
+      da[k] = mn ? smem_desc(sa + k * 1024, 4096, 512, 1) : smem_desc(sa + k * 32, 16, 1024);
+      db[k] = mn ? smem_desc(sb + k * 1024, 4096, 512, 1) : smem_desc(sb + k * 32, 16, 1024);
+    }
     long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      const uint32_t koff = (i & 3) * 32;
-      if (kind == 0 && mn) umma_tf32(tbase, smem_desc(sa + (i & 3) * 1024, 4096, 512, 1), smem_desc(sb + (i & 3) * 1024, 4096, 512, 1), idesc, 1u);
-      else if (kind == 0) umma_tf32(tbase, smem_desc(sa + koff, 16, 1024), smem_desc(sb + koff, 16, 1024), idesc, 1u);
-      else umma_f16(tbase, smem_desc(sa + koff, 16, 1024), smem_desc(sb + koff, 16, 1024), idesc, 1u);
+    if (kind == 0) {
+      for (int i = 0; i < iters; i += 4) {
+        umma_tf32(tbase, da[0], db[0], idesc, 1u);
+        umma_tf32(tbase, da[1], db[1], idesc, 1u);
+        umma_tf32(tbase, da[2], db[2], idesc, 1u);
+        umma_tf32(tbase, da[3], db[3], idesc, 1u);
+      }
+    } else {
+      for (int i = 0; i < iters; i += 4) {
+        umma_f16(tbase, da[0], db[0], idesc, 1u);
+        umma_f16(tbase, da[1], db[1], idesc, 1u);
+        umma_f16(tbase, da[2], db[2], idesc, 1u);
+        umma_f16(tbase, da[3], db[3], idesc, 1u);
+      }
     }
     umma_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
@@ -51,7 +65,7 @@ int main() {
   long long* d; cudaMalloc(&d, 148 * 8);
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int iters = 4000;
-  for (int mn = 0; mn < 2; ++mn) for (int grid : {1, 148}) for (int kind = 0; kind < 2 - mn; ++kind) for (int N : {64, 128, 240, 256}) {
+  for (int mn = 0; mn < 2; ++mn) for (int grid : {148}) for (int kind = 0; kind < 2 - mn; ++kind) for (int N : {16, 32, 64, 128, 192, 256}) {
     rate_kernel<<<grid, 128, 64 * 1024>>>(kind, N, iters, d, mn);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
