@@ -97,6 +97,8 @@ struct GemmTcParams {
   int act, round_out;
   float out_scale;
   double* stats;
+  int sub;           // row tiles per work item (1 or 2): with 2 the CTA runs two 128-row tiles against ONE W tile per
+                     // stage (two accumulators, no TMEM double buffering) - a third less shared-memory traffic per FLOP
   int epi_kind;      // which compiled epilogue variant serves (act, R, stats, round_out); see gemm_tc_body
   long long* trace;  // debug (SCV_TC_TRACE=<n events>): CTA 0 appends (role, event, tile, clock) records
 };
@@ -186,15 +188,17 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
   const int bnw = p.bn / kCtas;                       // W rows held by this CTA
-  const uint32_t a_bytes = kBM * kBK * 4;             // 16 KB
+  const int sub = kCtas == 1 ? p.sub : 1;
+  const uint32_t a_tile = kBM * kBK * 4;              // 16 KB per 128-row tile
+  const uint32_t a_bytes = a_tile * (uint32_t)sub;
   const uint32_t w_bytes = (uint32_t)bnw * kBK * 4;   // rows of 128 B (multiple of 2 KB)
   const uint32_t stage_bytes = a_bytes + w_bytes;
   uint8_t* ctl_raw = smem + (size_t)p.stages * stage_bytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(ctl_raw);
   float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtl) + 15) & ~size_t(15)));  // 4 warps x 32 x 32 floats
-  const uint32_t tile_tx = ((uint32_t)(p.bl * p.nb) * kBK * 4 + w_bytes) * kCtas;
-  // work items: (n tile, group of kCtas consecutive m tiles); the CTAs of a pair walk the same list
-  const int m_groups = (p.m_tiles + kCtas - 1) / kCtas;
+  const uint32_t tile_tx = ((uint32_t)(p.bl * p.nb) * kBK * 4 * (uint32_t)sub + w_bytes) * kCtas;
+  // work items: (n tile, group of kCtas * sub consecutive m tiles); the CTAs of a pair walk the same list
+  const int m_groups = (p.m_tiles + kCtas * sub - 1) / (kCtas * sub);
   const int total = p.n_tiles * m_groups;
   const int first = (int)blockIdx.x / kCtas, step = (int)gridDim.x / kCtas;
 
@@ -227,9 +231,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
       int s = 0;
       uint32_t ph = 0;
       for (int t = first; t < total; t += step) {
-        const int nt = t / m_groups, mt = (t - nt * m_groups) * kCtas + (int)rank;
+        const int nt = t / m_groups, mt = (t - nt * m_groups) * kCtas * sub + (int)rank;
         const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;  // mt >= m_tiles (odd tail): box fully out of bounds -> zeros
         const int l0 = lt_i * p.bl, b0 = bt_i * p.nb, n0 = nt * p.bn + (int)rank * bnw;
+        const int bt_2 = (mt + 1) / p.lt, lt_2 = (mt + 1) - bt_2 * p.lt;  // second row tile (sub == 2)
         tc_trace(p, 0, 0, t);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1);
@@ -245,6 +250,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             const uint32_t fb = smem_u32(&ctl->full[s]);
             mbar_expect_tx(fb, tile_tx);
             tma_load_3d(sa, &tmA, fb, kc * kBK, l0, b0);
+            if (sub == 2) tma_load_3d(sa + a_tile, &tmA, fb, kc * kBK, lt_2 * p.bl, bt_2 * p.nb);
             tma_load_2d(sa + a_bytes, &tmW, fb, kc * kBK, n0);
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -262,9 +268,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int t = first; t < total; t += step, ++it) {
-        const int acc = it & 1;
+        const int acc = sub == 2 ? 0 : (it & 1);  // sub == 2: both TMEM halves hold this item's two accumulators
         tc_trace(p, 1, 0, t);
-        mbar_wait(smem_u32(&ctl->tempty[acc]), ((it >> 1) & 1) ^ 1);
+        mbar_wait(smem_u32(&ctl->tempty[acc]), (sub == 2 ? (it & 1) : ((it >> 1) & 1)) ^ 1);
         tc_fence_after();
         tc_trace(p, 1, 1, t);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;
@@ -285,6 +291,13 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             umma_tf32_lh(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
             umma_tf32_lh(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
             umma_tf32_lh(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
+            if (sub == 2) {
+              const uint32_t a2 = a_lo + (a_tile >> 4), d2 = d_tmem + kMaxBN;
+              umma_tf32_lh(d2, a2, desc_hi, b_lo, desc_hi, idesc, acc0);
+              umma_tf32_lh(d2, a2 + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
+              umma_tf32_lh(d2, a2 + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
+              umma_tf32_lh(d2, a2 + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
+            }
           }
           if (kCtas == 2) umma2_commit(smem_u32(&ctl->empty[s])); else umma_commit(smem_u32(&ctl->empty[s]));
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -312,8 +325,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
                                      kCtas == 2 ? mapa_rank(smem_u32(&ctl->tempty[1]), 0) : smem_u32(&ctl->tempty[1])};
     int it = 0, cur_nt = -1;
     for (int t = first; t < total; t += step, ++it) {
-      const int nt = t / m_groups, mt = (t - nt * m_groups) * kCtas + (int)rank;
-      const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;
+      const int nt = t / m_groups, mt0 = (t - nt * m_groups) * kCtas * sub + (int)rank;
       const int n0 = nt * p.bn;
       const int ncols = min(p.bn, N - n0);
       if (has_stats && nt != cur_nt) {
@@ -330,6 +342,14 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         }
         cur_nt = nt;
       }
+      const int acc = sub == 2 ? 0 : (it & 1);
+      if (ew == 0 && lane == 0) tc_trace(p, 2, 0, t);
+      mbar_wait(smem_u32(&ctl->tfull[acc]), sub == 2 ? (it & 1) : ((it >> 1) & 1));
+      tc_fence_after();
+      if (ew == 0 && lane == 0) tc_trace(p, 2, 1, t);
+     for (int sj = 0; sj < sub; ++sj) {
+      const int mt = mt0 + sj;
+      const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;
       long long yoff[8], roff[8];
       int ncap[8];
 #pragma unroll
@@ -342,17 +362,12 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         roff[i] = (long long)(b * p.r_bs + l * p.r_ls);
         ncap[i] = ok ? ((l == p.Lo - 1) ? p.n_last : N) : 0;
       }
-      const int acc = it & 1;
-      if (ew == 0 && lane == 0) tc_trace(p, 2, 0, t);
-      mbar_wait(smem_u32(&ctl->tfull[acc]), (it >> 1) & 1);
-      tc_fence_after();
-      if (ew == 0 && lane == 0) tc_trace(p, 2, 1, t);
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kMaxBN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(sub == 2 ? sj : acc) * kMaxBN;
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
-        if (c0 + 32 >= ncols) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+        if (c0 + 32 >= ncols && sj == sub - 1) {  // accumulator(s) fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -402,6 +417,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         }
         __syncwarp();
       }
+     }  // sub tiles
       if (ew == 0 && lane == 0) tc_trace(p, 2, 2, t);
     }
     if (has_stats && cur_nt >= 0) {
@@ -721,7 +737,21 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   const int nt0 = (int)cdiv(n16, kMaxBN);
   q.bn = (int)cdiv(cdiv(n16, nt0), ng) * ng;
   q.n_tiles = (int)cdiv(p->N, q.bn);
-  const size_t stage_bytes = (size_t)kBM * kBK * 4 + (size_t)(q.bn / ctas) * kBK * 4;
+  // two row tiles per work item when that still fills the machine and K is long enough for the shared-memory
+  // traffic (not the epilogue, which is no longer overlapped) to dominate; SCV_TC_SUB=1/2 forces the choice
+  static const int force_sub = [] { const char* e = getenv("SCV_TC_SUB"); return e ? atoi(e) : 0; }();
+  q.sub = 1;
+  if (ctas == 1) {
+    const int items2 = q.n_tiles * (int)cdiv(q.m_tiles, 2);
+    // measured rule (profiles/r01_sub2_vs_sub1.md): enough items for 3/4 of the SMs, and a main loop (8 MMAs per
+    // 32-float K chunk, >= 48 cycles each) at least 1.5x the two un-overlapped epilogues (~1500 cycles per 32 columns)
+    const int64_t mainloop = (int64_t)q.k_chunks * 8 * (q.bn / 2 > 48 ? q.bn / 2 : 48);
+    const int64_t epi = 2 * cdiv(q.bn, 32) * 1500;
+    if (items2 >= (sm_count() * 3) / 4 && 2 * mainloop >= 3 * epi) q.sub = 2;
+    if (force_sub == 1 || force_sub == 2) q.sub = force_sub;
+    if (q.m_tiles < 2) q.sub = 1;
+  }
+  const size_t stage_bytes = (size_t)kBM * kBK * 4 * q.sub + (size_t)(q.bn / ctas) * kBK * 4;
   const size_t fixed = 1024 + ((sizeof(SmemCtl) + 15) & ~size_t(15)) + 4 * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -766,7 +796,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
     gemm_tc2_kernel<<<2 * pairs, kThreads, smem, st>>>(tmA, tmW, q);
     return check_launch("gemm_tc2_kernel");
   }
-  const int total = q.n_tiles * q.m_tiles;
+  const int total = q.n_tiles * (int)cdiv(q.m_tiles, q.sub);
   const int grid = total < sm_count() ? total : sm_count();
   gemm_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, q);
   return check_launch("gemm_tc_kernel");
