@@ -113,43 +113,184 @@ __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, c
   }
 }
 
-constexpr int FK_THREADS = 64;
-__global__ void __launch_bounds__(FK_THREADS) recon_loss_kernel(const float* __restrict__ xh, int64_t ld,
-                                                                const float* __restrict__ offsets,
-                                                                const float* __restrict__ target,
-                                                                const float* __restrict__ root,
-                                                                const float* __restrict__ arena,
-                                                                const int32_t* __restrict__ tree, int n_tree,
-                                                                double* loss, float* __restrict__ root_hat,
-                                                                float* __restrict__ dxh, int64_t F, int B, int J) {
-  __shared__ int32_t stree[SCV_MAX_J * 3];
-  __shared__ double shd[32];
-  for (int i = threadIdx.x; i < n_tree; i += blockDim.x) stree[i] = tree[i];
-  __syncthreads();
-  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nx = J * 6;
-  double ljpe = 0.0, lroot = 0.0;
-  if (f < F) {
-    float c6[SCV_MAX_J * 6], off[SCV_MAX_J * 3], tgt[SCV_MAX_J * 3], gc[SCV_MAX_J * 6];
-    const float* xr = xh + f * ld;
-    for (int q = 0; q < nx; ++q) c6[q] = xr[q];
-    for (int q = 0; q < J * 3; ++q) { off[q] = offsets[f * J * 3 + q]; tgt[q] = target[f * J * 3 + q]; }
-    const float scale = 1.f / ((float)B * 3.f * (float)J);
-    float l = scvfk::fk_jpe_frame(c6, off, tgt, stree, J, 1e-8f, scale, gc);
-    ljpe = (double)l * (double)scale;
-    float* dr = dxh + f * ld;
-    for (int q = 0; q < nx; ++q) dr[q] = gc[q];
-    const float invB = 1.f / (float)B;
+// One WARP per frame, one LANE per joint.  The kinematic tree is turned into per-joint tables once per block
+// (chain index, rotation parent, position parent, position children); chain products, positions, subtree sums of
+// the position gradients and the rotation gradients then move between lanes with warp shuffles, level by level.
+// Everything a lane owns (its joint's 3x3 matrices) stays in registers: no local-memory arrays, coalesced row reads
+// and writes.  Semantics: fwd_kin_cont6d_torch (every chain restarts from the ROOT joint's rotation) + mpjpe_loss +
+// root MSE, as scvfk::fk_jpe_frame (scv_fk.h, kept as the host-testable statement of the same math).
+constexpr int FK_WARPS = 8;
+constexpr int FK_MAXCH = 6;  // position children per joint
+
+struct FkTables {
+  int8_t cidx[32], rp[32], pp[32], pdepth[32], rc[32], nchild[32], child[32][FK_MAXCH];
+  int maxc, maxd, maxch, bad;
+};
+
+__device__ __forceinline__ void shfl9(const float* v, int src, float* o) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      float a0 = arena[d], a1 = arena[3 + d];
-      float rh = 0.5f * (xr[nx + d] + 1.f) * (a1 - a0) + a0;
+  for (int q = 0; q < 9; ++q) o[q] = __shfl_sync(0xffffffffu, v[q], src);
+}
+
+__global__ void __launch_bounds__(FK_WARPS * 32) recon_loss_kernel(const float* __restrict__ xh, int64_t ld,
+                                                                   const float* __restrict__ offsets,
+                                                                   const float* __restrict__ target,
+                                                                   const float* __restrict__ root,
+                                                                   const float* __restrict__ arena,
+                                                                   const int32_t* __restrict__ tree, int n_tree,
+                                                                   double* loss, float* __restrict__ root_hat,
+                                                                   float* __restrict__ dxh, int64_t F, int B, int J) {
+  __shared__ FkTables T;
+  __shared__ double shd[32];
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < 32; ++j) {
+      T.cidx[j] = j == 0 ? 0 : -1; T.rp[j] = 0; T.pp[j] = -1; T.pdepth[j] = 0; T.rc[j] = -1; T.nchild[j] = 0;
+      for (int c = 0; c < FK_MAXCH; ++c) T.child[j][c] = -1;
+    }
+    T.bad = 0;
+    int pos = 1;
+    for (int ch = 0; ch < tree[0]; ++ch) {
+      const int len = tree[pos];
+      const int32_t* cj = tree + pos + 1;
+      for (int i = 1; i < len; ++i) {
+        const int j = cj[i];
+        T.cidx[j] = (int8_t)i;
+        T.pp[j] = (int8_t)cj[i - 1];
+        T.rp[j] = (int8_t)(i == 1 ? 0 : cj[i - 1]);
+        if (i >= 2) T.rc[cj[i - 1]] = (int8_t)j;
+      }
+      pos += 1 + len;
+    }
+    int maxc = 0, maxd = 0, maxch = 0;
+    for (int it = 0; it < J; ++it)  // depths: parents may be defined by any chain
+      for (int j = 1; j < J; ++j)
+        if (T.pp[j] >= 0) T.pdepth[j] = (int8_t)(T.pdepth[T.pp[j]] + 1);
+    for (int j = 1; j < J; ++j) {
+      if (T.pp[j] >= 0) {
+        const int pj = T.pp[j];
+        if (T.nchild[pj] < FK_MAXCH) T.child[pj][T.nchild[pj]++] = (int8_t)j; else T.bad = 1;
+      }
+      maxc = max(maxc, (int)T.cidx[j]);
+      maxd = max(maxd, (int)T.pdepth[j]);
+    }
+    for (int j = 0; j < J; ++j) maxch = max(maxch, (int)T.nchild[j]);
+    T.maxc = maxc; T.maxd = maxd; T.maxch = maxch;
+  }
+  __syncthreads();
+  if (T.bad) {  // a joint with more than FK_MAXCH children: not a skeleton this kernel was built for
+    if (threadIdx.x == 0 && blockIdx.x == 0) printf("libscv: recon_loss: kinematic tree has a joint with too many children\n");
+    __trap();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = lane;
+  const bool act = j < J;
+  const int cidx = act ? T.cidx[j] : -1, rp = act ? T.rp[j] : 0, pp = (act && T.pp[j] >= 0) ? T.pp[j] : 0;
+  const int pdepth = act ? T.pdepth[j] : -1, rc = act ? T.rc[j] : -1, nchild = act ? T.nchild[j] : 0;
+  int child[FK_MAXCH];
+#pragma unroll
+  for (int c = 0; c < FK_MAXCH; ++c) child[c] = act ? T.child[j][c] : -1;
+  const int maxc = T.maxc, maxd = T.maxd, maxch = T.maxch;
+  const int nx = J * 6;
+  const float scale = 1.f / ((float)B * 3.f * (float)J), invB = 1.f / (float)B;
+  double ljpe = 0.0, lroot = 0.0;
+  for (int64_t f = (int64_t)blockIdx.x * FK_WARPS + warp; f < F; f += (int64_t)gridDim.x * FK_WARPS) {
+    const float* xr = xh + f * ld;
+    float* dr = dxh + f * ld;
+    float c6[6] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f}, off[3] = {0.f, 0.f, 0.f}, tgt[3] = {0.f, 0.f, 0.f};
+    if (act) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) c6[q] = xr[j * 6 + q];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) { off[q] = offsets[f * J * 3 + j * 3 + q]; tgt[q] = target[f * J * 3 + j * 3 + q]; }
+    }
+    float M[9], R[9], Rp[9], tmp[9];
+    scvfk::c6d_to_mat(c6, 1e-8f, M);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) { R[q] = M[q]; Rp[q] = 0.f; }
+    for (int s = 1; s <= maxc; ++s) {  // chain products, one chain level at a time
+      shfl9(R, rp, tmp);
+      if (cidx == s) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Rp[q] = tmp[q];
+        scvfk::mat_mul(Rp, M, R);
+      }
+    }
+    float v[3] = {0.f, 0.f, 0.f}, pose[3] = {0.f, 0.f, 0.f};
+    if (cidx >= 1) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) v[r] = R[r * 3] * off[0] + R[r * 3 + 1] * off[1] + R[r * 3 + 2] * off[2];
+    }
+    for (int d = 1; d <= maxd; ++d) {  // positions, one tree level at a time
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float pv = __shfl_sync(0xffffffffu, pose[r], pp);
+        if (pdepth == d) pose[r] = v[r] + pv;
+      }
+    }
+    float S[3], lsum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float dlt = act ? pose[r] - tgt[r] : 0.f;
+      lsum += dlt * dlt;
+      S[r] = 2.f * scale * dlt;
+    }
+    lsum = scv::warp_sum(lsum);
+    if (lane == 0) ljpe += (double)lsum * (double)scale;
+    for (int d = maxd - 1; d >= 0; --d) {  // subtree sums of the position gradients
+#pragma unroll
+      for (int ci = 0; ci < FK_MAXCH; ++ci) {
+        if (ci < maxch) {  // warp-uniform
+          const int c = child[ci];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float cv = __shfl_sync(0xffffffffu, S[r], c >= 0 ? c : 0);
+            if (pdepth == d && ci < nchild) S[r] += cv;
+          }
+        }
+      }
+    }
+    float gR[9], gM[9], Tm[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { gR[r * 3 + c] = cidx >= 1 ? S[r] * off[c] : 0.f; gM[r * 3 + c] = 0.f; }
+    for (int s = maxc; s >= 1; --s) {  // rotation gradients back along the chains
+#pragma unroll
+      for (int q = 0; q < 9; ++q) Tm[q] = 0.f;
+      if (cidx == s) {
+        scvfk::mat_mul_at_acc(Rp, gR, gM);  // gM += Rp^T gR
+        scvfk::mat_mul_bt(gR, M, Tm);       // to the rotation parent: gR M^T
+      }
+      if (s >= 2) {
+        shfl9(Tm, rc >= 0 ? rc : 0, tmp);
+        if (cidx == s - 1 && rc >= 0) {
+#pragma unroll
+          for (int q = 0; q < 9; ++q) gR[q] += tmp[q];
+        }
+      } else {  // the root joint's matrix starts every chain: sum over all first chain elements
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          const float tot = scv::warp_sum(Tm[q]);
+          if (j == 0) gM[q] += tot;
+        }
+      }
+    }
+    if (act) {
+      float gc[6];
+      scvfk::c6d_to_mat_bwd(c6, 1e-8f, gM, gc);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) dr[j * 6 + q] = gc[q];
+    }
+    if (lane < 3) {  // root channels: inverse normalisation, squared error, unit gradient
+      const int d = lane;
+      const float a0 = arena[d], a1 = arena[3 + d];
+      const float rh = 0.5f * (xr[nx + d] + 1.f) * (a1 - a0) + a0;
       if (root_hat) root_hat[f * 3 + d] = rh;
-      float diff = rh - root[f * 3 + d];
+      const float diff = rh - root[f * 3 + d];
       lroot += (double)(diff * diff) * (double)invB;
       dr[nx + d] = 2.f * diff * 0.5f * (a1 - a0) * invB;
     }
-    for (int q = nx + 3; q < ld; ++q) dr[q] = 0.f;
+    for (int q = nx + 3 + lane; q < ld; q += 32) dr[q] = 0.f;
   }
   double s0 = scv::block_sum_d(ljpe, shd);
   if (threadIdx.x == 0) atomicAdd(loss, s0);
@@ -255,7 +396,10 @@ int scv_recon_loss(const float* xh, int64_t ld, const float* offsets, const floa
                    int64_t F, int64_t B, int64_t J, void* stream) {
   SCV_REQUIRE(J <= SCV_MAX_J && n_tree <= SCV_MAX_J * 3 && ld >= J * 6 + 3, "scv_recon_loss: bad J/tree/ld");
   if (F <= 0) return 0;
-  recon_loss_kernel<<<(unsigned)((F + FK_THREADS - 1) / FK_THREADS), FK_THREADS, 0, (cudaStream_t)stream>>>(
+  int64_t blocks = (F + FK_WARPS - 1) / FK_WARPS;
+  const int64_t cap = (int64_t)scv::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  recon_loss_kernel<<<(unsigned)blocks, FK_WARPS * 32, 0, (cudaStream_t)stream>>>(
       xh, ld, offsets, target, root, arena, tree, (int)n_tree, loss, root_hat, dxh, F, (int)B, (int)J);
   return scv::check_launch("recon_loss_kernel");
 }

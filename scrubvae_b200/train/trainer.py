@@ -89,8 +89,100 @@ def predict_batch(model, data, disentangle_keys=None):
     return model(data_i)
 
 
-def train_test_epoch(config, model, loader, device, epoch, optimizer=None, scheduler=None, mode="train"):
-    """Reference train/trainer.py:101-212."""
+def _fused_train_epoch(config, model, loader, device, epoch, optimizer, scheduler, step_callback=None):
+    """train-mode body of train_test_epoch as ONE captured launch sequence per step (engine.TrainStep: forward, losses,
+    backward, gradient all-reduce, clip, optimizer replayed from a CUDA graph) with the next batch's host->device copy
+    prefetched on a side stream while the current step runs.  Same kernels, order and results as the piecewise
+    path below (predict_batch -> get_batch_loss -> backward -> clip_grad_norm_ -> optimizer.step)."""
+    from ..engine import TrainStep
+    eng = model.engine
+    steps = model.__dict__.setdefault("_train_steps", {})
+    main = torch.cuda.current_stream()
+    copy_stream = model.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=eng.device))
+    it = iter(loader)
+    # two persistent device staging slots (no per-step allocation): slot s is refilled on the copy stream once the
+    # step that read it has been enqueued-and-passed on the main stream
+    stage = model.__dict__.setdefault("_stage", [dict(), dict()])
+    consumed = [None, None]
+    count = [0]
+
+    def fetch():
+        try:
+            host = next(it)
+        except StopIteration:
+            return None
+        slot = count[0] & 1
+        count[0] += 1
+        bufs = stage[slot]
+        for k, v in host.items():
+            if torch.is_tensor(v) and (k not in bufs or bufs[k].shape != v.shape or bufs[k].dtype != v.dtype):
+                bufs[k] = torch.empty(v.shape, dtype=v.dtype, device=device)
+        if consumed[slot] is not None:
+            copy_stream.wait_event(consumed[slot])
+        else:
+            copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            dev = {}
+            for k, v in host.items():
+                if torch.is_tensor(v):
+                    bufs[k].copy_(v, non_blocking=True)
+                    dev[k] = bufs[k]
+                else:
+                    dev[k] = v
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return dev, ev, slot
+
+    names = None
+    acc = None
+    n_batches = 0
+    nxt = fetch()
+    while nxt is not None:
+        data, ev, slot = nxt
+        nxt = fetch()  # overlaps with this step's kernels
+        main.wait_event(ev)
+        B = data["x6d"].shape[0]
+        key = (B, id(optimizer))
+        st = steps.get(key)
+        if st is None:
+            st = TrainStep(model, optimizer, config["loss"], B, max_norm=1e6, use_graph=True, comm=eng.comm)
+            steps[key] = st
+        if names is None:
+            names = st.plan.loss_names
+            for k in config["loss"].keys():  # every configured loss must be produced, and vice versa (reference :125,:181)
+                if k not in names:
+                    raise KeyError(k)
+            for k in names:
+                if k.endswith("_gr"):
+                    config["loss"][k]
+        st.plan.set_loss_scale(config["loss"])  # the KL weight may have been annealed since the last epoch
+        vec = st.run(data)  # copies the slot into the plan's static input buffers, then replays the step
+        consumed[slot] = torch.cuda.Event()
+        consumed[slot].record(main)
+        if step_callback is not None:
+            step_callback(n_batches, vec)
+        if scheduler is not None:
+            scheduler.step(epoch + n_batches / len(loader))
+        acc = vec.clone() if acc is None else acc + vec
+        n_batches += 1
+    epoch_metrics = {}
+    host = acc.cpu() if acc is not None else None
+    for k in ["total"] + list(config["loss"].keys()):
+        idx = len(names) if k == "total" else names.index(k)
+        epoch_metrics[k] = host[idx].item() / max(1, n_batches)
+        print("====> Epoch: {} Average {} loss: {:.4f}".format(epoch, k, epoch_metrics[k]))
+    return epoch_metrics
+
+
+def train_test_epoch(config, model, loader, device, epoch, optimizer=None, scheduler=None, mode="train",
+                     step_callback=None):
+    """Reference train/trainer.py:101-212.  `step_callback(batch_idx, loss_vector)` is an optional extension (the
+    per-step losses as one device vector [jpe, root, prior, <feat>_gr..., total])."""
+    if (mode == "train" and isinstance(optimizer, FusedOptimizer) and torch.device(device).type == "cuda"
+            and (config.get("train") or {}).get("fused_step", True)):
+        model.train()
+        model.mi_estimator = None
+        return _fused_train_epoch(config, model, loader, device, epoch, optimizer, scheduler, step_callback)
     if mode == "train":
         model.train()
         grad_env = torch.enable_grad
@@ -116,6 +208,8 @@ def train_test_epoch(config, model, loader, device, epoch, optimizer=None, sched
                 if scheduler is not None:
                     scheduler.step(epoch + batch_idx / len(loader))
             epoch_metrics = {k: v + batch_loss[k].detach() for k, v in epoch_metrics.items()}
+            if step_callback is not None:
+                step_callback(batch_idx, batch_loss["total"].detach().reshape(1))
 
         for k, v in epoch_metrics.items():
             epoch_metrics[k] = v.item() / len(loader)
