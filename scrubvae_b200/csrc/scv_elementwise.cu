@@ -126,24 +126,44 @@ __global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, cons
       p.running_var[ch] = (float)((1.0 - p.momentum) * (double)p.running_var[ch] + p.momentum * unb);
     }
   }
-  const int64_t L = p.L;
+  const uint32_t L = (uint32_t)p.L;
   const bool rnd = mode & SCV_MODE_ROUND_TF32;
-  for (int64_t r = t.r0; r < t.rend; r += t.rstep) {
-    int64_t b = r / L, l = r - b * L;
-    const float* xr = p.X + b * p.x_bs + l * p.x_ls + t.c * 4;
-    float4 a = bn_prelu(ld4(xr), cb, has_act, slope);
-    if (p.H) st4(p.H + b * p.h_bs + l * p.h_ls + t.c * 4, rnd ? scv::round_tf32(a) : a);
-    if (p.U) {
-      float4 am = l > 0 ? bn_prelu(ld4(xr - p.x_ls), cb, has_act, slope) : a;
-      float4 ap = l < L - 1 ? bn_prelu(ld4(xr + p.x_ls), cb, has_act, slope) : a;
-      float4 e, o;
-      e.x = 0.25f * am.x + 0.75f * a.x; e.y = 0.25f * am.y + 0.75f * a.y;
-      e.z = 0.25f * am.z + 0.75f * a.z; e.w = 0.25f * am.w + 0.75f * a.w;
-      o.x = 0.75f * a.x + 0.25f * ap.x; o.y = 0.75f * a.y + 0.25f * ap.y;
-      o.z = 0.75f * a.z + 0.25f * ap.z; o.w = 0.75f * a.w + 0.25f * ap.w;
-      float* ur = p.U + b * p.u_bs + (2 * l) * p.u_ls + t.c * 4;
-      st4(ur, rnd ? scv::round_tf32(e) : e);
-      st4(ur + p.u_ls, rnd ? scv::round_tf32(o) : o);
+  // 4 rows per iteration, loads first: one thread keeps 4 (12 with the upsample neighbours) float4 loads in flight
+  for (int64_t r = t.r0; r < t.rend; r += 4 * (int64_t)t.rstep) {
+    float4 xc[4], xm[4], xp[4];
+    uint32_t bb[4], ll[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t rr = r + u * (int64_t)t.rstep;
+      ok[u] = rr < t.rend;
+      if (ok[u]) {
+        bb[u] = (uint32_t)rr / L;
+        ll[u] = (uint32_t)rr - bb[u] * L;
+        const float* xr = p.X + (int64_t)bb[u] * p.x_bs + (int64_t)ll[u] * p.x_ls + t.c * 4;
+        xc[u] = ld4(xr);
+        if (p.U) {
+          xm[u] = ll[u] > 0 ? ld4(xr - p.x_ls) : xc[u];
+          xp[u] = ll[u] < L - 1 ? ld4(xr + p.x_ls) : xc[u];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const float4 a = bn_prelu(xc[u], cb, has_act, slope);
+      if (p.H) st4(p.H + (int64_t)bb[u] * p.h_bs + (int64_t)ll[u] * p.h_ls + t.c * 4, rnd ? scv::round_tf32(a) : a);
+      if (p.U) {
+        const float4 am = bn_prelu(xm[u], cb, has_act, slope), ap = bn_prelu(xp[u], cb, has_act, slope);
+        float4 e, o;
+        e.x = 0.25f * am.x + 0.75f * a.x; e.y = 0.25f * am.y + 0.75f * a.y;
+        e.z = 0.25f * am.z + 0.75f * a.z; e.w = 0.25f * am.w + 0.75f * a.w;
+        o.x = 0.75f * a.x + 0.25f * ap.x; o.y = 0.75f * a.y + 0.25f * ap.y;
+        o.z = 0.75f * a.z + 0.25f * ap.z; o.w = 0.75f * a.w + 0.25f * ap.w;
+        float* ur = p.U + (int64_t)bb[u] * p.u_bs + (int64_t)(2 * ll[u]) * p.u_ls + t.c * 4;
+        st4(ur, rnd ? scv::round_tf32(e) : e);
+        st4(ur + p.u_ls, rnd ? scv::round_tf32(o) : o);
+      }
     }
   }
 }
@@ -180,18 +200,32 @@ __global__ void __launch_bounds__(NT) bnact_bwd_reduce_kernel(const scv_bnact_bw
     chan_bn(cb, t.c * 4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, nullptr, nullptr);
     const bool has_act = mode & 2;
     const float slope = has_act ? __ldg(p.slope) : 0.f;
-    for (int64_t r = t.r0; r < t.rend; r += t.rstep) {
-      int64_t b = r / L, l = r - b * L;
-      float4 x4 = ld4(p.X + b * p.x_bs + l * p.x_ls + t.c * 4);
-      float4 g4 = load_dout(p, b, l, t.c);
-      float x[4] = {x4.x, x4.y, x4.z, x4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+    const uint32_t L32 = (uint32_t)L;
+    for (int64_t r = t.r0; r < t.rend; r += 4 * (int64_t)t.rstep) {
+      float4 xv[4], gv[4];
+      bool ok[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v = fmaf(x[q], cb.scale[q], cb.shift[q]);
-        float gg = g[q];
-        if (has_act && v < 0.f) { ds += gg * v; gg *= slope; }
-        sg[q] += gg;
-        sgx[q] += gg * (x[q] - cb.mean[q]) * cb.rstd[q];
+      for (int u = 0; u < 4; ++u) {  // loads first
+        const int64_t rr = r + u * (int64_t)t.rstep;
+        ok[u] = rr < t.rend;
+        if (ok[u]) {
+          const uint32_t b = (uint32_t)rr / L32, l = (uint32_t)rr - b * L32;
+          xv[u] = ld4(p.X + (int64_t)b * p.x_bs + (int64_t)l * p.x_ls + t.c * 4);
+          gv[u] = load_dout(p, b, l, t.c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        const float x[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, g[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v = fmaf(x[q], cb.scale[q], cb.shift[q]);
+          float gg = g[q];
+          if (has_act && v < 0.f) { ds += gg * v; gg *= slope; }
+          sg[q] += gg;
+          sgx[q] += gg * (x[q] - cb.mean[q]) * cb.rstd[q];
+        }
       }
     }
   }
@@ -253,46 +287,76 @@ __global__ void __launch_bounds__(NT) bnact_bwd_apply_kernel(const scv_bnact_bwd
     }
   }
   if (!p.dX) return;
-  for (int64_t r = t.r0; r < t.rend; r += t.rstep) {
-    int64_t b = r / L, l = r - b * L;
-    float4 x4 = ld4(p.X + b * p.x_bs + l * p.x_ls + t.c * 4);
-    float4 g4 = load_dout(p, b, l, t.c);
-    float x[4] = {x4.x, x4.y, x4.z, x4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w}, d[4];
+  const uint32_t L32 = (uint32_t)L;
+  for (int64_t r = t.r0; r < t.rend; r += 4 * (int64_t)t.rstep) {
+    float4 xv[4], gv[4];
+    uint32_t bb[4], ll[4];
+    bool ok[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float v = fmaf(x[q], cb.scale[q], cb.shift[q]);
-      float gg = g[q];
-      if (has_act && v < 0.f) gg *= slope;
-      if (mode & 1) {
-        float xh = (x[q] - cb.mean[q]) * cb.rstd[q];
-        d[q] = cb.scale[q] * (gg - mg[q] - xh * mgx[q]);
-      } else {
-        d[q] = gg;
+    for (int u = 0; u < 4; ++u) {  // loads first
+      const int64_t rr = r + u * (int64_t)t.rstep;
+      ok[u] = rr < t.rend;
+      if (ok[u]) {
+        bb[u] = (uint32_t)rr / L32;
+        ll[u] = (uint32_t)rr - bb[u] * L32;
+        xv[u] = ld4(p.X + (int64_t)bb[u] * p.x_bs + (int64_t)ll[u] * p.x_ls + t.c * 4);
+        gv[u] = load_dout(p, bb[u], ll[u], t.c);
       }
     }
-    float4 dv = make_float4(d[0], d[1], d[2], d[3]);
-    st4(p.dX + b * p.d_bs + l * p.d_ls + t.c * 4, (mode & SCV_MODE_ROUND_TF32) ? scv::round_tf32(dv) : dv);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const float x[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, g[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+      float d[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v = fmaf(x[q], cb.scale[q], cb.shift[q]);
+        float gg = g[q];
+        if (has_act && v < 0.f) gg *= slope;
+        if (mode & 1) {
+          float xh = (x[q] - cb.mean[q]) * cb.rstd[q];
+          d[q] = cb.scale[q] * (gg - mg[q] - xh * mgx[q]);
+        } else {
+          d[q] = gg;
+        }
+      }
+      const float4 dv = make_float4(d[0], d[1], d[2], d[3]);
+      st4(p.dX + (int64_t)bb[u] * p.d_bs + (int64_t)ll[u] * p.d_ls + t.c * 4,
+          (mode & SCV_MODE_ROUND_TF32) ? scv::round_tf32(dv) : dv);
+    }
   }
 }
 
+// one thread per 4 output columns (C % 4 == 0): float4 reads of the x6d row when nx % 4 == 0, 32-bit index math
 __global__ void __launch_bounds__(NT) pack_input_kernel(const float* __restrict__ x6d, const float* __restrict__ root,
                                                         const float* __restrict__ arena, float* __restrict__ out,
                                                         int64_t rows, int W, int nx, int C, int halo, int rnd) {
-  const int64_t total = rows * C;
+  const uint32_t C4 = (uint32_t)C >> 2;
+  const int64_t total = rows * C4;
+  const bool vec = (nx & 3) == 0;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
-    int64_t r = i / C;
-    int c = (int)(i - r * C);
-    int64_t b = r / W;
-    int w = (int)(r - b * W);
-    float v = 0.f;
-    if (c < nx) {
-      v = x6d[r * nx + c];
-    } else if (c < nx + 3) {
-      int d = c - nx;
-      float a0 = arena[d], a1 = arena[3 + d];
-      v = 2.f * (root[r * 3 + d] - a0) / (a1 - a0) - 1.f;
+    const uint32_t r = (uint32_t)(i / C4), c = ((uint32_t)i - r * C4) * 4;
+    const uint32_t b = r / (uint32_t)W, w = r - b * (uint32_t)W;
+    float v[4];
+    if (vec && (int)c + 4 <= nx) {
+      const float4 t = ld4(x6d + (int64_t)r * nx + c);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cc = (int)c + q;
+        v[q] = 0.f;
+        if (cc < nx) {
+          v[q] = x6d[(int64_t)r * nx + cc];
+        } else if (cc < nx + 3) {
+          const int d = cc - nx;
+          const float a0 = arena[d], a1 = arena[3 + d];
+          v[q] = 2.f * (root[(int64_t)r * 3 + d] - a0) / (a1 - a0) - 1.f;
+        }
+      }
     }
-    out[(b * (W + 2 * halo) + halo + w) * C + c] = rnd ? scv::round_tf32(v) : v;
+    float4 o = make_float4(v[0], v[1], v[2], v[3]);
+    st4(out + ((int64_t)b * (W + 2 * halo) + halo + w) * C + c, rnd ? scv::round_tf32(o) : o);
   }
 }
 
@@ -400,7 +464,9 @@ extern "C" {
 int scv_pack_input(const float* x6d, const float* root, const float* arena, float* out, int64_t B, int64_t W,
                    int64_t nx, int64_t C, int64_t halo, int64_t flags, void* stream) {
   SCV_REQUIRE(nx + 3 <= C, "scv_pack_input: C too small");
-  pack_input_kernel<<<grid1d(B * W * C, 8), NT, 0, (cudaStream_t)stream>>>(x6d, root, arena, out, B * W, (int)W,
+  SCV_REQUIRE(C % 4 == 0 && scv::aligned16(out) && scv::aligned16(x6d) && B * W < (1LL << 31),
+              "scv_pack_input: C must be a multiple of 4 and the buffers 16-byte aligned");
+  pack_input_kernel<<<grid1d(B * W * (C / 4), 8), NT, 0, (cudaStream_t)stream>>>(x6d, root, arena, out, B * W, (int)W,
                                                                           (int)nx, (int)C, (int)halo,
                                                                           (int)(flags & SCV_F_ROUND_TF32));
   return scv::check_launch("pack_input_kernel");
@@ -418,6 +484,7 @@ int scv_bnact_fwd(const scv_bnact_t* p, void* stream) {
   SCV_REQUIRE(!(p->mode & 1) || (p->gamma && p->beta), "scv_bnact_fwd: BN needs gamma/beta");
   SCV_REQUIRE(!((p->mode & 5) == 5) || p->stats, "scv_bnact_fwd: training BN needs stats");
   SCV_REQUIRE(!((p->mode & 5) == 1) || (p->running_mean && p->running_var), "scv_bnact_fwd: eval BN needs running stats");
+  SCV_REQUIRE(p->B * p->L < (1LL << 31), "scv_bnact_fwd: more than 2^31 rows");
   Launch2D l = plan2d(p->C / 4, p->B * p->L, 8);
   bnact_fwd_kernel<<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
   return scv::check_launch("bnact_fwd_kernel");
@@ -428,6 +495,7 @@ int scv_bnact_bwd_reduce(const scv_bnact_bwd_t* p, void* stream) {
   if (p->dO && check_rows("scv_bnact_bwd dO", p->C, p->dO, p->o_bs, p->o_ls)) return -1;
   if (p->dU && check_rows("scv_bnact_bwd dU", p->C, p->dU, p->u_bs, p->u_ls)) return -1;
   SCV_REQUIRE(p->sums, "scv_bnact_bwd_reduce: sums required");
+  SCV_REQUIRE(p->B * p->L < (1LL << 31), "scv_bnact_bwd_reduce: more than 2^31 rows");
   Launch2D l = plan2d(p->C / 4, p->B * p->L, 4);
   bnact_bwd_reduce_kernel<<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
   return scv::check_launch("bnact_bwd_reduce_kernel");
@@ -439,6 +507,7 @@ int scv_bnact_bwd_apply(const scv_bnact_bwd_t* p, void* stream) {
   if (p->dU && check_rows("scv_bnact_bwd dU", p->C, p->dU, p->u_bs, p->u_ls)) return -1;
   if (p->dX && check_rows("scv_bnact_bwd dX", p->C, p->dX, p->d_bs, p->d_ls)) return -1;
   SCV_REQUIRE(!(p->mode & 3) || p->sums, "scv_bnact_bwd_apply: sums required");
+  SCV_REQUIRE(p->B * p->L < (1LL << 31), "scv_bnact_bwd_apply: more than 2^31 rows");
   Launch2D l = plan2d(p->C / 4, p->B * p->L, 8);
   bnact_bwd_apply_kernel<<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
   return scv::check_launch("bnact_bwd_apply_kernel");

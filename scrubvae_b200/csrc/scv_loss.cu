@@ -298,21 +298,29 @@ __global__ void __launch_bounds__(FK_WARPS * 32) recon_loss_kernel(const float* 
   if (threadIdx.x == 0) atomicAdd(loss + 1, s1);
 }
 
+// float4 per thread (ld % 4 == 0, nx % 4 == 0: the 3 root channels + 1 pad share the last group), 32-bit index math
 __global__ void __launch_bounds__(256) out_bwd_kernel(const float* __restrict__ xh, const float* __restrict__ dxh,
                                                       int ld, const float* g_jpe, const float* g_root, int nx,
                                                       float* __restrict__ draw, int64_t d_bs, int64_t d_ls,
                                                       int64_t rows, int W, int rnd) {
   const float gj = g_jpe ? *g_jpe : 0.f, gr = g_root ? *g_root : 0.f;
-  const int64_t total = rows * ld;
+  const uint32_t ld4n = (uint32_t)ld >> 2;
+  const int64_t total = rows * ld4n;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    int64_t r = i / ld;
-    int c = (int)(i - r * ld);
-    int64_t b = r / W;
-    int w = (int)(r - b * W);
-    float y = xh[i];
-    float g = dxh[i] * (c < nx ? gj : (c < nx + 3 ? gr : 0.f));
-    const float dv = g * (1.f - y * y);
-    draw[b * d_bs + w * d_ls + c] = rnd ? scv::round_tf32(dv) : dv;
+    const uint32_t r = (uint32_t)(i / ld4n), c = ((uint32_t)i - r * ld4n) * 4;
+    const uint32_t b = r / (uint32_t)W, w = r - b * (uint32_t)W;
+    const float4 y = *reinterpret_cast<const float4*>(xh + (int64_t)r * ld + c);
+    const float4 g = *reinterpret_cast<const float4*>(dxh + (int64_t)r * ld + c);
+    const float yy[4] = {y.x, y.y, y.z, y.w}, gg[4] = {g.x, g.y, g.z, g.w};
+    float dv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int cc = (int)c + q;
+      const float sc = cc < nx ? gj : (cc < nx + 3 ? gr : 0.f);
+      dv[q] = gg[q] * sc * (1.f - yy[q] * yy[q]);
+    }
+    float4 o = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    *reinterpret_cast<float4*>(draw + (int64_t)b * d_bs + (int64_t)w * d_ls + c) = rnd ? scv::round_tf32(o) : o;
   }
 }
 
@@ -406,7 +414,10 @@ int scv_recon_loss(const float* xh, int64_t ld, const float* offsets, const floa
 
 int scv_out_bwd(const float* xh, const float* dxh, int64_t ld, const float* g_jpe, const float* g_root, int64_t nx,
                 float* draw, int64_t d_bs, int64_t d_ls, int64_t B, int64_t W, int64_t flags, void* stream) {
-  int64_t total = B * W * ld;
+  SCV_REQUIRE(ld % 4 == 0 && d_bs % 4 == 0 && d_ls % 4 == 0 && scv::aligned16(xh) && scv::aligned16(dxh) &&
+                  scv::aligned16(draw) && B * W < (1LL << 31),
+              "scv_out_bwd: rows must be 16-byte aligned groups of 4 columns");
+  int64_t total = B * W * (ld / 4);
   int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)scv::sm_count() * 8;
   if (blocks > cap) blocks = cap;
