@@ -455,6 +455,8 @@ struct WgradTcParams {
   int bl, nb, lt, bt;   // row boxes as above; R = bl*nb rows (multiple of 8) reduced per stage
   int bnk;              // k tile width (UMMA N), multiple of 16, <= 256
   int n_tiles, k_tiles, splits, groups, gps, stages;
+  int sub;  // 128-row n tiles per work item (1 or 2).  2: both share the A slabs of a stage (two accumulators in the
+            // two TMEM halves, no double buffering) - a third less L2 -> shared-memory traffic per FLOP
   float* dW;
   float* dbias;  // bias gradient = column sums of dY: one extra N=16 MMA per 8 rows against a tile of ones (k tile 0 only)
   int bias_mod, bias_n;
@@ -477,7 +479,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const int R = p.bl * p.nb;
   const uint32_t slab = (uint32_t)R * 128;  // one 32-wide slab of R rows (R % 8 == 0 -> 1 KB multiple)
   const int a_slabs = (p.bnk + 31) / 32;
-  const uint32_t y_bytes = 4 * slab, a_bytes = (uint32_t)a_slabs * slab;
+  const int sub = p.sub;
+  const uint32_t y_bytes = 4 * slab * (uint32_t)sub, a_bytes = (uint32_t)a_slabs * slab;
   const uint32_t stage_bytes = y_bytes + a_bytes;
   float* ones = reinterpret_cast<float*>(smem);  // 1 KB = 8 k-rows x 128 B of 1.0f (B operand of the bias MMA)
   smem += 1024;
@@ -536,7 +539,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           mbar_expect_tx(fb, stage_bytes);
           const uint32_t sy = smem_u32(smem + (size_t)s * stage_bytes);
           // one TMA per operand: 4-D boxes (32 floats, bl, nb, slabs) land slab-major, exactly the MN-major layout
-          tma_load_4d(sy, &tmY, fb, 0, l0, b0, nt * (kBM / 32));
+          tma_load_4d(sy, &tmY, fb, 0, l0, b0, nt * sub * (kBM / 32));
           tma_load_4d(sy + y_bytes, &tmA, fb, 0, l0, b0, kt * (p.bnk / 32));
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -559,8 +562,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         int nt, kt, g0, g1;
         decode(t, nt, kt, g0, g1);
         const bool do_bias = p.dbias != nullptr && kt == 0;
-        const int acc = it & 1;
-        mbar_wait(smem_u32(&ctl->tempty[acc]), ((it >> 1) & 1) ^ 1);
+        const int acc = sub == 2 ? 0 : (it & 1);
+        mbar_wait(smem_u32(&ctl->tempty[acc]), (sub == 2 ? (it & 1) : ((it >> 1) & 1)) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;
         for (int g = g0; g < g1; ++g) {
@@ -573,6 +576,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           for (int r8 = 0; r8 < R / 8; ++r8) {  // 8 reduction rows = 1024 B = 64 units per MMA
             umma_tf32_lh(d_tmem, y_lo + r8 * 64, desc_hi, a_lo + r8 * 64, desc_hi, idesc, accf);
             if (do_bias) umma_tf32_lh(d_tmem + kBiasCol, y_lo + r8 * 64, desc_hi, ones_lo, ones_hi, idesc_b, accf);
+            if (sub == 2) {  // second n tile: dY slabs 4..7 of the same stage, same A slabs
+              const uint32_t y2 = y_lo + ((4 * slab) >> 4) + r8 * 64;
+              umma_tf32_lh(d_tmem + kMaxBN, y2, desc_hi, a_lo + r8 * 64, desc_hi, idesc, accf);
+              if (do_bias) umma_tf32_lh(d_tmem + kMaxBN + kBiasCol, y2, desc_hi, ones_lo, ones_hi, idesc_b, accf);
+            }
             accf = 1u;
           }
           umma_commit(smem_u32(&ctl->empty[s]));
@@ -590,13 +598,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       int nt, kt, g0, g1;
       decode(t, nt, kt, g0, g1);
-      const int acc = it & 1;
-      mbar_wait(smem_u32(&ctl->tfull[acc]), (it >> 1) & 1);
+      const int acc = sub == 2 ? 0 : (it & 1);
+      mbar_wait(smem_u32(&ctl->tfull[acc]), sub == 2 ? (it & 1) : ((it >> 1) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kMaxBN;
-      const int nbase = nt * kBM + ew * 32;
       const int kbase = kt * p.bnk;
       const int kcols = min(p.bnk, p.K - kbase);
+     for (int sj = 0; sj < sub; ++sj) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(sub == 2 ? sj : acc) * kMaxBN;
+      const int nbase = (nt * sub + sj) * kBM + ew * 32;
       if (g1 > g0 && nbase < p.N) {
         const int nrows = min(32, p.N - nbase);
         for (int c0 = 0; c0 < kcols; c0 += 32) {
@@ -626,6 +635,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           if (n < p.N && n < p.bias_n) atomicAdd(p.dbias + (n % p.bias_mod), __uint_as_float(bv[0]));
         }
       }
+     }  // n tiles of the item
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ctl->tempty[acc]));
@@ -827,16 +837,23 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   const int kt0 = (int)cdiv(k32, kWgradMaxBNK);
   q.bnk = (int)cdiv(cdiv(k32, kt0), 32) * 32;
   q.k_tiles = (int)cdiv(p->K, q.bnk);
-  q.n_tiles = (int)cdiv(p->N, kBM);
+  // two n tiles per item (sharing the A slabs) measured 7-10 % SLOWER than one on every large layer
+  // (profiles/r01_wgrad_sub.md: fewer stages in flight and an un-overlapped epilogue cost more than the saved
+  // traffic), so one tile per item is the default; SCV_TC_WSUB=2 selects the two-tile variant for experiments
+  static const int force_wsub = [] { const char* e = getenv("SCV_TC_WSUB"); return e ? atoi(e) : 0; }();
+  q.sub = force_wsub == 2 ? 2 : 1;
+  if (p->N <= kBM) q.sub = 1;
+  q.n_tiles = (int)cdiv(p->N, kBM * q.sub);
   const int tiles = q.n_tiles * q.k_tiles;
-  // row splits: fill the SMs ~2x over, but keep at least 4 row groups per item
-  int splits = (int)cdiv(2 * sm_count(), tiles);
+  // row splits: fill the SMs ~2x over (once over for the two-tile items: their epilogue is not overlapped, so
+  // fewer, longer items), but keep at least 4 row groups per item
+  int splits = (int)cdiv((q.sub == 2 ? 1 : 2) * sm_count(), tiles);
   if (splits > q.groups / 4) splits = q.groups / 4;
   if (splits < 1) splits = 1;
   q.gps = (int)cdiv(q.groups, splits);
   q.splits = (int)cdiv(q.groups, q.gps);
   const int R = q.bl * q.nb;
-  const size_t stage_bytes = (size_t)(4 + (q.bnk + 31) / 32) * R * 128;
+  const size_t stage_bytes = (size_t)(4 * q.sub + (q.bnk + 31) / 32) * R * 128;
   const size_t fixed = 1024 + 1024 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + 4 * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -850,7 +867,7 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   {
     const int64_t dims[4] = {32, p->Lo, p->B, cdiv(p->N, 32)};
     const int64_t str[4] = {1, p->y_ls ? p->y_ls : p->y_bs, p->y_bs ? p->y_bs : 4, 32};
-    const int box[4] = {32, q.bl, q.nb, 4};
+    const int box[4] = {32, q.bl, q.nb, 4 * q.sub};
     rc = tc::make_tmap(&tmY, p->dY, 4, dims, str, box, "scv_wgrad dY", true);
     if (rc) return rc;
   }
