@@ -152,3 +152,31 @@ def test_trainstep_sequence_equals_api_path(golden_dir):
     assert abs(res[0][1].item() - res[1][1].item()) <= 1e-6 * abs(res[0][1].item())
     for k in res[0][0]:
         assert torch.equal(res[0][0][k], res[1][0][k]), k
+
+
+@pytest.mark.parametrize("ch,zd,window,B", [([8, 16, 32, 64, 128], 8, 101, 3), ([8, 16, 32], 16, 51, 4)])
+def test_engine_other_geometries_vs_oracle(ch, zd, window, B):
+    """BASELINE config 5 geometry (longer windows, other depths / latent sizes): the launch plan is generic in
+    window length, block count and z; one step vs the CPU oracle."""
+    torch.manual_seed(5)
+    m, dcfg = build_model(ch, zd, ["heading"], ["heading"], window=window)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    cfg = orc.Cfg(ch=ch, z_dim=zd, window=window)
+    data = orc.synth_batch(B, window=window, seed=3)
+    eps = orc.synth_eps(B, zd, seed=4)
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "heading_gr": 1.0}
+    lref, gref, _, _, _ = orc.train_step(sd, data, cfg, scale, eps)
+    m._engine = Engine(m, ops=EmuOps())
+    m.train()
+    m._noise = eps
+    data_o = sv.train.predict_batch(m, data, m.disentangle_keys)
+    losses = sv.train.get_batch_loss(m, data, data_o, scale, dcfg)
+    for k, v in lref.items():
+        assert abs(losses[k].item() - v.item()) <= 2e-5 * abs(v.item()) + 1e-6, k
+    for p in m.parameters():
+        p.grad = None
+    losses["total"].backward()
+    gnorm = np.sqrt(sum(float((v.double() ** 2).sum()) for v in gref.values()))
+    for n, p in m.named_parameters():
+        err = (p.grad.double() - gref[n].double()).norm().item()
+        assert _rel(p.grad, gref[n]) < 3e-4 or err < 2e-6 * gnorm, (n, _rel(p.grad, gref[n]), err)

@@ -207,3 +207,36 @@ def test_trainer_epoch_api_runs_and_learns():
     assert e2["total"] < e1["total"]
     e3 = sv.train.train_test_epoch(config, m, loader, "cuda", 3, mode="test")
     assert np.isfinite(e3["total"])
+
+
+@pytest.mark.parametrize("ch,zd,window,B,precision", [
+    ([128, 256, 512, 1024, 2048], 128, 101, 2, "fp32"),   # BASELINE config 5: 194.98 M parameters
+    ([128, 256, 512, 1024, 2048], 128, 101, 2, "tf32"),
+    ([32, 64, 128], 32, 51, 9, "fp32"),                    # other depth
+])
+def test_scaled_architectures_vs_oracle(ch, zd, window, B, precision):
+    """The launch plan is generic in width, depth, window and z (BASELINE configs 5): one step vs the CPU oracle."""
+    cfg = orc.Cfg(ch=ch, z_dim=zd, window=window)
+    torch.manual_seed(7)
+    m, dcfg = build_model(ch, zd, ["heading"], ["heading"], window=window, device="cpu")
+    m.precision = precision
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    if len(ch) == 5 and ch[-1] == 2048:
+        assert sum(p.numel() for p in m.parameters()) == 194980766 - sum(
+            v.numel() for k, v in sd.items() if "running" in k or "num_batches" in k or k == "arena_size")
+    data = orc.synth_batch(B, window=window, seed=0)
+    eps = orc.synth_eps(B, zd, seed=2)
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "heading_gr": 1.0}
+    lref, gref, _, _, _ = orc.train_step(sd, data, cfg, scale, eps)
+    m = m.to("cuda").train()
+    m._noise = eps.cuda()
+    data_o = sv.train.predict_batch(m, _to_cuda(data), m.disentangle_keys)
+    losses = sv.train.get_batch_loss(m, _to_cuda(data), data_o, scale, dcfg)
+    ltol = 5e-5 if precision == "fp32" else 2e-3
+    for k, v in lref.items():
+        assert abs(losses[k].item() - v.item()) <= ltol * abs(v.item()) + 1e-5, (k, losses[k].item(), v.item())
+    if precision == "fp32":
+        for p in m.parameters():
+            p.grad = None
+        losses["total"].backward()
+        _check_grads([(n, p.grad) for n, p in m.named_parameters()], gref, 1e-3, "vs fp32 oracle")
