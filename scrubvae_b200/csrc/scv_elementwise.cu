@@ -91,6 +91,21 @@ __device__ __forceinline__ void chan_bn(ChanBN& cb, int ch0, int C, int mode, co
   }
 }
 
+// The per-channel constants need fp64 divisions and a square root (~1500 instructions for 4 channels): computed ONCE
+// per block by the first `cw` threads (one float4 column each) and handed to the rest through shared memory —
+// every thread recomputing them cost more instructions than the streaming work itself (ncu, round 1).
+__device__ __forceinline__ void chan_bn_block(ChanBN& cb, int cw, int C4, int C, int mode, const double* stats, int fold,
+                                              double count, double eps, const float* gamma, const float* beta,
+                                              const float* rmean, const float* rvar) {
+  __shared__ ChanBN sh[32];
+  if ((int)threadIdx.x < cw) {
+    const int c = blockIdx.x * cw + threadIdx.x;
+    if (c < C4) chan_bn(sh[threadIdx.x], c * 4, C, mode, stats, fold, count, eps, gamma, beta, rmean, rvar);
+  }
+  __syncthreads();
+  cb = sh[(threadIdx.x & 31) % cw];
+}
+
 __device__ __forceinline__ float4 bn_prelu(float4 x, const ChanBN& cb, bool has_act, float slope) {
   float v[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -106,10 +121,10 @@ __global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, cons
   const int mode = (int)p.mode;
   const int64_t rows = p.B * p.L;
   Tile2D t = make_tile(C4, cw, rows, rpb);
-  if (!t.cok) return;
   ChanBN cb;
-  chan_bn(cb, t.c * 4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, p.running_mean,
-          p.running_var);
+  chan_bn_block(cb, cw, C4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, p.running_mean,
+                p.running_var);
+  if (!t.cok) return;
   const bool has_act = mode & 2;
   const float slope = has_act ? __ldg(p.slope) : 0.f;
   // running statistics: one thread per channel group (block row 0, first row lane)
@@ -195,9 +210,9 @@ __global__ void __launch_bounds__(NT) bnact_bwd_reduce_kernel(const scv_bnact_bw
   const int64_t rows = p.B * p.L, L = p.L;
   Tile2D t = make_tile(C4, cw, rows, rpb);
   float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f}, ds = 0.f;
+  ChanBN cb;
+  chan_bn_block(cb, cw, C4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, nullptr, nullptr);
   if (t.cok) {
-    ChanBN cb;
-    chan_bn(cb, t.c * 4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, nullptr, nullptr);
     const bool has_act = mode & 2;
     const float slope = has_act ? __ldg(p.slope) : 0.f;
     const uint32_t L32 = (uint32_t)L;
@@ -267,9 +282,9 @@ __global__ void __launch_bounds__(NT) bnact_bwd_apply_kernel(const scv_bnact_bwd
   Tile2D t = make_tile(C4, cw, rows, rpb);
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (mode & 2) && p.dslope)
     p.dslope[0] += (float)p.sums[2 * C];
-  if (!t.cok) return;
   ChanBN cb;
-  chan_bn(cb, t.c * 4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, nullptr, nullptr);
+  chan_bn_block(cb, cw, C4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, nullptr, nullptr);
+  if (!t.cok) return;
   const bool has_act = mode & 2;
   const bool train_bn = (mode & 5) == 5;
   const float slope = has_act ? __ldg(p.slope) : 0.f;
@@ -485,7 +500,7 @@ int scv_bnact_fwd(const scv_bnact_t* p, void* stream) {
   SCV_REQUIRE(!((p->mode & 5) == 5) || p->stats, "scv_bnact_fwd: training BN needs stats");
   SCV_REQUIRE(!((p->mode & 5) == 1) || (p->running_mean && p->running_var), "scv_bnact_fwd: eval BN needs running stats");
   SCV_REQUIRE(p->B * p->L < (1LL << 31), "scv_bnact_fwd: more than 2^31 rows");
-  Launch2D l = plan2d(p->C / 4, p->B * p->L, 8);
+  Launch2D l = plan2d(p->C / 4, p->B * p->L, 3);
   bnact_fwd_kernel<<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
   return scv::check_launch("bnact_fwd_kernel");
 }
@@ -496,7 +511,7 @@ int scv_bnact_bwd_reduce(const scv_bnact_bwd_t* p, void* stream) {
   if (p->dU && check_rows("scv_bnact_bwd dU", p->C, p->dU, p->u_bs, p->u_ls)) return -1;
   SCV_REQUIRE(p->sums, "scv_bnact_bwd_reduce: sums required");
   SCV_REQUIRE(p->B * p->L < (1LL << 31), "scv_bnact_bwd_reduce: more than 2^31 rows");
-  Launch2D l = plan2d(p->C / 4, p->B * p->L, 4);
+  Launch2D l = plan2d(p->C / 4, p->B * p->L, 2);
   bnact_bwd_reduce_kernel<<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
   return scv::check_launch("bnact_bwd_reduce_kernel");
 }
@@ -508,7 +523,7 @@ int scv_bnact_bwd_apply(const scv_bnact_bwd_t* p, void* stream) {
   if (p->dX && check_rows("scv_bnact_bwd dX", p->C, p->dX, p->d_bs, p->d_ls)) return -1;
   SCV_REQUIRE(!(p->mode & 3) || p->sums, "scv_bnact_bwd_apply: sums required");
   SCV_REQUIRE(p->B * p->L < (1LL << 31), "scv_bnact_bwd_apply: more than 2^31 rows");
-  Launch2D l = plan2d(p->C / 4, p->B * p->L, 8);
+  Launch2D l = plan2d(p->C / 4, p->B * p->L, 3);
   bnact_bwd_apply_kernel<<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
   return scv::check_launch("bnact_bwd_apply_kernel");
 }
