@@ -63,6 +63,44 @@ SCV_HD void c6d_to_mat_bwd(const float* c, float eps, const float* gm, float* gc
   gc[3] = gbx; gc[4] = gby; gc[5] = gbz;
 }
 
+// Same two functions with the divisions hoisted: one reciprocal per norm (2 sqrt + 2 div forward, 2 sqrt + 4 div
+// backward instead of 6 / 14 divisions).  Results differ from the exact-division forms above by <= 1 ulp per
+// element; the loss kernels (instruction-bound on exactly these divisions) use them, the preprocessing kernel keeps
+// the exact forms.
+SCV_HD void c6d_to_mat_r(const float* c, float eps, float* m) {
+  const float ax = c[0], ay = c[1], az = c[2], bx = c[3], by = c[4], bz = c[5];
+  const float ina = 1.f / (sqrtf(ax * ax + ay * ay + az * az) + eps);
+  const float xx = ax * ina, xy = ay * ina, xz = az * ina;
+  const float wx = xy * bz - xz * by, wy = xz * bx - xx * bz, wz = xx * by - xy * bx;
+  const float inw = 1.f / (sqrtf(wx * wx + wy * wy + wz * wz) + eps);
+  const float zx = wx * inw, zy = wy * inw, zz = wz * inw;
+  m[0] = xx; m[1] = zy * xz - zz * xy; m[2] = zx;
+  m[3] = xy; m[4] = zz * xx - zx * xz; m[5] = zy;
+  m[6] = xz; m[7] = zx * xy - zy * xx; m[8] = zz;
+}
+
+SCV_HD void c6d_to_mat_bwd_r(const float* c, float eps, const float* gm, float* gc) {
+  const float ax = c[0], ay = c[1], az = c[2], bx = c[3], by = c[4], bz = c[5];
+  const float ra = sqrtf(ax * ax + ay * ay + az * az), ina = 1.f / (ra + eps);
+  const float xx = ax * ina, xy = ay * ina, xz = az * ina;
+  const float wx = xy * bz - xz * by, wy = xz * bx - xx * bz, wz = xx * by - xy * bx;
+  const float rw = sqrtf(wx * wx + wy * wy + wz * wz), inw = 1.f / (rw + eps);
+  const float zx = wx * inw, zy = wy * inw, zz = wz * inw;
+  float gxx = gm[0], gxy = gm[3], gxz = gm[6];
+  const float gyx = gm[1], gyy = gm[4], gyz = gm[7];
+  float gzx = gm[2], gzy = gm[5], gzz = gm[8];
+  gzx += xy * gyz - xz * gyy; gzy += xz * gyx - xx * gyz; gzz += xx * gyy - xy * gyx;
+  gxx += gyy * zz - gyz * zy; gxy += gyz * zx - gyx * zz; gxz += gyx * zy - gyy * zx;
+  const float dzw = gzx * wx + gzy * wy + gzz * wz;
+  const float k = rw > 0.f ? dzw * inw * inw / rw : 0.f;
+  const float gwx = gzx * inw - wx * k, gwy = gzy * inw - wy * k, gwz = gzz * inw - wz * k;
+  gxx += by * gwz - bz * gwy; gxy += bz * gwx - bx * gwz; gxz += bx * gwy - by * gwx;
+  const float dxa = gxx * ax + gxy * ay + gxz * az;
+  const float ka = ra > 0.f ? dxa * ina * ina / ra : 0.f;
+  gc[0] = gxx * ina - ax * ka; gc[1] = gxy * ina - ay * ka; gc[2] = gxz * ina - az * ka;
+  gc[3] = gwy * xz - gwz * xy; gc[4] = gwz * xx - gwx * xz; gc[5] = gwx * xy - gwy * xx;
+}
+
 SCV_HD void mat_mul(const float* a, const float* b, float* o) {  // o = a b
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) o[r * 3 + c] = a[r * 3] * b[c] + a[r * 3 + 1] * b[3 + c] + a[r * 3 + 2] * b[6 + c];
