@@ -309,8 +309,16 @@ def run_ours(args, rank, world, local_rank):
     try:
         gp = gemm_profile(step, B)
         ach = gp["flops"] / gp["seconds"] / 1e12
+        traffic = None
+        try:  # DRAM bytes of the same launches from the committed ncu pass (profiles/, cold cache): informational
+            with open(os.path.join(ROOT, "profiles", "r01_gemm_family_dram.json")) as f:
+                traffic = json.load(f)["dram_bytes_per_step"]
+        except Exception:
+            pass
         line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                            "frac": ach / tf32_peak, "traffic": None,
+                            "frac": ach / tf32_peak, "traffic": traffic,
+                            "traffic_note": "dram__bytes_read+write summed over the family's launches of one step "
+                                            "(profiles/r01_gemm_family_dram.json), bytes per step",
                             "kernel": "tcgen05 overlapping-row GEMM family (gemm_tc_kernel + wgrad_tc_kernel): all its "
                                       "launches of one step replayed back to back from one CUDA graph, CUDA events",
                             "launches_per_step": gp["launches"], "gemm_seconds_per_step": gp["seconds"],
