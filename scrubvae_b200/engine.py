@@ -617,10 +617,13 @@ class Plan:
                 acts_k.append(acts)
                 dacts_k.append(dacts)
             self.gr_act[key], self.gr_dact[key] = acts_k, dacts_k
+        self._f_heads0 = len(F)
         for li in sorted(fwd_levels):
             for grp in chunks(fwd_levels[li]):
                 F.append(lambda grp=grp: ops.gemm_group(grp))
         self._n_head_launches = sum(len(chunks(v)) for v in fwd_levels.values())
+        # the heads only read mu: on CUDA they run on a side stream, concurrently with the decoder (forward and backward)
+        self.side = torch.cuda.Stream(device=dev) if (dev.type == "cuda" and eng.gr_keys) else None
 
         self.F = F
 
@@ -691,6 +694,7 @@ class Plan:
         Bw.append(wgrad(gin, self.zc, eng.zc_ld, 0, 1, dX0.at(0), dX0.bs, 0))
         self.dzc = torch.zeros(B, eng.zc_ld, **f32)
         Bw.append(dgemm(gin, dX0.at(0), dX0.bs, 0, 1, self.dzc, eng.zc_ld, 0))
+        self._bw_heads0 = len(Bw)
         # scrubber heads: dpred from the loss, then level by level from the output side — the weight gradients and
         # the data gradients of all ensemble members at the same distance from the output are one grouped launch
         # each; the gradient-reversed gradient into mu is one GEMM per key over the concatenated first layers
@@ -811,8 +815,11 @@ class Plan:
                 self.stats.zero_()
                 eng.nbt.add_(1)
             eng.repack()
-            for f in (self.F[:self._n_enc] if upto == "encode" else self.F):
-                f()
+            if upto == "encode":
+                for f in self.F[:self._n_enc]:
+                    f()
+            else:
+                self.run_forward()
         else:  # decode(z, data): decoder only
             self.load_inputs(data, need_loss_inputs=False)
             if training:
@@ -859,18 +866,45 @@ class Plan:
             f()
         return self.loss_out
 
+    def run_forward(self):
+        """All forward launches; the scrubber heads fork onto the side stream right after the latent is final."""
+        if self.side is None:
+            for f in self.F:
+                f()
+            return
+        main = torch.cuda.current_stream()
+        for f in self.F[:self._n_enc]:
+            f()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            for f in self.F[self._f_heads0:]:
+                f()
+        for f in self.F[self._n_enc:self._f_heads0]:
+            f()
+        main.wait_stream(self.side)
+
     def backward(self, comm=None):
         """Runs the backward launch list; `self.gscale` must hold d total / d loss_k.
         `comm(engine, phase)` (data parallelism, parallel.py) is called when the decoder + scrubber-head weight
         gradients are final ("decoder_done": their all-reduce overlaps the encoder backward) and again before
         the final gather of the packed gradients ("encoder_done")."""
         last = len(self.Bw) - 1
+        main = torch.cuda.current_stream() if self.side is not None else None
         for i, f in enumerate(self.Bw):
+            if self.side is not None and i == 1:  # gradients zeroed: the head backward forks off, beside the decoder's
+                self.side.wait_stream(main)
+                with torch.cuda.stream(self.side):
+                    for g in self.Bw[self._bw_heads0:self._bw_dec_end]:
+                        g()
+            if i == self._bw_dec_end and self.side is not None:
+                main.wait_stream(self.side)
             if comm is not None:
                 if i == self._bw_dec_end:
                     comm(self.eng, "decoder_done")
                 if i == last:
                     comm(self.eng, "encoder_done")
+            if self.side is not None and self._bw_heads0 <= i < self._bw_dec_end:
+                continue  # launched on the side stream above
             f()
 
 
@@ -908,8 +942,7 @@ class TrainStep:
         plan.stats.zero_()
         eng.nbt.add_(1)
         eng.repack()
-        for f in plan.F:
-            f()
+        plan.run_forward()
         for f in plan.Lk:
             f()
         plan.gscale.copy_(plan.loss_scale)
