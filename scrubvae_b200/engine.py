@@ -21,6 +21,7 @@ of the ABI to check this host logic without a GPU.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -56,6 +57,19 @@ class Act:
 
     def view(self) -> torch.Tensor:
         return self.t[:self.B * self.rows * self.C].view(self.B, self.rows, self.C)[:, self.hl:self.hl + self.L]
+
+
+class SideLaunch:
+    """A backward launch that only feeds the weight gradients (scv_wgrad): nothing downstream on the main stream
+    reads its result before the final gather, so on CUDA it runs on a second stream and fills the SMs the
+    dependent chain (dgrad -> BN backward -> dgrad ...) leaves idle: wave tails, HBM-bound passes, launch gaps."""
+    __slots__ = ("fn",)
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self):
+        self.fn()
 
 
 class GemmW:
@@ -454,7 +468,7 @@ class Plan:
             kw = dict(A=Aref, a_bs=a_bs, a_ls=a_ls, B=B, Lo=Lo, K=g.K, N=g.N, dY=dY, y_bs=y_bs, y_ls=y_ls,
                       dW=eng.gwref(g), dbias=eng.gbref(g), bias_mod=g.bias_mod,
                       bias_n=(g.N if bias_n is None else bias_n) if g.b is not None else 0, precision=prec)
-            return lambda: ops.wgrad(**kw)
+            return SideLaunch(lambda: ops.wgrad(**kw))
 
         def dgemm(g: GemmW, Aref, a_bs, a_ls, Lo, Y, y_bs, y_ls, n_last=None, R=None, r_bs=0, r_ls=0, act=ACT_NONE,
                   out_scale=1.0):
@@ -624,6 +638,7 @@ class Plan:
         self._n_head_launches = sum(len(chunks(v)) for v in fwd_levels.values())
         # the heads only read mu: on CUDA they run on a side stream, concurrently with the decoder (forward and backward)
         self.side = torch.cuda.Stream(device=dev) if (dev.type == "cuda" and eng.gr_keys) else None
+        self.wside = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None  # weight-gradient stream
 
         self.F = F
 
@@ -889,7 +904,8 @@ class Plan:
         gradients are final ("decoder_done": their all-reduce overlaps the encoder backward) and again before
         the final gather of the packed gradients ("encoder_done")."""
         last = len(self.Bw) - 1
-        main = torch.cuda.current_stream() if self.side is not None else None
+        main = torch.cuda.current_stream() if (self.side is not None or self.wside is not None) else None
+        wside = self.wside if os.environ.get("SCV_WGRAD_STREAM", "1") != "0" else None
         for i, f in enumerate(self.Bw):
             if self.side is not None and i == 1:  # gradients zeroed: the head backward forks off, beside the decoder's
                 self.side.wait_stream(main)
@@ -898,6 +914,8 @@ class Plan:
                         g()
             if i == self._bw_dec_end and self.side is not None:
                 main.wait_stream(self.side)
+            if wside is not None and ((i == self._bw_dec_end and comm is not None) or i == last):
+                main.wait_stream(wside)  # the all-reduce / the final gather read the weight gradients
             if comm is not None:
                 if i == self._bw_dec_end:
                     comm(self.eng, "decoder_done")
@@ -905,6 +923,11 @@ class Plan:
                     comm(self.eng, "encoder_done")
             if self.side is not None and self._bw_heads0 <= i < self._bw_dec_end:
                 continue  # launched on the side stream above
+            if wside is not None and isinstance(f, SideLaunch):
+                wside.wait_stream(main)  # its dY is ready at this point of the main stream
+                with torch.cuda.stream(wside):
+                    f()
+                continue
             f()
 
 
