@@ -72,6 +72,17 @@ class SideLaunch:
         self.fn()
 
 
+class AfterSide:
+    """A forward launch that consumes the result of an earlier SideLaunch (the block's skip convolution)."""
+    __slots__ = ("fn",)
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self):
+        self.fn()
+
+
 class GemmW:
     """One GEMM layer's packed weights: forward matrix [N][K] (+ bias) and optional dgrad matrix."""
     __slots__ = ("name", "N", "K", "w", "b", "bias_mod", "bias_n", "gw", "gb", "dN", "dK", "wd", "nnz", "nnz_d")
@@ -416,9 +427,12 @@ class Plan:
         def bn_mode(has_bn=True, has_act=True):
             return (BN if has_bn else 0) | (PRELU if has_act else 0) | rmode
 
-        def gemm(**kw):
+        def gemm(role=None, **kw):
+            """role "side": independent of the launches that follow until the next "join" launch (the skip convolution
+            of a residual block runs beside residual.0 -> BN -> PReLU); role "join": consumes the side result."""
             kw.setdefault("precision", prec)
-            F.append(lambda: ops.gemm(**kw))
+            fn = lambda: ops.gemm(**kw)  # noqa: E731
+            F.append(SideLaunch(fn) if role == "side" else AfterSide(fn) if role == "join" else fn)
 
         def bnact_fwd(bn_name, slope_name, X, L, Cc, st_off, fold, H=None, U=None):
             kw = dict(X=X.at(0), x_bs=X.bs, x_ls=X.ls, B=B, L=L, Cc=Cc, fold=fold, count=float(B * L), eps=1e-4,
@@ -498,8 +512,8 @@ class Plan:
             pre = f"encoder.res_layers.{i}."
             gs, g0, g3 = WG[f"enc.{i}.skip"], WG[f"enc.{i}.r0"], WG[f"enc.{i}.r3"]
             S, R0 = A(Lo, Co), A(Lo, Co // 2)
-            gemm(A=H.at(-p2), a_bs=H.bs, a_ls=2 * Ci, B=B, Lo=Lo, K=gs.K, N=gs.N, W=eng.wref(gs), bias=eng.bref(gs),
-                 bias_mod=gs.bias_mod, bias_n=gs.N, Y=S.at(0), y_bs=S.bs, y_ls=S.ls)
+            gemm(role="side", A=H.at(-p2), a_bs=H.bs, a_ls=2 * Ci, B=B, Lo=Lo, K=gs.K, N=gs.N, W=eng.wref(gs),
+                 bias=eng.bref(gs), bias_mod=gs.bias_mod, bias_n=gs.N, Y=S.at(0), y_bs=S.bs, y_ls=S.ls)
             st1 = stats(Co // 2)
             gemm(A=H.at(-p2), a_bs=H.bs, a_ls=2 * Ci, B=B, Lo=Lo, K=g0.K, N=g0.N, W=eng.wref(g0), bias=eng.bref(g0),
                  bias_mod=g0.bias_mod, bias_n=g0.N, Y=R0.at(0), y_bs=R0.bs, y_ls=R0.ls, stats=st1)
@@ -507,7 +521,7 @@ class Plan:
             bnact_fwd(pre + "residual.1", pre + "residual.2.weight", R0, Lo, Co // 2, st1, 1, H=R0a)
             T = A(Lo, Co)
             st2 = stats(Co)
-            gemm(A=R0a.at(-p2), a_bs=R0a.bs, a_ls=Co // 2, B=B, Lo=Lo, K=g3.K, N=g3.N, W=eng.wref(g3),
+            gemm(role="join", A=R0a.at(-p2), a_bs=R0a.bs, a_ls=Co // 2, B=B, Lo=Lo, K=g3.K, N=g3.N, W=eng.wref(g3),
                  bias=eng.bref(g3), bias_mod=g3.bias_mod, bias_n=g3.N, Y=T.at(0), y_bs=T.bs, y_ls=T.ls,
                  R=S.at(0), r_bs=S.bs, r_ls=S.ls, stats=st2)
             last = i == eng.nblk - 1
@@ -553,8 +567,8 @@ class Plan:
             gs, g0, g3 = WG[f"dec.{i}.skip"], WG[f"dec.{i}.r0"], WG[f"dec.{i}.r3"]
             Lo2 = 2 * L - 1
             S = A(Lo2, Co)
-            gemm(A=U.at(-p2), a_bs=U.bs, a_ls=Ci, B=B, Lo=Lo2, K=gs.K, N=gs.N, W=eng.wref(gs), bias=eng.bref(gs),
-                 bias_mod=gs.bias_mod, bias_n=gs.N, Y=S.at(0), y_bs=S.bs, y_ls=S.ls)
+            gemm(role="side", A=U.at(-p2), a_bs=U.bs, a_ls=Ci, B=B, Lo=Lo2, K=gs.K, N=gs.N, W=eng.wref(gs),
+                 bias=eng.bref(gs), bias_mod=gs.bias_mod, bias_n=gs.N, Y=S.at(0), y_bs=S.bs, y_ls=S.ls)
             R0 = A(L, Ci // 2)
             st1 = stats(Ci // 2)
             gemm(A=H.at(-p2), a_bs=H.bs, a_ls=Ci, B=B, Lo=L, K=g0.K, N=g0.N, W=eng.wref(g0), bias=eng.bref(g0),
@@ -563,7 +577,7 @@ class Plan:
             bnact_fwd(pre + "residual.1", pre + "residual.2.weight", R0, L, Ci // 2, st1, 1, H=R0a)
             T = A(Lo2, Co)
             st2 = stats(2 * Co)
-            gemm(A=R0a.at(-wl), a_bs=R0a.bs, a_ls=Ci // 2, B=B, Lo=L, K=g3.K, N=g3.N, W=eng.wref(g3),
+            gemm(role="join", A=R0a.at(-wl), a_bs=R0a.bs, a_ls=Ci // 2, B=B, Lo=L, K=g3.K, N=g3.N, W=eng.wref(g3),
                  bias=eng.bref(g3), bias_mod=Co, bias_n=2 * Co, Y=T.at(0), y_bs=T.bs, y_ls=2 * Co, n_last=Co,
                  R=S.at(0), r_bs=S.bs, r_ls=2 * Co, stats=st2)
             last = i == eng.nblk - 1
@@ -830,11 +844,7 @@ class Plan:
                 self.stats.zero_()
                 eng.nbt.add_(1)
             eng.repack()
-            if upto == "encode":
-                for f in self.F[:self._n_enc]:
-                    f()
-            else:
-                self.run_forward()
+            self.run_forward(upto=upto)
         else:  # decode(z, data): decoder only
             self.load_inputs(data, need_loss_inputs=False)
             if training:
@@ -844,8 +854,7 @@ class Plan:
             self.zc[:, :m.z_dim].copy_(z_given)
             if eng.cond_dim > 0:
                 self.zc[:, m.z_dim:m.z_dim + eng.cond_dim].copy_(self.var)
-            for f in self.F[self._n_enc:len(self.F) - self._n_head_launches]:
-                f()
+            self.run_forward(decode_only=True)
         out = {}
         if z_given is None:
             out["mu"], out["L"] = self.mu, self.Lmat
@@ -881,21 +890,47 @@ class Plan:
             f()
         return self.loss_out
 
-    def run_forward(self):
-        """All forward launches; the scrubber heads fork onto the side stream right after the latent is final."""
-        if self.side is None:
-            for f in self.F:
+    def _run_main(self, fns):
+        """Launches in order on the current stream; SideLaunch entries go to the second stream (forked here), the
+        matching AfterSide entry waits for them."""
+        ws = self.wside if os.environ.get("SCV_SKIP_STREAM", "1") != "0" else None
+        if ws is None:
+            for f in fns:
                 f()
             return
         main = torch.cuda.current_stream()
-        for f in self.F[:self._n_enc]:
+        pending = False
+        for f in fns:
+            if isinstance(f, SideLaunch):
+                ws.wait_stream(main)
+                with torch.cuda.stream(ws):
+                    f()
+                pending = True
+                continue
+            if isinstance(f, AfterSide) and pending:
+                main.wait_stream(ws)
+                pending = False
             f()
+        if pending:
+            main.wait_stream(ws)
+
+    def run_forward(self, upto=None, decode_only=False):
+        """All forward launches; the scrubber heads fork onto the side stream right after the latent is final."""
+        if decode_only:
+            self._run_main(self.F[self._n_enc:self._f_heads0])
+            return
+        self._run_main(self.F[:self._n_enc])
+        if upto == "encode":
+            return
+        if self.side is None:
+            self._run_main(self.F[self._n_enc:])
+            return
+        main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             for f in self.F[self._f_heads0:]:
                 f()
-        for f in self.F[self._n_enc:self._f_heads0]:
-            f()
+        self._run_main(self.F[self._n_enc:self._f_heads0])
         main.wait_stream(self.side)
 
     def backward(self, comm=None):
