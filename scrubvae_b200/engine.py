@@ -72,6 +72,18 @@ class SideLaunch:
         self.fn()
 
 
+class SideData:
+    """A backward data-gradient launch off the dependent chain (the skip path's dgrad): third stream, joined by the
+    next AfterSide launch (its consumer)."""
+    __slots__ = ("fn",)
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self):
+        self.fn()
+
+
 class AfterSide:
     """A forward launch that consumes the result of an earlier SideLaunch (the block's skip convolution)."""
     __slots__ = ("fn",)
@@ -653,6 +665,7 @@ class Plan:
         # the heads only read mu: on CUDA they run on a side stream, concurrently with the decoder (forward and backward)
         self.side = torch.cuda.Stream(device=dev) if (dev.type == "cuda" and eng.gr_keys) else None
         self.wside = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None  # weight-gradient stream
+        self.dside = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None  # skip-path data-gradient stream
 
         self.F = F
 
@@ -698,13 +711,16 @@ class Plan:
             Ci, Co, L, Lo2, pre = blk["Ci"], blk["Co"], blk["L"], blk["Lo2"], blk["pre"]
             gs, g0, g3 = blk["gs"], blk["g0"], blk["g3"]
             dT = A(Lo2, Co, k - p2, p2 + 1, even=True)
-            Bw += bnact_bwd(pre + "add.0", pre + "add.1.weight", blk["T"], Lo2, Co, blk["st2"], 2, dH, dU, dT,
+            lst = bnact_bwd(pre + "add.0", pre + "add.1.weight", blk["T"], Lo2, Co, blk["st2"], 2, dH, dU, dT,
                             sums(Co))
+            if dU is not None:
+                lst[0] = AfterSide(lst[0])  # dU comes from the previous block's skip dgrad on the side stream
+            Bw += lst
             # skip conv (k+1, stride 1, pad k//2) on the upsampled input
             Bw.append(wgrad(gs, blk["U"].at(-p2), blk["U"].bs, Ci, Lo2, dT.at(0), dT.bs, dT.ls))
             dUin = A(2 * L, Ci)
             hl_s = (k + 1) - 1 - p2
-            Bw.append(dgemm(gs, dT.at(-hl_s), dT.bs, Co, 2 * L, dUin.at(0), dUin.bs, dUin.ls))
+            Bw.append(SideData(dgemm(gs, dT.at(-hl_s), dT.bs, Co, 2 * L, dUin.at(0), dUin.bs, dUin.ls)))
             # stride-2 transposed conv (polyphase forward; plain strided-window dgrad)
             Bw.append(wgrad(g3, blk["R0a"].at(-wl), blk["R0a"].bs, Ci // 2, L, dT.at(0), dT.bs, 2 * Co,
                             bias_n=2 * Co))
@@ -719,7 +735,9 @@ class Plan:
             dH, dU = dHin, dUin
         # fc_in (input of decoder block 0 has no BN / activation: only the upsample transpose)
         dX0 = A(Ll, Cl)
-        Bw += bnact_bwd(None, None, dec_in["H"], Ll, Cl, None, 1, dH, dU, dX0, None)
+        lst = bnact_bwd(None, None, dec_in["H"], Ll, Cl, None, 1, dH, dU, dX0, None)
+        lst[0] = AfterSide(lst[0])
+        Bw += lst
         Bw.append(wgrad(gin, self.zc, eng.zc_ld, 0, 1, dX0.at(0), dX0.bs, 0))
         self.dzc = torch.zeros(B, eng.zc_ld, **f32)
         Bw.append(dgemm(gin, dX0.at(0), dX0.bs, 0, 1, self.dzc, eng.zc_ld, 0))
@@ -779,6 +797,11 @@ class Plan:
             dT = A(Lo, Co, p2, p2)
             Bw += bnact_bwd(pre + "add.0", pre + "add.1.weight", blk["T"], Lo, Co, blk["st2"], 1, dH, None, dT,
                             sums(Co))
+            # the skip path's data gradient needs only dT: side stream, beside residual.3 dgrad -> BN backward
+            dHin = A(blk["Lin"], Ci)
+            Lg = (blk["Lin"] + 1) // 2
+            nlast = Ci if blk["Lin"] % 2 else 2 * Ci
+            Bw.append(SideData(dgemm(gs, dT.at(-wl), dT.bs, Co, Lg, dHin.at(0), dHin.bs, 2 * Ci, n_last=nlast)))
             Bw.append(wgrad(g3, blk["R0a"].at(-p2), blk["R0a"].bs, Co // 2, Lo, dT.at(0), dT.bs, dT.ls))
             dR0a = A(Lo, Co // 2)
             Bw.append(dgemm(g3, dT.at(-(k - 1 - p2)), dT.bs, Co, Lo, dR0a.at(0), dR0a.bs, dR0a.ls))
@@ -788,12 +811,8 @@ class Plan:
             Hin = blk["Hin"]
             Bw.append(wgrad(g0, Hin.at(-p2), Hin.bs, 2 * Ci, Lo, dR0.at(0), dR0.bs, dR0.ls))
             Bw.append(wgrad(gs, Hin.at(-p2), Hin.bs, 2 * Ci, Lo, dT.at(0), dT.bs, dT.ls))
-            dHin = A(Lin, Ci)
-            Lg = (Lin + 1) // 2
-            nlast = Ci if Lin % 2 else 2 * Ci
-            Bw.append(dgemm(gs, dT.at(-wl), dT.bs, Co, Lg, dHin.at(0), dHin.bs, 2 * Ci, n_last=nlast))
-            Bw.append(dgemm(g0, dR0.at(-wl), dR0.bs, Co // 2, Lg, dHin.at(0), dHin.bs, 2 * Ci, n_last=nlast,
-                            R=dHin.at(0), r_bs=dHin.bs, r_ls=2 * Ci))
+            Bw.append(AfterSide(dgemm(g0, dR0.at(-wl), dR0.bs, Co // 2, Lg, dHin.at(0), dHin.bs, 2 * Ci, n_last=nlast,
+                                      R=dHin.at(0), r_bs=dHin.bs, r_ls=2 * Ci)))
             dH = dHin
         dY0 = A(W, ch[0])
         Bw += bnact_bwd(None, "encoder.activation.weight", enc_in["Y0"], W, ch[0], None, 1, dH, None, dY0, sums(ch[0]))
@@ -941,6 +960,8 @@ class Plan:
         last = len(self.Bw) - 1
         main = torch.cuda.current_stream() if (self.side is not None or self.wside is not None) else None
         wside = self.wside if os.environ.get("SCV_WGRAD_STREAM", "1") != "0" else None
+        dside = self.dside if os.environ.get("SCV_SKIP_STREAM", "1") != "0" else None
+        dpending = False
         for i, f in enumerate(self.Bw):
             if self.side is not None and i == 1:  # gradients zeroed: the head backward forks off, beside the decoder's
                 self.side.wait_stream(main)
@@ -963,6 +984,15 @@ class Plan:
                 with torch.cuda.stream(wside):
                     f()
                 continue
+            if dside is not None and isinstance(f, SideData):
+                dside.wait_stream(main)
+                with torch.cuda.stream(dside):
+                    f()
+                dpending = True
+                continue
+            if dpending and isinstance(f, AfterSide):
+                main.wait_stream(dside)
+                dpending = False
             f()
 
 
