@@ -333,8 +333,13 @@ class Engine:
     def gbref(self, g: GemmW) -> Optional[Ref]:
         return None if g.b is None else Ref(self.gpacked, g.b)
 
-    def repack(self):
-        self.ops.gather(self.flat, self.pack_idx, self.packed, self.packed.numel(), False, round_tf32=self.rnd)
+    def repack(self, part: str = "all"):
+        """Refreshes the packed GEMM matrices from the flat parameters: "fwd" = forward matrices + biases,
+        "dgrad" = data-gradient matrices (only the backward pass reads them), "all" = both."""
+        n0 = 0 if part in ("all", "fwd") else self._n_fwd
+        n1 = self._n_fwd if part == "fwd" else self.packed.numel()
+        if n1 > n0:
+            self.ops.gather(self.flat, Ref(self.pack_idx, n0), Ref(self.packed, n0), n1 - n0, False, round_tf32=self.rnd)
 
     # ------------------------------------------------------------------ API
     def plan(self, B: int) -> "Plan":
@@ -1029,10 +1034,23 @@ class TrainStep:
             plan.eps.normal_()
         plan.stats.zero_()
         eng.nbt.add_(1)
-        eng.repack()
-        plan.run_forward()
-        for f in plan.Lk:
-            f()
+        if plan.dside is not None:
+            # forward matrices first; the data-gradient matrices (read only by backward) are repacked on a side stream
+            # while the forward pass runs, and the gradient buffers are zeroed there too
+            main = torch.cuda.current_stream()
+            eng.repack("fwd")
+            plan.dside.wait_stream(main)
+            with torch.cuda.stream(plan.dside):
+                eng.repack("dgrad")
+            plan.run_forward()
+            for f in plan.Lk:
+                f()
+            main.wait_stream(plan.dside)
+        else:
+            eng.repack()
+            plan.run_forward()
+            for f in plan.Lk:
+                f()
         plan.gscale.copy_(plan.loss_scale)
         plan.backward(self.comm)
         eng.sumsq.zero_()
