@@ -234,16 +234,19 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step.run()
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
-        sampler.start()
+        sampler.start()  # before the barrier: NVML start-up on one rank must not delay its peers inside the timed region
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         step.run()
+        marks[i].record()  # per-step marks (diagnostic: median / max step time), same stream, no host sync
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    per_step = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))
     dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -288,13 +291,14 @@ def run_ours(args, rank, world, local_rank):
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            _shutdown(dist)
         return
     pk, src = peaks()
     tf32_peak = pk["bf16_tflops_sustained"] / 2.0
     line = {
         "metric": "pose windows/sec per training step", "value": world * B * args.steps / dt, "unit": "windows/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3,
+        "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_max": per_step[-1],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"tf32": "tf32 (fp32 storage, fp32 accumulate)", "fp32": "fp32"}[args.precision],
         "data": "synthetic",
@@ -337,7 +341,18 @@ def run_ours(args, rank, world, local_rank):
                                     "sample": "failed: " + repr(ex)[:160]}
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _shutdown(dist)
+
+
+def _shutdown(dist):
+    """Leave the process group without waiting on peers that may already be gone."""
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    # no destroy_process_group / interpreter teardown: ranks finish at different times (rank 0 alone runs the GEMM
+    # profile) and CUDA graphs holding captured collectives stalled the teardown on 2 GPUs
+    os._exit(0)
 
 
 def main():

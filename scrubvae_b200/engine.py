@@ -975,11 +975,12 @@ class Plan:
                         g()
             if i == self._bw_dec_end and self.side is not None:
                 main.wait_stream(self.side)
-            if wside is not None and ((i == self._bw_dec_end and comm is not None) or i == last):
-                main.wait_stream(wside)  # the all-reduce / the final gather read the weight gradients
+            if wside is not None and i == last:
+                main.wait_stream(wside)  # the final gather reads the weight gradients
             if comm is not None:
                 if i == self._bw_dec_end:
-                    comm(self.eng, "decoder_done")
+                    # the all-reduce stream (not the main stream) waits for the decoder's weight gradients
+                    comm(self.eng, "decoder_done", wait=[wside] if wside is not None else [])
                 if i == last:
                     comm(self.eng, "encoder_done")
             if self.side is not None and self._bw_heads0 <= i < self._bw_dec_end:

@@ -51,7 +51,8 @@ class GradAllReduce:
     def _reduce(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
-    def __call__(self, eng, phase: str):
+    def __call__(self, eng, phase: str, wait=()):
+        """`wait`: extra streams whose work the reduced buffers depend on (the weight-gradient stream)."""
         if self.world == 1:
             return
         if phase == "post_backward":
@@ -66,6 +67,8 @@ class GradAllReduce:
             return
         main = torch.cuda.current_stream()
         self.stream.wait_stream(main)
+        for st in wait:
+            self.stream.wait_stream(st)
         with torch.cuda.stream(self.stream):
             if phase == "decoder_done":
                 self._reduce(eng.gpacked[eng.gp_split:])
