@@ -5,9 +5,11 @@
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
   value        whole-job windows/s, inputs resident in HBM, one CUDA-graph replay per step
-  e2e          same step through the public module/loss/optimizer API with HOST (pinned) inputs:
-               H2D of the batch and D2H of the loss inside the timed region
-  roofline     tensor-pipe roofline of the dominant kernel class (the overlapping-row GEMMs)
+  e2e          the same steps through the public API scrubvae_b200.train.train_test_epoch(mode="train") over a
+               loader of HOST (pinned) batches: every step's H2D copy (prefetched on a side stream) and the D2H
+               read of its loss are inside the timed region
+  roofline     tensor-pipe roofline of the dominant kernel class (the tcgen05 overlapping-row GEMMs): their
+               launches of one step replayed back to back from one CUDA graph between CUDA events
   cpu_baseline the CPU oracle port (oracle/scvae_oracle.py) of the reference step on the host cores
 `--impl reference` times that CPU port alone (the reference is pure Python/PyTorch and its tree does
 not travel to the GPU box; the port is pinned to it by tests/golden)."""

@@ -7,10 +7,14 @@
 //            implicit-GEMM im2col is done by the tensor map; W tile = 2-D box (32 k, bn) of the packed
 //            [N][K] weights.  128-byte swizzle, out-of-bounds -> 0 (K tail, ragged l / b / n edges).
 //   warp 1   one elected thread issues tcgen05.mma (M=128, N=bn<=256, K=8 per instruction), both operands
-//            K-major from shared memory, accumulators double-buffered in TMEM (2 x 256 columns).
+//            K-major from shared memory (descriptors built once, the low word advances per MMA).  Work item =
+//            one 128-row tile with the accumulator double-buffered in TMEM (2 x 256 columns), or (sub = 2) two
+//            row tiles against ONE W tile per stage, one accumulator each (less shared-memory traffic per FLOP).
 //   warp 2   TMEM allocation.
-//   warps 4-7 epilogue: tcgen05.ld -> per-warp transpose through shared memory -> out_scale, bias,
-//            residual, BatchNorm column sums (sum / sum of squares), activation, coalesced row stores.
+//   warps 4-7 epilogue: tcgen05.ld -> swizzled float4 transpose through shared memory -> out_scale, bias,
+//            residual, BatchNorm column sums, activation, TF32 rounding, float4 row stores; the arithmetic is
+//            compiled per (activation, residual, sums, rounding) variant (epi_rows).
+// gemm_tc2_kernel is the same body for CTA pairs (cta_group::2), kept as an experiment (SCV_TC_PAIR=1).
 // Weight gradient (wgrad_tc_kernel): D[n][k] = sum_m dY[m][n] A[m][k]; both operands are MN-major in
 // shared memory (dY rows are n-contiguous, A rows k-contiguous; 128B swizzle with 32-byte atoms, the only
 // layout tcgen05 takes for MN-major tf32), the reduction runs over the rows of
