@@ -314,7 +314,11 @@ def run_ours(args, rank, world, local_rank):
     }
     try:
         gp = gemm_profile(step, B)
-        ach = gp["flops"] / gp["seconds"] / 1e12
+        # numerator: SURVEY.md §8(d)'s algorithmic figure (759.0 MFLOP per window, layer GEMMs only).  The launches'
+        # own count (2 x rows x nnz(W), boundary taps of the transposed convolutions included) is 1.1 % higher and
+        # is reported beside it, not used.
+        alg = FLOP_PER_WINDOW * B
+        ach = alg / gp["seconds"] / 1e12
         traffic = None
         try:  # DRAM bytes of the same launches from the committed ncu pass (profiles/, cold cache): informational
             with open(os.path.join(ROOT, "profiles", "r01_gemm_family_dram.json")) as f:
@@ -329,7 +333,7 @@ def run_ours(args, rank, world, local_rank):
                                       "launches of one step replayed back to back from one CUDA graph, CUDA events",
                             "launches_per_step": gp["launches"], "gemm_seconds_per_step": gp["seconds"],
                             "gemm_share_of_step": gp["seconds"] / (dt / args.steps),
-                            "alg_flops_per_step": gp["flops"], "peak_source": f"{src}: bf16_tflops_sustained/2 (TF32)"}
+                            "alg_flops_per_step": alg, "launch_counted_flops_per_step": gp["flops"], "peak_source": f"{src}: bf16_tflops_sustained/2 (TF32)"}
     except Exception as ex:
         line["roofline"] = {"bound": "tensor", "achieved": None, "peak": tf32_peak, "unit": "TFLOP/s", "frac": None,
                             "traffic": None, "error": repr(ex)[:200]}
