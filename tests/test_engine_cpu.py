@@ -180,3 +180,32 @@ def test_engine_other_geometries_vs_oracle(ch, zd, window, B):
     for n, p in m.named_parameters():
         err = (p.grad.double() - gref[n].double()).norm().item()
         assert _rel(p.grad, gref[n]) < 3e-4 or err < 2e-6 * gnorm, (n, _rel(p.grad, gref[n]), err)
+
+
+def test_train_loop_api_on_emulation(tmp_path):
+    """The epoch loop of reference train/trainer.py:321-399 through scrubvae_b200.train.train: beta annealing of the
+    KL weight, per-epoch re-initialisation of the GR scrubber (optimizer moments kept), weight / optimizer
+    checkpoints with the reference's file names and state-dict keys."""
+    torch.manual_seed(2)
+    ch, zd = [8, 16, 32], 8
+    m, dcfg = build_model(ch, zd, ["heading"], ["heading"])
+    m._engine = Engine(m, ops=EmuOps())
+    data = orc.synth_batch(6, seed=9)
+    config = {"out_path": str(tmp_path), "disentangle": dcfg,
+              "loss": {"prior": "cyclical", "jpe": 1.0, "root": 1.0, "heading_gr": 1.0},
+              "model": {"load_model": None, "start_epoch": None},
+              "train": {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": "cawr", "num_epochs": 5, "beta_anneal": 1e-3}}
+    gr_w = "disentangle.grad_reversal.heading.reversal.1.mlp1.0.weight"
+    before = m.state_dict()[gr_w].clone()
+    model, metrics = sv.train.train(config, m, {"train": [data, data]}, device="cpu")
+    assert model is m and np.isfinite(metrics["total"]) and "time" in metrics
+    # cyclical annealing wrote the epoch-5 KL weight into the config (reference :349-351): beta_max * 4 / 50
+    assert abs(config["loss"]["prior"] - 1e-3 * 4 / 50) < 1e-12
+    after = m.state_dict()[gr_w]
+    assert not torch.equal(before, after)
+    bound = 1.0 / np.sqrt(after.shape[1])  # freshly re-initialised nn.Linear: U(-1/sqrt(in), 1/sqrt(in))
+    assert after.abs().max().item() <= bound + 1e-6
+    saved = torch.load(tmp_path / "weights" / "epoch_5.pth")
+    assert set(saved.keys()) == set(m.state_dict().keys())
+    for k, v in saved.items():
+        assert torch.equal(v, m.state_dict()[k].cpu()), k
