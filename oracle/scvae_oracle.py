@@ -333,12 +333,13 @@ def encoder(sd, x, cfg: Cfg, training, new_stats):
     flat = h.flatten(1)
     mu = F.linear(flat, sd[p + "fc_mu.weight"], sd[p + "fc_mu.bias"])
     sig = F.linear(flat, sd[p + "fc_sigma.0.weight"], sd[p + "fc_sigma.0.bias"])
-    return mu, cholesky_L(sig, cfg.z_dim)
+    return mu, cholesky_L(sig, cfg.z_dim, cfg.is_diag)
 
 
-def cholesky_L(sig, z):
-    """model/residual.py:39-68 (non-diagonal): row-major tril scatter, softplus on diag."""
-    idx = torch.tril_indices(z, z)
+def cholesky_L(sig, z, is_diag=False):
+    """model/residual.py:39-68: row-major tril scatter (is_diag: the z values go on the diagonal, :55-56),
+    softplus on the diagonal."""
+    idx = torch.arange(z)[None, :].repeat(2, 1) if is_diag else torch.tril_indices(z, z)
     L = torch.zeros(sig.shape[0], z, z, dtype=sig.dtype)
     L = L.index_put((torch.arange(sig.shape[0])[:, None], idx[0][None], idx[1][None]), sig)
     d = F.softplus(torch.diagonal(L, dim1=-2, dim2=-1))
@@ -526,7 +527,7 @@ def state_dict_shapes(cfg: Cfg) -> Dict[str, tuple]:
         L = (L + 2 * (k // 2) - (k - 1) - 1) // 2 + 1
     flat = L * ch[-1]
     s["encoder.fc_mu.weight"] = (z, flat); s["encoder.fc_mu.bias"] = (z,)
-    sig = z * (z + 1) // 2
+    sig = z if cfg.is_diag else z * (z + 1) // 2  # model/residual.py:216
     s["encoder.fc_sigma.0.weight"] = (sig, flat); s["encoder.fc_sigma.0.bias"] = (sig,)
     cd = sum(cfg.feat_dim(c) for c in cfg.conditional)
     s["decoder.fc_in.weight"] = (flat, z + cd); s["decoder.fc_in.bias"] = (flat,)

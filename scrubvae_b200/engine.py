@@ -237,10 +237,21 @@ class Engine:
         self.Cl = ch[-1]
         self.nsig = z * (z + 1) // 2
         self.ms_ld = pad16(z + self.nsig)
-        wf = torch.cat([lay.fc_enc_fprop(I(e + "fc_mu.weight"), self.Cl, self.Ll),
-                        lay.fc_enc_fprop(I(e + "fc_sigma.0.weight"), self.Cl, self.Ll)], 0)
+        w_sig = lay.fc_enc_fprop(I(e + "fc_sigma.0.weight"), self.Cl, self.Ll)
+        b_sig = I(e + "fc_sigma.0.bias")
+        if getattr(m, "is_diag", False):
+            # CholeskyL(is_diag=True) (reference model/residual.py:55-56): the z outputs are the DIAGONAL of L.  The
+            # kernels keep the packed lower-triangular row layout; the off-diagonal rows of the fc_sigma matrix become
+            # structural zeros (weight and bias), so L's off-diagonals are exactly 0 and their gradients are dropped.
+            diag_pos = torch.tensor([i * (i + 1) // 2 + i for i in range(z)])
+            full_w = torch.full((self.nsig, w_sig.shape[1]), -1, dtype=torch.long)
+            full_b = torch.full((self.nsig,), -1, dtype=torch.long)
+            full_w[diag_pos] = w_sig
+            full_b[diag_pos] = b_sig
+            w_sig, b_sig = full_w, full_b
+        wf = torch.cat([lay.fc_enc_fprop(I(e + "fc_mu.weight"), self.Cl, self.Ll), w_sig], 0)
         wf = lay.pad_rows(wf, self.ms_ld)
-        bf = lay.pad_cols(torch.cat([I(e + "fc_mu.bias"), I(e + "fc_sigma.0.bias")]).reshape(1, -1), self.ms_ld)
+        bf = lay.pad_cols(torch.cat([I(e + "fc_mu.bias"), b_sig]).reshape(1, -1), self.ms_ld)
         add("enc.fc", wf, bf.reshape(-1), d_idx=lay.transpose_pad(wf, self.ms_ld))
 
         d = "decoder."

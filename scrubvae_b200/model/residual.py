@@ -92,8 +92,8 @@ class ResidualEncoder(_EngineOnly):
     def __init__(self, in_channels, ch=[64, 128, 256, 512, 1024], kernel=5, z_dim=128, window=200,
                  activation="prelu", is_diag=False, prior="gaussian", init_dilation=None):
         super().__init__()
-        if prior != "gaussian" or is_diag:
-            raise NotImplementedError("scrubvae_b200: only the full-covariance gaussian prior is built")
+        if prior != "gaussian":
+            raise NotImplementedError("scrubvae_b200: only the gaussian prior is built (reference default)")
         if init_dilation is not None:
             raise NotImplementedError("scrubvae_b200: init_dilation is not supported")
         self.prior = prior
@@ -105,7 +105,7 @@ class ResidualEncoder(_EngineOnly):
             *[ResidualBlock(ch[i], ch[i + 1], kernel, activation, 1) for i in range(len(ch) - 1)])
         self.flatten = nn.Flatten()
         flatten_dim = find_latent_dim(window, kernel, len(ch) - 1) * ch[-1]
-        sig_dim = z_dim * (z_dim + 1) // 2
+        sig_dim = z_dim if is_diag else z_dim * (z_dim + 1) // 2  # reference model/residual.py:216
         self.fc_mu = nn.Linear(flatten_dim, z_dim)
         self.fc_sigma = nn.Sequential(nn.Linear(flatten_dim, sig_dim), CholeskyL(z_dim, is_diag))
 

@@ -19,9 +19,9 @@ import _refimport  # noqa: E402
 from oracle import scvae_oracle as orc  # noqa: E402  (only for the synthetic input generator)
 
 
-def build_ref_model(sv, ch, z_dim, feats_cond, feats_gr, discrete_classes=None, window=51, seed=1):
+def build_ref_model(sv, ch, z_dim, feats_cond, feats_gr, discrete_classes=None, window=51, seed=1, diag=False):
     mc = dict(type="rcnn", channel=list(ch), kernel=5, z_dim=z_dim, window=window,
-              activation="prelu", diag=False, init_dilation=None, prior="gaussian",
+              activation="prelu", diag=diag, init_dilation=None, prior="gaussian",
               load_model=None, start_epoch=None)
     dc = dict(method={"conditional": list(feats_cond), "grad_reversal": list(feats_gr)},
               features=sorted(set(feats_cond) | set(feats_gr)), alpha=1.0)
@@ -60,8 +60,8 @@ def run_step(sv, m, dc, data, eps, loss_scale, lr=1e-4):
     return data_o, losses, grads
 
 
-def golden_step(sv, tag, ch, z_dim, cond, gr, B, discrete_classes=None, full=True):
-    m, dc = build_ref_model(sv, ch, z_dim, cond, gr, discrete_classes)
+def golden_step(sv, tag, ch, z_dim, cond, gr, B, discrete_classes=None, full=True, diag=False):
+    m, dc = build_ref_model(sv, ch, z_dim, cond, gr, discrete_classes, diag=diag)
     sd0 = {k: v.clone() for k, v in m.state_dict().items()}
     data = orc.synth_batch(B, seed=0)
     eps = orc.synth_eps(B, z_dim, seed=2)
@@ -138,6 +138,7 @@ if __name__ == "__main__":
     golden_step(sv, "small_heading", [8, 16, 32, 64, 128], 8, ["heading"], ["heading"], B=6)
     golden_step(sv, "small_3head", [8, 16, 32, 64, 128], 8, ["heading", "avg_speed_3d", "ids"],
                 ["heading", "avg_speed_3d", "ids"], B=5, discrete_classes={"ids": [0, 1, 2, 3]})
+    golden_step(sv, "small_diag", [8, 16, 32, 64, 128], 8, ["heading"], ["heading"], B=6, diag=True)
     golden_step(sv, "default_heading_digest", [64, 128, 256, 512, 1024], 64, ["heading"], ["heading"],
                 B=4, full=False)
     golden_preprocess(sv)

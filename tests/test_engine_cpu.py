@@ -21,8 +21,8 @@ def _rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-30)).item()
 
 
-def build_model(ch, z, cond, gr, dc=None, window=51, device="cpu"):
-    mc = dict(type="rcnn", channel=list(ch), kernel=5, z_dim=z, window=window, activation="prelu", diag=False,
+def build_model(ch, z, cond, gr, dc=None, window=51, device="cpu", diag=False):
+    mc = dict(type="rcnn", channel=list(ch), kernel=5, z_dim=z, window=window, activation="prelu", diag=diag,
               init_dilation=None, prior="gaussian", load_model=None, start_epoch=None)
     dcfg = dict(method={"conditional": list(cond), "grad_reversal": list(gr)},
                 features=sorted(set(cond) | set(gr)), alpha=1.0)
@@ -36,12 +36,13 @@ def build_model(ch, z, cond, gr, dc=None, window=51, device="cpu"):
     ("step_small_heading.npz", ["heading"], ["heading"], None),
     ("step_small_3head.npz", ["heading", "avg_speed_3d", "ids"], ["heading", "avg_speed_3d", "ids"],
      {"ids": [0, 1, 2, 3]}),
+    ("step_small_diag.npz", ["heading"], ["heading"], None),  # model.diag = True
 ])
 def test_engine_step_matches_reference_golden(golden_dir, name, cond, gr, dc):
     z = np.load(os.path.join(golden_dir, name))
     g = {k: z[k] for k in z.files}
     ch, zd, B = [int(c) for c in g["meta_ch"]], int(g["meta_z"]), int(g["meta_B"])
-    m, dcfg = build_model(ch, zd, cond, gr, dc)
+    m, dcfg = build_model(ch, zd, cond, gr, dc, diag="diag" in name)
     sd = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd0.")}
     assert set(m.state_dict().keys()) == set(sd.keys())
     for k, v in m.state_dict().items():

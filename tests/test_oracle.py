@@ -23,9 +23,9 @@ def _load(golden_dir, name):
     return {k: z[k] for k in z.files}
 
 
-def _cfg_from(g, cond, gr, dc=None):
+def _cfg_from(g, cond, gr, dc=None, is_diag=False):
     return orc.Cfg(ch=[int(c) for c in g["meta_ch"]], z_dim=int(g["meta_z"]), conditional=cond,
-                   grad_reversal=gr, discrete_classes=dc)
+                   grad_reversal=gr, discrete_classes=dc, is_diag=is_diag)
 
 
 def _rel(a, b):
@@ -37,10 +37,11 @@ def _rel(a, b):
     ("step_small_heading.npz", ["heading"], ["heading"], None),
     ("step_small_3head.npz", ["heading", "avg_speed_3d", "ids"], ["heading", "avg_speed_3d", "ids"],
      {"ids": [0, 1, 2, 3]}),
+    ("step_small_diag.npz", ["heading"], ["heading"], None),  # model.diag = True: diagonal Cholesky factor
 ])
 def test_oracle_step_matches_reference_golden(golden_dir, name, cond, gr, dc):
     g = _load(golden_dir, name)
-    cfg = _cfg_from(g, cond, gr, dc)
+    cfg = _cfg_from(g, cond, gr, dc, is_diag="diag" in name)
     B = int(g["meta_B"])
     sd = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd0.")}
     assert set(orc.state_dict_shapes(cfg)) == set(sd)
