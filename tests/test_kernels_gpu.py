@@ -192,6 +192,31 @@ def test_recon_loss_and_out_bwd(ops):
     run_both(ops, T, call, tol=3e-5, check=["loss", "rh", "rh2", "dxh", "draw"])
 
 
+@pytest.mark.parametrize("tree,J", [
+    ([[0, 1, 2, 3, 4, 5, 6], [0, 7], [7, 8, 9]], 10),                      # a chain longer than the fast path takes
+    ([[0, 1], [0, 2], [0, 3], [1, 4], [2, 5], [3, 6], [4, 7], [5, 8], [6, 9]], 10),   # more chains than the fast path
+    ([[0, 1, 2], [1, 3, 4], [3, 5]], 6),                                    # small skeleton on the fast path, 3 levels
+])
+def test_recon_loss_other_skeletons(ops, tree, J):
+    """Both FK kernels on skeletons other than the mouse: the generic lane-per-joint kernel (long / many chains) and
+    the lane-per-chain fast path with nested attachment levels, against the oracle FK through the ABI emulation."""
+    from oracle import scvae_oracle as orc
+    F, B = 37, 5
+    C = (J * 6 + 3 + 3) // 4 * 4
+    tr = [len(tree)]
+    for c in tree:
+        tr += [len(c)] + list(c)
+    T = {"xh": torch.tanh(torch.randn(F, C, generator=g(1))), "off": torch.randn(F, J, 3, generator=g(2)) * 10,
+         "tgt": torch.randn(F, J, 3, generator=g(3)) * 10, "root": torch.randn(F, 3, generator=g(4)) * 50,
+         "arena": torch.tensor(orc.ARENA), "tree": torch.tensor(tr, dtype=torch.int32),
+         "loss": torch.zeros(2, dtype=torch.double), "rh": torch.zeros(F, 3), "dxh": torch.zeros(F, C)}
+
+    def call(o, t):
+        o.recon_loss(t["xh"], C, t["off"], t["tgt"], t["root"], t["arena"], t["tree"], len(tr), t["loss"], t["rh"],
+                     t["dxh"], F, B, J)
+    run_both(ops, T, call, tol=3e-5, check=["loss", "rh", "dxh"])
+
+
 @pytest.mark.parametrize("d,ce", [(2, False), (3, False), (4, True)])
 def test_gr_loss(ops, d, ce):
     B, ld, n = 37, 4, 4
