@@ -165,6 +165,9 @@ class Engine:
             self.nbt[i] = mod.num_batches_tracked.to(dev)
             mod.num_batches_tracked = self.nbt[i]
         self.bn_index = {n: i for i, (n, _) in enumerate(bns)}
+        # encode() / decode() alone advance only their own half's num_batches_tracked (torch counts per module call)
+        enc = torch.tensor([1 if n.startswith("encoder.") else 0 for n, _ in bns] or [0], dtype=torch.long)
+        self.nbt_enc, self.nbt_dec = enc.to(dev), (1 - enc).to(dev)
 
     def pref(self, name: str) -> Ref:
         return Ref(self.flat, self.poff[name])
@@ -877,18 +880,29 @@ class Plan:
                 else:
                     self.eps.normal_()
                 self.stats.zero_()
-                eng.nbt.add_(1)
+                if upto == "encode":
+                    eng.nbt.add_(eng.nbt_enc)
+                else:
+                    eng.nbt.add_(1)
             eng.repack()
             self.run_forward(upto=upto)
         else:  # decode(z, data): decoder only
             self.load_inputs(data, need_loss_inputs=False)
             if training:
                 self.stats.zero_()
+                eng.nbt.add_(eng.nbt_dec)
             eng.repack()
-            self.zc.zero_()
-            self.zc[:, :m.z_dim].copy_(z_given)
-            if eng.cond_dim > 0:
-                self.zc[:, m.z_dim:m.z_dim + eng.cond_dim].copy_(self.var)
+            # zc = [z | var | 0] through the same kernel as the full forward (eps = None: z = "mu" row), so the given
+            # latent gets the operand rounding the tensor-core GEMM expects; mu / L outputs go to scratch, never to
+            # the buffers an earlier encode() handed out
+            if getattr(self, "_dec_scratch", None) is None:
+                f32 = dict(device=eng.device, dtype=torch.float32)
+                self._dec_scratch = (torch.zeros(self.B, eng.ms_ld, **f32), torch.zeros(self.B, m.z_dim, **f32),
+                                     torch.zeros(self.B, m.z_dim, m.z_dim, **f32))
+            ms_t, mu_t, L_t = self._dec_scratch
+            ms_t[:, :m.z_dim].copy_(z_given)
+            eng.ops.reparam_fwd(ms_t, eng.ms_ld, None, self.var if eng.cond_dim > 0 else None, eng.cond_dim, mu_t, L_t,
+                                self.zc, eng.zc_ld, self.B, m.z_dim, round_tf32=eng.rnd)
             self.run_forward(decode_only=True)
         out = {}
         if z_given is None:
@@ -1081,9 +1095,7 @@ class TrainStep:
             plan.load_inputs(data, need_loss_inputs=True)
             plan.load_targets(data)
         opt._steps += 1
-        opt.hyper_host[0] = float(opt.param_groups[0]["lr"])
-        opt.hyper_host[1] = float(opt._steps)
-        opt.hyper.copy_(opt.hyper_host, non_blocking=True)
+        opt.push_hyper()  # ring of pinned slots: safe when the host runs several steps ahead of the device
         if not self.use_graph:
             n0 = self.eng.ops.launch_count()
             self._sequence()

@@ -15,6 +15,13 @@ class FusedOptimizer(torch.optim.Optimizer):
         if weight_decay is None:
             weight_decay = 0.01 if kind == "adamw" else 0.0
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, momentum=momentum)
+        # the keys torch.optim.Adam / AdamW / SGD read in step(): a checkpoint written by state_dict() below loads into
+        # the reference's torch optimizers (train/trainer.py:60-70, :81-87) and steps there
+        if kind == "sgd":
+            defaults.update(dampening=0, nesterov=True, maximize=False, foreach=None, differentiable=False, fused=None)
+        else:
+            defaults.update(amsgrad=False, maximize=False, foreach=None, capturable=False, differentiable=False,
+                            fused=None, decoupled_weight_decay=(kind == "adamw"))
         super().__init__(list(model.parameters()), defaults)
         self.model, self.kind = model, kind
         self._steps = 0
@@ -31,7 +38,14 @@ class FusedOptimizer(torch.optim.Optimizer):
             if old is not None and old[0].numel() == self.m.numel():
                 self.m.copy_(old[0])
                 self.v.copy_(old[1])
-            self.hyper_host = torch.zeros(2, dtype=torch.double, pin_memory=eng.device.type == "cuda")
+            # per-step [lr, step] reach the kernel through a RING of pinned slots: an asynchronous copy reads pinned
+            # memory when the DMA executes, not when it is enqueued, so a single slot would be overwritten by the host
+            # running ahead of the GPU (steps k+1.. queued before step k's copy ran).  A slot is reused only after the
+            # copy that read it has completed (event per slot).
+            cuda = eng.device.type == "cuda"
+            self.hyper_ring = torch.zeros(self.RING, 2, dtype=torch.double, pin_memory=cuda)
+            self.hyper_events = [None] * self.RING
+            self.hyper_pos = 0
             self.hyper = torch.zeros(2, dtype=torch.double, device=eng.device)
             names = [n for n, _ in self.model.named_parameters()]
             for n, p in zip(names, eng.params):
@@ -45,14 +59,30 @@ class FusedOptimizer(torch.optim.Optimizer):
                     st["exp_avg_sq"] = self.v[o:o + p.numel()].view(p.shape)
         return eng
 
+    RING = 16
+
+    def push_hyper(self):
+        """Enqueues the copy of this step's [lr, step count] to the device vector the optimizer kernel reads."""
+        i = self.hyper_pos
+        self.hyper_pos = (i + 1) % self.RING
+        ev = self.hyper_events[i]
+        if ev is not None:
+            ev.synchronize()  # only ever waits if the host is RING steps ahead of the device
+        slot = self.hyper_ring[i]
+        slot[0] = float(self.param_groups[0]["lr"])
+        slot[1] = float(self._steps)
+        self.hyper.copy_(slot, non_blocking=True)
+        if self.hyper.is_cuda:
+            ev = ev or torch.cuda.Event()
+            ev.record()
+            self.hyper_events[i] = ev
+
     @torch.no_grad()
     def step(self, closure=None):
         eng = self._bind()
         grp = self.param_groups[0]
         self._steps += 1
-        self.hyper_host[0] = float(grp["lr"])
-        self.hyper_host[1] = float(self._steps)
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        self.push_hyper()
         clip = getattr(eng, "clip", None)
         b1 = grp["momentum"] if self.kind == "sgd" else grp["betas"][0]
         eng.ops.optim_step(eng.flat, eng.gflat, self.m, self.v, eng.n_flat, clip[0] if clip else None,
@@ -84,5 +114,5 @@ class FusedOptimizer(torch.optim.Optimizer):
                     self._steps = max(self._steps, 1)
         for g, sg in zip(self.param_groups, state_dict["param_groups"]):
             for k, v in sg.items():
-                if k != "params":
+                if k != "params" and k in g:  # hyper-parameters this optimizer knows; foreign keys are ignored
                     g[k] = v

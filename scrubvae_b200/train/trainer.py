@@ -7,6 +7,7 @@ EMA updates and the MI estimator rebuild."""
 from __future__ import annotations
 
 import time
+import weakref
 from pathlib import Path
 
 import torch
@@ -96,13 +97,15 @@ def _fused_train_epoch(config, model, loader, device, epoch, optimizer, schedule
     path below (predict_batch -> get_batch_loss -> backward -> clip_grad_norm_ -> optimizer.step)."""
     from ..engine import TrainStep
     eng = model.engine
-    steps = model.__dict__.setdefault("_train_steps", {})
+    # captured steps, staging slots and the copy stream live ON the engine: a new engine (model.to(...), .float() ...)
+    # starts with none of them, so no graph bound to the old engine's buffers can be replayed
+    steps = eng.__dict__.setdefault("_train_steps", {})
     main = torch.cuda.current_stream()
-    copy_stream = model.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=eng.device))
+    copy_stream = eng.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=eng.device))
     it = iter(loader)
     # two persistent device staging slots (no per-step allocation): slot s is refilled on the copy stream once the
     # step that read it has been enqueued-and-passed on the main stream
-    stage = model.__dict__.setdefault("_stage", [dict(), dict()])
+    stage = eng.__dict__.setdefault("_stage", [dict(), dict()])
     consumed = [None, None]
     count = [0]
 
@@ -111,6 +114,10 @@ def _fused_train_epoch(config, model, loader, device, epoch, optimizer, schedule
             host = next(it)
         except StopIteration:
             return None
+        if any(torch.is_tensor(v) and v.is_cuda for v in host.values()):
+            # device-resident loader (data.DevicePoseWindows): the batch was produced by kernels on the MAIN stream and
+            # is consumed there (plan.load_inputs) — staging it on the copy stream would race with its producer
+            return {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}, None, None
         slot = count[0] & 1
         count[0] += 1
         bufs = stage[slot]
@@ -133,6 +140,18 @@ def _fused_train_epoch(config, model, loader, device, epoch, optimizer, schedule
             ev.record(copy_stream)
         return dev, ev, slot
 
+    def step_for(B):
+        """The captured step for this batch size, optimizer and the hyper-parameters baked in at capture."""
+        grp = optimizer.param_groups[0]
+        key = (B, id(optimizer), optimizer.kind, tuple(grp["betas"]), grp["eps"], grp["weight_decay"], grp["momentum"],
+               optimizer.grad_scale)
+        hit = steps.get(key)
+        if hit is not None and hit[0]() is optimizer:
+            return hit[1]
+        st = TrainStep(model, optimizer, config["loss"], B, max_norm=1e6, use_graph=True, comm=eng.comm)
+        steps[key] = (weakref.ref(optimizer), st)
+        return st
+
     names = None
     acc = None
     n_batches = 0
@@ -140,13 +159,10 @@ def _fused_train_epoch(config, model, loader, device, epoch, optimizer, schedule
     while nxt is not None:
         data, ev, slot = nxt
         nxt = fetch()  # overlaps with this step's kernels
-        main.wait_event(ev)
+        if ev is not None:
+            main.wait_event(ev)
         B = data["x6d"].shape[0]
-        key = (B, id(optimizer))
-        st = steps.get(key)
-        if st is None:
-            st = TrainStep(model, optimizer, config["loss"], B, max_norm=1e6, use_graph=True, comm=eng.comm)
-            steps[key] = st
+        st = step_for(B)
         if names is None:
             names = st.plan.loss_names
             for k in config["loss"].keys():  # every configured loss must be produced, and vice versa (reference :125,:181)
@@ -157,8 +173,9 @@ def _fused_train_epoch(config, model, loader, device, epoch, optimizer, schedule
                     config["loss"][k]
         st.plan.set_loss_scale(config["loss"])  # the KL weight may have been annealed since the last epoch
         vec = st.run(data)  # copies the slot into the plan's static input buffers, then replays the step
-        consumed[slot] = torch.cuda.Event()
-        consumed[slot].record(main)
+        if slot is not None:
+            consumed[slot] = torch.cuda.Event()
+            consumed[slot].record(main)
         if step_callback is not None:
             step_callback(n_batches, vec)
         if scheduler is not None:
