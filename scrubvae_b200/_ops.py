@@ -74,7 +74,8 @@ BnactBwdT = _struct("BnactBwdT", [
 OptimT = _struct("OptimT", [
     ("p", _vp), ("g", _vp), ("m", _vp), ("v", _vp), ("n", _i64), ("sumsq", _vp), ("max_norm", _f64),
     ("gscale", _f64), ("lr", _f64), ("beta1", _f64), ("beta2", _f64), ("eps", _f64),
-    ("weight_decay", _f64), ("step", _i64), ("hyper", _vp), ("kind", _i64)])
+    ("weight_decay", _f64), ("step", _i64), ("hyper", _vp), ("kind", _i64),
+    ("inv_idx", _vp), ("gpacked", _vp), ("packed_w", _vp), ("inv_d", _vp), ("packed_d", _vp), ("flags", _i64)])
 
 _SIGS = {
     "scv_version": (C.c_int, []),
@@ -97,6 +98,8 @@ _SIGS = {
     "scv_gather": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "scv_sumsq": (C.c_int, [_vp, _i64, _vp, _vp]),
     "scv_optim_step": (C.c_int, [C.POINTER(OptimT), _vp]),
+    "scv_sumsq_packed": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "scv_zero": (C.c_int, [_vp, _i64, _vp]),
     "scv_d2f": (C.c_int, [_vp, _vp, _i64, _vp]),
     "scv_loss_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "scv_unpack_root": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _i64, _vp]),
@@ -238,10 +241,19 @@ class CudaOps:
         self._check(self.lib.scv_sumsq(_ptr(g), n, _ptr(out), self._stream()), "scv_sumsq")
 
     def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind,
-                   hyper=None):
+                   hyper=None, inv_idx=None, gpacked=None, packed_w=None, inv_d=None, packed_d=None, round_tf32=False):
         s = OptimT(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, _ptr(sumsq), max_norm, gscale, lr, beta1, beta2, eps,
-                   weight_decay, step, _ptr(hyper), kind)
+                   weight_decay, step, _ptr(hyper), kind, _ptr(inv_idx), _ptr(gpacked), _ptr(packed_w), _ptr(inv_d),
+                   _ptr(packed_d), int(bool(round_tf32)))
         self._check(self.lib.scv_optim_step(C.byref(s), self._stream()), "scv_optim_step")
+
+    def sumsq_packed(self, gpacked, pack_idx, n_packed, gdirect, n_direct, out):
+        self._check(self.lib.scv_sumsq_packed(_ptr(gpacked), _ptr(pack_idx), n_packed, _ptr(gdirect), n_direct,
+                                              _ptr(out), self._stream()), "scv_sumsq_packed")
+
+    def zero(self, t):
+        """cudaMemsetAsync over a whole tensor (a memset node when captured)."""
+        self._check(self.lib.scv_zero(t.data_ptr(), t.numel() * t.element_size(), self._stream()), "scv_zero")
 
     def loss_finalize(self, acc, scale, out, n):
         self._check(self.lib.scv_loss_finalize(_ptr(acc), _ptr(scale), _ptr(out), n, self._stream()),

@@ -296,9 +296,10 @@ class Engine:
                         wi = I(f"{pre}mlp{mi + 1}.{li}.weight")
                         assert wi.shape[1] % 4 == 0, "scrubvae_b200: z_dim must be a multiple of 8"
                         npad = pad4(wi.shape[0])
+                        # (first layers have no data-gradient matrix of their own: the gradient into mu uses gr_cat below)
                         g = add(f"gr.{key}.{mi}.{li}", lay.pad_rows(wi, npad),
                                 lay.pad_cols(I(f"{pre}mlp{mi + 1}.{li}.bias").reshape(1, -1), npad).reshape(-1),
-                                d_idx=lay.transpose_pad(lay.pad_rows(wi, npad), npad))
+                                d_idx=lay.transpose_pad(lay.pad_rows(wi, npad), npad) if li > 0 else None)
                         layers.append(g)
                     mlps.append(layers)
                 self.gr_layers[key] = mlps
@@ -325,6 +326,12 @@ class Engine:
         self.packed = torch.zeros(self._n_fwd + self._n_d, device=dev)
         self.gpacked = torch.zeros(self._n_fwd, device=dev)
         self.inv_idx = lay.inverse_map(fwd_idx, self.n_flat).to(torch.int32).to(dev)
+        # flat weight -> its position in the data-gradient matrices (each weight appears there at most once): the fused
+        # optimizer writes both packed copies itself (TrainStep), no repack pass
+        self.inv_d = lay.inverse_map(d_idx, self.n_flat).to(torch.int32).to(dev) if d_idx.numel() else None
+        self.packed_dirty = True   # packed matrices do not reflect `flat` (set by anything that edits parameters)
+        self.grads_dirty = False   # gpacked / gflat hold gradients of a piecewise backward (TrainStep zeroes them)
+        self._pversions = None
         del self._pack_parts, self._pack_parts_d
         self.max_k = max(max(g.K, g.dK if g.wd is not None else 0) for g in self.W.values())
         for gc in getattr(self, "gr_cat", {}).values():
@@ -354,6 +361,16 @@ class Engine:
         n1 = self._n_fwd if part == "fwd" else self.packed.numel()
         if n1 > n0:
             self.ops.gather(self.flat, Ref(self.pack_idx, n0), Ref(self.packed, n0), n1 - n0, False, round_tf32=self.rnd)
+
+    def sync_packed(self):
+        """TrainStep keeps the packed matrices current itself (the optimizer writes them); they are rebuilt from the
+        flat parameters only when something else edited the parameters: load_state_dict / reset_parameters (seen
+        through the parameters' version counters), a piecewise optimizer step or a broadcast (packed_dirty)."""
+        pv = sum(p._version for p in self.params)
+        if self.packed_dirty or pv != self._pversions:
+            self.repack()
+            self.packed_dirty = False
+            self._pversions = pv
 
     # ------------------------------------------------------------------ API
     def plan(self, B: int) -> "Plan":
@@ -424,7 +441,14 @@ class Plan:
         # ---- loss bookkeeping: acc (double) / out (float): [jpe, root, prior, gr keys...]
         self.loss_names = ["jpe", "root", "prior"] + [kk + "_gr" for kk in eng.gr_keys]
         nl = len(self.loss_names)
-        self.loss_acc = torch.zeros(nl, dtype=torch.double, device=dev)
+        nbn = sum(mod.num_features for mod in m.modules() if isinstance(mod, nn.BatchNorm1d))
+        n_stats, n_sums = 4 * nbn + 8, 2 * nbn + 2 * ch[0] + 64
+        # every per-step accumulator in ONE buffer: [BN statistics | BN backward sums | loss terms | grad norm^2];
+        # the fused step clears it with one memset, the piecewise API path clears the parts as it reaches them
+        self.zbuf = torch.zeros(n_stats + n_sums + nl + 1, dtype=torch.double, device=dev)
+        self.loss_acc = self.zbuf[n_stats + n_sums:n_stats + n_sums + nl]
+        self.sumsq = self.zbuf[n_stats + n_sums + nl:]
+        self._fused_tail = False  # True while TrainStep drives the plan (see TrainStep._sequence)
         self.loss_out = torch.zeros(nl + 1, **f32)
         self.anchor = torch.zeros((), device=dev, requires_grad=True)  # autograd attachment point
         self.loss_scale = torch.zeros(nl, **f32)    # total = sum scale*loss
@@ -432,9 +456,8 @@ class Plan:
         self._scale_host = None
 
         # ---- BN statistics / backward sums (double), zeroed once per step
-        nbn = sum(mod.num_features for mod in m.modules() if isinstance(mod, nn.BatchNorm1d))
-        self.stats = torch.zeros(4 * nbn + 8, dtype=torch.double, device=dev)
-        self.sums = torch.zeros(2 * nbn + 2 * ch[0] + 64, dtype=torch.double, device=dev)
+        self.stats = self.zbuf[:n_stats]
+        self.sums = self.zbuf[n_stats:n_stats + n_sums]
         self._stats_n = 0
         self._sums_n = 0
 
@@ -691,7 +714,7 @@ class Plan:
         # =============================================================== loss launches
         self.dxh = torch.zeros(B * W, C0, **f32)
         Lk: List = []
-        Lk.append(lambda: self.loss_acc.zero_())
+        Lk.append(lambda: None if self._fused_tail else self.loss_acc.zero_())
         self._loss_has = {"jpe": False, "root": False, "prior": False}
 
         def recon():
@@ -714,9 +737,12 @@ class Plan:
         Bw: List = []
 
         def zero_grads():
+            if self._fused_tail:
+                return  # TrainStep: accumulators cleared by its one memset, gradients zeroed by the optimizer as it reads them
             self.sums.zero_()
             eng.gpacked.zero_()
             eng.gflat.zero_()
+            eng.grads_dirty = True  # this path leaves the gradients in place; TrainStep expects zeroed buffers
         Bw.append(zero_grads)
         # conv_out + tanh
         dOut = A(W, C0, 3, 3)
@@ -837,7 +863,8 @@ class Plan:
         Bw += bnact_bwd(None, "encoder.activation.weight", enc_in["Y0"], W, ch[0], None, 1, dH, None, dY0, sums(ch[0]))
         g = enc_in["g"]
         Bw.append(wgrad(g, X0.at(-3), X0.bs, C0, W, dY0.at(0), dY0.bs, dY0.ls))
-        Bw.append(lambda: ops.gather(eng.gpacked, eng.inv_idx, eng.gflat, eng.n_flat, True))
+        # public-API path only: weight gradients back into the reference layout (p.grad views of gflat)
+        Bw.append(lambda: None if self._fused_tail else ops.gather(eng.gpacked, eng.inv_idx, eng.gflat, eng.n_flat, True))
         self.Bw = Bw
 
     # ------------------------------------------------------------------ running
@@ -1036,16 +1063,18 @@ class TrainStep:
     `comm` (optional): callable(engine, phase) hook used by data parallelism (parallel.py) to launch the
     bucketed gradient all-reduce from inside the backward launch list (Plan.backward)."""
 
-    def __init__(self, model, optimizer, loss_scale, B, max_norm=1e6, use_graph=True, comm=None):
+    def __init__(self, model, optimizer, loss_scale, B, max_norm=1e6, use_graph=True, comm=None, keep_grads=False):
         self.model, self.opt = model, optimizer
+        # keep_grads (tests / debugging): the step's (all-reduced, unscaled) gradients are copied out in the reference
+        # parameter layout before the optimizer consumes them — see named_grads()
+        self.keep_grads = keep_grads
+        self.grad_snapshot = None
         self.eng = model.engine
         self.plan = self.eng.plan(B)
         self.max_norm = float(max_norm)
         self.comm = comm
         self.plan.set_loss_scale(loss_scale)
         self.opt._bind()
-        if not hasattr(self.eng, "sumsq"):
-            self.eng.sumsq = torch.zeros(1, dtype=torch.double, device=self.eng.device)
         self.graph = None
         self.use_graph = use_graph and self.eng.device.type == "cuda"
         self.n_launch = None
@@ -1053,40 +1082,38 @@ class TrainStep:
     def _sequence(self):
         plan, eng, opt = self.plan, self.eng, self.opt
         m = self.model
+        ops = eng.ops
         plan._training = True
-        if m._noise is not None:
-            plan.eps.copy_(m._noise)
-        else:
-            plan.eps.normal_()
-        plan.stats.zero_()
-        eng.nbt.add_(1)
-        if plan.dside is not None:
-            # forward matrices first; the data-gradient matrices (read only by backward) are repacked on a side stream
-            # while the forward pass runs, and the gradient buffers are zeroed there too
-            main = torch.cuda.current_stream()
-            eng.repack("fwd")
-            plan.dside.wait_stream(main)
-            with torch.cuda.stream(plan.dside):
-                eng.repack("dgrad")
+        plan._fused_tail = True
+        try:
+            ops.zero(plan.zbuf)  # BN statistics, BN backward sums, loss terms, grad norm: one memset
+            if m._noise is not None:
+                plan.eps.copy_(m._noise)
+            else:
+                plan.eps.normal_()
+            eng.nbt.add_(1)
+            # the packed GEMM matrices are current: the previous step's optimizer wrote them (run() rebuilds them when
+            # something else edited the parameters)
             plan.run_forward()
             for f in plan.Lk:
                 f()
-            main.wait_stream(plan.dside)
-        else:
-            eng.repack()
-            plan.run_forward()
-            for f in plan.Lk:
-                f()
-        plan.gscale.copy_(plan.loss_scale)
-        plan.backward(self.comm)
-        eng.sumsq.zero_()
-        eng.ops.sumsq(eng.gflat, eng.n_flat, eng.sumsq)
-        grp = opt.param_groups[0]
-        from .train.optim import KIND
-        b1 = grp["momentum"] if opt.kind == "sgd" else grp["betas"][0]
-        eng.ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, eng.n_flat, eng.sumsq, self.max_norm, opt.grad_scale,
+            plan.gscale.copy_(plan.loss_scale)
+            plan.backward(self.comm)
+            if self.keep_grads:
+                if self.grad_snapshot is None:
+                    self.grad_snapshot = torch.zeros_like(eng.gflat)
+                self.grad_snapshot.copy_(eng.gflat)  # BatchNorm / PReLU gradients
+                ops.gather(eng.gpacked, eng.inv_idx, self.grad_snapshot, eng.n_flat, True)
+            ops.sumsq_packed(eng.gpacked, eng.pack_idx, eng._n_fwd, eng.gflat, eng.n_direct, plan.sumsq)
+            grp = opt.param_groups[0]
+            from .train.optim import KIND
+            b1 = grp["momentum"] if opt.kind == "sgd" else grp["betas"][0]
+            ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, eng.n_flat, plan.sumsq, self.max_norm, opt.grad_scale,
                            float(grp["lr"]), b1, grp["betas"][1], grp["eps"], grp["weight_decay"], 1, KIND[opt.kind],
-                           hyper=opt.hyper)
+                           hyper=opt.hyper, inv_idx=eng.inv_idx, gpacked=eng.gpacked, packed_w=eng.packed,
+                           inv_d=eng.inv_d, packed_d=Ref(eng.packed, eng._n_fwd), round_tf32=eng.rnd)
+        finally:
+            plan._fused_tail = False
 
     def run(self, data=None):
         """Returns the static loss vector [jpe, root, prior, <gr>..., total] (device, overwritten each step)."""
@@ -1096,6 +1123,11 @@ class TrainStep:
             plan.load_targets(data)
         opt._steps += 1
         opt.push_hyper()  # ring of pinned slots: safe when the host runs several steps ahead of the device
+        self.eng.sync_packed()
+        if self.eng.grads_dirty:
+            self.eng.gpacked.zero_()
+            self.eng.gflat.zero_()
+            self.eng.grads_dirty = False
         if not self.use_graph:
             n0 = self.eng.ops.launch_count()
             self._sequence()
@@ -1118,6 +1150,14 @@ class TrainStep:
         else:
             self.graph.replay()
         return plan.loss_out
+
+    def named_grads(self):
+        """{parameter name: gradient of the last step} (needs keep_grads=True); under data parallelism the SUM over ranks."""
+        if self.grad_snapshot is None:
+            raise RuntimeError("TrainStep(keep_grads=True) is required to read the step's gradients")
+        eng = self.eng
+        return {n: self.grad_snapshot[eng.poff[n]:eng.poff[n] + p.numel()].view(p.shape)
+                for (n, p) in self.model.named_parameters()}
 
     def losses(self):
         """dict view of the last step's losses (0-d device tensors)."""

@@ -25,7 +25,13 @@ def _v(ref, shape, strides):
     if ref is None:
         return None
     t, off = (ref, 0) if isinstance(ref, torch.Tensor) else (ref.t, ref.off)
-    return torch.as_strided(t, shape, strides, off)
+    return torch.as_strided(t, shape, strides, t.storage_offset() + off)  # offsets count from the tensor (it may be a view)
+
+
+def _tail(ref):
+    """1-D view of a buffer from the referenced element to the end of its storage"""
+    t, off = (ref, 0) if isinstance(ref, torch.Tensor) else (ref.t, ref.off)
+    return t.reshape(-1)[off:]
 
 
 class EmuOps:
@@ -384,13 +390,41 @@ class EmuOps:
         self.n += 1
         _v(out, (1,), (1,)).add_((_v(g, (n,), (1,)).double() ** 2).sum())
 
+    def sumsq_packed(self, gpacked, pack_idx, n_packed, gdirect, n_direct, out):
+        self.n += 1
+        G, I = _v(gpacked, (n_packed,), (1,)), _v(pack_idx, (n_packed,), (1,))
+        G[I < 0] = 0.0
+        tot = (G.double() ** 2).sum()
+        if gdirect is not None and n_direct:
+            tot = tot + (_v(gdirect, (n_direct,), (1,)).double() ** 2).sum()
+        _v(out, (1,), (1,)).add_(tot)
+
+    def zero(self, t):
+        t.zero_()
+
     def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind,
-                   hyper=None):
+                   hyper=None, inv_idx=None, gpacked=None, packed_w=None, inv_d=None, packed_d=None, round_tf32=False):
         self.n += 1
         if hyper is not None:
             hy = _v(hyper, (2,), (1,))
             lr, step = float(hy[0]), int(round(float(hy[1])))
         P, G = _v(p, (n,), (1,)), _v(g, (n,), (1,))
+        if inv_idx is not None:  # packed-weights mode: gather the gradient, zero what was read, scatter the update
+            inv = _v(inv_idx, (n,), (1,)).long()
+            live = inv >= 0
+            GP, PW = _tail(gpacked), _tail(packed_w)
+            Gfull = G.clone()
+            Gfull[live] = GP[inv[live]]
+            GP[inv[live]] = 0.0
+            G[~live] = 0.0
+            self.optim_step(p, Gfull, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind)
+            self.n -= 1
+            PW[inv[live]] = rtf32(P[live]) if round_tf32 else P[live]
+            if inv_d is not None:
+                invd = _v(inv_d, (n,), (1,)).long()
+                ld = invd >= 0
+                _tail(packed_d)[invd[ld]] = rtf32(P[ld]) if round_tf32 else P[ld]
+            return
         coef = gscale
         if sumsq is not None:
             norm = math.sqrt(float(_v(sumsq, (1,), (1,)))) * gscale

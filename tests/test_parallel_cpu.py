@@ -46,7 +46,7 @@ def _worker(rank, world, port, q):
     data = orc.synth_batch(BL, seed=100 + rank)
     eps = orc.synth_eps(BL, Z, seed=200 + rank)
     m._noise = eps
-    step = TrainStep(m, opt, SCALE, BL, use_graph=False, comm=comm)
+    step = TrainStep(m, opt, SCALE, BL, use_graph=False, comm=comm, keep_grads=True)
     step.run(data)
     losses = {k: v.item() for k, v in step.losses().items()}
     # oracle: every shard on this rank (so that each rank can check alone), gradients averaged, one AdamW step
@@ -60,7 +60,7 @@ def _worker(rank, world, port, q):
     gavg = {k: v / world for k, v in gsum.items()}
     errs = {}
     gn = sum(float((v.double() ** 2).sum()) for v in gavg.values()) ** 0.5
-    for (n, p), gv in zip(m.named_parameters(), m.engine.gviews):
+    for n, gv in step.named_grads().items():
         e = ((gv / world).double() - gavg[n].double()).norm().item()
         errs[n] = (_rel(gv / world, gavg[n]), e / gn)
     new = {n: p.detach().clone() for n, p in m.named_parameters()}

@@ -165,11 +165,11 @@ def test_default_arch_step_vs_oracle(precision, B):
     m = m.to("cuda").train()
     m._noise = eps.cuda()
     opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-4, "lr_schedule": None})
-    step = TrainStep(m, opt, scale, B, use_graph=True)
+    step = TrainStep(m, opt, scale, B, use_graph=True, keep_grads=True)
     ltol, gtol = (5e-5, 1e-3) if precision == "fp32" else (1e-3, 5e-3)
     step.run(_to_cuda(data))
     got1 = {k: v.item() for k, v in step.losses().items()}
-    grads = [(n, gv) for (n, p), gv in zip(m.named_parameters(), m.engine.gviews)]
+    grads = [(n, gv.clone()) for n, gv in step.named_grads().items()]
     if precision == "fp32":
         _check_grads(grads, g1, gtol, "vs fp32 oracle")
     else:  # see the module docstring: gradients are held to ideal TF32 arithmetic
