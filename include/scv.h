@@ -28,6 +28,9 @@ extern "C" {
 #define SCV_ACT_TANH 2
 #define SCV_ACT_RELUMASK 3 /* y = (R > 0) ? y : 0 ; R is a mask, not added */
 #define SCV_ACT_ROUND_TF32 16 /* OR-ed into act: round the stored Y to TF32 (it feeds a tensor-core GEMM) */
+#define SCV_ACT_ACCUM 32 /* OR-ed into act: Y += result instead of Y = result (activation NONE, no R, no stats).  The
+                          * tensor-core path then cuts a long reduction over several CTAs (split-K) and adds the partial
+                          * tiles with red.global.add: the caller zeroes Y first. */
 
 /* `flags` arguments of the kernels that PRODUCE tensor-core GEMM operands: round what is stored to TF32
  * (round-to-nearest, ties away: cvt.rna.tf32.f32).  tcgen05 kind::tf32 truncates fp32 operands; rounding at

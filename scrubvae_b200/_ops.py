@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libscv.so")
 
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELUMASK = 0, 1, 2, 3
 ACT_ROUND_TF32 = 16  # OR-ed into act: the stored output is rounded to TF32 (it feeds a tensor-core GEMM)
+ACT_ACCUM = 32  # OR-ed into act: Y += result (split-K on the tensor-core path; the caller zeroes Y)
 PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
 MAX_GROUP = 6  # problems per scv_gemm_group / scv_wgrad_group launch
 BN, PRELU, TRAIN, ROUND_TF32 = 1, 2, 4, 8  # bnact mode bits

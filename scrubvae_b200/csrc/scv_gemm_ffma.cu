@@ -102,6 +102,7 @@ __device__ __forceinline__ void gemm_ffma_body(const scv_gemm_t& p, const int ve
   const float osc = (float)p.out_scale;
   const int act = (int)(p.act & 15);
   const bool rnd = p.act & SCV_ACT_ROUND_TF32;
+  const bool accum = p.act & SCV_ACT_ACCUM;  // Y += result (one thread owns each output element here: plain read-add-write)
   float csum[8], csq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) csum[j] = csq[j] = 0.f;
@@ -141,7 +142,11 @@ __device__ __forceinline__ void gemm_ffma_body(const scv_gemm_t& p, const int ve
         v[q] = apply_act(t, act, r[q]);
         if (rnd) v[q] = scv::round_tf32(v[q]);
       }
-      if (vec) {
+      if (accum) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (nb + q < ncap) yrow[nb + q] += v[q];
+      } else if (vec) {
         *reinterpret_cast<float4*>(yrow + nb) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
 #pragma unroll

@@ -104,6 +104,9 @@ struct GemmTcParams {
   int sub;           // row tiles per work item (1 or 2): with 2 the CTA runs two 128-row tiles against ONE W tile per
                      // stage (two accumulators, no TMEM double buffering) - a third less shared-memory traffic per FLOP
   int epi_kind;      // which compiled epilogue variant serves (act, R, stats, round_out); see gemm_tc_body
+  int ksplit;        // split-K: the reduction is cut into `ksplit` chunk ranges, one work item each, and the epilogue ADDS
+                     // (red.global.add) into a pre-zeroed Y - for GEMMs with few output tiles and a long K (SCV_ACT_ACCUM)
+  int kc_per;        // k chunks per split
   long long* trace;  // debug (SCV_TC_TRACE=<n events>): CTA 0 appends (role, event, tile, clock) records
 };
 
@@ -140,7 +143,7 @@ __device__ __forceinline__ float act_apply(float v, int act, float r) {
 
 // Epilogue arithmetic of one 32x32 chunk for lane (rq, cq): rows 4 i + rq (i < 8), columns n .. n + 3.
 // ACT >= 0 / RD / ST / RND are compile-time; ACT = -1 is the generic path (activation, rounding from p at run time).
-template <int ACT, bool RD, bool ST, bool RND>
+template <int ACT, bool RD, bool ST, bool RND, bool ACC = false>
 __device__ __forceinline__ void epi_rows(const GemmTcParams& p, const float4* xp4, const int rq, const int cq, const bool col_ok,
                                          const int n, const float4 bv, const long long (&yoff)[8], const long long (&roff)[8],
                                          const int (&ncap)[8], float4& s1, float4& s2) {
@@ -175,7 +178,8 @@ __device__ __forceinline__ void epi_rows(const GemmTcParams& p, const float4* xp
         yv = make_float4(act_apply(tv.x, act, r4.x), act_apply(tv.y, act, r4.y), act_apply(tv.z, act, r4.z),
                          act_apply(tv.w, act, r4.w));
       if (rnd) yv = scv::round_tf32(yv);
-      *reinterpret_cast<float4*>(p.Y + yoff[i] + n) = yv;
+      if (ACC) red_add_v4(p.Y + yoff[i] + n, yv);
+      else *reinterpret_cast<float4*>(p.Y + yoff[i] + n) = yv;
     }
   }
 }
@@ -184,13 +188,19 @@ __device__ __forceinline__ void epi_rows(const GemmTcParams& p, const float4* xp
 // (cta_group::2): each loads its own 128 A rows and HALF of the W tile, the leader's single thread issues M = 256
 // MMAs that read W from both shared memories — per SM the shared-memory fill and operand-read traffic per FLOP
 // drops by a third, which is what paces the large TF32 layers.
-template <int kCtas>
+// kMc (kCtas = 1 only): the two CTAs of a cluster work on different row tiles of the SAME n tile in lock step; each loads
+// half of the W tile and MULTICASTS it into both shared memories, so W crosses the L2 -> SM fabric once per pair.  The
+// layers of this network are paced by that fabric (12.3 TB/s chip-wide, ~42 B/cycle per SM, against the 64-96 B/cycle a
+// 128x256 TF32 tile consumes), not by the tensor pipe.
+template <int kCtas, bool kMc = false>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmTcParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const uint32_t crank = kMc ? cluster_ctarank() : 0u;
+  constexpr int kGroup = kMc ? 2 : kCtas;  // CTAs walking one work-item list together
   const int bnw = p.bn / kCtas;                       // W rows held by this CTA
   const int sub = kCtas == 1 ? p.sub : 1;
   const uint32_t a_tile = kBM * kBK * 4;              // 16 KB per 128-row tile
@@ -202,9 +212,11 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
   float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtl) + 15) & ~size_t(15)));  // 4 warps x 32 x 32 floats
   const uint32_t tile_tx = ((uint32_t)(p.bl * p.nb) * kBK * 4 * (uint32_t)sub + w_bytes) * kCtas;
   // work items: (n tile, group of kCtas * sub consecutive m tiles); the CTAs of a pair walk the same list
-  const int m_groups = (p.m_tiles + kCtas * sub - 1) / (kCtas * sub);
-  const int total = p.n_tiles * m_groups;
-  const int first = (int)blockIdx.x / kCtas, step = (int)gridDim.x / kCtas;
+  const int mper = kGroup * sub;
+  const int m_groups = (p.m_tiles + mper - 1) / mper;
+  const int tiles = p.n_tiles * m_groups;
+  const int total = tiles * p.ksplit;  // item t: k split t / tiles, then (n tile, m group)
+  const int first = (int)blockIdx.x / kGroup, step = (int)gridDim.x / kGroup;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -213,7 +225,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&ctl->full[s]), kCtas);   // pair: the leader's expect_tx arrive + the peer's arrive
-      mbar_init(smem_u32(&ctl->empty[s]), 1);
+      mbar_init(smem_u32(&ctl->empty[s]), kMc ? 2 : 1);  // multicast pair: both CTAs' MMAs must be done with the stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&ctl->tfull[i]), 1);
@@ -226,7 +238,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     else tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
   }
   tc_fence_before();
-  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
+  if (kCtas == 2 || kMc) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
@@ -235,14 +247,16 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
       int s = 0;
       uint32_t ph = 0;
       for (int t = first; t < total; t += step) {
-        const int nt = t / m_groups, mt = (t - nt * m_groups) * kCtas * sub + (int)rank;
+        const int ks = t / tiles, tt = t - ks * tiles;
+        const int nt = tt / m_groups, mt = (tt - nt * m_groups) * mper + (kMc ? (int)crank * sub : (int)rank);
         const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;  // mt >= m_tiles (odd tail): box fully out of bounds -> zeros
         const int l0 = lt_i * p.bl, b0 = bt_i * p.nb, n0 = nt * p.bn + (int)rank * bnw;
         const int bt_2 = (mt + 1) / p.lt, lt_2 = (mt + 1) - bt_2 * p.lt;  // second row tile (sub == 2)
+        const int kc0 = ks * p.kc_per, kc1 = min(p.k_chunks, kc0 + p.kc_per);
         tc_trace(p, 0, 0, t);
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        for (int kc = kc0; kc < kc1; ++kc) {
           mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1);
-          if (kc == 0 || kc == p.k_chunks - 1) tc_trace(p, 0, 1 + (kc != 0), t);
+          if (kc == kc0 || kc == kc1 - 1) tc_trace(p, 0, 1 + (kc != kc0), t);
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           if (kCtas == 2) {
             const uint32_t fb = mapa_rank(smem_u32(&ctl->full[s]), 0);  // the leader's barrier counts both CTAs' bytes
@@ -255,7 +269,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             mbar_expect_tx(fb, tile_tx);
             tma_load_3d(sa, &tmA, fb, kc * kBK, l0, b0);
             if (sub == 2) tma_load_3d(sa + a_tile, &tmA, fb, kc * kBK, lt_2 * p.bl, bt_2 * p.nb);
-            tma_load_2d(sa + a_bytes, &tmW, fb, kc * kBK, n0);
+            if (kMc)  // my half of the W tile, into both CTAs' stage
+              tma_load_2d_mc(sa + a_bytes + crank * (w_bytes >> 1), &tmW, fb, kc * kBK, n0 + (int)crank * (p.bn >> 1), (uint16_t)3);
+            else
+              tma_load_2d(sa + a_bytes, &tmW, fb, kc * kBK, n0);
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -278,13 +295,15 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         tc_fence_after();
         tc_trace(p, 1, 1, t);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int ks = t / tiles;
+        const int kc0 = ks * p.kc_per, kc1 = min(p.k_chunks, kc0 + p.kc_per);
+        for (int kc = kc0; kc < kc1; ++kc) {
           mbar_wait(smem_u32(&ctl->full[s]), ph);
           tc_fence_after();
-          if (kc == 0 || kc == p.k_chunks - 1) tc_trace(p, 1, 2 + (kc != 0), t);
+          if (kc == kc0 || kc == kc1 - 1) tc_trace(p, 1, 2 + (kc != kc0), t);
           // descriptor low words of this stage; each k step of 8 floats advances the start address by 32 B = 2 units
           const uint32_t a_lo = desc_lo0 + (uint32_t)s * stage_units, b_lo = a_lo + (a_bytes >> 4);
-          const uint32_t acc0 = kc != 0 ? 1u : 0u;
+          const uint32_t acc0 = kc != kc0 ? 1u : 0u;
           if (kCtas == 2) {
             umma2_tf32_lh(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, acc0);
             umma2_tf32_lh(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
@@ -303,7 +322,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
               umma_tf32_lh(d2, a2 + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
             }
           }
-          if (kCtas == 2) umma2_commit(smem_u32(&ctl->empty[s])); else umma_commit(smem_u32(&ctl->empty[s]));
+          if (kCtas == 2) umma2_commit(smem_u32(&ctl->empty[s]));
+          else if (kMc) umma_commit_mc(smem_u32(&ctl->empty[s]), (uint16_t)3);
+          else umma_commit(smem_u32(&ctl->empty[s]));
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (kCtas == 2) umma2_commit(smem_u32(&ctl->tfull[acc])); else umma_commit(smem_u32(&ctl->tfull[acc]));
@@ -329,7 +350,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
                                      kCtas == 2 ? mapa_rank(smem_u32(&ctl->tempty[1]), 0) : smem_u32(&ctl->tempty[1])};
     int it = 0, cur_nt = -1;
     for (int t = first; t < total; t += step, ++it) {
-      const int nt = t / m_groups, mt0 = (t - nt * m_groups) * kCtas * sub + (int)rank;
+      const int ks = t / tiles, tt = t - ks * tiles;
+      const int nt = tt / m_groups, mt0 = (tt - nt * m_groups) * mper + (kMc ? (int)crank * sub : (int)rank);
       const int n0 = nt * p.bn;
       const int ncols = min(p.bn, N - n0);
       if (has_stats && nt != cur_nt) {
@@ -387,7 +409,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         const int n = n0 + cc;
         const bool col_ok = cc < ncols;
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok && n < p.bias_n) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (n % p.bias_mod)));
+        if (p.bias && col_ok && n < p.bias_n && ks == 0) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (n % p.bias_mod)));
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
         const bool rd = p.R != nullptr;
         // one instantiation per (activation, residual, sums, rounding) combination the step uses: the per-element
@@ -400,6 +422,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
           case 3: epi_rows<SCV_ACT_NONE, true, true, false>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
           case 4: epi_rows<SCV_ACT_NONE, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
           case 5: epi_rows<SCV_ACT_TANH, false, false, false>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
+          case 6: epi_rows<SCV_ACT_NONE, false, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
           default:
             if (rd) epi_rows<-1, true, true, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2);
             else epi_rows<-1, false, true, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2);
@@ -434,7 +457,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     }
   }
   tc_fence_before();
-  if (kCtas == 2) cluster_sync_all(); else __syncthreads();  // pair: no CTA may exit while its peer still signals it
+  if (kCtas == 2 || kMc) cluster_sync_all(); else __syncthreads();  // pair: no CTA may exit while its peer still signals it
   if (warp == 2) {
     tc_fence_after();
     if (kCtas == 2) tmem_dealloc2(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
@@ -444,6 +467,11 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcParams p) {
   gemm_tc_body<1>(tmA, tmW, p);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcParams p) {
+  gemm_tc_body<1, true>(tmA, tmW, p);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -475,8 +503,11 @@ struct SmemCtlW {
   uint32_t pad;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmA, const WgradTcParams p) {
+// kMc: the two CTAs of a cluster take ADJACENT n tiles of the same (k tile, row split): they need the same A slabs, so each
+// loads half of them and multicasts into both shared memories (dY slabs are private).  L2 -> SM traffic per FLOP drops by a
+// third (30 KB instead of 44 KB per 32-row stage), which is what bounds this kernel.
+template <bool kMc>
+__device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUtensorMap& tmA, const WgradTcParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -491,7 +522,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   uint8_t* ctl_raw = smem + (size_t)p.stages * stage_bytes;
   SmemCtlW* ctl = reinterpret_cast<SmemCtlW*>(ctl_raw);
   float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtlW) + 15) & ~size_t(15)));
-  const int total = p.n_tiles * p.k_tiles * p.splits;
+  const uint32_t crank = kMc ? cluster_ctarank() : 0u;
+  const int n_items = kMc ? (p.n_tiles + 1) / 2 : p.n_tiles;  // n tiles (pairs of n tiles) per (k tile, split)
+  const int total = n_items * p.k_tiles * p.splits;
+  const int first = kMc ? (int)blockIdx.x / 2 : (int)blockIdx.x, step = kMc ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int h0 = (a_slabs + 1) / 2;  // kMc: A slabs loaded (and multicast) per CTA; an odd middle slab is delivered twice
+  const uint32_t stage_tx = kMc ? y_bytes + 2u * (uint32_t)h0 * slab : stage_bytes;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmY);
@@ -500,7 +536,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&ctl->full[s]), 1);
-      mbar_init(smem_u32(&ctl->empty[s]), 1);
+      mbar_init(smem_u32(&ctl->empty[s]), kMc ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&ctl->tfull[i]), 1);
@@ -514,16 +550,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
   }
   tc_fence_before();
-  __syncthreads();
+  if (kMc) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
   // item -> (split, k tile, n tile): consecutive CTAs share the row range (A / dY slabs hit in L2)
   auto decode = [&](int t, int& nt, int& kt, int& g0, int& g1) {
-    const int tiles = p.n_tiles * p.k_tiles;
+    const int tiles = n_items * p.k_tiles;
     const int sp = t / tiles, r = t - sp * tiles;
-    kt = r / p.n_tiles;
-    nt = r - kt * p.n_tiles;
+    kt = r / n_items;
+    nt = r - kt * n_items;
+    if (kMc) nt = 2 * nt + (int)crank;  // may be == n_tiles (odd count): dY slabs out of bounds -> zeros, nothing stored
     g0 = sp * p.gps;
     g1 = min(p.groups, g0 + p.gps);
   };
@@ -532,7 +569,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      for (int t = first; t < total; t += step) {
         int nt, kt, g0, g1;
         decode(t, nt, kt, g0, g1);
         for (int g = g0; g < g1; ++g) {
@@ -540,10 +577,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           const int l0 = lt_i * p.bl, b0 = bt_i * p.nb;
           mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1);
           const uint32_t fb = smem_u32(&ctl->full[s]);
-          mbar_expect_tx(fb, stage_bytes);
+          mbar_expect_tx(fb, stage_tx);
           const uint32_t sy = smem_u32(smem + (size_t)s * stage_bytes);
           // one TMA per operand: 4-D boxes (32 floats, bl, nb, slabs) land slab-major, exactly the MN-major layout
           tma_load_4d(sy, &tmY, fb, 0, l0, b0, nt * sub * (kBM / 32));
+          if (kMc) {
+            const int sl0 = crank ? a_slabs - h0 : 0;  // my half of the A slabs, into both CTAs' stage
+            tma_load_4d_mc(sy + y_bytes + (uint32_t)sl0 * slab, &tmA, fb, 0, l0, b0, kt * (p.bnk / 32) + sl0, (uint16_t)3);
+          } else
           tma_load_4d(sy + y_bytes, &tmA, fb, 0, l0, b0, kt * (p.bnk / 32));
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -562,7 +603,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       const uint32_t stage_units = stage_bytes >> 4;
       int s = 0, it = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      for (int t = first; t < total; t += step, ++it) {
         int nt, kt, g0, g1;
         decode(t, nt, kt, g0, g1);
         const bool do_bias = p.dbias != nullptr && kt == 0;
@@ -587,7 +628,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
             }
             accf = 1u;
           }
-          umma_commit(smem_u32(&ctl->empty[s]));
+          if (kMc) umma_commit_mc(smem_u32(&ctl->empty[s]), (uint16_t)3); else umma_commit(smem_u32(&ctl->empty[s]));
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         umma_commit(smem_u32(&ctl->tfull[acc]));
@@ -599,7 +640,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     const int rq = lane >> 3, cq = lane & 7;
     float4* xp4 = reinterpret_cast<float4*>(xpose + ew * kXposeFloats);
     int it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    for (int t = first; t < total; t += step, ++it) {
       int nt, kt, g0, g1;
       decode(t, nt, kt, g0, g1);
       const int acc = sub == 2 ? 0 : (it & 1);
@@ -646,15 +687,38 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kMc) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmA, const WgradTcParams p) {
+  wgrad_tc_body<false>(tmY, tmA, p);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+wgrad_tc_mc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmA, const WgradTcParams p) {
+  wgrad_tc_body<true>(tmY, tmA, p);
+}
+
 int g_attr_done = 0;
 int g_pair_capacity = -1;
+int g_mc_capacity = -1;
+
+// why the tensor-core path declined a shape (falls back to the fp32 FFMA kernels): logged once per distinct reason
+int decline(const char* who, const char* why, int64_t M, int64_t N, int64_t K) {
+  static int logged = 0;
+  static const bool quiet = [] { const char* e = getenv("SCV_QUIET"); return e && atoi(e); }();
+  if (!quiet && M * N * K >= (1LL << 24) && logged < 8) {  // tiny problems (scrubber heads) are FFMA by design
+    ++logged;
+    fprintf(stderr, "libscv: %s takes the fp32 FFMA path for M=%lld N=%lld K=%lld (%s)\n", who, (long long)M, (long long)N,
+            (long long)K, why);
+  }
+  return 1;
+}
 
 // number of CTA pairs (clusters of 2) of the 2-CTA GEMM that can be resident at once
 int pair_capacity() { return g_pair_capacity; }
@@ -663,6 +727,8 @@ int ensure_attrs() {
   if (g_attr_done) return 0;
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * (scv::sm_count() / 2));
@@ -676,6 +742,8 @@ int ensure_attrs() {
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel, &cfg) == cudaSuccess) g_pair_capacity = n;
     else { g_pair_capacity = 0; cudaGetLastError(); }
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_mc_kernel, &cfg) == cudaSuccess) g_mc_capacity = n;
+    else { g_mc_capacity = 0; cudaGetLastError(); }
   }
   if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e != cudaSuccess) {
@@ -721,13 +789,20 @@ namespace scv {
 int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   const int64_t M = p->B * p->Lo;
   // shapes the tensor-core path does not take (tiny scrubber-head layers, unaligned views)
-  if (p->N < 16 || p->K < 32 || M < 64) return 1;
-  if (p->K % 4 || p->a_bs % 4 || p->a_ls % 4 || !aligned16(p->A) || !aligned16(p->W)) return 1;
-  if (p->K > (1 << 30) || p->N > (1 << 30) || p->B >= (1LL << 31) || p->Lo >= (1LL << 31)) return 1;
+  if (p->N < 16 || p->K < 32 || M < 64) return decline("scv_gemm", "N < 16, K < 32 or fewer than 64 rows", M, p->N, p->K);
+  if (p->K % 4 || p->a_bs % 4 || p->a_ls % 4 || !aligned16(p->A) || !aligned16(p->W))
+    return decline("scv_gemm", "A / W not 16-byte aligned", M, p->N, p->K);
+  if (p->K > (1 << 30) || p->N > (1 << 30) || p->B >= (1LL << 31) || p->Lo >= (1LL << 31))
+    return decline("scv_gemm", "extent beyond 2^30", M, p->N, p->K);
   // the epilogue moves float4s: rows of Y / R / bias must be 16-byte aligned at every 4-column group
-  if (p->N % 4 || p->n_last % 4 || p->y_bs % 4 || p->y_ls % 4 || !aligned16(p->Y)) return 1;
-  if (p->R && (p->r_bs % 4 || p->r_ls % 4 || !aligned16(p->R))) return 1;
-  if (p->bias && (p->bias_mod % 4 || p->bias_n % 4 || !aligned16(p->bias))) return 1;
+  if (p->N % 4 || p->n_last % 4 || p->y_bs % 4 || p->y_ls % 4 || !aligned16(p->Y))
+    return decline("scv_gemm", "Y rows not float4-aligned", M, p->N, p->K);
+  if (p->R && (p->r_bs % 4 || p->r_ls % 4 || !aligned16(p->R))) return decline("scv_gemm", "R rows not float4-aligned", M, p->N, p->K);
+  if (p->bias && (p->bias_mod % 4 || p->bias_n % 4 || !aligned16(p->bias)))
+    return decline("scv_gemm", "bias not float4-aligned", M, p->N, p->K);
+  const bool accum = (p->act & SCV_ACT_ACCUM) != 0;
+  if (accum && ((p->act & 15) != SCV_ACT_NONE || (p->act & SCV_ACT_ROUND_TF32) || p->R || p->stats))
+    return decline("scv_gemm", "SCV_ACT_ACCUM with an activation / residual / statistics", M, p->N, p->K);
   int rc = ensure_attrs();
   if (rc) return rc;
 
@@ -753,7 +828,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   q.n_tiles = (int)cdiv(p->N, q.bn);
   // two row tiles per work item when that still fills the machine and K is long enough for the shared-memory
   // traffic (not the epilogue, which is no longer overlapped) to dominate; SCV_TC_SUB=1/2 forces the choice
-  static const int force_sub = [] { const char* e = getenv("SCV_TC_SUB"); return e ? atoi(e) : 0; }();
+  const int force_sub = [] { const char* e = getenv("SCV_TC_SUB"); return e ? atoi(e) : 0; }();  // per call (tests)
   q.sub = 1;
   if (ctas == 1) {
     const int items2 = q.n_tiles * (int)cdiv(q.m_tiles, 2);
@@ -765,11 +840,27 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
     if (force_sub == 1 || force_sub == 2) q.sub = force_sub;
     if (q.m_tiles < 2) q.sub = 1;
   }
+  // W multicast across a cluster of two CTAs (same n tile, adjacent row-tile groups): on by default wherever there are
+  // at least two groups of row tiles; SCV_TC_MC=0 turns it off for A/B measurements
+  const int mc_env = [] { const char* e = getenv("SCV_TC_MC"); return e ? atoi(e) : 1; }();  // read per call: tests toggle it
+  const bool mc = ctas == 1 && mc_env != 0 && g_mc_capacity >= 1 && q.m_tiles >= 2 * q.sub && q.bn % 16 == 0;
+  // split-K (accumulating GEMMs only): few output tiles, long reduction
+  q.ksplit = 1;
+  q.kc_per = q.k_chunks;
+  if (accum && ctas == 1) {
+    const int tiles0 = q.n_tiles * (int)cdiv(q.m_tiles, q.sub * (mc ? 2 : 1)) * (mc ? 2 : 1);
+    int want = sm_count() / (tiles0 > 0 ? tiles0 : 1);
+    if (want > q.k_chunks / 4) want = q.k_chunks / 4;
+    if (want > 1) {
+      q.kc_per = (int)cdiv(q.k_chunks, want);
+      q.ksplit = (int)cdiv(q.k_chunks, q.kc_per);
+    }
+  }
   const size_t stage_bytes = (size_t)kBM * kBK * 4 * q.sub + (size_t)(q.bn / ctas) * kBK * 4;
   const size_t fixed = 1024 + ((sizeof(SmemCtl) + 15) & ~size_t(15)) + 4 * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > q.k_chunks + 1) stages = q.k_chunks + 1;
+  if (stages > q.kc_per + 1) stages = q.kc_per + 1;
   if (stages < 2) stages = 2;
   q.stages = stages;
   q.bias = p->bias; q.bias_mod = (int)(p->bias ? p->bias_mod : 1); q.bias_n = (int)(p->bias ? p->bias_n : 0);
@@ -778,7 +869,8 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   q.act = (int)(p->act & 15); q.round_out = (p->act & SCV_ACT_ROUND_TF32) ? 1 : 0; q.out_scale = (float)p->out_scale; q.stats = p->stats;
   {
     const bool rd = q.R != nullptr, stt = q.stats != nullptr, rn = q.round_out != 0;
-    if (q.act == SCV_ACT_NONE && !rn) q.epi_kind = (rd ? 2 : 0) + (stt ? 1 : 0);
+    if (accum) q.epi_kind = 6;
+    else if (q.act == SCV_ACT_NONE && !rn) q.epi_kind = (rd ? 2 : 0) + (stt ? 1 : 0);
     else if (q.act == SCV_ACT_NONE && rn && !rd && !stt) q.epi_kind = 4;
     else if (q.act == SCV_ACT_TANH && !rn && !rd && !stt) q.epi_kind = 5;
     else q.epi_kind = 99;  // generic
@@ -799,7 +891,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   {
     const int64_t dims[2] = {p->K, p->N};
     const int64_t str[2] = {1, p->K};
-    const int box[2] = {kBK, q.bn / ctas};
+    const int box[2] = {kBK, q.bn / (mc ? 2 : ctas)};
     rc = tc::make_tmap(&tmW, p->W, 2, dims, str, box, "scv_gemm W");
     if (rc) return rc;
   }
@@ -810,7 +902,13 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
     gemm_tc2_kernel<<<2 * pairs, kThreads, smem, st>>>(tmA, tmW, q);
     return check_launch("gemm_tc2_kernel");
   }
-  const int total = q.n_tiles * (int)cdiv(q.m_tiles, q.sub);
+  if (mc) {
+    const int items = q.n_tiles * (int)cdiv(q.m_tiles, 2 * q.sub) * q.ksplit;
+    const int pairs = items < g_mc_capacity ? items : g_mc_capacity;
+    gemm_tc_mc_kernel<<<2 * pairs, kThreads, smem, st>>>(tmA, tmW, q);
+    return check_launch("gemm_tc_mc_kernel");
+  }
+  const int total = q.n_tiles * (int)cdiv(q.m_tiles, q.sub) * q.ksplit;
   const int grid = total < sm_count() ? total : sm_count();
   gemm_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, q);
   return check_launch("gemm_tc_kernel");
@@ -818,11 +916,12 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
 
 int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   const int64_t M = p->B * p->Lo;
-  if (p->N < 16 || p->K < 32 || M < 256) return 1;
+  if (p->N < 16 || p->K < 32 || M < 256) return decline("scv_wgrad", "N < 16, K < 32 or fewer than 256 rows", M, p->N, p->K);
   if (p->K % 4 || p->N % 4 || p->a_bs % 4 || p->a_ls % 4 || p->y_bs % 4 || p->y_ls % 4 || !aligned16(p->A) ||
       !aligned16(p->dY) || !aligned16(p->dW))
-    return 1;
-  if (p->K > (1 << 30) || p->N > (1 << 30) || p->B >= (1LL << 31) || p->Lo >= (1LL << 31)) return 1;
+    return decline("scv_wgrad", "operands not float4-aligned", M, p->N, p->K);
+  if (p->K > (1 << 30) || p->N > (1 << 30) || p->B >= (1LL << 31) || p->Lo >= (1LL << 31))
+    return decline("scv_wgrad", "extent beyond 2^30", M, p->N, p->K);
   int rc = ensure_attrs();
   if (rc) return rc;
 
@@ -848,7 +947,10 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.sub = force_wsub == 2 ? 2 : 1;
   if (p->N <= kBM) q.sub = 1;
   q.n_tiles = (int)cdiv(p->N, kBM * q.sub);
-  const int tiles = q.n_tiles * q.k_tiles;
+  // A multicast across a cluster of two CTAs holding adjacent n tiles (SCV_TC_WMC=0 turns it off)
+  const int wmc_env = [] { const char* e = getenv("SCV_TC_WMC"); return e ? atoi(e) : 1; }();
+  const bool mc = wmc_env != 0 && g_mc_capacity >= 1 && q.sub == 1 && q.n_tiles >= 2 && q.bnk >= 64;
+  const int tiles = (mc ? (q.n_tiles + 1) / 2 * 2 : q.n_tiles) * q.k_tiles;
   // row splits: fill the SMs ~2x over (once over for the two-tile items: their epilogue is not overlapped, so
   // fewer, longer items), but keep at least 4 row groups per item
   int splits = (int)cdiv((q.sub == 2 ? 1 : 2) * sm_count(), tiles);
@@ -861,7 +963,7 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   const size_t fixed = 1024 + 1024 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + 4 * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return 1;
+  if (stages < 2) return decline("scv_wgrad", "a stage does not fit shared memory twice", M, p->N, p->K);
   q.stages = stages;
 
   CUtensorMap tmY, tmA;
@@ -878,13 +980,19 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   {
     const int64_t dims[4] = {32, p->Lo, p->B, cdiv(p->K, 32)};
     const int64_t str[4] = {1, p->a_ls ? p->a_ls : p->a_bs, p->a_bs ? p->a_bs : 4, 32};
-    const int box[4] = {32, q.bl, q.nb, q.bnk / 32};
+    const int box[4] = {32, q.bl, q.nb, mc ? (q.bnk / 32 + 1) / 2 : q.bnk / 32};
     rc = tc::make_tmap(&tmA, p->A, 4, dims, str, box, "scv_wgrad A", true);
     if (rc) return rc;
   }
+  const size_t smem = fixed + (size_t)stages * stage_bytes;
+  if (mc) {
+    const int items = (q.n_tiles + 1) / 2 * q.k_tiles * q.splits;
+    const int pairs = items < g_mc_capacity ? items : g_mc_capacity;
+    wgrad_tc_mc_kernel<<<2 * pairs, kThreads, smem, st>>>(tmY, tmA, q);
+    return check_launch("wgrad_tc_mc_kernel");
+  }
   const int total = tiles * q.splits;
   const int grid = total < sm_count() ? total : sm_count();
-  const size_t smem = fixed + (size_t)stages * stage_bytes;
   wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tmY, tmA, q);
   rc = check_launch("wgrad_tc_kernel");
   if (rc) return rc;

@@ -76,6 +76,31 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
+// ---- multicast variants (cluster of 2, cta_group::1 MMAs): the box lands at the SAME shared-memory offset in every CTA
+// of `mask` and completes `bytes` on the mbarrier at the same offset in each of them.  One L2 read serves both SMs.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], "
+      "[%2], %3;" ::"r"(dst),
+      "l"(tm), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, "
+      "%6, %7}], [%2], %3;" ::"r"(dst),
+      "l"(tm), "r"(bar), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// completion of this thread's MMAs arrives on the barrier at the same offset in every CTA of `mask` (a stage is free only
+// when BOTH CTAs' tensor cores have read it: each producer writes its multicast half into both shared memories)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 // ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster of 2 act as one 256-row MMA ---------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import layout as lay
-from ._ops import ACT_NONE, ACT_RELU, ACT_RELUMASK, ACT_ROUND_TF32, ACT_TANH, BN, PREC, PRELU, ROUND_TF32, TRAIN, Ref
+from ._ops import ACT_ACCUM, ACT_NONE, ACT_RELU, ACT_RELUMASK, ACT_ROUND_TF32, ACT_TANH, BN, PREC, PRELU, ROUND_TF32, TRAIN, Ref
 
 FEAT_FLOAT = ("avg_speed", "part_speed", "frame_speed", "avg_speed_3d", "heading", "heading_change", "fluorescence")
 
@@ -784,8 +784,10 @@ class Plan:
         lst[0] = AfterSide(lst[0])
         Bw += lst
         Bw.append(wgrad(gin, self.zc, eng.zc_ld, 0, 1, dX0.at(0), dX0.bs, 0))
+        # 16 output tiles against a 4096-long reduction: split-K, partial tiles added into the zeroed buffer
         self.dzc = torch.zeros(B, eng.zc_ld, **f32)
-        Bw.append(dgemm(gin, dX0.at(0), dX0.bs, 0, 1, self.dzc, eng.zc_ld, 0))
+        Bw.append(lambda: ops.zero(self.dzc))
+        Bw.append(dgemm(gin, dX0.at(0), dX0.bs, 0, 1, self.dzc, eng.zc_ld, 0, act=ACT_ACCUM))
         self._bw_heads0 = len(Bw)
         # scrubber heads: dpred from the loss, then level by level from the output side — the weight gradients and
         # the data gradients of all ensemble members at the same distance from the output are one grouped launch
@@ -834,6 +836,9 @@ class Plan:
         Bw.append(lambda: ops.reparam_bwd(self.ms, eng.ms_ld, self.eps, self.dmu_kl, self.dmu_gr, 1.0, self.dzc,
                                           eng.zc_ld, self.dL_kl, self.dms, eng.ms_ld, B, z, round_tf32=rnd))
         Bw.append(wgrad(gfc, Hflat.at(0), Hflat.bs, 0, 1, self.dms, eng.ms_ld, 0))
+        # data parallelism: all-reduce buckets of the encoder's weight gradients, launched as soon as their last wgrad is
+        # enqueued — (index in Bw after which gpacked[lo:hi] is final, lo, hi), last layers first
+        self._bw_buckets = [(len(Bw), gfc.w, eng.gp_split)]
         dH = A(Ll, Cl)
         Bw.append(dgemm(gfc, self.dms, eng.ms_ld, 0, 1, dH.at(0), dH.bs, 0))
         for bi, blk in reversed(list(enumerate(enc_blocks))):
@@ -858,6 +863,8 @@ class Plan:
             Bw.append(wgrad(gs, Hin.at(-p2), Hin.bs, 2 * Ci, Lo, dT.at(0), dT.bs, dT.ls))
             Bw.append(AfterSide(dgemm(g0, dR0.at(-wl), dR0.bs, Co // 2, Lg, dHin.at(0), dHin.bs, 2 * Ci, n_last=nlast,
                                       R=dHin.at(0), r_bs=dHin.bs, r_ls=2 * Ci)))
+            if bi >= eng.nblk - 2:  # the two widest blocks (6.5 M and 1.6 M weights at the default widths); the small rest goes last
+                self._bw_buckets.append((len(Bw), gs.w, self._bw_buckets[-1][1]))
             dH = dHin
         dY0 = A(W, ch[0])
         Bw += bnact_bwd(None, "encoder.activation.weight", enc_in["Y0"], W, ch[0], None, 1, dH, None, dY0, sums(ch[0]))
@@ -1030,6 +1037,9 @@ class Plan:
             if wside is not None and i == last:
                 main.wait_stream(wside)  # the final gather reads the weight gradients
             if comm is not None:
+                for at, lo, hi in self._bw_buckets:
+                    if at == i:
+                        comm(self.eng, "range", wait=[wside] if wside is not None else [], lo=lo, hi=hi)
                 if i == self._bw_dec_end:
                     # the all-reduce stream (not the main stream) waits for the decoder's weight gradients
                     comm(self.eng, "decoder_done", wait=[wside] if wside is not None else [])

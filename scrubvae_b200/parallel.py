@@ -38,9 +38,13 @@ def broadcast_parameters(model, src: int = 0):
 
 
 class GradAllReduce:
-    """The `comm` hook of Plan.backward / TrainStep.  phases:
-       "decoder_done"  -> all-reduce gpacked[gp_split:] on the comm stream (overlaps the encoder backward)
-       "encoder_done"  -> all-reduce gpacked[:gp_split] and gflat[:n_direct]; the launching stream waits for both
+    """The `comm` hook of Plan.backward / TrainStep.  Buckets follow the order in which backward finishes weight
+    gradients, each launched on the comm stream the moment its last wgrad kernel is enqueued (the comm stream waits for
+    the weight-gradient stream), so only the last small bucket is exposed:
+       "decoder_done"  -> gpacked[gp_split:]  (decoder + scrubber heads; overlaps the whole encoder backward)
+       "range" lo, hi  -> gpacked[lo:hi]      (enc.fc right after its wgrad, then encoder blocks 3, 2 as they finish)
+       "encoder_done"  -> what is left of gpacked (conv_in, blocks 1 and 0) + gflat[:n_direct] (BatchNorm / PReLU
+                          gradients); the launching stream then waits for every bucket
        "post_backward" -> un-overlapped fallback for callers that ran the whole backward first: all-reduce gflat."""
 
     def __init__(self, engine, world: int, group=None):
@@ -48,11 +52,26 @@ class GradAllReduce:
         self.cuda = engine.device.type == "cuda"
         self.stream = torch.cuda.Stream(device=engine.device) if self.cuda else None
         self.bytes_per_step = 4 * (engine.gpacked.numel() + engine.n_direct)
+        self._lo = engine.gp_split  # gpacked[_lo:gp_split] of the encoder part is already reduced this step
 
     def _reduce(self, t):
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        if t.numel():
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
-    def __call__(self, eng, phase: str, wait=()):
+    def _run(self, eng, phase, lo, hi):
+        if phase == "decoder_done":
+            self._lo = eng.gp_split
+            self._reduce(eng.gpacked[eng.gp_split:])
+        elif phase == "range":
+            assert hi == self._lo and lo < hi, "encoder buckets must be contiguous, last layer first"
+            self._reduce(eng.gpacked[lo:hi])
+            self._lo = lo
+        elif phase == "encoder_done":
+            self._reduce(eng.gpacked[:self._lo])
+            self._reduce(eng.gflat[:eng.n_direct])
+            self._lo = eng.gp_split
+
+    def __call__(self, eng, phase: str, wait=(), lo=None, hi=None):
         """`wait`: extra streams whose work the reduced buffers depend on (the weight-gradient stream)."""
         if self.world == 1:
             return
@@ -60,21 +79,53 @@ class GradAllReduce:
             self._reduce(eng.gflat)
             return
         if not self.cuda:
-            if phase == "decoder_done":
-                self._reduce(eng.gpacked[eng.gp_split:])
-            elif phase == "encoder_done":
-                self._reduce(eng.gpacked[:eng.gp_split])
-                self._reduce(eng.gflat[:eng.n_direct])
+            self._run(eng, phase, lo, hi)
             return
         main = torch.cuda.current_stream()
         self.stream.wait_stream(main)
         for st in wait:
             self.stream.wait_stream(st)
         with torch.cuda.stream(self.stream):
-            if phase == "decoder_done":
-                self._reduce(eng.gpacked[eng.gp_split:])
-            elif phase == "encoder_done":
-                self._reduce(eng.gpacked[:eng.gp_split])
-                self._reduce(eng.gflat[:eng.n_direct])
+            self._run(eng, phase, lo, hi)
         if phase == "encoder_done":
             main.wait_stream(self.stream)
+
+
+def setup(model, optimizer=None, group=None):
+    """Public entry of data parallelism (call once per process after torch.distributed is initialised and the model is
+    on its device): identical replicas (rank 0's parameters and buffers), the bucketed gradient all-reduce hooked into
+    the engine's backward (both the fused TrainStep path and `total.backward()`), 1/world folded into the optimizer's
+    gradient scale.  Returns the GradAllReduce hook (None when the world is one process)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return None
+    broadcast_parameters(model)
+    eng = model.engine
+    comm = GradAllReduce(eng, world, group)
+    eng.comm = comm
+    if optimizer is not None:
+        optimizer.grad_scale = 1.0 / world
+    return comm
+
+
+def resync(model):
+    """After anything that re-draws parameters on every rank from its own RNG (the per-epoch GRScrubber.reset_parameters
+    of train(), reference train/trainer.py:368-370): rank 0's values everywhere again."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        broadcast_parameters(model)
+
+
+def shutdown(model=None):
+    """Release the CUDA graphs that hold captured NCCL kernels BEFORE the process group goes away: destroying the
+    communicator under a live graph is what stalled interpreter teardown in round 1."""
+    import gc
+    if model is not None:
+        eng = getattr(model, "_engine", None)
+        if eng is not None:
+            for _, st in list(eng.__dict__.get("_train_steps", {}).values()):
+                st.graph = None
+            eng.__dict__.pop("_train_steps", None)
+            eng.comm = None
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()

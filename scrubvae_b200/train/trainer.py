@@ -264,6 +264,8 @@ def train(config, model, loader_dict, run=None, device="cuda"):
         if "grad_reversal" in model.disentangle.keys():
             for key in model.disentangle["grad_reversal"].keys():
                 model.disentangle["grad_reversal"][key].reset_parameters()
+            from ..parallel import resync
+            resync(model)  # data parallelism: every rank drew its own re-initialisation; rank 0's everywhere
         metrics["time"] = time.time() - t0
         if epoch % 5 == 0:
             Path("{}/weights".format(config["out_path"])).mkdir(parents=True, exist_ok=True)

@@ -12,6 +12,7 @@ import torch
 
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELUMASK = 0, 1, 2, 3
 ACT_ROUND_TF32 = 16
+ACT_ACCUM = 32
 BN, PRELU, TRAIN, ROUND_TF32 = 1, 2, 4, 8
 
 
@@ -46,7 +47,7 @@ class EmuOps:
     def gemm(self, A, a_bs, a_ls, B, Lo, K, N, W, Y, y_bs, y_ls, bias=None, bias_mod=1, bias_n=0, n_last=None,
              R=None, r_bs=0, r_ls=0, act=ACT_NONE, out_scale=1.0, stats=None, precision=0):
         self.n += 1
-        rnd, act = bool(act & ACT_ROUND_TF32), act & 15
+        rnd, accum, act = bool(act & ACT_ROUND_TF32), bool(act & ACT_ACCUM), act & 15
         n_last = N if n_last is None else n_last
         a = _v(A, (B, Lo, K), (a_bs, a_ls, 1))
         w = _v(W, (N, K), (K, 1))
@@ -76,6 +77,8 @@ class EmuOps:
         if rnd:
             y = rtf32(y)
         out = _v(Y, (B, Lo, N), (y_bs, y_ls, 1))
+        if accum:
+            y = y + out
         if n_last == N:
             out.copy_(y)
         else:

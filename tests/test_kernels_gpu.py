@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from emu_ops import EmuOps, rtf32
-from scrubvae_b200._ops import Ref, BN, PRELU, TRAIN, ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELUMASK
+from scrubvae_b200._ops import Ref, BN, PRELU, TRAIN, ACT_ACCUM, ACT_NONE, ACT_RELU, ACT_TANH, ACT_RELUMASK
 
 pytestmark = pytest.mark.gpu
 
@@ -78,6 +78,50 @@ def test_gemm(ops, case, prec):
                bias_n=N, n_last=n_last, R=t["R"] if resid else None, r_bs=Lo * N, r_ls=N, act=act, out_scale=0.5,
                stats=t["stats"] if stats else None, precision=prec)
     run_both(ops, T, call, tol=1e-5 if prec == 0 else 2e-5, check=["Y", "stats"])
+
+
+# many row tiles: the cluster-multicast kernels (two CTAs share the W tile / the A slabs), odd tile counts (one CTA of
+# the last pair has nothing to store), two row tiles per item, several n tiles, ragged edges
+BIG_CASES = [
+    (701, 4, 8, 128, 1, 5, 528, None, ACT_NONE, True, True),     # 22 row tiles, 3 n tiles of 176
+    (330, 7, 16, 64, 2, 5, 160, 80, ACT_NONE, True, True),       # stride 2, ragged last row
+    (1100, 1, 1, 256, 1, 1, 272, None, ACT_RELU, False, False),  # linear layer, 9 row tiles
+    (257, 13, 18, 64, 1, 6, 48, None, ACT_NONE, False, True),    # narrow N
+    (513, 2, 6, 512, 1, 5, 1040, None, ACT_NONE, False, False),  # K = 2560, 5 n tiles
+]
+
+
+@pytest.mark.parametrize("mc", ["0", "1"])
+@pytest.mark.parametrize("sub", ["0", "1", "2"])
+@pytest.mark.parametrize("case", BIG_CASES)
+def test_gemm_multitile(ops, case, sub, mc, monkeypatch):
+    monkeypatch.setenv("SCV_TC_MC", mc)
+    monkeypatch.setenv("SCV_TC_SUB", sub)
+    test_gemm(ops, case, 1)
+
+
+@pytest.mark.parametrize("mc", ["0", "1"])
+@pytest.mark.parametrize("case", BIG_CASES)
+def test_wgrad_multitile(ops, case, mc, monkeypatch):
+    monkeypatch.setenv("SCV_TC_WMC", mc)
+    test_wgrad(ops, case, 1)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("mc", ["0", "1"])
+@pytest.mark.parametrize("B,K,N", [(2048, 4096, 68), (300, 1024, 44), (64, 8192, 272)])
+def test_gemm_accumulate_split_k(ops, B, K, N, mc, prec, monkeypatch):
+    """SCV_ACT_ACCUM: Y += A.W^T + bias; on the tensor-core path the reduction is split over CTAs (red.global.add)."""
+    monkeypatch.setenv("SCV_TC_MC", mc)
+    T = {"A": torch.randn(B * K + K, generator=g(1)), "W": torch.randn(N * K, generator=g(2)) / math.sqrt(K),
+         "bias": torch.randn(N, generator=g(3)), "Y": torch.randn(B * N, generator=g(5))}
+    if prec:
+        T["A"], T["W"] = rtf32(T["A"]), rtf32(T["W"])
+
+    def call(o, t):
+        o.gemm(t["A"], K, 0, B, 1, K, N, t["W"], t["Y"], N, 0, bias=t["bias"], bias_mod=N, bias_n=N, act=ACT_ACCUM,
+               out_scale=0.5, precision=prec)
+    run_both(ops, T, call, tol=2e-5, check=["Y"])
 
 
 @pytest.mark.parametrize("prec", [0, 1])

@@ -30,19 +30,17 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import scrubvae_b200 as sv
     from scrubvae_b200.engine import Engine, TrainStep
-    from scrubvae_b200.parallel import GradAllReduce, broadcast_parameters
+    from scrubvae_b200 import parallel
     from oracle import scvae_oracle as orc
     from emu_ops import EmuOps
     from test_engine_cpu import build_model, _rel
     torch.manual_seed(10 + rank)  # replicas start DIFFERENT: broadcast_parameters must make them equal
     m, dcfg = build_model(CH, Z, ["heading"], ["heading"])
     m._engine = Engine(m, ops=EmuOps())
-    broadcast_parameters(m)
-    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
     m.train()
     opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
-    opt.grad_scale = 1.0 / world
-    comm = GradAllReduce(m.engine, world)
+    comm = parallel.setup(m, opt)  # broadcast + bucketed all-reduce hook + 1/world gradient scale
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
     data = orc.synth_batch(BL, seed=100 + rank)
     eps = orc.synth_eps(BL, Z, seed=200 + rank)
     m._noise = eps
