@@ -117,3 +117,20 @@ def test_device_windows_loader_feeds_the_step():
         assert batch["x6d"].is_cuda
         seen += 1
     assert seen == len(loader)
+
+
+def test_skeleton_constants_match_the_reference_config():
+    """data/skeleton.py carries the mouse skeleton of the reference's configs/mouse_skeleton.yaml; the staged copy
+    (oracle/_ref/configs, build container: /root/reference/configs) must parse to the same tree and offsets."""
+    import os
+    from scrubvae_b200.data import skeleton
+    from oracle import scvae_oracle as orc
+    assert skeleton.KINEMATIC_TREE == orc.KINEMATIC_TREE and skeleton.OFFSET == orc.OFFSET
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in (os.path.join(root, "oracle", "_ref", "configs", "mouse_skeleton.yaml"),
+                 "/root/reference/configs/mouse_skeleton.yaml"):
+        if os.path.exists(path):
+            cfg = skeleton.read_skeleton(path)
+            assert [list(c) for c in cfg["KINEMATIC_TREE"]] == skeleton.KINEMATIC_TREE
+            assert [list(o) for o in cfg["OFFSET"]] == skeleton.OFFSET
+            break
