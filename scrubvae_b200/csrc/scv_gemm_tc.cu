@@ -77,7 +77,9 @@ namespace {
 
 using namespace scv::tc;
 
-constexpr int kThreads = 256;       // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue
+constexpr int kEpiWarps = 8;        // two epilogue warps per TMEM lane quarter (they split the 32-column chunks): with one
+                                    // warp per scheduler every instruction's latency was exposed (~2000 cycles per chunk)
+constexpr int kThreads = 128 + 32 * kEpiWarps;  // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
 constexpr int kBM = 128;            // UMMA M (TMEM lanes)
 constexpr int kBK = 32;             // k floats per stage row = one 128-byte swizzle span
 constexpr int kMaxBN = 256;         // UMMA N limit (cta_group::1)
@@ -129,7 +131,7 @@ struct SmemCtl {  // lives after the operand stages
 };
 
 // epilogue warps only (threads 128..255): named barrier 1
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -229,7 +231,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&ctl->tfull[i]), 1);
-      mbar_init(smem_u32(&ctl->tempty[i]), 4 * kCtas);
+      mbar_init(smem_u32(&ctl->tempty[i]), kEpiWarps * kCtas);
     }
     fence_barrier_init();
   }
@@ -335,7 +337,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     // Epilogue.  Warp ew owns TMEM lanes [32 ew, 32 ew + 32) = tile rows.  Per 32-column chunk: tcgen05.ld (thread =
     // row) -> swizzled float4 transpose through shared memory -> lane (rq, cq) holds 4 consecutive columns of rows
     // 4 i + rq (i < 8): 128-byte contiguous row segments per 8 lanes for the residual loads and the stores.
-    const int ew = warp - 4;
+    // warp -> TMEM lane quarter q (a warp can only read lanes 32 (warp % 4) .. +31) and column phase h: the kEpiWarps / 4
+    // warps of a quarter take every (kEpiWarps / 4)-th 32-column chunk
+    const int ew = warp - 4, q = ew & 3, h = ew >> 2;
+    constexpr int kColStep = 32 * (kEpiWarps / 4);
     const int rq = lane >> 3, cq = lane & 7;
     float4* xp4 = reinterpret_cast<float4*>(xpose + ew * kXposeFloats);
     const int rows_in_box = p.bl * p.nb;
@@ -343,7 +348,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     const int et = threadIdx.x - 128;
     const bool has_stats = p.stats != nullptr;
     if (has_stats) {
-      for (int c = et; c < 2 * kMaxBN; c += 128) (&ctl->sacc[0][0])[c] = 0.f;
+      for (int c = et; c < 2 * kMaxBN; c += 32 * kEpiWarps) (&ctl->sacc[0][0])[c] = 0.f;
       epi_bar();
     }
     const uint32_t tempty_addr[2] = {kCtas == 2 ? mapa_rank(smem_u32(&ctl->tempty[0]), 0) : smem_u32(&ctl->tempty[0]),
@@ -358,7 +363,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         if (cur_nt >= 0) {  // flush the finished n tile's column sums
           epi_bar();
           const int pn0 = cur_nt * p.bn, pc = min(p.bn, N - pn0);
-          for (int c = et; c < pc; c += 128) {
+          for (int c = et; c < pc; c += 32 * kEpiWarps) {
             atomicAdd(p.stats + pn0 + c, (double)ctl->sacc[0][c]);
             atomicAdd(p.stats + N + pn0 + c, (double)ctl->sacc[1][c]);
             ctl->sacc[0][c] = 0.f;
@@ -373,6 +378,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
       mbar_wait(smem_u32(&ctl->tfull[acc]), sub == 2 ? (it & 1) : ((it >> 1) & 1));
       tc_fence_after();
       if (ew == 0 && lane == 0) tc_trace(p, 2, 1, t);
+      bool released = false;
      for (int sj = 0; sj < sub; ++sj) {
       const int mt = mt0 + sj;
       const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;
@@ -380,7 +386,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
       int ncap[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int row = ew * 32 + i * 4 + rq;
+        const int row = q * 32 + i * 4 + rq;
         const int bi = row / p.bl, li = row - bi * p.bl;
         const int64_t b = (int64_t)bt_i * p.nb + bi, l = (int64_t)lt_i * p.bl + li;
         const bool ok = row < rows_in_box && mt < p.m_tiles && b < p.B && l < p.Lo;
@@ -388,12 +394,13 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         roff[i] = (long long)(b * p.r_bs + l * p.r_ls);
         ncap[i] = ok ? ((l == p.Lo - 1) ? p.n_last : N) : 0;
       }
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(sub == 2 ? sj : acc) * kMaxBN;
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub == 2 ? sj : acc) * kMaxBN;
+      for (int c0 = h * 32; c0 < ncols; c0 += kColStep) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
-        if (c0 + 32 >= ncols && sj == sub - 1) {  // accumulator(s) fully read: hand the TMEM buffer back to the MMA warp
+        if (c0 + kColStep >= ncols && sj == sub - 1) {  // this warp's last read of the accumulator(s): hand the buffer back
+          released = true;
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -445,12 +452,19 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         __syncwarp();
       }
      }  // sub tiles
+      if (!released) {  // no chunk of the last tile fell to this warp: it still owes its arrival
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCtas == 2) mbar_arrive_cluster(tempty_addr[acc]); else mbar_arrive(tempty_addr[acc]);
+        }
+      }
       if (ew == 0 && lane == 0) tc_trace(p, 2, 2, t);
     }
     if (has_stats && cur_nt >= 0) {
       epi_bar();
       const int pn0 = cur_nt * p.bn, pc = min(p.bn, N - pn0);
-      for (int c = et; c < pc; c += 128) {
+      for (int c = et; c < pc; c += 32 * kEpiWarps) {
         atomicAdd(p.stats + pn0 + c, (double)ctl->sacc[0][c]);
         atomicAdd(p.stats + N + pn0 + c, (double)ctl->sacc[1][c]);
       }
@@ -540,7 +554,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&ctl->tfull[i]), 1);
-      mbar_init(smem_u32(&ctl->tempty[i]), 4);
+      mbar_init(smem_u32(&ctl->tempty[i]), kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -636,7 +650,8 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int ew = warp - 4;
+    const int ew = warp - 4, q = ew & 3, h = ew >> 2;
+    constexpr int kColStep = 32 * (kEpiWarps / 4);
     const int rq = lane >> 3, cq = lane & 7;
     float4* xp4 = reinterpret_cast<float4*>(xpose + ew * kXposeFloats);
     int it = 0;
@@ -649,11 +664,11 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
       const int kbase = kt * p.bnk;
       const int kcols = min(p.bnk, p.K - kbase);
      for (int sj = 0; sj < sub; ++sj) {
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(sub == 2 ? sj : acc) * kMaxBN;
-      const int nbase = (nt * sub + sj) * kBM + ew * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub == 2 ? sj : acc) * kMaxBN;
+      const int nbase = (nt * sub + sj) * kBM + q * 32;
       if (g1 > g0 && nbase < p.N) {
         const int nrows = min(32, p.N - nbase);
-        for (int c0 = 0; c0 < kcols; c0 += 32) {
+        for (int c0 = h * 32; c0 < kcols; c0 += kColStep) {
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
@@ -672,7 +687,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
           }
           __syncwarp();
         }
-        if (p.dbias != nullptr && kt == 0) {  // every one of the 16 bias columns holds sum_rows dY[row][n] for n = TMEM lane
+        if (p.dbias != nullptr && kt == 0 && h == 0) {  // every one of the 16 bias columns holds sum_rows dY[row][n] for n = TMEM lane
           uint32_t bv[16];
           tmem_ld16(taddr + kBiasCol, bv);
           tmem_ld_wait();
@@ -840,9 +855,10 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
     if (force_sub == 1 || force_sub == 2) q.sub = force_sub;
     if (q.m_tiles < 2) q.sub = 1;
   }
-  // W multicast across a cluster of two CTAs (same n tile, adjacent row-tile groups): on by default wherever there are
-  // at least two groups of row tiles; SCV_TC_MC=0 turns it off for A/B measurements
-  const int mc_env = [] { const char* e = getenv("SCV_TC_MC"); return e ? atoi(e) : 1; }();  // read per call: tests toggle it
+  // W multicast across a cluster of two CTAs (same n tile, adjacent row-tile groups).  MEASURED: no gain — 2-4 % slower on
+  // every layer (profiles/r02_multicast_vs_unicast.md): each SM still has to take delivery of the full W tile, and L2
+  // already merges the two CTAs' unicast requests.  Off by default; SCV_TC_MC=1 selects it (the kernel tests cover both).
+  const int mc_env = [] { const char* e = getenv("SCV_TC_MC"); return e ? atoi(e) : 0; }();  // read per call: tests toggle it
   const bool mc = ctas == 1 && mc_env != 0 && g_mc_capacity >= 1 && q.m_tiles >= 2 * q.sub && q.bn % 16 == 0;
   // split-K (accumulating GEMMs only): few output tiles, long reduction
   q.ksplit = 1;
@@ -857,7 +873,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
     }
   }
   const size_t stage_bytes = (size_t)kBM * kBK * 4 * q.sub + (size_t)(q.bn / ctas) * kBK * 4;
-  const size_t fixed = 1024 + ((sizeof(SmemCtl) + 15) & ~size_t(15)) + 4 * kXposeFloats * 4;
+  const size_t fixed = 1024 + ((sizeof(SmemCtl) + 15) & ~size_t(15)) + kEpiWarps * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > q.kc_per + 1) stages = q.kc_per + 1;
@@ -947,8 +963,8 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.sub = force_wsub == 2 ? 2 : 1;
   if (p->N <= kBM) q.sub = 1;
   q.n_tiles = (int)cdiv(p->N, kBM * q.sub);
-  // A multicast across a cluster of two CTAs holding adjacent n tiles (SCV_TC_WMC=0 turns it off)
-  const int wmc_env = [] { const char* e = getenv("SCV_TC_WMC"); return e ? atoi(e) : 1; }();
+  // A multicast across a cluster of two CTAs holding adjacent n tiles: measured 0-4 % slower (same profile); SCV_TC_WMC=1
+  const int wmc_env = [] { const char* e = getenv("SCV_TC_WMC"); return e ? atoi(e) : 0; }();
   const bool mc = wmc_env != 0 && g_mc_capacity >= 1 && q.sub == 1 && q.n_tiles >= 2 && q.bnk >= 64;
   const int tiles = (mc ? (q.n_tiles + 1) / 2 * 2 : q.n_tiles) * q.k_tiles;
   // row splits: fill the SMs ~2x over (once over for the two-tile items: their epilogue is not overlapped, so
@@ -960,7 +976,7 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.splits = (int)cdiv(q.groups, q.gps);
   const int R = q.bl * q.nb;
   const size_t stage_bytes = (size_t)(4 * q.sub + (q.bnk + 31) / 32) * R * 128;
-  const size_t fixed = 1024 + 1024 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + 4 * kXposeFloats * 4;
+  const size_t fixed = 1024 + 1024 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + kEpiWarps * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return decline("scv_wgrad", "a stage does not fit shared memory twice", M, p->N, p->K);
