@@ -191,14 +191,11 @@ typedef struct {
   double lr, beta1, beta2, eps, weight_decay; int64_t step;
   const double* hyper; /* optional device [lr, step]: overrides lr/step (CUDA-graph replay) */
   int64_t kind; /* 0 adam (L2 wd folded in grad), 1 adamw (decoupled), 2 sgd nesterov (m = momentum buf, beta1 = momentum) */
-  /* packed-weights mode (inv_idx != NULL): the GEMM weight gradients are read where the wgrad kernels accumulated
-   * them, gpacked[inv_idx[i]] (g[i] where inv_idx[i] < 0: BatchNorm / PReLU gradients), the gradient word is zeroed
-   * once read (next step accumulates from zero), and the updated weight is written, rounded to the operand precision,
-   * straight into the packed K-major matrices the next forward / data-gradient GEMMs load: no repack pass, no
-   * gradient unpack pass (the two gather launches of the round-1 step). */
-  const int32_t* inv_idx; float* gpacked; float* packed_w;
-  const int32_t* inv_d; float* packed_d; /* second packed copy (data-gradient layout), inv_d[i] < 0: none */
-  int64_t flags;                         /* SCV_F_ROUND_TF32: packed copies are rounded to TF32 */
+  /* packed-gradient mode (inv_idx != NULL): the GEMM weight gradients are read where the wgrad kernels accumulated them,
+   * gpacked[inv_idx[i]] (g[i] where inv_idx[i] < 0: BatchNorm / PReLU gradients, zeroed once read) — no gradient-unpack
+   * pass.  (Round 2 also tried WRITING the packed weight copies from this kernel: 4-byte scattered stores made it 25x
+   * slower, 3.8 ms; the packed matrices are rebuilt by scv_gather, whose stores are coalesced.) */
+  const int32_t* inv_idx; const float* gpacked;
 } scv_optim_t;
 int scv_optim_step(const scv_optim_t* p, void* stream);
 /* global gradient norm in packed-weights mode: sumsq[0] += sum_{j < n_packed, pack_idx[j] >= 0} gpacked[j]^2

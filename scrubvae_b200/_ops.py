@@ -76,7 +76,7 @@ OptimT = _struct("OptimT", [
     ("p", _vp), ("g", _vp), ("m", _vp), ("v", _vp), ("n", _i64), ("sumsq", _vp), ("max_norm", _f64),
     ("gscale", _f64), ("lr", _f64), ("beta1", _f64), ("beta2", _f64), ("eps", _f64),
     ("weight_decay", _f64), ("step", _i64), ("hyper", _vp), ("kind", _i64),
-    ("inv_idx", _vp), ("gpacked", _vp), ("packed_w", _vp), ("inv_d", _vp), ("packed_d", _vp), ("flags", _i64)])
+    ("inv_idx", _vp), ("gpacked", _vp)])
 
 _SIGS = {
     "scv_version": (C.c_int, []),
@@ -242,10 +242,9 @@ class CudaOps:
         self._check(self.lib.scv_sumsq(_ptr(g), n, _ptr(out), self._stream()), "scv_sumsq")
 
     def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind,
-                   hyper=None, inv_idx=None, gpacked=None, packed_w=None, inv_d=None, packed_d=None, round_tf32=False):
+                   hyper=None, inv_idx=None, gpacked=None):
         s = OptimT(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, _ptr(sumsq), max_norm, gscale, lr, beta1, beta2, eps,
-                   weight_decay, step, _ptr(hyper), kind, _ptr(inv_idx), _ptr(gpacked), _ptr(packed_w), _ptr(inv_d),
-                   _ptr(packed_d), int(bool(round_tf32)))
+                   weight_decay, step, _ptr(hyper), kind, _ptr(inv_idx), _ptr(gpacked))
         self._check(self.lib.scv_optim_step(C.byref(s), self._stream()), "scv_optim_step")
 
     def sumsq_packed(self, gpacked, pack_idx, n_packed, gdirect, n_direct, out):

@@ -451,14 +451,13 @@ __global__ void __launch_bounds__(NT) optim_kernel(const scv_optim_t p) {
   const bool first = stepd < 1.5;
   const int kind = (int)p.kind;
   const bool packed = p.inv_idx != nullptr;
-  const bool rnd = (p.flags & SCV_F_ROUND_TF32) != 0;
   float* gw = const_cast<float*>(p.g);
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * NT) {
     float g, w = p.p[i];
     int32_t j = -1;
     if (packed) {
       j = __ldg(p.inv_idx + i);
-      if (j >= 0) { g = p.gpacked[j]; p.gpacked[j] = 0.f; }
+      if (j >= 0) g = __ldg(p.gpacked + j);  // gathered READ: sector-mates are read by neighbouring threads, L2 absorbs it
       else { g = gw[i]; gw[i] = 0.f; }
     } else {
       g = p.g[i];
@@ -480,14 +479,6 @@ __global__ void __launch_bounds__(NT) optim_kernel(const scv_optim_t p) {
       wn = w - step_size * (m / denom);
     }
     p.p[i] = wn;
-    if (j >= 0) {
-      const float wr = rnd ? scv::round_tf32(wn) : wn;
-      p.packed_w[j] = wr;
-      if (p.inv_d) {
-        const int32_t jd = __ldg(p.inv_d + i);
-        if (jd >= 0) p.packed_d[jd] = wr;
-      }
-    }
   }
 }
 
@@ -614,8 +605,7 @@ int scv_zero(void* p, int64_t bytes, void* stream) {
 
 int scv_optim_step(const scv_optim_t* p, void* stream) {
   SCV_REQUIRE(p->kind >= 0 && p->kind <= 2 && (p->hyper || p->step >= 1), "scv_optim_step: bad kind/step");
-  SCV_REQUIRE(!p->inv_idx || (p->gpacked && p->packed_w && p->g), "scv_optim_step: packed mode needs gpacked / packed_w / g");
-  SCV_REQUIRE(!p->inv_d || p->packed_d, "scv_optim_step: inv_d needs packed_d");
+  SCV_REQUIRE(!p->inv_idx || (p->gpacked && p->g), "scv_optim_step: packed-gradient mode needs gpacked and g");
   optim_kernel<<<grid1d(p->n, 8), NT, 0, (cudaStream_t)stream>>>(*p);
   return scv::check_launch("optim_kernel");
 }

@@ -127,8 +127,10 @@ struct SmemCtl {  // lives after the operand stages
   uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
   uint32_t tmem_base;
   uint32_t pad;
-  float sacc[2][kMaxBN];  // BatchNorm column sums / sums of squares of this CTA's tiles (flushed when the n tile changes)
 };
+// BatchNorm column sums / sums of squares of this CTA's tiles (flushed when the n tile changes): 2 x kMaxBN floats placed
+// behind the transpose tiles ONLY for launches that collect statistics — 2 KB that decide whether a third 64 KB stage
+// fits for the 256 x 256 work items.
 
 // epilogue warps only (threads 128..255): named barrier 1
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
@@ -211,7 +213,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
   const uint32_t stage_bytes = a_bytes + w_bytes;
   uint8_t* ctl_raw = smem + (size_t)p.stages * stage_bytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(ctl_raw);
-  float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtl) + 15) & ~size_t(15)));  // 4 warps x 32 x 32 floats
+  float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtl) + 15) & ~size_t(15)));  // kEpiWarps x 32 x 32 floats
+  float* sacc = xpose + kEpiWarps * kXposeFloats;  // [2][kMaxBN], present only when p.stats != nullptr
   const uint32_t tile_tx = ((uint32_t)(p.bl * p.nb) * kBK * 4 * (uint32_t)sub + w_bytes) * kCtas;
   // work items: (n tile, group of kCtas * sub consecutive m tiles); the CTAs of a pair walk the same list
   const int mper = kGroup * sub;
@@ -348,7 +351,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     const int et = threadIdx.x - 128;
     const bool has_stats = p.stats != nullptr;
     if (has_stats) {
-      for (int c = et; c < 2 * kMaxBN; c += 32 * kEpiWarps) (&ctl->sacc[0][0])[c] = 0.f;
+      for (int c = et; c < 2 * kMaxBN; c += 32 * kEpiWarps) sacc[c] = 0.f;
       epi_bar();
     }
     const uint32_t tempty_addr[2] = {kCtas == 2 ? mapa_rank(smem_u32(&ctl->tempty[0]), 0) : smem_u32(&ctl->tempty[0]),
@@ -364,10 +367,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
           epi_bar();
           const int pn0 = cur_nt * p.bn, pc = min(p.bn, N - pn0);
           for (int c = et; c < pc; c += 32 * kEpiWarps) {
-            atomicAdd(p.stats + pn0 + c, (double)ctl->sacc[0][c]);
-            atomicAdd(p.stats + N + pn0 + c, (double)ctl->sacc[1][c]);
-            ctl->sacc[0][c] = 0.f;
-            ctl->sacc[1][c] = 0.f;
+            atomicAdd(p.stats + pn0 + c, (double)sacc[c]);
+            atomicAdd(p.stats + N + pn0 + c, (double)sacc[kMaxBN + c]);
+            sacc[c] = 0.f;
+            sacc[kMaxBN + c] = 0.f;
           }
           epi_bar();
         }
@@ -443,10 +446,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
           }
           if (rq == 0 && col_ok) {
-            atomicAdd(&ctl->sacc[0][cc], s1.x); atomicAdd(&ctl->sacc[0][cc + 1], s1.y);
-            atomicAdd(&ctl->sacc[0][cc + 2], s1.z); atomicAdd(&ctl->sacc[0][cc + 3], s1.w);
-            atomicAdd(&ctl->sacc[1][cc], s2.x); atomicAdd(&ctl->sacc[1][cc + 1], s2.y);
-            atomicAdd(&ctl->sacc[1][cc + 2], s2.z); atomicAdd(&ctl->sacc[1][cc + 3], s2.w);
+            atomicAdd(sacc + cc, s1.x); atomicAdd(sacc + cc + 1, s1.y);
+            atomicAdd(sacc + cc + 2, s1.z); atomicAdd(sacc + cc + 3, s1.w);
+            atomicAdd(sacc + kMaxBN + cc, s2.x); atomicAdd(sacc + kMaxBN + cc + 1, s2.y);
+            atomicAdd(sacc + kMaxBN + cc + 2, s2.z); atomicAdd(sacc + kMaxBN + cc + 3, s2.w);
           }
         }
         __syncwarp();
@@ -465,8 +468,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
       epi_bar();
       const int pn0 = cur_nt * p.bn, pc = min(p.bn, N - pn0);
       for (int c = et; c < pc; c += 32 * kEpiWarps) {
-        atomicAdd(p.stats + pn0 + c, (double)ctl->sacc[0][c]);
-        atomicAdd(p.stats + N + pn0 + c, (double)ctl->sacc[1][c]);
+        atomicAdd(p.stats + pn0 + c, (double)sacc[c]);
+        atomicAdd(p.stats + N + pn0 + c, (double)sacc[kMaxBN + c]);
       }
     }
   }
@@ -855,6 +858,13 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
     if (force_sub == 1 || force_sub == 2) q.sub = force_sub;
     if (q.m_tiles < 2) q.sub = 1;
   }
+  const size_t fixed = 1024 + ((sizeof(SmemCtl) + 15) & ~size_t(15)) + kEpiWarps * kXposeFloats * 4 +
+                       (p->stats ? 2 * kMaxBN * sizeof(float) : 0);
+  size_t stage_bytes = (size_t)kBM * kBK * 4 * q.sub + (size_t)(q.bn / ctas) * kBK * 4;
+  if (q.sub == 2 && (kSmemLimit - fixed) / stage_bytes < 3 && force_sub != 2) {
+    q.sub = 1;  // two stages cannot hide the TMA latency (measured: 256 x 256 items with 2 stages lose 30 %)
+    stage_bytes = (size_t)kBM * kBK * 4 + (size_t)(q.bn / ctas) * kBK * 4;
+  }
   // W multicast across a cluster of two CTAs (same n tile, adjacent row-tile groups).  MEASURED: no gain — 2-4 % slower on
   // every layer (profiles/r02_multicast_vs_unicast.md): each SM still has to take delivery of the full W tile, and L2
   // already merges the two CTAs' unicast requests.  Off by default; SCV_TC_MC=1 selects it (the kernel tests cover both).
@@ -872,8 +882,6 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
       q.ksplit = (int)cdiv(q.k_chunks, q.kc_per);
     }
   }
-  const size_t stage_bytes = (size_t)kBM * kBK * 4 * q.sub + (size_t)(q.bn / ctas) * kBK * 4;
-  const size_t fixed = 1024 + ((sizeof(SmemCtl) + 15) & ~size_t(15)) + kEpiWarps * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > q.kc_per + 1) stages = q.kc_per + 1;

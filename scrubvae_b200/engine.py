@@ -326,12 +326,7 @@ class Engine:
         self.packed = torch.zeros(self._n_fwd + self._n_d, device=dev)
         self.gpacked = torch.zeros(self._n_fwd, device=dev)
         self.inv_idx = lay.inverse_map(fwd_idx, self.n_flat).to(torch.int32).to(dev)
-        # flat weight -> its position in the data-gradient matrices (each weight appears there at most once): the fused
-        # optimizer writes both packed copies itself (TrainStep), no repack pass
-        self.inv_d = lay.inverse_map(d_idx, self.n_flat).to(torch.int32).to(dev) if d_idx.numel() else None
-        self.packed_dirty = True   # packed matrices do not reflect `flat` (set by anything that edits parameters)
         self.grads_dirty = False   # gpacked / gflat hold gradients of a piecewise backward (TrainStep zeroes them)
-        self._pversions = None
         del self._pack_parts, self._pack_parts_d
         self.max_k = max(max(g.K, g.dK if g.wd is not None else 0) for g in self.W.values())
         for gc in getattr(self, "gr_cat", {}).values():
@@ -361,16 +356,6 @@ class Engine:
         n1 = self._n_fwd if part == "fwd" else self.packed.numel()
         if n1 > n0:
             self.ops.gather(self.flat, Ref(self.pack_idx, n0), Ref(self.packed, n0), n1 - n0, False, round_tf32=self.rnd)
-
-    def sync_packed(self):
-        """TrainStep keeps the packed matrices current itself (the optimizer writes them); they are rebuilt from the
-        flat parameters only when something else edited the parameters: load_state_dict / reset_parameters (seen
-        through the parameters' version counters), a piecewise optimizer step or a broadcast (packed_dirty)."""
-        pv = sum(p._version for p in self.params)
-        if self.packed_dirty or pv != self._pversions:
-            self.repack()
-            self.packed_dirty = False
-            self._pversions = pv
 
     # ------------------------------------------------------------------ API
     def plan(self, B: int) -> "Plan":
@@ -1102,11 +1087,26 @@ class TrainStep:
             else:
                 plan.eps.normal_()
             eng.nbt.add_(1)
-            # the packed GEMM matrices are current: the previous step's optimizer wrote them (run() rebuilds them when
-            # something else edited the parameters)
-            plan.run_forward()
-            for f in plan.Lk:
-                f()
+            # packed forward matrices first (coalesced-store gather from the flat parameters, 0.1 ms); the data-gradient
+            # matrices, which only backward reads, and the clearing of the weight-gradient accumulators run on a side
+            # stream beside the forward pass
+            eng.repack("fwd")
+            if plan.dside is not None:
+                main = torch.cuda.current_stream()
+                plan.dside.wait_stream(main)
+                with torch.cuda.stream(plan.dside):
+                    eng.repack("dgrad")
+                    ops.zero(eng.gpacked)
+                plan.run_forward()
+                for f in plan.Lk:
+                    f()
+                main.wait_stream(plan.dside)
+            else:
+                eng.repack("dgrad")
+                ops.zero(eng.gpacked)
+                plan.run_forward()
+                for f in plan.Lk:
+                    f()
             plan.gscale.copy_(plan.loss_scale)
             plan.backward(self.comm)
             if self.keep_grads:
@@ -1120,8 +1120,7 @@ class TrainStep:
             b1 = grp["momentum"] if opt.kind == "sgd" else grp["betas"][0]
             ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, eng.n_flat, plan.sumsq, self.max_norm, opt.grad_scale,
                            float(grp["lr"]), b1, grp["betas"][1], grp["eps"], grp["weight_decay"], 1, KIND[opt.kind],
-                           hyper=opt.hyper, inv_idx=eng.inv_idx, gpacked=eng.gpacked, packed_w=eng.packed,
-                           inv_d=eng.inv_d, packed_d=Ref(eng.packed, eng._n_fwd), round_tf32=eng.rnd)
+                           hyper=opt.hyper, inv_idx=eng.inv_idx, gpacked=eng.gpacked)
         finally:
             plan._fused_tail = False
 
@@ -1133,9 +1132,7 @@ class TrainStep:
             plan.load_targets(data)
         opt._steps += 1
         opt.push_hyper()  # ring of pinned slots: safe when the host runs several steps ahead of the device
-        self.eng.sync_packed()
-        if self.eng.grads_dirty:
-            self.eng.gpacked.zero_()
+        if self.eng.grads_dirty:  # a piecewise backward left BatchNorm / PReLU gradients in gflat: this path accumulates
             self.eng.gflat.zero_()
             self.eng.grads_dirty = False
         if not self.use_graph:

@@ -29,7 +29,6 @@ def broadcast_parameters(model, src: int = 0):
     with torch.no_grad():
         if eng is not None:
             dist.broadcast(eng.flat, src)
-            eng.packed_dirty = True
         else:
             for p in model.parameters():
                 dist.broadcast(p.data, src)

@@ -89,7 +89,6 @@ class FusedOptimizer(torch.optim.Optimizer):
                            clip[1] if clip else 0.0, self.grad_scale, float(grp["lr"]), b1, grp["betas"][1],
                            grp["eps"], grp["weight_decay"], self._steps, KIND[self.kind], hyper=self.hyper)
         eng.clip = None
-        eng.packed_dirty = True  # the packed GEMM matrices no longer match `flat` (engine.Engine.sync_packed)
         if self.kind != "sgd":
             for st in self.state.values():
                 if "step" in st:

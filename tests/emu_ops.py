@@ -406,27 +406,20 @@ class EmuOps:
         t.zero_()
 
     def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind,
-                   hyper=None, inv_idx=None, gpacked=None, packed_w=None, inv_d=None, packed_d=None, round_tf32=False):
+                   hyper=None, inv_idx=None, gpacked=None):
         self.n += 1
         if hyper is not None:
             hy = _v(hyper, (2,), (1,))
             lr, step = float(hy[0]), int(round(float(hy[1])))
         P, G = _v(p, (n,), (1,)), _v(g, (n,), (1,))
-        if inv_idx is not None:  # packed-weights mode: gather the gradient, zero what was read, scatter the update
+        if inv_idx is not None:  # packed-gradient mode: gather the weight gradients, zero the direct ones once read
             inv = _v(inv_idx, (n,), (1,)).long()
             live = inv >= 0
-            GP, PW = _tail(gpacked), _tail(packed_w)
             Gfull = G.clone()
-            Gfull[live] = GP[inv[live]]
-            GP[inv[live]] = 0.0
+            Gfull[live] = _tail(gpacked)[inv[live]]
             G[~live] = 0.0
             self.optim_step(p, Gfull, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind)
             self.n -= 1
-            PW[inv[live]] = rtf32(P[live]) if round_tf32 else P[live]
-            if inv_d is not None:
-                invd = _v(inv_d, (n,), (1,)).long()
-                ld = invd >= 0
-                _tail(packed_d)[invd[ld]] = rtf32(P[ld]) if round_tf32 else P[ld]
             return
         coef = gscale
         if sumsq is not None:
