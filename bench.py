@@ -214,10 +214,11 @@ def gemm_profile(step, B, reps=5):
     calls = []
     orig_gemm, orig_wgrad = ops.gemm, ops.wgrad
     nnz_by_w = {}
+    pk = eng.packed16 if getattr(eng, "packed16", None) is not None else eng.packed
     for g in eng.W.values():
-        nnz_by_w[eng.packed.data_ptr() + eng.packed.element_size() * g.w] = g.nnz
+        nnz_by_w[pk.data_ptr() + pk.element_size() * g.w] = g.nnz
         if g.wd is not None:
-            nnz_by_w[eng.packed.data_ptr() + eng.packed.element_size() * (eng._n_fwd + g.wd)] = g.nnz_d
+            nnz_by_w[pk.data_ptr() + pk.element_size() * (eng._n_fwd + g.wd)] = g.nnz_d
         nnz_by_w[("g", eng.gpacked.data_ptr() + 4 * g.w)] = g.nnz
     from scrubvae_b200._ops import _ptr
 
@@ -289,8 +290,9 @@ def hbm_kernel_table(step, hbm_gbs, reps=3):
         "recon_loss": lambda a, kw: B * W * (C0 + J * 3 * 2 + 3 + C0) * esz,
         "out_bwd": lambda a, kw: B * W * C0 * esz * 3,
         "unpack_root": lambda a, kw: B * W * 6 * esz,
-        "sumsq_packed": lambda a, kw: (eng._n_fwd + eng.n_direct) * esz,
-        "optim_step": lambda a, kw: eng.n_flat * esz * 9,  # p, m, v read + write; gradient read; two packed copies written
+        "sumsq": lambda a, kw: eng.n_flat * esz,
+        "gather": lambda a, kw: a[3] * esz * 2,  # weight repack / gradient unpack: one read + one write per element
+        "optim_step": lambda a, kw: eng.n_flat * esz * 7,  # p, m, v read + write; gradient read
     }
     recs = []
     saved = {}

@@ -36,13 +36,19 @@ extern "C" {
  * (round-to-nearest, ties away: cvt.rna.tf32.f32).  tcgen05 kind::tf32 truncates fp32 operands; rounding at
  * the producer makes the operand error unbiased.  0 keeps plain fp32 (the SCV_PREC_FP32 path). */
 #define SCV_F_ROUND_TF32 1
+#define SCV_F_OUT_BF16 2 /* the produced operand buffer holds bf16 elements (pointer typed float* in the prototype; strides
+                          * and offsets count ELEMENTS): what SCV_PREC_BF16 GEMMs read as A / dY */
 #define SCV_GATHER_SKIP_NEG 1
 #define SCV_GATHER_ROUND_TF32 2
+#define SCV_GATHER_OUT_BF16 4 /* dst holds bf16 elements (packed bf16 weight matrices) */
 #define SCV_MODE_ROUND_TF32 8 /* scv_bnact_*: mode bit3 */
+#define SCV_MODE_OUT_BF16 16  /* scv_bnact_*: mode bit4: H / U (forward) or dX (backward) hold bf16 elements */
 
 #define SCV_PREC_FP32 0 /* FFMA, fp32 exact */
 #define SCV_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
-#define SCV_PREC_BF16 2 /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate */
+#define SCV_PREC_BF16 2 /* tcgen05 kind::f16: A and W (scv_gemm) / A and dY (scv_wgrad) point to bf16 elements, their strides
+                         * and K count elements; fp32 accumulate in TMEM; Y, R, bias, dW, dbias stay fp32.  No FFMA
+                         * fallback: a shape the tensor-core path declines is an error. */
 
 int scv_version(void);
 const char* scv_last_error(void);

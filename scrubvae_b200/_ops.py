@@ -21,7 +21,7 @@ ACT_ROUND_TF32 = 16  # OR-ed into act: the stored output is rounded to TF32 (it 
 ACT_ACCUM = 32  # OR-ed into act: Y += result (split-K on the tensor-core path; the caller zeroes Y)
 PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
 MAX_GROUP = 6  # problems per scv_gemm_group / scv_wgrad_group launch
-BN, PRELU, TRAIN, ROUND_TF32 = 1, 2, 4, 8  # bnact mode bits
+BN, PRELU, TRAIN, ROUND_TF32, OUT_BF16 = 1, 2, 4, 8, 16  # bnact mode bits
 
 
 class Ref:
@@ -234,7 +234,9 @@ class CudaOps:
                                          _ptr(gscale), self._stream()), "scv_gr_loss")
 
     def gather(self, src, idx, dst, n, skip_neg=False, round_tf32=False):
-        self._check(self.lib.scv_gather(_ptr(src), _ptr(idx), _ptr(dst), n, int(bool(skip_neg)) | (2 if round_tf32 else 0),
+        # round_tf32: 0 plain, 1 round to TF32, 2 dst holds bf16 elements
+        self._check(self.lib.scv_gather(_ptr(src), _ptr(idx), _ptr(dst), n,
+                                        int(bool(skip_neg)) | (4 if round_tf32 == 2 else 2 if round_tf32 else 0),
                                         self._stream()),
                     "scv_gather")
 

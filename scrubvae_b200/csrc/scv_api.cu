@@ -48,6 +48,8 @@ int scv_gemm(const scv_gemm_t* p, void* stream) {
   if (p->precision != SCV_PREC_FP32) {
     int r = scv::gemm_tc(p, (cudaStream_t)stream);
     if (r != 1) return r;
+    SCV_REQUIRE(p->precision != SCV_PREC_BF16, "scv_gemm: bf16 operands need the tensor-core path, which declined this shape "
+                "(N >= 16, K %% 8 == 0, strides %% 8 == 0, 16-byte aligned pointers, Y / R / bias float4-aligned)");
   }
   return scv::gemm_ffma(p, (cudaStream_t)stream);
 }
@@ -80,6 +82,7 @@ int scv_wgrad(const scv_wgrad_t* p, void* stream) {
   if (p->precision != SCV_PREC_FP32) {
     int r = scv::wgrad_tc(p, (cudaStream_t)stream);
     if (r != 1) return r;
+    SCV_REQUIRE(p->precision != SCV_PREC_BF16, "scv_wgrad: bf16 operands need the tensor-core path, which declined this shape");
   }
   return scv::wgrad_ffma(p, (cudaStream_t)stream);
 }

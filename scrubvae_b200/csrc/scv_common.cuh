@@ -1,6 +1,7 @@
 // Shared helpers for libscv (sm_100a).  No torch headers: the library is a plain C-ABI .so.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -41,6 +42,25 @@ __device__ __forceinline__ float round_tf32(float x) {
 }
 __device__ __forceinline__ float4 round_tf32(float4 v) {
   return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+}
+
+// Stores of kernels that PRODUCE tensor-core GEMM operands.  omode 0: fp32 as is; 1: fp32 rounded to TF32; 2: bf16 — `base`
+// then addresses bf16 elements (idx counts elements either way).
+__device__ __forceinline__ int out_mode(int64_t flags) { return (flags & 2) ? 2 : (int)(flags & 1); }
+__device__ __forceinline__ void store_out(float* base, int64_t idx, float v, int omode) {
+  if (omode == 2) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+  else base[idx] = omode == 1 ? round_tf32(v) : v;
+}
+__device__ __forceinline__ void store_out4(float* base, int64_t idx, float4 v, int omode) {  // idx % 4 == 0
+  if (omode == 2) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = u;
+  } else {
+    *reinterpret_cast<float4*>(base + idx) = omode == 1 ? round_tf32(v) : v;
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

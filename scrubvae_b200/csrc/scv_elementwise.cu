@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, cons
     }
   }
   const uint32_t L = (uint32_t)p.L;
-  const bool rnd = mode & SCV_MODE_ROUND_TF32;
+  const int om = (mode & SCV_MODE_OUT_BF16) ? 2 : ((mode & SCV_MODE_ROUND_TF32) ? 1 : 0);
   // 4 rows per iteration, loads first: one thread keeps 4 (12 with the upsample neighbours) float4 loads in flight
   for (int64_t r = t.r0; r < t.rend; r += 4 * (int64_t)t.rstep) {
     float4 xc[4], xm[4], xp[4];
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, cons
     for (int u = 0; u < 4; ++u) {
       if (!ok[u]) continue;
       const float4 a = bn_prelu(xc[u], cb, has_act, slope);
-      if (p.H) st4(p.H + (int64_t)bb[u] * p.h_bs + (int64_t)ll[u] * p.h_ls + t.c * 4, rnd ? scv::round_tf32(a) : a);
+      if (p.H) scv::store_out4(p.H, (int64_t)bb[u] * p.h_bs + (int64_t)ll[u] * p.h_ls + t.c * 4, a, om);
       if (p.U) {
         const float4 am = bn_prelu(xm[u], cb, has_act, slope), ap = bn_prelu(xp[u], cb, has_act, slope);
         float4 e, o;
@@ -175,9 +175,9 @@ __global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, cons
         e.z = 0.25f * am.z + 0.75f * a.z; e.w = 0.25f * am.w + 0.75f * a.w;
         o.x = 0.75f * a.x + 0.25f * ap.x; o.y = 0.75f * a.y + 0.25f * ap.y;
         o.z = 0.75f * a.z + 0.25f * ap.z; o.w = 0.75f * a.w + 0.25f * ap.w;
-        float* ur = p.U + (int64_t)bb[u] * p.u_bs + (int64_t)(2 * ll[u]) * p.u_ls + t.c * 4;
-        st4(ur, rnd ? scv::round_tf32(e) : e);
-        st4(ur + p.u_ls, rnd ? scv::round_tf32(o) : o);
+        const int64_t ui = (int64_t)bb[u] * p.u_bs + (int64_t)(2 * ll[u]) * p.u_ls + t.c * 4;
+        scv::store_out4(p.U, ui, e, om);
+        scv::store_out4(p.U, ui + p.u_ls, o, om);
       }
     }
   }
@@ -336,8 +336,8 @@ __global__ void __launch_bounds__(NT) bnact_bwd_apply_kernel(const scv_bnact_bwd
         }
       }
       const float4 dv = make_float4(d[0], d[1], d[2], d[3]);
-      st4(p.dX + (int64_t)bb[u] * p.d_bs + (int64_t)ll[u] * p.d_ls + t.c * 4,
-          (mode & SCV_MODE_ROUND_TF32) ? scv::round_tf32(dv) : dv);
+      scv::store_out4(p.dX, (int64_t)bb[u] * p.d_bs + (int64_t)ll[u] * p.d_ls + t.c * 4, dv,
+                      (mode & SCV_MODE_OUT_BF16) ? 2 : ((mode & SCV_MODE_ROUND_TF32) ? 1 : 0));
     }
   }
 }
@@ -371,17 +371,17 @@ __global__ void __launch_bounds__(NT) pack_input_kernel(const float* __restrict_
       }
     }
     float4 o = make_float4(v[0], v[1], v[2], v[3]);
-    st4(out + ((int64_t)b * (W + 2 * halo) + halo + w) * C + c, rnd ? scv::round_tf32(o) : o);
+    scv::store_out4(out, ((int64_t)b * (W + 2 * halo) + halo + w) * C + c, o, rnd);
   }
 }
 
 __global__ void __launch_bounds__(NT) gather_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
                                                     float* __restrict__ dst, int64_t n, int flags) {
-  const bool rnd = flags & SCV_GATHER_ROUND_TF32;
+  const int om = (flags & SCV_GATHER_OUT_BF16) ? 2 : ((flags & SCV_GATHER_ROUND_TF32) ? 1 : 0);
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * NT) {
     int32_t j = idx[i];
-    if (j >= 0) { float v = __ldg(src + j); dst[i] = rnd ? scv::round_tf32(v) : v; }
-    else if (!(flags & SCV_GATHER_SKIP_NEG)) dst[i] = 0.f;
+    if (j >= 0) scv::store_out(dst, i, __ldg(src + j), om);
+    else if (!(flags & SCV_GATHER_SKIP_NEG)) scv::store_out(dst, i, 0.f, om);
   }
 }
 
@@ -527,7 +527,7 @@ int scv_pack_input(const float* x6d, const float* root, const float* arena, floa
               "scv_pack_input: C must be a multiple of 4 and the buffers 16-byte aligned");
   pack_input_kernel<<<grid1d(B * W * (C / 4), 8), NT, 0, (cudaStream_t)stream>>>(x6d, root, arena, out, B * W, (int)W,
                                                                           (int)nx, (int)C, (int)halo,
-                                                                          (int)(flags & SCV_F_ROUND_TF32));
+                                                                          (flags & SCV_F_OUT_BF16) ? 2 : (int)(flags & SCV_F_ROUND_TF32));
   return scv::check_launch("pack_input_kernel");
 }
 

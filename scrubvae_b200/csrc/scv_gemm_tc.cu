@@ -40,8 +40,8 @@ encode_tiled_fn get_encode_tiled() {
   return fn;
 }
 
-int make_tmap(CUtensorMap* tm, const float* base, int rank, const int64_t* dims, const int64_t* strides_elems,
-              const int* box, const char* what, bool atom32) {
+int make_tmap(CUtensorMap* tm, const void* base, int rank, const int64_t* dims, const int64_t* strides_elems,
+              const int* box, const char* what, bool atom32, bool bf16) {
   encode_tiled_fn fn = get_encode_tiled();
   if (!fn) {
     set_error("%s: cuTensorMapEncodeTiled is not available from the driver", what);
@@ -54,9 +54,9 @@ int make_tmap(CUtensorMap* tm, const float* base, int rank, const int64_t* dims,
     gd[i] = (cuuint64_t)dims[i];
     bx[i] = (cuuint32_t)box[i];
     es[i] = 1;
-    if (i > 0) gs[i - 1] = (cuuint64_t)strides_elems[i] * sizeof(float);
+    if (i > 0) gs[i - 1] = (cuuint64_t)strides_elems[i] * (bf16 ? 2 : sizeof(float));
   }
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gd, gs, bx, es,
+  CUresult r = fn(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -81,7 +81,8 @@ constexpr int kEpiWarps = 8;        // two epilogue warps per TMEM lane quarter 
                                     // warp per scheduler every instruction's latency was exposed (~2000 cycles per chunk)
 constexpr int kThreads = 128 + 32 * kEpiWarps;  // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
 constexpr int kBM = 128;            // UMMA M (TMEM lanes)
-constexpr int kBK = 32;             // k floats per stage row = one 128-byte swizzle span
+constexpr int kBK = 32;             // k floats per stage row = one 128-byte swizzle span (TF32); bf16: 64 elements
+constexpr int kRowBytes = 128;      // operand row of a stage, either element type
 constexpr int kMaxBN = 256;         // UMMA N limit (cta_group::1)
 constexpr int kTmemCols = 512;      // two accumulator buffers of 256 columns
 constexpr int kXposeFloats = 32 * 32;  // per-warp epilogue transpose tile: 32 rows x 32 floats, 16-byte chunks XOR-swizzled
@@ -196,7 +197,7 @@ __device__ __forceinline__ void epi_rows(const GemmTcParams& p, const float4* xp
 // half of the W tile and MULTICASTS it into both shared memories, so W crosses the L2 -> SM fabric once per pair.  The
 // layers of this network are paced by that fabric (12.3 TB/s chip-wide, ~42 B/cycle per SM, against the 64-96 B/cycle a
 // 128x256 TF32 tile consumes), not by the tensor pipe.
-template <int kCtas, bool kMc = false>
+template <int kCtas, bool kMc = false, bool kBf16 = false>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmTcParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
@@ -207,15 +208,16 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
   constexpr int kGroup = kMc ? 2 : kCtas;  // CTAs walking one work-item list together
   const int bnw = p.bn / kCtas;                       // W rows held by this CTA
   const int sub = kCtas == 1 ? p.sub : 1;
-  const uint32_t a_tile = kBM * kBK * 4;              // 16 KB per 128-row tile
+  constexpr int kEK = kBf16 ? 64 : 32;                // operand elements per 128-byte stage row
+  const uint32_t a_tile = kBM * kRowBytes;            // 16 KB per 128-row tile
   const uint32_t a_bytes = a_tile * (uint32_t)sub;
-  const uint32_t w_bytes = (uint32_t)bnw * kBK * 4;   // rows of 128 B (multiple of 2 KB)
+  const uint32_t w_bytes = (uint32_t)bnw * kRowBytes; // rows of 128 B (multiple of 2 KB)
   const uint32_t stage_bytes = a_bytes + w_bytes;
   uint8_t* ctl_raw = smem + (size_t)p.stages * stage_bytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(ctl_raw);
   float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtl) + 15) & ~size_t(15)));  // kEpiWarps x 32 x 32 floats
   float* sacc = xpose + kEpiWarps * kXposeFloats;  // [2][kMaxBN], present only when p.stats != nullptr
-  const uint32_t tile_tx = ((uint32_t)(p.bl * p.nb) * kBK * 4 * (uint32_t)sub + w_bytes) * kCtas;
+  const uint32_t tile_tx = ((uint32_t)(p.bl * p.nb) * kRowBytes * (uint32_t)sub + w_bytes) * kCtas;
   // work items: (n tile, group of kCtas * sub consecutive m tiles); the CTAs of a pair walk the same list
   const int mper = kGroup * sub;
   const int m_groups = (p.m_tiles + mper - 1) / mper;
@@ -267,17 +269,17 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             const uint32_t fb = mapa_rank(smem_u32(&ctl->full[s]), 0);  // the leader's barrier counts both CTAs' bytes
             if (rank == 0) mbar_expect_tx(smem_u32(&ctl->full[s]), tile_tx);
             else mbar_arrive_cluster(fb);
-            tma2_load_3d(sa, &tmA, fb, kc * kBK, l0, b0);
-            tma2_load_2d(sa + a_bytes, &tmW, fb, kc * kBK, n0);
+            tma2_load_3d(sa, &tmA, fb, kc * kEK, l0, b0);
+            tma2_load_2d(sa + a_bytes, &tmW, fb, kc * kEK, n0);
           } else {
             const uint32_t fb = smem_u32(&ctl->full[s]);
             mbar_expect_tx(fb, tile_tx);
-            tma_load_3d(sa, &tmA, fb, kc * kBK, l0, b0);
-            if (sub == 2) tma_load_3d(sa + a_tile, &tmA, fb, kc * kBK, lt_2 * p.bl, bt_2 * p.nb);
+            tma_load_3d(sa, &tmA, fb, kc * kEK, l0, b0);
+            if (sub == 2) tma_load_3d(sa + a_tile, &tmA, fb, kc * kEK, lt_2 * p.bl, bt_2 * p.nb);
             if (kMc)  // my half of the W tile, into both CTAs' stage
-              tma_load_2d_mc(sa + a_bytes + crank * (w_bytes >> 1), &tmW, fb, kc * kBK, n0 + (int)crank * (p.bn >> 1), (uint16_t)3);
+              tma_load_2d_mc(sa + a_bytes + crank * (w_bytes >> 1), &tmW, fb, kc * kEK, n0 + (int)crank * (p.bn >> 1), (uint16_t)3);
             else
-              tma_load_2d(sa + a_bytes, &tmW, fb, kc * kBK, n0);
+              tma_load_2d(sa + a_bytes, &tmW, fb, kc * kEK, n0);
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -286,7 +288,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = idesc_tf32(kBM * kCtas, p.bn, 0, 0);
+      const uint32_t idesc = kBf16 ? idesc_bf16(kBM, p.bn, 0, 0) : idesc_tf32(kBM * kCtas, p.bn, 0, 0);
       // K-major, 128B swizzle: LBO 16 B (unused), SBO 1024 B; the stage base addresses are 1024-byte aligned
       const uint64_t desc0 = smem_desc(smem_u32(smem), 16, 1024);
       const uint32_t desc_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
@@ -315,16 +317,17 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             umma2_tf32_lh(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
             umma2_tf32_lh(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
           } else {
-            umma_tf32_lh(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, acc0);
-            umma_tf32_lh(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
-            umma_tf32_lh(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
-            umma_tf32_lh(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
+            // 4 k steps of 32 bytes (8 tf32 / 16 bf16 elements) inside the 128-byte swizzle span
+            umma_lh<kBf16>(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, acc0);
+            umma_lh<kBf16>(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
+            umma_lh<kBf16>(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
+            umma_lh<kBf16>(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
             if (sub == 2) {
               const uint32_t a2 = a_lo + (a_tile >> 4), d2 = d_tmem + kMaxBN;
-              umma_tf32_lh(d2, a2, desc_hi, b_lo, desc_hi, idesc, acc0);
-              umma_tf32_lh(d2, a2 + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
-              umma_tf32_lh(d2, a2 + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
-              umma_tf32_lh(d2, a2 + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
+              umma_lh<kBf16>(d2, a2, desc_hi, b_lo, desc_hi, idesc, acc0);
+              umma_lh<kBf16>(d2, a2 + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
+              umma_lh<kBf16>(d2, a2 + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
+              umma_lh<kBf16>(d2, a2 + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
             }
           }
           if (kCtas == 2) umma2_commit(smem_u32(&ctl->empty[s]));
@@ -486,6 +489,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   gemm_tc_body<1>(tmA, tmW, p);
 }
 
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcParams p) {
+  gemm_tc_body<1, false, true>(tmA, tmW, p);
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcParams p) {
   gemm_tc_body<1, true>(tmA, tmW, p);
@@ -523,19 +531,24 @@ struct SmemCtlW {
 // kMc: the two CTAs of a cluster take ADJACENT n tiles of the same (k tile, row split): they need the same A slabs, so each
 // loads half of them and multicasts into both shared memories (dY slabs are private).  L2 -> SM traffic per FLOP drops by a
 // third (30 KB instead of 44 KB per 32-row stage), which is what bounds this kernel.
-template <bool kMc>
+// kBf16: bf16 operands — slabs are 64 elements wide (still 128 bytes per row), one MMA reduces 16 rows, plain 128-byte
+// swizzle (layout type 2, 8-row atoms) instead of the 32-byte-atom variant fp32 MN-major operands need.
+template <bool kMc, bool kBf16 = false>
 __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUtensorMap& tmA, const WgradTcParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = p.bl * p.nb;
-  const uint32_t slab = (uint32_t)R * 128;  // one 32-wide slab of R rows (R % 8 == 0 -> 1 KB multiple)
-  const int a_slabs = (p.bnk + 31) / 32;
+  constexpr int SW = kBf16 ? 64 : 32;       // slab width in operand elements (128 bytes)
+  constexpr int kYSlabs = kBM / SW;         // dY slabs per 128-row n tile
+  constexpr int kRowsPerMma = kBf16 ? 16 : 8;
+  const uint32_t slab = (uint32_t)R * 128;  // one slab of R rows (R % 8 == 0 -> 1 KB multiple)
+  const int a_slabs = (p.bnk + SW - 1) / SW;
   const int sub = p.sub;
-  const uint32_t y_bytes = 4 * slab * (uint32_t)sub, a_bytes = (uint32_t)a_slabs * slab;
+  const uint32_t y_bytes = kYSlabs * slab * (uint32_t)sub, a_bytes = (uint32_t)a_slabs * slab;
   const uint32_t stage_bytes = y_bytes + a_bytes;
-  float* ones = reinterpret_cast<float*>(smem);  // 1 KB = 8 k-rows x 128 B of 1.0f (B operand of the bias MMA)
-  smem += 1024;
+  float* ones = reinterpret_cast<float*>(smem);  // 8 (16) k-rows x 128 B of 1.0 (B operand of the bias MMA)
+  smem += 2048;
   uint8_t* ctl_raw = smem + (size_t)p.stages * stage_bytes;
   SmemCtlW* ctl = reinterpret_cast<SmemCtlW*>(ctl_raw);
   float* xpose = reinterpret_cast<float*>(ctl_raw + ((sizeof(SmemCtlW) + 15) & ~size_t(15)));
@@ -563,7 +576,8 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
   }
   if (warp == 2) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
   if (warp == 3) {
-    for (int i = lane; i < 256; i += 32) ones[i] = 1.0f;
+    if (kBf16) for (int i = lane; i < 512; i += 32) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;  // two bf16 1.0
+    else for (int i = lane; i < 256; i += 32) ones[i] = 1.0f;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
   }
   tc_fence_before();
@@ -597,12 +611,12 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
           mbar_expect_tx(fb, stage_tx);
           const uint32_t sy = smem_u32(smem + (size_t)s * stage_bytes);
           // one TMA per operand: 4-D boxes (32 floats, bl, nb, slabs) land slab-major, exactly the MN-major layout
-          tma_load_4d(sy, &tmY, fb, 0, l0, b0, nt * sub * (kBM / 32));
+          tma_load_4d(sy, &tmY, fb, 0, l0, b0, nt * sub * kYSlabs);
           if (kMc) {
             const int sl0 = crank ? a_slabs - h0 : 0;  // my half of the A slabs, into both CTAs' stage
-            tma_load_4d_mc(sy + y_bytes + (uint32_t)sl0 * slab, &tmA, fb, 0, l0, b0, kt * (p.bnk / 32) + sl0, (uint16_t)3);
+            tma_load_4d_mc(sy + y_bytes + (uint32_t)sl0 * slab, &tmA, fb, 0, l0, b0, kt * (p.bnk / SW) + sl0, (uint16_t)3);
           } else
-          tma_load_4d(sy + y_bytes, &tmA, fb, 0, l0, b0, kt * (p.bnk / 32));
+          tma_load_4d(sy + y_bytes, &tmA, fb, 0, l0, b0, kt * (p.bnk / SW));
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -610,12 +624,14 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(kBM, p.bnk, 1, 1);
-      const uint32_t idesc_b = idesc_tf32(kBM, 16, 1, 1);
-      const uint64_t ones_desc = smem_desc(smem_u32(ones), 1024, 512, 1);
+      const uint32_t idesc = kBf16 ? idesc_bf16(kBM, p.bnk, 1, 1) : idesc_tf32(kBM, p.bnk, 1, 1);
+      const uint32_t idesc_b = kBf16 ? idesc_bf16(kBM, 16, 1, 1) : idesc_tf32(kBM, 16, 1, 1);
+      const uint64_t ones_desc = kBf16 ? smem_desc(smem_u32(ones), 2048, 1024, 2) : smem_desc(smem_u32(ones), 1024, 512, 1);
       const uint32_t ones_lo = (uint32_t)ones_desc, ones_hi = (uint32_t)(ones_desc >> 32);
-      // MN-major, 128B swizzle with 32-byte atoms: LBO = slab pitch, SBO = 512 B (4 k-rows)
-      const uint64_t ydesc0 = smem_desc(smem_u32(smem), slab, 512, 1);
+      // MN-major: LBO = slab pitch; fp32: 128B swizzle with 32-byte atoms, SBO = 512 B (4 k-rows); bf16: plain 128B
+      // swizzle, SBO = 1024 B (8 k-rows)
+      const uint64_t ydesc0 = kBf16 ? smem_desc(smem_u32(smem), slab, 1024, 2) : smem_desc(smem_u32(smem), slab, 512, 1);
+      constexpr uint32_t kAdv = kRowsPerMma * 128 / 16;  // descriptor units per MMA (8 or 16 reduction rows of 128 B)
       const uint32_t ydesc_lo0 = (uint32_t)ydesc0, desc_hi = (uint32_t)(ydesc0 >> 32);
       const uint32_t stage_units = stage_bytes >> 4;
       int s = 0, it = 0;
@@ -635,13 +651,13 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
           const uint32_t sa = sy + y_bytes;
           const uint32_t y_lo = ydesc_lo0 + (uint32_t)s * stage_units, a_lo = y_lo + (y_bytes >> 4);
           uint32_t accf = g > g0 ? 1u : 0u;
-          for (int r8 = 0; r8 < R / 8; ++r8) {  // 8 reduction rows = 1024 B = 64 units per MMA
-            umma_tf32_lh(d_tmem, y_lo + r8 * 64, desc_hi, a_lo + r8 * 64, desc_hi, idesc, accf);
-            if (do_bias) umma_tf32_lh(d_tmem + kBiasCol, y_lo + r8 * 64, desc_hi, ones_lo, ones_hi, idesc_b, accf);
-            if (sub == 2) {  // second n tile: dY slabs 4..7 of the same stage, same A slabs
-              const uint32_t y2 = y_lo + ((4 * slab) >> 4) + r8 * 64;
-              umma_tf32_lh(d_tmem + kMaxBN, y2, desc_hi, a_lo + r8 * 64, desc_hi, idesc, accf);
-              if (do_bias) umma_tf32_lh(d_tmem + kMaxBN + kBiasCol, y2, desc_hi, ones_lo, ones_hi, idesc_b, accf);
+          for (int r8 = 0; r8 < R / kRowsPerMma; ++r8) {  // 8 (16) reduction rows = 1024 (2048) B per MMA
+            umma_lh<kBf16>(d_tmem, y_lo + r8 * kAdv, desc_hi, a_lo + r8 * kAdv, desc_hi, idesc, accf);
+            if (do_bias) umma_lh<kBf16>(d_tmem + kBiasCol, y_lo + r8 * kAdv, desc_hi, ones_lo, ones_hi, idesc_b, accf);
+            if (sub == 2) {  // second n tile: the next dY slabs of the same stage, same A slabs
+              const uint32_t y2 = y_lo + ((kYSlabs * slab) >> 4) + r8 * kAdv;
+              umma_lh<kBf16>(d_tmem + kMaxBN, y2, desc_hi, a_lo + r8 * kAdv, desc_hi, idesc, accf);
+              if (do_bias) umma_lh<kBf16>(d_tmem + kMaxBN + kBiasCol, y2, desc_hi, ones_lo, ones_hi, idesc_b, accf);
             }
             accf = 1u;
           }
@@ -717,6 +733,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   wgrad_tc_body<false>(tmY, tmA, p);
 }
 
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_bf16_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmA, const WgradTcParams p) {
+  wgrad_tc_body<false, true>(tmY, tmA, p);
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 wgrad_tc_mc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmA, const WgradTcParams p) {
   wgrad_tc_body<true>(tmY, tmA, p);
@@ -746,6 +767,8 @@ int ensure_attrs() {
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
@@ -777,17 +800,18 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // rows of a (bl x nb) box, at most `rmax`; forward wants the best use of the 128 MMA rows,
 // the weight gradient wants rows % 8 == 0 and as few zero-filled rows as possible
-void choose_box(int64_t Lo, int64_t B, int rmax, bool mult8, int& bl, int& nb) {
+void choose_box(int64_t Lo, int64_t B, int rmax, int mult, int& bl, int& nb) {  // mult: rows must be a multiple of it (0: any)
+  const bool mult8 = mult > 1;
   double best = -1.0;
   bl = 1;
-  nb = mult8 ? 8 : 1;
-  int lmax = (int)(mult8 ? (Lo + 7) / 8 * 8 : Lo);
+  nb = mult8 ? mult : 1;
+  int lmax = (int)(mult8 ? (Lo + mult - 1) / mult * mult : Lo);
   if (lmax > rmax) lmax = rmax;
   if (lmax > 256) lmax = 256;
   for (int l = lmax; l >= 1; --l) {
     for (int n = 1; n * l <= rmax && n <= 256; ++n) {
       const int r = l * n;
-      if (mult8 && r % 8) continue;
+      if (mult8 && r % mult) continue;
       const double covered = (double)(cdiv(Lo, l) * l) * (double)(cdiv(B, n) * n);
       double eff = (double)Lo * (double)B / covered;
       eff *= (double)r / rmax;  // forward: unused MMA rows; wgrad: short stages pay more barrier round trips
@@ -806,9 +830,13 @@ namespace scv {
 
 int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   const int64_t M = p->B * p->Lo;
-  // shapes the tensor-core path does not take (tiny scrubber-head layers, unaligned views)
-  if (p->N < 16 || p->K < 32 || M < 64) return decline("scv_gemm", "N < 16, K < 32 or fewer than 64 rows", M, p->N, p->K);
-  if (p->K % 4 || p->a_bs % 4 || p->a_ls % 4 || !aligned16(p->A) || !aligned16(p->W))
+  const bool bf16 = p->precision == SCV_PREC_BF16;
+  const int ea = bf16 ? 8 : 4;  // operand elements per 16 bytes
+  // shapes the tensor-core path does not take (tiny scrubber-head layers, unaligned views); bf16 operands have no FFMA
+  // fallback, so only the hard limits apply to them
+  if (p->N < 16 || p->K < (bf16 ? 8 : 32) || (!bf16 && M < 64))
+    return decline("scv_gemm", "N < 16, K < 32 or fewer than 64 rows", M, p->N, p->K);
+  if (p->K % ea || p->a_bs % ea || p->a_ls % ea || !aligned16(p->A) || !aligned16(p->W))
     return decline("scv_gemm", "A / W not 16-byte aligned", M, p->N, p->K);
   if (p->K > (1 << 30) || p->N > (1 << 30) || p->B >= (1LL << 31) || p->Lo >= (1LL << 31))
     return decline("scv_gemm", "extent beyond 2^30", M, p->N, p->K);
@@ -826,18 +854,18 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
 
   GemmTcParams q;
   q.B = p->B; q.Lo = p->Lo; q.K = (int)p->K; q.N = (int)p->N;
-  choose_box(p->Lo, p->B, kBM, false, q.bl, q.nb);
+  choose_box(p->Lo, p->B, kBM, 0, q.bl, q.nb);
   q.lt = (int)cdiv(p->Lo, q.bl);
   q.bt = (int)cdiv(p->B, q.nb);
   q.m_tiles = q.lt * q.bt;
-  q.k_chunks = (int)cdiv(p->K, kBK);
+  q.k_chunks = (int)cdiv(p->K, bf16 ? 64 : kBK);
   // CTA pairs (cta_group::2, gemm_tc2_kernel) are correct (kernel tests pass with SCV_TC_PAIR=1) but measured
   // SLOWER on every layer of the step (profiles/r01_pair_vs_single.md: the M=256 pair MMA issues at the same
   // 162 cycles as two M=128 MMAs, tools/cu/mma_rate2.cu, and the cross-SM operand fetch costs on top), so the
   // single-CTA kernel is the default; SCV_TC_PAIR=1 selects the pair kernel for experiments.
   static const int force_pair = [] { const char* e = getenv("SCV_TC_PAIR"); return e ? atoi(e) : 0; }();
   int ctas = force_pair ? 2 : 1;
-  if (q.m_tiles < 2 || pair_capacity() < 1) ctas = 1;
+  if (q.m_tiles < 2 || pair_capacity() < 1 || bf16) ctas = 1;
   // N tile: as wide as the MMA allows, balanced over the tiles, multiple of 16 (of 32 for a pair: each CTA holds half)
   const int ng = 16 * ctas;
   const int n16 = (int)cdiv(p->N, ng) * ng;
@@ -869,7 +897,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   // every layer (profiles/r02_multicast_vs_unicast.md): each SM still has to take delivery of the full W tile, and L2
   // already merges the two CTAs' unicast requests.  Off by default; SCV_TC_MC=1 selects it (the kernel tests cover both).
   const int mc_env = [] { const char* e = getenv("SCV_TC_MC"); return e ? atoi(e) : 0; }();  // read per call: tests toggle it
-  const bool mc = ctas == 1 && mc_env != 0 && g_mc_capacity >= 1 && q.m_tiles >= 2 * q.sub && q.bn % 16 == 0;
+  const bool mc = ctas == 1 && !bf16 && mc_env != 0 && g_mc_capacity >= 1 && q.m_tiles >= 2 * q.sub && q.bn % 16 == 0;
   // split-K (accumulating GEMMs only): few output tiles, long reduction
   q.ksplit = 1;
   q.kc_per = q.k_chunks;
@@ -907,16 +935,16 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   CUtensorMap tmA, tmW;
   {
     const int64_t dims[3] = {p->K, p->Lo, p->B};
-    const int64_t str[3] = {1, p->a_ls ? p->a_ls : p->a_bs, p->a_bs ? p->a_bs : 4};
-    const int box[3] = {kBK, q.bl, q.nb};
-    rc = tc::make_tmap(&tmA, p->A, 3, dims, str, box, "scv_gemm A");
+    const int64_t str[3] = {1, p->a_ls ? p->a_ls : p->a_bs, p->a_bs ? p->a_bs : ea};
+    const int box[3] = {bf16 ? 64 : kBK, q.bl, q.nb};
+    rc = tc::make_tmap(&tmA, p->A, 3, dims, str, box, "scv_gemm A", false, bf16);
     if (rc) return rc;
   }
   {
     const int64_t dims[2] = {p->K, p->N};
     const int64_t str[2] = {1, p->K};
-    const int box[2] = {kBK, q.bn / (mc ? 2 : ctas)};
-    rc = tc::make_tmap(&tmW, p->W, 2, dims, str, box, "scv_gemm W");
+    const int box[2] = {bf16 ? 64 : kBK, q.bn / (mc ? 2 : ctas)};
+    rc = tc::make_tmap(&tmW, p->W, 2, dims, str, box, "scv_gemm W", false, bf16);
     if (rc) return rc;
   }
   const size_t smem = fixed + (size_t)stages * stage_bytes;
@@ -934,16 +962,23 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   }
   const int total = q.n_tiles * (int)cdiv(q.m_tiles, q.sub) * q.ksplit;
   const int grid = total < sm_count() ? total : sm_count();
+  if (bf16) {
+    gemm_tc_bf16_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, q);
+    return check_launch("gemm_tc_bf16_kernel");
+  }
   gemm_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, q);
   return check_launch("gemm_tc_kernel");
 }
 
 int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   const int64_t M = p->B * p->Lo;
-  if (p->N < 16 || p->K < 32 || M < 256) return decline("scv_wgrad", "N < 16, K < 32 or fewer than 256 rows", M, p->N, p->K);
-  if (p->K % 4 || p->N % 4 || p->a_bs % 4 || p->a_ls % 4 || p->y_bs % 4 || p->y_ls % 4 || !aligned16(p->A) ||
+  const bool bf16 = p->precision == SCV_PREC_BF16;
+  const int ea = bf16 ? 8 : 4, SW = bf16 ? 64 : 32;
+  if (p->N < 16 || p->K < (bf16 ? 8 : 32) || (!bf16 && M < 256))
+    return decline("scv_wgrad", "N < 16, K < 32 or fewer than 256 rows", M, p->N, p->K);
+  if (p->K % 4 || p->N % 4 || p->a_bs % ea || p->a_ls % ea || p->y_bs % ea || p->y_ls % ea || !aligned16(p->A) ||
       !aligned16(p->dY) || !aligned16(p->dW))
-    return decline("scv_wgrad", "operands not float4-aligned", M, p->N, p->K);
+    return decline("scv_wgrad", "operands not 16-byte aligned", M, p->N, p->K);
   if (p->K > (1 << 30) || p->N > (1 << 30) || p->B >= (1LL << 31) || p->Lo >= (1LL << 31))
     return decline("scv_wgrad", "extent beyond 2^30", M, p->N, p->K);
   int rc = ensure_attrs();
@@ -955,25 +990,25 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.dbias = want_bias ? p->dbias : nullptr;
   q.bias_mod = (int)(want_bias ? p->bias_mod : 1);
   q.bias_n = (int)(want_bias ? p->bias_n : 0);
-  choose_box(p->Lo, p->B, 32, true, q.bl, q.nb);
+  choose_box(p->Lo, p->B, bf16 ? 64 : 32, bf16 ? 16 : 8, q.bl, q.nb);
   q.lt = (int)cdiv(p->Lo, q.bl);
   q.bt = (int)cdiv(p->B, q.nb);
   q.groups = q.lt * q.bt;
   // k tile: whole 32-float slabs (the TMA box counts slabs), balanced over the tiles
-  const int k32 = (int)cdiv(p->K, 32) * 32;
-  const int kt0 = (int)cdiv(k32, kWgradMaxBNK);
-  q.bnk = (int)cdiv(cdiv(k32, kt0), 32) * 32;
+  const int k32 = (int)cdiv(p->K, SW) * SW;
+  const int kt0 = (int)cdiv(k32, bf16 ? 192 : kWgradMaxBNK);
+  q.bnk = (int)cdiv(cdiv(k32, kt0), SW) * SW;
   q.k_tiles = (int)cdiv(p->K, q.bnk);
   // two n tiles per item (sharing the A slabs) measured 7-10 % SLOWER than one on every large layer
   // (profiles/r01_wgrad_sub.md: fewer stages in flight and an un-overlapped epilogue cost more than the saved
   // traffic), so one tile per item is the default; SCV_TC_WSUB=2 selects the two-tile variant for experiments
   static const int force_wsub = [] { const char* e = getenv("SCV_TC_WSUB"); return e ? atoi(e) : 0; }();
-  q.sub = force_wsub == 2 ? 2 : 1;
+  q.sub = (force_wsub == 2 && !bf16) ? 2 : 1;
   if (p->N <= kBM) q.sub = 1;
   q.n_tiles = (int)cdiv(p->N, kBM * q.sub);
   // A multicast across a cluster of two CTAs holding adjacent n tiles: measured 0-4 % slower (same profile); SCV_TC_WMC=1
   const int wmc_env = [] { const char* e = getenv("SCV_TC_WMC"); return e ? atoi(e) : 0; }();
-  const bool mc = wmc_env != 0 && g_mc_capacity >= 1 && q.sub == 1 && q.n_tiles >= 2 && q.bnk >= 64;
+  const bool mc = wmc_env != 0 && !bf16 && g_mc_capacity >= 1 && q.sub == 1 && q.n_tiles >= 2 && q.bnk >= 64;
   const int tiles = (mc ? (q.n_tiles + 1) / 2 * 2 : q.n_tiles) * q.k_tiles;
   // row splits: fill the SMs ~2x over (once over for the two-tile items: their epilogue is not overlapped, so
   // fewer, longer items), but keep at least 4 row groups per item
@@ -983,8 +1018,8 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.gps = (int)cdiv(q.groups, splits);
   q.splits = (int)cdiv(q.groups, q.gps);
   const int R = q.bl * q.nb;
-  const size_t stage_bytes = (size_t)(4 * q.sub + (q.bnk + 31) / 32) * R * 128;
-  const size_t fixed = 1024 + 1024 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + kEpiWarps * kXposeFloats * 4;
+  const size_t stage_bytes = (size_t)(kBM / SW * q.sub + (q.bnk + SW - 1) / SW) * R * 128;
+  const size_t fixed = 1024 + 2048 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + kEpiWarps * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return decline("scv_wgrad", "a stage does not fit shared memory twice", M, p->N, p->K);
@@ -995,17 +1030,17 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   // reads past the row's end (the next row / the buffer's slack): those columns only reach output rows n >= N or
   // output columns k >= K, which the epilogue does not store.
   {
-    const int64_t dims[4] = {32, p->Lo, p->B, cdiv(p->N, 32)};
-    const int64_t str[4] = {1, p->y_ls ? p->y_ls : p->y_bs, p->y_bs ? p->y_bs : 4, 32};
-    const int box[4] = {32, q.bl, q.nb, 4 * q.sub};
-    rc = tc::make_tmap(&tmY, p->dY, 4, dims, str, box, "scv_wgrad dY", true);
+    const int64_t dims[4] = {SW, p->Lo, p->B, cdiv(p->N, SW)};
+    const int64_t str[4] = {1, p->y_ls ? p->y_ls : p->y_bs, p->y_bs ? p->y_bs : ea, SW};
+    const int box[4] = {SW, q.bl, q.nb, kBM / SW * q.sub};
+    rc = tc::make_tmap(&tmY, p->dY, 4, dims, str, box, "scv_wgrad dY", !bf16, bf16);
     if (rc) return rc;
   }
   {
-    const int64_t dims[4] = {32, p->Lo, p->B, cdiv(p->K, 32)};
-    const int64_t str[4] = {1, p->a_ls ? p->a_ls : p->a_bs, p->a_bs ? p->a_bs : 4, 32};
-    const int box[4] = {32, q.bl, q.nb, mc ? (q.bnk / 32 + 1) / 2 : q.bnk / 32};
-    rc = tc::make_tmap(&tmA, p->A, 4, dims, str, box, "scv_wgrad A", true);
+    const int64_t dims[4] = {SW, p->Lo, p->B, cdiv(p->K, SW)};
+    const int64_t str[4] = {1, p->a_ls ? p->a_ls : p->a_bs, p->a_bs ? p->a_bs : ea, SW};
+    const int box[4] = {SW, q.bl, q.nb, mc ? (q.bnk / SW + 1) / 2 : q.bnk / SW};
+    rc = tc::make_tmap(&tmA, p->A, 4, dims, str, box, "scv_wgrad A", !bf16, bf16);
     if (rc) return rc;
   }
   const size_t smem = fixed + (size_t)stages * stage_bytes;
@@ -1017,6 +1052,10 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   }
   const int total = tiles * q.splits;
   const int grid = total < sm_count() ? total : sm_count();
+  if (bf16) {
+    wgrad_tc_bf16_kernel<<<grid, kThreads, smem, st>>>(tmY, tmA, q);
+    return check_launch("wgrad_tc_bf16_kernel");
+  }
   wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(tmY, tmA, q);
   rc = check_launch("wgrad_tc_kernel");
   if (rc) return rc;

@@ -29,11 +29,11 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(const float* __restric
     for (int j = 0; j < i; ++j) acc = fmaf(sig[tri + j], e[j], acc);
     acc = fmaf(softplus_f(sig[tri + i]), e[i], acc);
     if (mu) mu[b * z + i] = m;
-    if (zc) { float zv = eps ? acc : m; zc[b * zc_ld + i] = rnd ? scv::round_tf32(zv) : zv; }
+    if (zc) scv::store_out(zc, b * zc_ld + i, eps ? acc : m, rnd);
   }
   if (zc) {
     for (int t = threadIdx.x; t < (int)zc_ld - z; t += blockDim.x)
-      { float vv = t < nvar ? var[b * nvar + t] : 0.f; zc[b * zc_ld + z + t] = rnd ? scv::round_tf32(vv) : vv; }
+      scv::store_out(zc, b * zc_ld + z + t, t < nvar ? var[b * nvar + t] : 0.f, rnd);
   }
   if (L) {
     float* Lb = L + b * (int64_t)z * z;
@@ -65,11 +65,11 @@ __global__ void __launch_bounds__(256) reparam_bwd_kernel(const float* __restric
     if (dmu) g += dmu[b * z + i];
     if (dmu2) g += s2 * dmu2[b * z + i];
     if (dz) g += dz[b * dz_ld + i];
-    dms[b * dms_ld + i] = rnd ? scv::round_tf32(g) : g;
+    scv::store_out(dms, b * dms_ld + i, g, rnd);
   }
   __syncthreads();
   const float* sraw = ms + b * ms_ld + z;
-  float* drow = dms + b * dms_ld + z;
+  const int64_t drow = b * dms_ld + z;
   const float* dLb = dL ? dL + b * (int64_t)z * z : nullptr;
   for (int idx = threadIdx.x; idx < z * z; idx += blockDim.x) {
     int i = idx / z, j = idx - i * z;
@@ -78,9 +78,9 @@ __global__ void __launch_bounds__(256) reparam_bwd_kernel(const float* __restric
     if (dLb) g += dLb[idx];
     const int t = i * (i + 1) / 2 + j;
     if (j == i) g *= softplus_grad(sraw[t]);
-    drow[t] = rnd ? scv::round_tf32(g) : g;
+    scv::store_out(dms, drow + t, g, rnd);
   }
-  for (int t = z + nsig + threadIdx.x; t < dms_ld; t += blockDim.x) dms[b * dms_ld + t] = 0.f;
+  for (int t = z + nsig + threadIdx.x; t < dms_ld; t += blockDim.x) scv::store_out(dms, b * dms_ld + t, 0.f, rnd);
 }
 
 __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, const float* __restrict__ L,
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(256) out_bwd_kernel(const float* __restrict__ 
       dv[q] = gg[q] * sc * (1.f - yy[q] * yy[q]);
     }
     float4 o = make_float4(dv[0], dv[1], dv[2], dv[3]);
-    *reinterpret_cast<float4*>(draw + (int64_t)b * d_bs + (int64_t)w * d_ls + c) = rnd ? scv::round_tf32(o) : o;
+    scv::store_out4(draw, (int64_t)b * d_bs + (int64_t)w * d_ls + c, o, rnd);
   }
 }
 
@@ -619,7 +619,7 @@ int scv_reparam_fwd(const float* ms, int64_t ms_ld, const float* eps, const floa
   SCV_REQUIRE(!zc || zc_ld >= z + nvar, "scv_reparam_fwd: zc_ld too small");
   if (B <= 0) return 0;
   reparam_fwd_kernel<<<(unsigned)B, 256, sh, (cudaStream_t)stream>>>(ms, ms_ld, eps, var, (int)nvar, mu, L, zc, zc_ld,
-                                                                    (int)z, (int)(flags & SCV_F_ROUND_TF32));
+                                                                    (int)z, (flags & SCV_F_OUT_BF16) ? 2 : (int)(flags & SCV_F_ROUND_TF32));
   return scv::check_launch("reparam_fwd_kernel");
 }
 
@@ -628,7 +628,7 @@ int scv_reparam_bwd(const float* ms, int64_t ms_ld, const float* eps, const floa
                     int64_t B, int64_t z, int64_t flags, void* stream) {
   if (B <= 0) return 0;
   reparam_bwd_kernel<<<(unsigned)B, 256, (size_t)(2 * z) * sizeof(float), (cudaStream_t)stream>>>(
-      ms, ms_ld, eps, dmu, dmu2, (float)dmu2_scale, dz, dz_ld, dL, dms, dms_ld, (int)z, (int)(flags & SCV_F_ROUND_TF32));
+      ms, ms_ld, eps, dmu, dmu2, (float)dmu2_scale, dz, dz_ld, dL, dms, dms_ld, (int)z, (flags & SCV_F_OUT_BF16) ? 2 : (int)(flags & SCV_F_ROUND_TF32));
   return scv::check_launch("reparam_bwd_kernel");
 }
 
@@ -671,7 +671,7 @@ int scv_out_bwd(const float* xh, const float* dxh, int64_t ld, const float* g_jp
   if (blocks < 1) return 0;
   out_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(xh, dxh, (int)ld, g_jpe, g_root, (int)nx, draw,
                                                                     d_bs, d_ls, B * W, (int)W,
-                                                                    (int)(flags & SCV_F_ROUND_TF32));
+                                                                    (flags & SCV_F_OUT_BF16) ? 2 : (int)(flags & SCV_F_ROUND_TF32));
   return scv::check_launch("out_bwd_kernel");
 }
 

@@ -213,6 +213,24 @@ __device__ __forceinline__ void umma2_tf32_lh(uint32_t tmem_d, uint32_t a_lo, ui
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 with bf16 operands (16 elements = 32 bytes of K per instruction), fp32 accumulate
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool kBf16>
+__device__ __forceinline__ void umma_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t accumulate) {
+  if (kBf16) umma_bf16_lh(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  else umma_tf32_lh(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+}
 // all previously issued MMAs of this thread arrive on `bar` when they complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -267,6 +285,12 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Instruction descriptor, kind::f16 with BF16 operands (a_format = b_format = 1), fp32 accumulate
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // sum over the 32 lanes of v[j] for every j: afterwards lane j holds column j's total in v[0]
 __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 #pragma unroll
@@ -293,8 +317,8 @@ encode_tiled_fn get_encode_tiled();
 // fp32 tensor of `rank` dims (dims[0] contiguous), strides in ELEMENTS for dims 1.., 128B-swizzled boxes,
 // out-of-bounds elements read as zero.  Overlapping strides (stride < extent of the faster dims) are what
 // turns a halo-padded activation into the implicit-GEMM A operand.
-int make_tmap(CUtensorMap* tm, const float* base, int rank, const int64_t* dims, const int64_t* strides_elems,
-              const int* box, const char* what, bool atom32 = false);
+int make_tmap(CUtensorMap* tm, const void* base, int rank, const int64_t* dims, const int64_t* strides_elems,
+              const int* box, const char* what, bool atom32 = false, bool bf16 = false);
 
 }  // namespace tc
 }  // namespace scv

@@ -28,13 +28,18 @@ import torch
 import torch.nn as nn
 
 from . import layout as lay
-from ._ops import ACT_ACCUM, ACT_NONE, ACT_RELU, ACT_RELUMASK, ACT_ROUND_TF32, ACT_TANH, BN, PREC, PRELU, ROUND_TF32, TRAIN, Ref
+from ._ops import (ACT_ACCUM, ACT_NONE, ACT_RELU, ACT_RELUMASK, ACT_ROUND_TF32, ACT_TANH, BN, OUT_BF16, PREC, PRELU,
+                   ROUND_TF32, TRAIN, Ref)
 
 FEAT_FLOAT = ("avg_speed", "part_speed", "frame_speed", "avg_speed_3d", "heading", "heading_change", "fluorescence")
 
 
 def pad4(n: int) -> int:
     return (n + 3) // 4 * 4
+
+
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
 
 
 def pad16(n: int) -> int:
@@ -44,13 +49,13 @@ def pad16(n: int) -> int:
 class Act:
     """Halo-padded channels-last activation  t[b][hl + l][c]  (halo rows stay zero forever)."""
 
-    def __init__(self, dev, B, L, C, hl=0, hr=0, even=False, slack=0):
+    def __init__(self, dev, B, L, C, hl=0, hr=0, even=False, slack=0, dtype=torch.float32):
         rows = hl + L + hr
         if even and rows % 2:
             rows += 1
         self.B, self.L, self.C, self.hl, self.rows = B, L, C, hl, rows
         self.bs, self.ls = rows * C, C
-        self.t = torch.zeros(B * rows * C + slack, device=dev, dtype=torch.float32)
+        self.t = torch.zeros(B * rows * C + slack, device=dev, dtype=dtype)
 
     def at(self, l: int = 0) -> Ref:
         return Ref(self.t, (self.hl + l) * self.C)
@@ -108,9 +113,11 @@ class Engine:
         self.ops = ops
         self.m = model
         self.precision = PREC[getattr(model, "precision", "tf32")]
-        # tensor-core path: every kernel that PRODUCES a GEMM operand rounds it to TF32 (round-to-nearest); the
-        # MMA itself would truncate, which biases sums that cancel (BatchNorm backward subtracts batch means)
-        self.rnd = self.precision != 0
+        # tensor-core path: every kernel that PRODUCES a GEMM operand rounds it to TF32 (round-to-nearest; the MMA itself
+        # would truncate, which biases sums that cancel: BatchNorm backward subtracts batch means) or, in bf16 mode,
+        # stores it as bf16.  `rnd` is the producers' output mode: 0 fp32, 1 TF32-rounded fp32, 2 bf16 operand buffers.
+        self.rnd = self.precision
+        self.op_dtype = torch.bfloat16 if self.precision == 2 else torch.float32
         self.device = next(model.parameters()).device
         if ops.name == "cuda" and self.device.type != "cuda":
             raise RuntimeError("scrubvae_b200: the model must live on a CUDA device (there is no CPU path); "
@@ -259,7 +266,7 @@ class Engine:
 
         d = "decoder."
         self.cond_dim = m.conditional_dim
-        self.zc_ld = pad4(z + self.cond_dim)
+        self.zc_ld = pad8(z + self.cond_dim) if self.precision == 2 else pad4(z + self.cond_dim)
         wfi = lay.fc_dec_fprop(I(d + "fc_in.weight"), self.Cl, self.Ll, self.zc_ld)
         add("dec.fc_in", wfi, lay.fc_dec_bias(I(d + "fc_in.bias"), self.Cl, self.Ll),
             d_idx=lay.transpose_pad(wfi, self.Ll * self.Cl))
@@ -279,6 +286,7 @@ class Engine:
             d_idx=lay.convT_dgrad(I(d + "conv_out.weight"), self.C0))
 
         # gradient-reversal heads: model/disentangle.py:583-632
+        self._d_heads0 = self._n_d  # data-gradient matrices of the scrubber heads start here (they stay fp32: FFMA path)
         self.gr_keys: List[str] = []
         self.gr_layers: Dict[str, List[List[GemmW]]] = {}
         self.gr_alpha: Dict[str, float] = {}
@@ -324,6 +332,9 @@ class Engine:
         assert fwd_idx.numel() == self._n_fwd and d_idx.numel() == self._n_d
         self.pack_idx = torch.cat([fwd_idx, d_idx]).to(torch.int32).to(dev)
         self.packed = torch.zeros(self._n_fwd + self._n_d, device=dev)
+        # bf16 mode: the GEMMs read bf16 copies of the packed matrices (same element offsets); `packed` (fp32) then only
+        # serves the biases, which the epilogues add in fp32
+        self.packed16 = torch.zeros(self._n_fwd + self._n_d, device=dev, dtype=torch.bfloat16) if self.precision == 2 else None
         self.gpacked = torch.zeros(self._n_fwd, device=dev)
         self.inv_idx = lay.inverse_map(fwd_idx, self.n_flat).to(torch.int32).to(dev)
         self.grads_dirty = False   # gpacked / gflat hold gradients of a piecewise backward (TrainStep zeroes them)
@@ -335,12 +346,18 @@ class Engine:
         self.gp_split = self.W["dec.fc_in"].w
 
     def wref(self, g: GemmW) -> Ref:
-        return Ref(self.packed, g.w)
+        return Ref(self.packed16 if self.packed16 is not None else self.packed, g.w)
 
     def bref(self, g: GemmW) -> Optional[Ref]:
         return None if g.b is None else Ref(self.packed, g.b)
 
     def wdref(self, g: GemmW) -> Ref:
+        return Ref(self.packed16 if self.packed16 is not None else self.packed, self._n_fwd + g.wd)
+
+    def wref32(self, g: GemmW) -> Ref:  # scrubber heads: fp32 FFMA kernels in every precision mode
+        return Ref(self.packed, g.w)
+
+    def wdref32(self, g: GemmW) -> Ref:
         return Ref(self.packed, self._n_fwd + g.wd)
 
     def gwref(self, g: GemmW) -> Ref:
@@ -354,8 +371,17 @@ class Engine:
         "dgrad" = data-gradient matrices (only the backward pass reads them), "all" = both."""
         n0 = 0 if part in ("all", "fwd") else self._n_fwd
         n1 = self._n_fwd if part == "fwd" else self.packed.numel()
-        if n1 > n0:
-            self.ops.gather(self.flat, Ref(self.pack_idx, n0), Ref(self.packed, n0), n1 - n0, False, round_tf32=self.rnd)
+        if n1 <= n0:
+            return
+        if self.packed16 is not None:
+            self.ops.gather(self.flat, Ref(self.pack_idx, n0), Ref(self.packed16, n0), n1 - n0, False, round_tf32=2)
+            if n0 == 0:  # biases (and the scrubber heads' fp32 weights) live in the fp32 copy of the forward part
+                self.ops.gather(self.flat, self.pack_idx, self.packed, self._n_fwd, False, round_tf32=0)
+            h0 = self._n_fwd + self._d_heads0
+            if n1 > h0:  # fp32 data-gradient matrices of the scrubber heads
+                self.ops.gather(self.flat, Ref(self.pack_idx, h0), Ref(self.packed, h0), n1 - h0, False, round_tf32=0)
+            return
+        self.ops.gather(self.flat, Ref(self.pack_idx, n0), Ref(self.packed, n0), n1 - n0, False, round_tf32=self.rnd)
 
     # ------------------------------------------------------------------ API
     def plan(self, B: int) -> "Plan":
@@ -390,11 +416,15 @@ class Plan:
         C0 = eng.C0
         prec = eng.precision
         rnd = eng.rnd
-        rmode = ROUND_TF32 if rnd else 0
+        rmode = {0: 0, 1: ROUND_TF32, 2: OUT_BF16}[rnd]
+        bf16 = rnd == 2
         slack = eng.max_k + 64
         p2 = k // 2
         f32 = dict(device=dev, dtype=torch.float32)
-        A = lambda L, C, hl=0, hr=0, even=False: Act(dev, B, L, C, hl, hr, even, slack)  # noqa: E731
+        opd = dict(device=dev, dtype=eng.op_dtype)
+        A = lambda L, C, hl=0, hr=0, even=False: Act(dev, B, L, C, hl, hr, even, slack)  # noqa: E731  fp32: GEMM outputs
+        # GEMM OPERAND buffers (written by the elementwise producers, read by the GEMMs as A / dY): bf16 in bf16 mode
+        Ao = lambda L, C, hl=0, hr=0, even=False: Act(dev, B, L, C, hl, hr, even, slack, eng.op_dtype)  # noqa: E731
 
         # ---- static inputs
         self.inp = {
@@ -532,7 +562,7 @@ class Plan:
 
         WG = eng.W
         # =============================================================== encoder
-        X0 = A(W, C0, 3, 3)
+        X0 = Ao(W, C0, 3, 3)
         self.X0 = X0
         F.append(lambda: ops.pack_input(self.inp["x6d"], self.inp["root"], arena, X0.t, B, W, self.nx, C0, 3,
                                         round_tf32=rnd))
@@ -540,7 +570,7 @@ class Plan:
         g = WG["enc.conv_in"]
         gemm(A=X0.at(-3), a_bs=X0.bs, a_ls=C0, B=B, Lo=W, K=g.K, N=g.N, W=eng.wref(g), bias=eng.bref(g),
              bias_mod=g.bias_mod, bias_n=g.N, Y=Y0.at(0), y_bs=Y0.bs, y_ls=Y0.ls)
-        H = A(W, ch[0], p2, p2, even=True)
+        H = Ao(W, ch[0], p2, p2, even=True)
         bnact_fwd(None, "encoder.activation.weight", Y0, W, ch[0], None, 1, H=H)
         enc_in = dict(Y0=Y0, H0=H, g=g)
         L = W
@@ -556,7 +586,7 @@ class Plan:
             st1 = stats(Co // 2)
             gemm(A=H.at(-p2), a_bs=H.bs, a_ls=2 * Ci, B=B, Lo=Lo, K=g0.K, N=g0.N, W=eng.wref(g0), bias=eng.bref(g0),
                  bias_mod=g0.bias_mod, bias_n=g0.N, Y=R0.at(0), y_bs=R0.bs, y_ls=R0.ls, stats=st1)
-            R0a = A(Lo, Co // 2, p2, p2)
+            R0a = Ao(Lo, Co // 2, p2, p2)
             bnact_fwd(pre + "residual.1", pre + "residual.2.weight", R0, Lo, Co // 2, st1, 1, H=R0a)
             T = A(Lo, Co)
             st2 = stats(Co)
@@ -564,7 +594,7 @@ class Plan:
                  bias=eng.bref(g3), bias_mod=g3.bias_mod, bias_n=g3.N, Y=T.at(0), y_bs=T.bs, y_ls=T.ls,
                  R=S.at(0), r_bs=S.bs, r_ls=S.ls, stats=st2)
             last = i == eng.nblk - 1
-            Hn = A(Lo, Co) if last else A(Lo, Co, p2, p2, even=True)
+            Hn = Ao(Lo, Co) if last else Ao(Lo, Co, p2, p2, even=True)
             bnact_fwd(pre + "add.0", pre + "add.1.weight", T, Lo, Co, st2, 1, H=Hn)
             enc_blocks.append(dict(pre=pre, Hin=H, Lin=L, Ci=Ci, Co=Co, Lo=Lo, S=S, R0=R0, R0a=R0a, T=T, Hn=Hn,
                                    st1=st1, st2=st2, gs=gs, g0=g0, g3=g3))
@@ -577,7 +607,7 @@ class Plan:
              bias_mod=gfc.bias_mod, bias_n=gfc.N, Y=self.ms, y_bs=eng.ms_ld, y_ls=0)
         self.mu = torch.zeros(B, z, **f32)
         self.Lmat = torch.zeros(B, z, z, **f32)
-        self.zc = torch.zeros(B * eng.zc_ld + 64, **f32)[:B * eng.zc_ld].view(B, eng.zc_ld)  # + slab read slack (scv.h)
+        self.zc = torch.zeros(B * eng.zc_ld + 64, **opd)[:B * eng.zc_ld].view(B, eng.zc_ld)  # + slab read slack (scv.h)
 
         def reparam():
             ops.reparam_fwd(self.ms, eng.ms_ld, self.eps if self._training else None,
@@ -589,13 +619,22 @@ class Plan:
         # =============================================================== decoder
         Ll, Cl = eng.Ll, eng.Cl
         gin = WG["dec.fc_in"]
-        H = A(Ll, Cl, p2, p2)
-        gemm(A=self.zc, a_bs=eng.zc_ld, a_ls=0, B=B, Lo=1, K=gin.K, N=gin.N, W=eng.wref(gin), bias=eng.bref(gin),
-             bias_mod=gin.bias_mod, bias_n=gin.N, Y=H.at(0), y_bs=H.bs, y_ls=0,
-             act=ACT_ROUND_TF32 if rnd else ACT_NONE)  # fc_in output feeds the next GEMM directly
-        U = A(2 * Ll, Cl, p2, p2)
-        bnact_fwd(None, None, H, Ll, Cl, None, 1, U=U)
-        dec_in = dict(H=H, U=U, g=gin)
+        H = Ao(Ll, Cl, p2, p2)
+        U = Ao(2 * Ll, Cl, p2, p2)
+        if bf16:
+            # GEMM outputs are fp32: fc_in writes Hraw, the (BN-less, activation-less) pass that builds the upsampled
+            # copy also writes the bf16 operand copy H
+            Hraw = A(Ll, Cl)
+            gemm(A=self.zc, a_bs=eng.zc_ld, a_ls=0, B=B, Lo=1, K=gin.K, N=gin.N, W=eng.wref(gin), bias=eng.bref(gin),
+                 bias_mod=gin.bias_mod, bias_n=gin.N, Y=Hraw.at(0), y_bs=Hraw.bs, y_ls=0)
+            bnact_fwd(None, None, Hraw, Ll, Cl, None, 1, H=H, U=U)
+        else:
+            Hraw = H
+            gemm(A=self.zc, a_bs=eng.zc_ld, a_ls=0, B=B, Lo=1, K=gin.K, N=gin.N, W=eng.wref(gin), bias=eng.bref(gin),
+                 bias_mod=gin.bias_mod, bias_n=gin.N, Y=H.at(0), y_bs=H.bs, y_ls=0,
+                 act=ACT_ROUND_TF32 if rnd else ACT_NONE)  # fc_in output feeds the next GEMM directly
+            bnact_fwd(None, None, H, Ll, Cl, None, 1, U=U)
+        dec_in = dict(H=H, Hraw=Hraw, U=U, g=gin)
         wl, wr = lay.poly_window(k)
         hw = max(wl, wr)
         L = Ll
@@ -612,7 +651,7 @@ class Plan:
             st1 = stats(Ci // 2)
             gemm(A=H.at(-p2), a_bs=H.bs, a_ls=Ci, B=B, Lo=L, K=g0.K, N=g0.N, W=eng.wref(g0), bias=eng.bref(g0),
                  bias_mod=g0.bias_mod, bias_n=g0.N, Y=R0.at(0), y_bs=R0.bs, y_ls=R0.ls, stats=st1)
-            R0a = A(L, Ci // 2, hw, hw)
+            R0a = Ao(L, Ci // 2, hw, hw)
             bnact_fwd(pre + "residual.1", pre + "residual.2.weight", R0, L, Ci // 2, st1, 1, H=R0a)
             T = A(Lo2, Co)
             st2 = stats(2 * Co)
@@ -622,9 +661,9 @@ class Plan:
             last = i == eng.nblk - 1
             if last:
                 ho = eng.kf - 1 - 3
-                Hn, Un = A(Lo2, Co, ho, ho), None
+                Hn, Un = Ao(Lo2, Co, ho, ho), None
             else:
-                Hn, Un = A(Lo2, Co, p2, p2), A(2 * Lo2, Co, p2, p2)
+                Hn, Un = Ao(Lo2, Co, p2, p2), Ao(2 * Lo2, Co, p2, p2)
             bnact_fwd(pre + "add.0", pre + "add.1.weight", T, Lo2, Co, st2, 2, H=Hn, U=Un)
             dec_blocks.append(dict(pre=pre, H=H, U=U, L=L, Ci=Ci, Co=Co, Lo2=Lo2, S=S, R0=R0, R0a=R0a, T=T, Hn=Hn,
                                    Un=Un, st1=st1, st2=st2, gs=gs, g0=g0, g3=g3))
@@ -675,7 +714,7 @@ class Plan:
                         out, dout, o_ld = Ref(torch.zeros(B, gl.N, **f32)), Ref(torch.zeros(B, gl.N, **f32)), gl.N
                     lastl = li == len(layers) - 1
                     fwd_levels.setdefault(li, []).append(dict(
-                        A=hin, a_bs=h_ld, a_ls=0, B=B, Lo=1, K=gl.K, N=gl.N, W=eng.wref(gl), bias=eng.bref(gl),
+                        A=hin, a_bs=h_ld, a_ls=0, B=B, Lo=1, K=gl.K, N=gl.N, W=eng.wref32(gl), bias=eng.bref(gl),
                         bias_mod=gl.bias_mod, bias_n=gl.N, Y=out, y_bs=o_ld, y_ls=0,
                         act=ACT_NONE if lastl else ACT_RELU, precision=0))
                     acts.append((out, o_ld))
@@ -730,7 +769,7 @@ class Plan:
             eng.grads_dirty = True  # this path leaves the gradients in place; TrainStep expects zeroed buffers
         Bw.append(zero_grads)
         # conv_out + tanh
-        dOut = A(W, C0, 3, 3)
+        dOut = Ao(W, C0, 3, 3)
         Bw.append(lambda: ops.out_bwd(self.xh, self.dxh, C0, Ref(self.gscale, 0), Ref(self.gscale, 1), self.nx,
                                       dOut.at(0), dOut.bs, dOut.ls, B, W, round_tf32=rnd))
         Bw.append(wgrad(gout, Hlast.at(-ho), Hlast.bs, ch[0], W, dOut.at(0), dOut.bs, dOut.ls))
@@ -740,7 +779,7 @@ class Plan:
         for blk in reversed(dec_blocks):
             Ci, Co, L, Lo2, pre = blk["Ci"], blk["Co"], blk["L"], blk["Lo2"], blk["pre"]
             gs, g0, g3 = blk["gs"], blk["g0"], blk["g3"]
-            dT = A(Lo2, Co, k - p2, p2 + 1, even=True)
+            dT = Ao(Lo2, Co, k - p2, p2 + 1, even=True)
             lst = bnact_bwd(pre + "add.0", pre + "add.1.weight", blk["T"], Lo2, Co, blk["st2"], 2, dH, dU, dT,
                             sums(Co))
             if dU is not None:
@@ -756,7 +795,7 @@ class Plan:
                             bias_n=2 * Co))
             dR0a = A(L, Ci // 2)
             Bw.append(dgemm(g3, dT.at(-p2), dT.bs, 2 * Co, L, dR0a.at(0), dR0a.bs, dR0a.ls))
-            dR0 = A(L, Ci // 2, p2, p2)
+            dR0 = Ao(L, Ci // 2, p2, p2)
             Bw += bnact_bwd(pre + "residual.1", pre + "residual.2.weight", blk["R0"], L, Ci // 2, blk["st1"], 1,
                             dR0a, None, dR0, sums(Ci // 2))
             Bw.append(wgrad(g0, blk["H"].at(-p2), blk["H"].bs, Ci, L, dR0.at(0), dR0.bs, dR0.ls))
@@ -764,8 +803,8 @@ class Plan:
             Bw.append(dgemm(g0, dR0.at(-p2), dR0.bs, Ci // 2, L, dHin.at(0), dHin.bs, dHin.ls))
             dH, dU = dHin, dUin
         # fc_in (input of decoder block 0 has no BN / activation: only the upsample transpose)
-        dX0 = A(Ll, Cl)
-        lst = bnact_bwd(None, None, dec_in["H"], Ll, Cl, None, 1, dH, dU, dX0, None)
+        dX0 = Ao(Ll, Cl)
+        lst = bnact_bwd(None, None, dec_in["Hraw"], Ll, Cl, None, 1, dH, dU, dX0, None)
         lst[0] = AfterSide(lst[0])
         Bw += lst
         Bw.append(wgrad(gin, self.zc, eng.zc_ld, 0, 1, dX0.at(0), dX0.bs, 0))
@@ -800,7 +839,7 @@ class Plan:
                                    dW=eng.gwref(gl), dbias=eng.gbref(gl), bias_mod=gl.bias_mod, bias_n=gl.N, precision=0))
                     if li > 0:
                         dprev, dp_ld = dacts[li - 1]
-                        dg.append(dict(A=dy, a_bs=dy_ld, a_ls=0, B=B, Lo=1, K=gl.dK, N=gl.dN, W=eng.wdref(gl), Y=dprev,
+                        dg.append(dict(A=dy, a_bs=dy_ld, a_ls=0, B=B, Lo=1, K=gl.dK, N=gl.dN, W=eng.wdref32(gl), Y=dprev,
                                        y_bs=dp_ld, y_ls=0, R=hin, r_bs=h_ld, r_ls=0, act=ACT_RELUMASK, precision=0))
             for grp in chunks(wg):
                 Bw.append(lambda grp=grp: ops.wgrad_group(grp))
@@ -809,14 +848,14 @@ class Plan:
         for ki, key in enumerate(eng.gr_keys):  # gradient reversal: dmu_gr (+)= -alpha * dact0_cat . W_cat^T
             gc = eng.gr_cat[key]
             kw2 = dict(A=self.gr_dact0[key], a_bs=self.gr_cat_ld[key], a_ls=0, B=B, Lo=1, K=gc.dK, N=gc.dN,
-                       W=eng.wdref(gc), Y=self.dmu_gr, y_bs=z, y_ls=0, R=None if ki == 0 else self.dmu_gr, r_bs=z, r_ls=0,
+                       W=eng.wdref32(gc), Y=self.dmu_gr, y_bs=z, y_ls=0, R=None if ki == 0 else self.dmu_gr, r_bs=z, r_ls=0,
                        out_scale=-eng.gr_alpha[key], precision=0)
             Bw.append(lambda kw2=kw2: ops.gemm(**kw2))
         self._bw_dec_end = len(Bw)  # decoder + scrubber-head weight gradients are final from here on
         # latent
         self.dmu_kl = torch.zeros(B, z, **f32)
         self.dL_kl = torch.zeros(B, z, z, **f32)
-        self.dms = torch.zeros(B * eng.ms_ld + 64, **f32)[:B * eng.ms_ld].view(B, eng.ms_ld)
+        self.dms = torch.zeros(B * eng.ms_ld + 64, **opd)[:B * eng.ms_ld].view(B, eng.ms_ld)
         Bw.append(lambda: ops.kl(self.mu, self.Lmat, None, Ref(self.gscale, 2), self.dmu_kl, self.dL_kl, B, z))
         Bw.append(lambda: ops.reparam_bwd(self.ms, eng.ms_ld, self.eps, self.dmu_kl, self.dmu_gr, 1.0, self.dzc,
                                           eng.zc_ld, self.dL_kl, self.dms, eng.ms_ld, B, z, round_tf32=rnd))
@@ -829,7 +868,7 @@ class Plan:
         for bi, blk in reversed(list(enumerate(enc_blocks))):
             Ci, Co, Lo, Lin, pre = blk["Ci"], blk["Co"], blk["Lo"], blk["Lin"], blk["pre"]
             gs, g0, g3 = blk["gs"], blk["g0"], blk["g3"]
-            dT = A(Lo, Co, p2, p2)
+            dT = Ao(Lo, Co, p2, p2)
             Bw += bnact_bwd(pre + "add.0", pre + "add.1.weight", blk["T"], Lo, Co, blk["st2"], 1, dH, None, dT,
                             sums(Co))
             # the skip path's data gradient needs only dT: side stream, beside residual.3 dgrad -> BN backward
@@ -840,7 +879,7 @@ class Plan:
             Bw.append(wgrad(g3, blk["R0a"].at(-p2), blk["R0a"].bs, Co // 2, Lo, dT.at(0), dT.bs, dT.ls))
             dR0a = A(Lo, Co // 2)
             Bw.append(dgemm(g3, dT.at(-(k - 1 - p2)), dT.bs, Co, Lo, dR0a.at(0), dR0a.bs, dR0a.ls))
-            dR0 = A(Lo, Co // 2, hw, hw)
+            dR0 = Ao(Lo, Co // 2, hw, hw)
             Bw += bnact_bwd(pre + "residual.1", pre + "residual.2.weight", blk["R0"], Lo, Co // 2, blk["st1"], 1,
                             dR0a, None, dR0, sums(Co // 2))
             Hin = blk["Hin"]
@@ -851,7 +890,7 @@ class Plan:
             if bi >= eng.nblk - 2:  # the two widest blocks (6.5 M and 1.6 M weights at the default widths); the small rest goes last
                 self._bw_buckets.append((len(Bw), gs.w, self._bw_buckets[-1][1]))
             dH = dHin
-        dY0 = A(W, ch[0])
+        dY0 = Ao(W, ch[0])
         Bw += bnact_bwd(None, "encoder.activation.weight", enc_in["Y0"], W, ch[0], None, 1, dH, None, dY0, sums(ch[0]))
         g = enc_in["g"]
         Bw.append(wgrad(g, X0.at(-3), X0.bs, C0, W, dY0.at(0), dY0.bs, dY0.ls))
@@ -928,7 +967,7 @@ class Plan:
             out["mu"], out["L"] = self.mu, self.Lmat
             if upto == "encode":
                 return out
-            out["z"] = self.zc[:, :m.z_dim]
+            out["z"] = self.zc[:, :m.z_dim] if eng.precision != 2 else self.zc[:, :m.z_dim].float()
         if eng.cond_dim > 0:
             out["var"] = self.var
         B, W = self.B, m.window
@@ -1097,6 +1136,7 @@ class TrainStep:
                 with torch.cuda.stream(plan.dside):
                     eng.repack("dgrad")
                     ops.zero(eng.gpacked)
+                    ops.zero(eng.gflat[:eng.n_direct])  # BatchNorm / PReLU gradients accumulate
                 plan.run_forward()
                 for f in plan.Lk:
                     f()
@@ -1104,23 +1144,28 @@ class TrainStep:
             else:
                 eng.repack("dgrad")
                 ops.zero(eng.gpacked)
+                ops.zero(eng.gflat[:eng.n_direct])
                 plan.run_forward()
                 for f in plan.Lk:
                     f()
             plan.gscale.copy_(plan.loss_scale)
             plan.backward(self.comm)
+            # tail: weight gradients back to the parameter layout (coalesced-store gather), global norm, clip + optimizer.
+            # Measured alternatives (profiles/r02_optimizer_tail.md): an optimizer that WRITES the packed matrices with
+            # scattered 4-byte stores took 3.8 ms; one that only READS the packed gradients by gather 348 us against
+            # 110 (gather) + 132 (optimizer) here.
+            ops.gather(eng.gpacked, eng.inv_idx, eng.gflat, eng.n_flat, True)
             if self.keep_grads:
                 if self.grad_snapshot is None:
                     self.grad_snapshot = torch.zeros_like(eng.gflat)
-                self.grad_snapshot.copy_(eng.gflat)  # BatchNorm / PReLU gradients
-                ops.gather(eng.gpacked, eng.inv_idx, self.grad_snapshot, eng.n_flat, True)
-            ops.sumsq_packed(eng.gpacked, eng.pack_idx, eng._n_fwd, eng.gflat, eng.n_direct, plan.sumsq)
+                self.grad_snapshot.copy_(eng.gflat)
+            ops.sumsq(eng.gflat, eng.n_flat, plan.sumsq)
             grp = opt.param_groups[0]
             from .train.optim import KIND
             b1 = grp["momentum"] if opt.kind == "sgd" else grp["betas"][0]
             ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, eng.n_flat, plan.sumsq, self.max_norm, opt.grad_scale,
                            float(grp["lr"]), b1, grp["betas"][1], grp["eps"], grp["weight_decay"], 1, KIND[opt.kind],
-                           hyper=opt.hyper, inv_idx=eng.inv_idx, gpacked=eng.gpacked)
+                           hyper=opt.hyper)
         finally:
             plan._fused_tail = False
 
@@ -1132,9 +1177,6 @@ class TrainStep:
             plan.load_targets(data)
         opt._steps += 1
         opt.push_hyper()  # ring of pinned slots: safe when the host runs several steps ahead of the device
-        if self.eng.grads_dirty:  # a piecewise backward left BatchNorm / PReLU gradients in gflat: this path accumulates
-            self.eng.gflat.zero_()
-            self.eng.grads_dirty = False
         if not self.use_graph:
             n0 = self.eng.ops.launch_count()
             self._sequence()

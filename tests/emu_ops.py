@@ -51,7 +51,9 @@ class EmuOps:
         n_last = N if n_last is None else n_last
         a = _v(A, (B, Lo, K), (a_bs, a_ls, 1))
         w = _v(W, (N, K), (K, 1))
-        if precision != 0:  # TF32 tensor-core arithmetic: operands carry 10 mantissa bits, fp32 accumulation
+        if precision == 2:  # bf16 operands (the buffers hold bf16), fp32 accumulation
+            a, w = a.float(), w.float()
+        elif precision != 0:  # TF32 tensor-core arithmetic: operands carry 10 mantissa bits, fp32 accumulation
             a, w = rtf32(a), rtf32(w)
         y = out_scale * (a.reshape(B * Lo, K) @ w.t()).reshape(B, Lo, N)
         if bias is not None:
@@ -97,7 +99,10 @@ class EmuOps:
         self.n += 1
         a = _v(A, (B, Lo, K), (a_bs, a_ls, 1)).reshape(B * Lo, K)
         g = _v(dY, (B, Lo, N), (y_bs, y_ls, 1)).reshape(B * Lo, N)
-        if precision != 0:
+        if precision == 2:
+            a, g = a.float(), g.float()
+            gm = g
+        elif precision != 0:
             a, gm = rtf32(a), rtf32(g)
         else:
             gm = g
@@ -121,7 +126,7 @@ class EmuOps:
         o.zero_()
         o[..., :nx] = x
         o[..., nx:nx + 3] = 2 * (r - a[0]) / (a[1] - a[0]) - 1
-        if round_tf32:
+        if round_tf32 == 1:  # (2: the output buffer is bf16 — the assignments above already rounded)
             o.copy_(rtf32(o.clone()))
 
     # ---- BN + PReLU
@@ -256,7 +261,7 @@ class EmuOps:
                 o[:, :z] = m
             if nvar > 0:
                 o[:, z:z + nvar] = _v(var, (B, nvar), (nvar, 1))
-            if round_tf32:
+            if round_tf32 == 1:
                 o.copy_(rtf32(o.clone()))
 
     def reparam_bwd(self, ms, ms_ld, eps, dmu, dmu2, dmu2_scale, dz, dz_ld, dL, dms, dms_ld, B, z, round_tf32=False):
@@ -287,7 +292,7 @@ class EmuOps:
         sp = torch.where(sig > 20, torch.ones(()), torch.sigmoid(sig))
         gs = torch.where(isd[None, :], gs * sp, gs)
         out[:, z:z + nsig] = gs
-        if round_tf32:
+        if round_tf32 == 1:
             out.copy_(rtf32(out.clone()))
 
     def kl(self, mu, L, loss, gscale, dmu, dL, B, z):
@@ -350,7 +355,7 @@ class EmuOps:
         sc[:nx] = gj
         sc[nx:nx + 3] = gr
         dv = d * sc * (1 - y * y)
-        _v(draw, (B, W, ld), (d_bs, d_ls, 1)).copy_(rtf32(dv) if round_tf32 else dv)
+        _v(draw, (B, W, ld), (d_bs, d_ls, 1)).copy_(rtf32(dv) if round_tf32 == 1 else dv)
 
     @torch.enable_grad()
     def gr_loss(self, preds, dpreds, ld, target, labels, B, d, num_keys, loss, gscale):
@@ -382,12 +387,13 @@ class EmuOps:
         o = _v(dst, (n,), (1,))
         ok = i >= 0
         vals = s[i.clamp_min(0)]
-        if round_tf32:
+        if round_tf32 == 1:
             vals = rtf32(vals)
+        vals = vals.to(o.dtype)
         if skip_neg:
             o[ok] = vals[ok]
         else:
-            o.copy_(torch.where(ok, vals, torch.zeros(())))
+            o.copy_(torch.where(ok, vals, torch.zeros((), dtype=vals.dtype)))
 
     def sumsq(self, g, n, out):
         self.n += 1

@@ -52,10 +52,12 @@ GEMM_CASES = [
 ]
 
 
-@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("prec", [0, 1, 2])
 @pytest.mark.parametrize("case", GEMM_CASES)
 def test_gemm(ops, case, prec):
     B, Lo, rows, C, s, taps, N, n_last, act, resid, stats = case
+    if prec == 2 and N < 16:
+        pytest.skip("bf16 operands exist only on the tensor-core path (N >= 16)")
     K = taps * C
     a_bs, a_ls = rows * C, s * C
     T = {
@@ -70,8 +72,10 @@ def test_gemm(ops, case, prec):
         bias_mod = N // 2
     else:
         bias_mod = N
-    if prec:  # operands already TF32-representable: the tensor-core result must then be fp32-exact arithmetic
+    if prec == 1:  # operands already TF32-representable: the tensor-core result must then be fp32-exact arithmetic
         T["A"], T["W"] = rtf32(T["A"]), rtf32(T["W"])
+    elif prec == 2:  # bf16 operand buffers (SCV_PREC_BF16): products of bf16 values are exact in fp32
+        T["A"], T["W"] = T["A"].bfloat16(), T["W"].bfloat16()
 
     def call(o, t):
         o.gemm(t["A"], a_bs, a_ls, B, Lo, K, N, t["W"], t["Y"], Lo * N, N, bias=t["bias"], bias_mod=bias_mod,
@@ -98,6 +102,8 @@ def test_gemm_multitile(ops, case, sub, mc, monkeypatch):
     monkeypatch.setenv("SCV_TC_MC", mc)
     monkeypatch.setenv("SCV_TC_SUB", sub)
     test_gemm(ops, case, 1)
+    if mc == "0":
+        test_gemm(ops, case, 2)
 
 
 @pytest.mark.parametrize("mc", ["0", "1"])
@@ -105,6 +111,8 @@ def test_gemm_multitile(ops, case, sub, mc, monkeypatch):
 def test_wgrad_multitile(ops, case, mc, monkeypatch):
     monkeypatch.setenv("SCV_TC_WMC", mc)
     test_wgrad(ops, case, 1)
+    if mc == "0":
+        test_wgrad(ops, case, 2)
 
 
 @pytest.mark.parametrize("prec", [0, 1])
@@ -124,21 +132,25 @@ def test_gemm_accumulate_split_k(ops, B, K, N, mc, prec, monkeypatch):
     run_both(ops, T, call, tol=2e-5, check=["Y"])
 
 
-@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("prec", [0, 1, 2])
 @pytest.mark.parametrize("case", GEMM_CASES[:5] + GEMM_CASES[6:])
 def test_wgrad(ops, case, prec):
     B, Lo, rows, C, s, taps, N, n_last, act, resid, stats = case
+    if prec == 2 and N % 8:
+        pytest.skip("bf16 dY rows must be 16-byte aligned (N % 8 == 0)")
     K = taps * C
     a_bs, a_ls = rows * C, s * C
     T = {
         "A": torch.randn(B * rows * C + K, generator=g(1)),
-        "dY": torch.randn(B * Lo * N + 32, generator=g(2)),  # + read slack of one 32-float slab (include/scv.h)
+        "dY": torch.randn(B * Lo * N + 64, generator=g(2)),  # + read slack of one 128-byte slab (include/scv.h)
         "dW": torch.zeros(N * K),
         "db": torch.zeros(N),
     }
     bias_mod = N // 2 if n_last is not None else N
-    if prec:
+    if prec == 1:
         T["A"], T["dY"] = rtf32(T["A"]), rtf32(T["dY"])
+    elif prec == 2:
+        T["A"], T["dY"] = T["A"].bfloat16(), T["dY"].bfloat16()
 
     def call(o, t):
         o.wgrad(t["A"], a_bs, a_ls, B, Lo, K, N, t["dY"], Lo * N, N, t["dW"], dbias=t["db"], bias_mod=bias_mod,

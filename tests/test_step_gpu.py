@@ -246,3 +246,50 @@ def test_scaled_architectures_vs_oracle(ch, zd, window, B, precision):
             p.grad = None
         losses["total"].backward()
         _check_grads([(n, p.grad) for n, p in m.named_parameters()], gref, 1e-3, "vs fp32 oracle")
+
+
+@pytest.mark.parametrize("cond,gr,dc", [(["heading"], ["heading"], None),
+                                        (["heading", "avg_speed_3d", "ids"], ["heading", "avg_speed_3d", "ids"],
+                                         {"ids": [0, 1, 2, 3]})])
+def test_bf16_step_against_oracle_and_ideal_bf16(cond, gr, dc):
+    """precision="bf16" (BASELINE config 3: bf16 operands / fp32 accumulate / fp32 master weights and GEMM outputs).
+    The reference has no bf16 mode: losses are held to the fp32 oracle within 1e-2 (stated, looser tolerance), the
+    gradients to IDEAL bf16 arithmetic — the same step on CPU with every GEMM operand buffer in bf16 and exact fp32
+    accumulation (tests/emu_ops.py) — under the same floor criterion as the TF32 path."""
+    ch, zd, B = [32, 64, 128, 256, 512], 32, 48
+    torch.manual_seed(21)
+    m, dcfg = build_model(ch, zd, cond, gr, dc, device="cpu")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    cfg = orc.Cfg(ch=tuple(ch), z_dim=zd, conditional=tuple(cond), grad_reversal=tuple(gr), discrete_classes=dc)
+    data = orc.synth_batch(B, seed=0)
+    eps = orc.synth_eps(B, zd, seed=2)
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, **{k + "_gr": 1.0 for k in gr}}
+    lref, gref, _, _, _ = orc.train_step(sd, data, cfg, scale, eps)
+    # ideal bf16 on the CPU emulation
+    from scrubvae_b200.engine import Engine
+    from emu_ops import EmuOps
+    me, _ = build_model(ch, zd, cond, gr, dc, device="cpu")
+    me.precision = "bf16"
+    me.load_state_dict(sd)
+    me._engine = Engine(me, ops=EmuOps())
+    me.train()
+    me._noise = eps
+    lo = sv.train.get_batch_loss(me, data, sv.train.predict_batch(me, data, me.disentangle_keys), scale, dcfg)
+    for p in me.parameters():
+        p.grad = None
+    lo["total"].backward()
+    emu = {n: p.grad.clone() for n, p in me.named_parameters()}
+    # CUDA
+    m.precision = "bf16"
+    m = m.to("cuda").train()
+    m._noise = eps.cuda()
+    opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-4, "lr_schedule": None})
+    step = TrainStep(m, opt, scale, B, use_graph=False, keep_grads=True)
+    step.run(_to_cuda(data))
+    torch.cuda.synchronize()
+    got = {k: v.item() for k, v in step.losses().items()}
+    for k, v in lref.items():
+        assert abs(got[k] - v.item()) <= 1e-2 * abs(v.item()) + 1e-5, (k, got[k], v.item())
+        assert abs(got[k] - lo[k].item()) <= 2e-3 * abs(lo[k].item()) + 1e-5, ("vs ideal bf16", k, got[k], lo[k].item())
+    grads = [(n, g.clone()) for n, g in step.named_grads().items()]
+    _check_tf32_floor(grads, emu, gref)

@@ -19,7 +19,7 @@ ap.add_argument("--once", action="store_true", help="launch each selected call e
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
-m, dcfg = bench.build_model(dev, "tf32")
+m, dcfg = bench.build_model(dev, os.environ.get("SCV_BENCH_PREC", "tf32"))
 m.train()
 opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-4, "lr_schedule": None})
 host = bench.synth_host_batch(a.batch, seed=0)
@@ -29,9 +29,10 @@ step.run(data)
 eng, ops = step.eng, step.eng.ops
 names = {}
 for g in eng.W.values():
-    names[eng.packed.data_ptr() + 4 * g.w] = (g.name + ":fwd", g.nnz)
+    pk = eng.packed16 if eng.packed16 is not None else eng.packed
+    names[pk.data_ptr() + pk.element_size() * g.w] = (g.name + ":fwd", g.nnz)
     if g.wd is not None:
-        names[eng.packed.data_ptr() + 4 * (eng._n_fwd + g.wd)] = (g.name + ":dgrad", g.nnz_d)
+        names[pk.data_ptr() + pk.element_size() * (eng._n_fwd + g.wd)] = (g.name + ":dgrad", g.nnz_d)
     names[("g", eng.gpacked.data_ptr() + 4 * g.w)] = (g.name + ":wgrad", g.nnz)
 calls = []
 og, ow = ops.gemm, ops.wgrad
