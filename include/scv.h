@@ -245,6 +245,17 @@ int scv_preprocess_windows(const double* pose, const int64_t* starts, const int6
                            int64_t window, int64_t J, const int32_t* tree, const int32_t* offset, const double* yaw,
                            int64_t mode, float* x6d, float* root, float* offsets, float* target_pose, void* stream);
 
+/* ---- generative restrictiveness (eval): reference eval/eval.py:22-120.  For B decoded windows (xh rows of ld floats: the
+ * decoder output after tanh, 6-D channels first; root_hat (B*W,3) un-normalised root positions or NULL = 0; offsets
+ * (B*W,J,3)): forward kinematics (fwd_kin_cont6d_torch data/dataset.py:83-116, eps 1e-8) and, per window,
+ *   heading (B,2)  = (sin, cos) of yaw = -atan2 of the unit joint0->joint1 vector at the mid frame (:67-72)
+ *   avg3 (B,3)     = [mean root speed, mean speed of part 0's joints, mean of the means of parts 1 and 2] (:73-104),
+ *                    then (x - norm[0..3)) / norm[3..6) if norm != NULL (:105-118)
+ * parts = [n, len, ref, j.., len, ref, j..]; pose_out (B,W,J,3) optional.  Each may be NULL. */
+int scv_gen_features(const float* xh, int64_t ld, const float* root_hat, const float* offsets, const int32_t* tree,
+                     int64_t n_tree, const int32_t* parts, int64_t B, int64_t W, int64_t J, const float* norm,
+                     float* pose_out, float* heading, float* avg3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

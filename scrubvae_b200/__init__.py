@@ -3,3 +3,4 @@ from . import model
 from . import get
 from . import train
 from . import data
+from . import eval  # noqa: A004

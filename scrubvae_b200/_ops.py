@@ -99,6 +99,7 @@ _SIGS = {
     "scv_gather": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "scv_sumsq": (C.c_int, [_vp, _i64, _vp, _vp]),
     "scv_optim_step": (C.c_int, [C.POINTER(OptimT), _vp]),
+    "scv_gen_features": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "scv_sumsq_packed": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "scv_zero": (C.c_int, [_vp, _i64, _vp]),
     "scv_d2f": (C.c_int, [_vp, _vp, _i64, _vp]),
@@ -279,6 +280,12 @@ class CudaOps:
         self._check(self.lib.scv_preprocess_windows(_ptr(pose), _ptr(starts), _ptr(keep), n_keep, window, J, _ptr(tree),
                                                     _ptr(offset), _ptr(yaw), mode, _ptr(x6d), _ptr(root), _ptr(offsets),
                                                     _ptr(target_pose), self._stream()), "scv_preprocess_windows")
+
+    def gen_features(self, xh, ld, root_hat, offsets, tree, n_tree, parts, B, W, J, norm=None, pose_out=None, heading=None,
+                     avg3=None):
+        self._check(self.lib.scv_gen_features(_ptr(xh), ld, _ptr(root_hat), _ptr(offsets), _ptr(tree), n_tree, _ptr(parts),
+                                              B, W, J, _ptr(norm), _ptr(pose_out), _ptr(heading), _ptr(avg3),
+                                              self._stream()), "scv_gen_features")
 
     def d2f(self, src, dst, n):
         self._check(self.lib.scv_d2f(_ptr(src), _ptr(dst), n, self._stream()), "scv_d2f")

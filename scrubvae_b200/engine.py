@@ -973,6 +973,8 @@ class Plan:
         B, W = self.B, m.window
         out["root"] = self.root_hat
         out["x6d"] = self.xh.view(B, W, -1)[..., :self.nx].unflatten(-1, (self.J, 6))
+        if z_given is not None:
+            out["_plan"] = self  # eval.generative_restrictiveness reads the decoded rows straight from the plan
         if z_given is None:
             out["disentangle"] = {}
             if eng.gr_keys:

@@ -240,8 +240,37 @@ def train_epoch(config, model, loader, device, optimizer, scheduler, epoch):
 
 
 def test_epoch(config, model, loader, device="cuda", epoch=0):
-    """Loss part of reference train/trainer.py:215-303 (the sklearn decoders are out of scope)."""
-    return train_test_epoch(config, model, loader, device, epoch, mode="test")
+    """Reference train/trainer.py:215-303: eval-mode pass over the loader — per-loss epoch averages, the latent means of
+    every window, and the generative-restrictiveness R^2 of each conditioned variable except `ids` (decode with a
+    resampled conditional, FK, re-extract: eval.generative_restrictiveness).  Returns (epoch_metrics, z) like the
+    reference.  The `mcmi` estimator rebuild (:228-252) belongs to the MutInfo scrubber, outside the built path."""
+    from ..eval import generative_restrictiveness, r2_score
+    print("Running test epoch")
+    model.eval()
+    with torch.no_grad():
+        z = []
+        epoch_metrics = {k: 0 for k in ["total"] + list(config["loss"].keys())}
+        gen_res = {k1: {k2: [] for k2 in ["pred", "target"]} for k1 in model.disentangle_keys if k1 != "ids"}
+        tree = getattr(getattr(loader, "dataset", None), "kinematic_tree", None) or model.kinematic_tree
+        for batch_idx, data in enumerate(loader):
+            data = {k: v.to(device) for k, v in data.items()}
+            data_o = predict_batch(model, data, model.disentangle_keys)
+            mu = data_o["mu"].clone().detach()  # (the plan's static buffer is overwritten by the decodes below)
+            z += [mu]
+            batch_metrics = get_batch_loss(model, data, data_o, config["loss"], config["disentangle"])
+            batch_metrics = {k: v.detach().clone() for k, v in batch_metrics.items()}
+            for key in gen_res.keys():
+                key_pred, key_target = generative_restrictiveness(model, mu, data, key, tree)
+                gen_res[key]["pred"] += [key_pred.detach().cpu()]
+                gen_res[key]["target"] += [key_target.detach().cpu()]
+            epoch_metrics = {k: v + batch_metrics[k] for k, v in epoch_metrics.items()}
+    for k, v in epoch_metrics.items():
+        epoch_metrics[k] = v.item() / len(loader)
+        print("====> Epoch: {} Average {} loss: {:.4f}".format(epoch, k, epoch_metrics[k]))
+    for key in gen_res.keys():
+        epoch_metrics["r2_gen_restrict_{}".format(key)] = r2_score(torch.cat(gen_res[key]["target"], dim=0),
+                                                                   torch.cat(gen_res[key]["pred"], dim=0))
+    return epoch_metrics, torch.cat(z, dim=0).cpu()
 
 
 def train(config, model, loader_dict, run=None, device="cuda"):

@@ -462,6 +462,41 @@ class EmuOps:
         nr = torch.as_strided(t, (F, 3), (ld, 1), off + nx)
         _v(root_hat, (F, 3), (3, 1)).copy_(0.5 * (nr + 1) * (a[1] - a[0]) + a[0])
 
+    def gen_features(self, xh, ld, root_hat, offsets, tree, n_tree, parts, B, W, J, norm=None, pose_out=None, heading=None,
+                     avg3=None):
+        """eval/eval.py:58-118 (FK through the oracle's fwd_kin, then the feature formulas)"""
+        self.n += 1
+        from oracle import scvae_oracle as orc
+        tr = _v(tree, (n_tree,), (1,)).tolist()
+        chains, pos = [], 1
+        for _ in range(tr[0]):
+            chains.append(tr[pos + 1:pos + 1 + tr[pos]])
+            pos += 1 + tr[pos]
+        x6 = _v(xh, (B * W, J, 6), (ld, 6, 1))
+        off = _v(offsets, (B * W, J, 3), (J * 3, 3, 1))
+        root = _v(root_hat, (B * W, 3), (3, 1)) if root_hat is not None else torch.zeros(B * W, 3)
+        pose = orc.fwd_kin(x6, off, root, tree=chains, eps=1e-8).reshape(B, W, J, 3)
+        if pose_out is not None:
+            _v(pose_out, (B, W, J, 3), (W * J * 3, J * 3, 3, 1)).copy_(pose)
+        if heading is not None:
+            fwd = pose[:, W // 2, 1] - pose[:, W // 2, 0]
+            fwd = fwd / fwd.norm(dim=-1, keepdim=True)
+            yaw = -torch.atan2(fwd[:, 1], fwd[:, 0])
+            _v(heading, (B, 2), (2, 1)).copy_(torch.stack([torch.sin(yaw), torch.cos(yaw)], -1))
+        if avg3 is not None:
+            pr = (parts if isinstance(parts, torch.Tensor) else parts.t).reshape(-1).tolist()
+            plist, pos = [], 1
+            for _ in range(pr[0]):
+                plist.append(pr[pos + 1:pos + 1 + pr[pos]])
+                pos += 1 + pr[pos]
+            root_spd = (pose[:, 1:, 0] - pose[:, :-1, 0]).norm(dim=-1).mean(-1)
+            d = [(pose[:, 1:, p[1:]] - pose[:, :-1, p[1:]]).norm(dim=-1).mean((-1, -2)) for p in plist]
+            pred = torch.stack([root_spd, d[0], 0.5 * (d[1] + d[2])], -1)
+            if norm is not None:
+                nm = _v(norm, (6,), (1,))
+                pred = (pred - nm[:3]) / nm[3:]
+            _v(avg3, (B, 3), (3, 1)).copy_(pred)
+
     def d2f(self, src, dst, n):
         self.n += 1
         _v(dst, (n,), (1,)).copy_(_v(src, (n,), (1,)).float())

@@ -256,3 +256,41 @@ def test_checkpoint_resume_is_exact(kind):
         assert torch.isfinite(pa).all() and torch.equal(pa, pb), n
     for (n, ba), (_, bb) in zip(a.named_buffers(), b.named_buffers()):
         assert torch.equal(ba, bb), n
+
+
+def test_test_epoch_and_generative_restrictiveness_on_emulation():
+    """test_epoch (reference train/trainer.py:215-303) through the engine on the CPU emulation, against the live
+    reference when its tree is importable: eval-mode losses, the latent means, and generative_restrictiveness
+    (eval/eval.py:22-120) for heading and avg_speed_3d with the same random draws."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference not importable here")
+    from oracle import ref_runner as rr
+    ch, zd, B = [8, 16, 32, 64, 128], 8, 10
+    feats = ["heading", "avg_speed_3d"]
+    ref, dc = rr.build_model("cpu", ch=ch, z_dim=zd, cond=feats, gr=feats, seed=5)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    m, dcfg = build_model(ch, zd, feats, feats)
+    m.load_state_dict(sd)
+    m._engine = Engine(m, ops=EmuOps())
+    data = orc.synth_batch(B, seed=4)
+    keys = ("x6d", "root", "offsets", "target_pose", "heading", "avg_speed_3d")
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "heading_gr": 1.0, "avg_speed_3d_gr": 1.0}
+    cfg = {"loss": dict(scale), "disentangle": dcfg}
+
+    class Loader(list):
+        pass
+    from scrubvae.train import trainer as rtr
+    import scrubvae.eval as reval  # noqa: F401
+    outs = []
+    for mod, fn in ((ref, rtr.test_epoch), (m, sv.train.test_epoch)):
+        loader = Loader([{k: data[k].clone() for k in keys}, {k: data[k].clone().flip(0) for k in keys}])
+        loader.dataset = type("D", (), {"kinematic_tree": orc.KINEMATIC_TREE})()
+        torch.manual_seed(123)
+        outs.append(fn({"loss": dict(scale), "disentangle": dc if mod is ref else dcfg}, mod, loader, device="cpu", epoch=1))
+    (mr, zr), (mo, zo) = outs
+    assert set(mr.keys()) == set(mo.keys())
+    assert _rel(zo, zr) < 1e-5
+    for k in mr:
+        tol = 1e-4 if k.startswith("r2_") else 2e-5
+        assert abs(mo[k] - mr[k]) <= tol * max(1.0, abs(mr[k])), (k, mo[k], mr[k])

@@ -314,3 +314,24 @@ def test_library_fails_loudly_when_missing(tmp_path):
     from scrubvae_b200 import _ops
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _ops.load_library(str(tmp_path / "nope.so"))
+
+
+@pytest.mark.parametrize("W", [51, 101])
+def test_gen_features(ops, W):
+    """FK of decoded windows + re-extracted heading / avg_speed_3d (scv_gen_features) against the torch statement."""
+    from oracle import scvae_oracle as orc
+    B, J, ld = 7, 18, 112
+    d = orc.synth_batch(B, window=W, seed=3)
+    xh = torch.zeros(B * W, ld)
+    xh[:, :J * 6] = torch.tanh(torch.randn(B * W, J * 6, generator=g(5)))
+    tree = [len(orc.KINEMATIC_TREE)]
+    for c in orc.KINEMATIC_TREE:
+        tree += [len(c)] + list(c)
+    parts = [3, 6, 0, 1, 2, 3, 4, 5, 7, 1, 6, 7, 8, 9, 10, 11, 7, 5, 12, 13, 14, 15, 16, 17]
+    T = {"xh": xh, "root": torch.randn(B * W, 3, generator=g(6)) * 20, "off": d["offsets"].reshape(B * W, J, 3).contiguous(),
+         "tree": torch.tensor(tree, dtype=torch.int32), "parts": torch.tensor(parts, dtype=torch.int32),
+         "norm": torch.tensor([0.4993, 0.7112, 0.6663, 0.4038, 0.3586, 0.4169]),
+         "pose": torch.zeros(B, W, J, 3), "head": torch.zeros(B, 2), "avg3": torch.zeros(B, 3)}
+    run_both(ops, T, lambda o, t: o.gen_features(t["xh"], ld, t["root"], t["off"], t["tree"], len(tree), t["parts"], B, W, J,
+                                                 norm=t["norm"], pose_out=t["pose"], heading=t["head"], avg3=t["avg3"]),
+             tol=2e-5, check=["pose", "head", "avg3"])

@@ -153,3 +153,35 @@ def test_fused_epoch_over_device_loader_equals_piecewise_path():
     bad = {k: _rel(sa[k].float().cpu(), sb[k].float().cpu()) for k in sa
            if _rel(sa[k].float().cpu(), sb[k].float().cpu()) >= 5e-3 and not ZERO_GRAD_BIAS.search(k)}
     assert not bad, bad
+
+
+def test_test_epoch_matches_reference_on_gpu():
+    """test_epoch (reference train/trainer.py:215-303) incl. generative_restrictiveness (eval/eval.py:22-120) on the GPU:
+    same loader, same CUDA random draws for the resampled conditionals; losses, latent means and the R^2 metrics."""
+    from oracle import ref_runner as rr
+    from scrubvae.train import trainer as rtr
+    ch, zd, B = [16, 32, 64, 128, 256], 16, 32
+    feats = ["heading", "avg_speed_3d"]
+    ref, dc = rr.build_model("cuda", ch=ch, z_dim=zd, cond=feats, gr=feats, seed=5)
+    sd = {k: v.detach().cpu().clone() for k, v in ref.state_dict().items()}
+    m, dcfg = _ours_from(sd, ch, zd, "fp32", cond=feats, gr=feats)
+    data = orc.synth_batch(2 * B, seed=4)
+    keys = ("x6d", "root", "offsets", "target_pose", "heading", "avg_speed_3d")
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "heading_gr": 1.0, "avg_speed_3d_gr": 1.0}
+
+    class Loader(list):
+        pass
+    outs = []
+    for mod, fn, dcc in ((ref, rtr.test_epoch, dc), (m, sv.train.test_epoch, dcfg)):
+        loader = Loader([{k: data[k][:B].clone() for k in keys}, {k: data[k][B:].clone() for k in keys}])
+        loader.dataset = type("D", (), {"kinematic_tree": orc.KINEMATIC_TREE})()
+        torch.manual_seed(123)
+        torch.cuda.manual_seed(123)
+        with rr.precision("fp32"):
+            outs.append(fn({"loss": dict(scale), "disentangle": dcc}, mod, loader, device="cuda", epoch=1))
+    (mr, zr), (mo, zo) = outs
+    assert set(mr.keys()) == set(mo.keys())
+    assert _rel(zo, zr) < 1e-4
+    for k in mr:
+        tol = 1e-3 if k.startswith("r2_") else 1e-4
+        assert abs(mo[k] - mr[k]) <= tol * max(1.0, abs(mr[k])), (k, mo[k], mr[k])

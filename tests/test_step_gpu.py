@@ -65,7 +65,7 @@ def _check_grads(named_grads, ref, tol, what):
 TF32_FLOOR = 2.5
 
 
-def _check_tf32_floor(named_grads, emu, ref32):
+def _check_tf32_floor(named_grads, emu, ref32, min_cos=0.995):
     """CUDA TF32 gradients vs the fp32 reference: no farther than ideal TF32 arithmetic is (module docstring)."""
     d = lambda t: torch.as_tensor(t).double().cpu()  # noqa: E731
     gnorm = np.sqrt(sum(float((d(v) ** 2).sum()) for v in ref32.values()))
@@ -86,7 +86,7 @@ def _check_tf32_floor(named_grads, emu, ref32):
         ng += float((g * g).sum())
         ne += float((e * e).sum())
     assert np.sqrt(tg) <= 1.5 * np.sqrt(te) + 1e-4 * gnorm, (np.sqrt(tg) / gnorm, np.sqrt(te) / gnorm)
-    assert dot / np.sqrt(ng * ne) > 0.995, dot / np.sqrt(ng * ne)
+    assert dot / np.sqrt(ng * ne) > min_cos, dot / np.sqrt(ng * ne)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
@@ -292,4 +292,5 @@ def test_bf16_step_against_oracle_and_ideal_bf16(cond, gr, dc):
         assert abs(got[k] - v.item()) <= 1e-2 * abs(v.item()) + 1e-5, (k, got[k], v.item())
         assert abs(got[k] - lo[k].item()) <= 2e-3 * abs(lo[k].item()) + 1e-5, ("vs ideal bf16", k, got[k], lo[k].item())
     grads = [(n, g.clone()) for n, g in step.named_grads().items()]
-    _check_tf32_floor(grads, emu, gref)
+    # two bf16 evaluations that order their fp32 sums differently: 8 mantissa bits leave the direction a little looser
+    _check_tf32_floor(grads, emu, gref, min_cos=0.99)
