@@ -53,6 +53,21 @@ Launch2D plan2d(int64_t C4, int64_t rows, int ctas_per_sm) {
   return l;
 }
 
+// (window, position) of a row index, advanced by a fixed row step without dividing: the division by L per row was a fifth
+// of these kernels' instructions (ncu: they issue-bound at ~30 % of HBM bandwidth)
+struct RowIt {
+  uint32_t b, l, sb, sl, L;
+  __device__ __forceinline__ void init(int64_t r, int64_t step, uint32_t L_) {
+    L = L_;
+    b = (uint32_t)(r / L_); l = (uint32_t)(r - (int64_t)b * L_);
+    sb = (uint32_t)(step / L_); sl = (uint32_t)(step - (int64_t)sb * L_);
+  }
+  __device__ __forceinline__ void next() {
+    l += sl; b += sb;
+    if (l >= L) { l -= L; ++b; }
+  }
+};
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
@@ -144,6 +159,8 @@ __global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, cons
   const uint32_t L = (uint32_t)p.L;
   const int om = (mode & SCV_MODE_OUT_BF16) ? 2 : ((mode & SCV_MODE_ROUND_TF32) ? 1 : 0);
   // 4 rows per iteration, loads first: one thread keeps 4 (12 with the upsample neighbours) float4 loads in flight
+  RowIt it;
+  it.init(t.r0, t.rstep, L);
   for (int64_t r = t.r0; r < t.rend; r += 4 * (int64_t)t.rstep) {
     float4 xc[4], xm[4], xp[4];
     uint32_t bb[4], ll[4];
@@ -152,9 +169,10 @@ __global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, cons
     for (int u = 0; u < 4; ++u) {
       const int64_t rr = r + u * (int64_t)t.rstep;
       ok[u] = rr < t.rend;
+      bb[u] = it.b;
+      ll[u] = it.l;
+      it.next();
       if (ok[u]) {
-        bb[u] = (uint32_t)rr / L;
-        ll[u] = (uint32_t)rr - bb[u] * L;
         const float* xr = p.X + (int64_t)bb[u] * p.x_bs + (int64_t)ll[u] * p.x_ls + t.c * 4;
         xc[u] = ld4(xr);
         if (p.U) {
@@ -216,6 +234,8 @@ __global__ void __launch_bounds__(NT) bnact_bwd_reduce_kernel(const scv_bnact_bw
     const bool has_act = mode & 2;
     const float slope = has_act ? __ldg(p.slope) : 0.f;
     const uint32_t L32 = (uint32_t)L;
+    RowIt it;
+    it.init(t.r0, t.rstep, L32);
     for (int64_t r = t.r0; r < t.rend; r += 4 * (int64_t)t.rstep) {
       float4 xv[4], gv[4];
       bool ok[4];
@@ -223,8 +243,9 @@ __global__ void __launch_bounds__(NT) bnact_bwd_reduce_kernel(const scv_bnact_bw
       for (int u = 0; u < 4; ++u) {  // loads first
         const int64_t rr = r + u * (int64_t)t.rstep;
         ok[u] = rr < t.rend;
+        const uint32_t b = it.b, l = it.l;
+        it.next();
         if (ok[u]) {
-          const uint32_t b = (uint32_t)rr / L32, l = (uint32_t)rr - b * L32;
           xv[u] = ld4(p.X + (int64_t)b * p.x_bs + (int64_t)l * p.x_ls + t.c * 4);
           gv[u] = load_dout(p, b, l, t.c);
         }
@@ -303,6 +324,8 @@ __global__ void __launch_bounds__(NT) bnact_bwd_apply_kernel(const scv_bnact_bwd
   }
   if (!p.dX) return;
   const uint32_t L32 = (uint32_t)L;
+  RowIt it;
+  it.init(t.r0, t.rstep, L32);
   for (int64_t r = t.r0; r < t.rend; r += 4 * (int64_t)t.rstep) {
     float4 xv[4], gv[4];
     uint32_t bb[4], ll[4];
@@ -311,9 +334,10 @@ __global__ void __launch_bounds__(NT) bnact_bwd_apply_kernel(const scv_bnact_bwd
     for (int u = 0; u < 4; ++u) {  // loads first
       const int64_t rr = r + u * (int64_t)t.rstep;
       ok[u] = rr < t.rend;
+      bb[u] = it.b;
+      ll[u] = it.l;
+      it.next();
       if (ok[u]) {
-        bb[u] = (uint32_t)rr / L32;
-        ll[u] = (uint32_t)rr - bb[u] * L32;
         xv[u] = ld4(p.X + (int64_t)bb[u] * p.x_bs + (int64_t)ll[u] * p.x_ls + t.c * 4);
         gv[u] = load_dout(p, bb[u], ll[u], t.c);
       }

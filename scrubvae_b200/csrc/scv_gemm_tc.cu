@@ -231,7 +231,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&ctl->full[s]), kCtas);   // pair: the leader's expect_tx arrive + the peer's arrive
+      // pair: ONE arrival (the leader's expect_tx for both CTAs' bytes).  Round 1 also had the peer arrive on the leader's
+      // barrier every chunk: that mbarrier.arrive.release.cluster stalled the peer's producer ~1500 cycles per stage
+      // and made the pair kernel 2x slower than one CTA (tools/cu/pair_pipe.cu: the pipeline itself runs at the MMA rate)
+      mbar_init(smem_u32(&ctl->full[s]), 1);
       mbar_init(smem_u32(&ctl->empty[s]), kMc ? 2 : 1);  // multicast pair: both CTAs' MMAs must be done with the stage
     }
     for (int i = 0; i < 2; ++i) {
@@ -268,7 +271,6 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
           if (kCtas == 2) {
             const uint32_t fb = mapa_rank(smem_u32(&ctl->full[s]), 0);  // the leader's barrier counts both CTAs' bytes
             if (rank == 0) mbar_expect_tx(smem_u32(&ctl->full[s]), tile_tx);
-            else mbar_arrive_cluster(fb);
             tma2_load_3d(sa, &tmA, fb, kc * kEK, l0, b0);
             tma2_load_2d(sa + a_bytes, &tmW, fb, kc * kEK, n0);
           } else {
