@@ -73,6 +73,16 @@ typedef struct {
   int64_t act; double out_scale;
   double* stats;                        /* [2][N] accumulators or NULL */
   int64_t precision;
+  /* Optional fused BatchNorm(+PReLU) BACKWARD REDUCTION (bnr_sums != NULL; activation NONE, no stats / ROUND / ACCUM):
+   * the stored Y(b,l,n) is the gradient g w.r.t. the output of a BN(+PReLU) layer (model/residual.py:88-89,112-119,
+   * 146-147,172-180) whose pre-normalisation input is bnr_x, addressed like Y with (bnr_bs, bnr_ls), channel n % bnr_c.
+   * With y = scale x + shift (bnr_chan = [scale | shift | mean | rstd] x bnr_c, as scv_bnact_fwd writes to chan_out;
+   * NULL = no BatchNorm) and g' = (y < 0 ? slope : 1) g (bnr_slope NULL = no PReLU):
+   *   bnr_sums[c] += sum g',  bnr_sums[C + c] += sum g' (x - mean) rstd,  bnr_sums[2C] += sum_{y<0} g y
+   * i.e. exactly what scv_bnact_bwd_reduce accumulates, without its extra pass over X and Y. */
+  const float* bnr_x; int64_t bnr_bs, bnr_ls;
+  const float* bnr_chan; const float* bnr_slope; int64_t bnr_c;
+  double* bnr_sums;
 } scv_gemm_t;
 int scv_gemm(const scv_gemm_t* p, void* stream);
 
@@ -118,6 +128,7 @@ typedef struct {
   float* H; int64_t h_bs, h_ls;
   float* U; int64_t u_bs, u_ls;
   int64_t mode;
+  float* chan_out; /* optional [4][C]: per-channel scale, shift, mean, rstd of this normalisation (for scv_gemm's bnr_chan) */
 } scv_bnact_t;
 int scv_bnact_fwd(const scv_bnact_t* p, void* stream);
 
@@ -135,6 +146,7 @@ typedef struct {
   float* dX; int64_t d_bs, d_ls;
   float* dgamma; float* dbeta; float* dslope;
   int64_t mode;
+  const float* chan; /* optional [4][C] table from scv_bnact_fwd (chan_out): used instead of recomputing from stats */
 } scv_bnact_bwd_t;
 int scv_bnact_bwd_reduce(const scv_bnact_bwd_t* p, void* stream);
 int scv_bnact_bwd_apply(const scv_bnact_bwd_t* p, void* stream);

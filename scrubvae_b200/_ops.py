@@ -55,7 +55,9 @@ GemmT = _struct("GemmT", [
     ("W", _vp), ("bias", _vp), ("bias_mod", _i64), ("bias_n", _i64),
     ("Y", _vp), ("y_bs", _i64), ("y_ls", _i64), ("n_last", _i64),
     ("R", _vp), ("r_bs", _i64), ("r_ls", _i64), ("act", _i64), ("out_scale", _f64),
-    ("stats", _vp), ("precision", _i64)])
+    ("stats", _vp), ("precision", _i64),
+    ("bnr_x", _vp), ("bnr_bs", _i64), ("bnr_ls", _i64), ("bnr_chan", _vp), ("bnr_slope", _vp), ("bnr_c", _i64),
+    ("bnr_sums", _vp)])
 WgradT = _struct("WgradT", [
     ("A", _vp), ("a_bs", _i64), ("a_ls", _i64), ("B", _i64), ("Lo", _i64), ("K", _i64), ("N", _i64),
     ("dY", _vp), ("y_bs", _i64), ("y_ls", _i64), ("dW", _vp), ("dbias", _vp), ("bias_mod", _i64),
@@ -64,14 +66,15 @@ BnactT = _struct("BnactT", [
     ("X", _vp), ("x_bs", _i64), ("x_ls", _i64), ("B", _i64), ("L", _i64), ("C", _i64),
     ("stats", _vp), ("fold", _i64), ("count", _f64), ("eps", _f64), ("momentum", _f64),
     ("gamma", _vp), ("beta", _vp), ("running_mean", _vp), ("running_var", _vp), ("slope", _vp),
-    ("H", _vp), ("h_bs", _i64), ("h_ls", _i64), ("U", _vp), ("u_bs", _i64), ("u_ls", _i64), ("mode", _i64)])
+    ("H", _vp), ("h_bs", _i64), ("h_ls", _i64), ("U", _vp), ("u_bs", _i64), ("u_ls", _i64), ("mode", _i64),
+    ("chan_out", _vp)])
 BnactBwdT = _struct("BnactBwdT", [
     ("X", _vp), ("x_bs", _i64), ("x_ls", _i64), ("B", _i64), ("L", _i64), ("C", _i64),
     ("stats", _vp), ("fold", _i64), ("count", _f64), ("eps", _f64),
     ("gamma", _vp), ("beta", _vp), ("slope", _vp),
     ("dO", _vp), ("o_bs", _i64), ("o_ls", _i64), ("dU", _vp), ("u_bs", _i64), ("u_ls", _i64),
     ("sums", _vp), ("dX", _vp), ("d_bs", _i64), ("d_ls", _i64),
-    ("dgamma", _vp), ("dbeta", _vp), ("dslope", _vp), ("mode", _i64)])
+    ("dgamma", _vp), ("dbeta", _vp), ("dslope", _vp), ("mode", _i64), ("chan", _vp)])
 OptimT = _struct("OptimT", [
     ("p", _vp), ("g", _vp), ("m", _vp), ("v", _vp), ("n", _i64), ("sumsq", _vp), ("max_norm", _f64),
     ("gscale", _f64), ("lr", _f64), ("beta1", _f64), ("beta2", _f64), ("eps", _f64),
@@ -147,9 +150,11 @@ class CudaOps:
     # -- kernels
     @staticmethod
     def _gemm_struct(A, a_bs, a_ls, B, Lo, K, N, W, Y, y_bs, y_ls, bias=None, bias_mod=1, bias_n=0, n_last=None,
-                     R=None, r_bs=0, r_ls=0, act=ACT_NONE, out_scale=1.0, stats=None, precision=0):
+                     R=None, r_bs=0, r_ls=0, act=ACT_NONE, out_scale=1.0, stats=None, precision=0,
+                     bnr_x=None, bnr_bs=0, bnr_ls=0, bnr_chan=None, bnr_slope=None, bnr_c=0, bnr_sums=None):
         return GemmT(_ptr(A), a_bs, a_ls, B, Lo, K, N, _ptr(W), _ptr(bias), bias_mod, bias_n, _ptr(Y), y_bs, y_ls,
-                     N if n_last is None else n_last, _ptr(R), r_bs, r_ls, act, out_scale, _ptr(stats), precision)
+                     N if n_last is None else n_last, _ptr(R), r_bs, r_ls, act, out_scale, _ptr(stats), precision,
+                     _ptr(bnr_x), bnr_bs, bnr_ls, _ptr(bnr_chan), _ptr(bnr_slope), bnr_c, _ptr(bnr_sums))
 
     @staticmethod
     def _wgrad_struct(A, a_bs, a_ls, B, Lo, K, N, dY, y_bs, y_ls, dW, dbias=None, bias_mod=1, bias_n=0, precision=0):
@@ -179,16 +184,17 @@ class CudaOps:
 
     def bnact_fwd(self, X, x_bs, x_ls, B, L, Cc, mode, stats=None, fold=1, count=1.0, eps=1e-4, momentum=0.1,
                   gamma=None, beta=None, running_mean=None, running_var=None, slope=None,
-                  H=None, h_bs=0, h_ls=0, U=None, u_bs=0, u_ls=0):
+                  H=None, h_bs=0, h_ls=0, U=None, u_bs=0, u_ls=0, chan_out=None):
         p = BnactT(_ptr(X), x_bs, x_ls, B, L, Cc, _ptr(stats), fold, count, eps, momentum, _ptr(gamma), _ptr(beta),
-                   _ptr(running_mean), _ptr(running_var), _ptr(slope), _ptr(H), h_bs, h_ls, _ptr(U), u_bs, u_ls, mode)
+                   _ptr(running_mean), _ptr(running_var), _ptr(slope), _ptr(H), h_bs, h_ls, _ptr(U), u_bs, u_ls, mode,
+                   _ptr(chan_out))
         self._check(self.lib.scv_bnact_fwd(C.byref(p), self._stream()), "scv_bnact_fwd")
 
     def _bwd_struct(self, X, x_bs, x_ls, B, L, Cc, mode, stats, fold, count, eps, gamma, beta, slope, dO, o_bs, o_ls,
                     dU, u_bs, u_ls, sums, dX, d_bs, d_ls, dgamma, dbeta, dslope):
         return BnactBwdT(_ptr(X), x_bs, x_ls, B, L, Cc, _ptr(stats), fold, count, eps, _ptr(gamma), _ptr(beta),
                          _ptr(slope), _ptr(dO), o_bs, o_ls, _ptr(dU), u_bs, u_ls, _ptr(sums), _ptr(dX), d_bs, d_ls,
-                         _ptr(dgamma), _ptr(dbeta), _ptr(dslope), mode)
+                         _ptr(dgamma), _ptr(dbeta), _ptr(dslope), mode, None)
 
     def bnact_bwd_reduce(self, X, x_bs, x_ls, B, L, Cc, mode, sums, stats=None, fold=1, count=1.0, eps=1e-4,
                          gamma=None, beta=None, slope=None, dO=None, o_bs=0, o_ls=0, dU=None, u_bs=0, u_ls=0):

@@ -51,7 +51,25 @@ int scv_gemm(const scv_gemm_t* p, void* stream) {
     SCV_REQUIRE(p->precision != SCV_PREC_BF16, "scv_gemm: bf16 operands need the tensor-core path, which declined this shape "
                 "(N >= 16, K %% 8 == 0, strides %% 8 == 0, 16-byte aligned pointers, Y / R / bias float4-aligned)");
   }
-  return scv::gemm_ffma(p, (cudaStream_t)stream);
+  int rc = scv::gemm_ffma(p, (cudaStream_t)stream);
+  if (rc == 0 && p->bnr_sums) {
+    // the FFMA path has no fused reduction: the stand-alone pass over X and the Y just written, same sums
+    const int64_t C = p->bnr_c;
+    SCV_REQUIRE(C > 0 && p->N % C == 0 && (p->Lo == 1 || (p->y_ls == p->N && p->bnr_ls == p->N)),
+                "scv_gemm: fused BatchNorm reduction needs rows that are contiguous groups of bnr_c channels");
+    scv_bnact_bwd_t q;
+    memset(&q, 0, sizeof(q));
+    q.X = p->bnr_x; q.x_bs = p->bnr_bs; q.x_ls = C;
+    q.B = p->B; q.L = p->Lo * (p->N / C) - (p->N - p->n_last) / C; q.C = C;
+    q.fold = 1; q.count = 1.0; q.eps = 0.0;
+    q.slope = p->bnr_slope;
+    q.dO = p->Y; q.o_bs = p->y_bs; q.o_ls = C;
+    q.sums = p->bnr_sums;
+    q.mode = (p->bnr_chan ? 1 : 0) | (p->bnr_slope ? 2 : 0) | 4;
+    q.chan = p->bnr_chan;
+    rc = scv_bnact_bwd_reduce(&q, stream);
+  }
+  return rc;
 }
 
 int scv_gemm_group(const scv_gemm_t* p, int64_t n, void* stream) {

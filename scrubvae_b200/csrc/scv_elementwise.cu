@@ -111,11 +111,22 @@ __device__ __forceinline__ void chan_bn(ChanBN& cb, int ch0, int C, int mode, co
 // every thread recomputing them cost more instructions than the streaming work itself (ncu, round 1).
 __device__ __forceinline__ void chan_bn_block(ChanBN& cb, int cw, int C4, int C, int mode, const double* stats, int fold,
                                               double count, double eps, const float* gamma, const float* beta,
-                                              const float* rmean, const float* rvar) {
+                                              const float* rmean, const float* rvar, const float* chan = nullptr) {
   __shared__ ChanBN sh[32];
   if ((int)threadIdx.x < cw) {
     const int c = blockIdx.x * cw + threadIdx.x;
-    if (c < C4) chan_bn(sh[threadIdx.x], c * 4, C, mode, stats, fold, count, eps, gamma, beta, rmean, rvar);
+    if (c < C4) {
+      if (chan && (mode & 1)) {  // constants already finalised by the forward pass (scv_bnact_fwd chan_out)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ch = c * 4 + q;
+          sh[threadIdx.x].scale[q] = chan[ch]; sh[threadIdx.x].shift[q] = chan[C + ch];
+          sh[threadIdx.x].mean[q] = chan[2 * C + ch]; sh[threadIdx.x].rstd[q] = chan[3 * C + ch];
+        }
+      } else {
+        chan_bn(sh[threadIdx.x], c * 4, C, mode, stats, fold, count, eps, gamma, beta, rmean, rvar);
+      }
+    }
   }
   __syncthreads();
   cb = sh[(threadIdx.x & 31) % cw];
@@ -143,6 +154,14 @@ __global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, cons
   const bool has_act = mode & 2;
   const float slope = has_act ? __ldg(p.slope) : 0.f;
   // running statistics: one thread per channel group (block row 0, first row lane)
+  if (p.chan_out && blockIdx.y == 0 && t.r0 == 0) {  // the per-channel constants, for fused backward reductions
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ch = t.c * 4 + q;
+      p.chan_out[ch] = cb.scale[q]; p.chan_out[C + ch] = cb.shift[q];
+      p.chan_out[2 * C + ch] = cb.mean[q]; p.chan_out[3 * C + ch] = cb.rstd[q];
+    }
+  }
   if ((mode & 5) == 5 && p.running_mean && blockIdx.y == 0 && t.r0 == 0) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -229,7 +248,7 @@ __global__ void __launch_bounds__(NT) bnact_bwd_reduce_kernel(const scv_bnact_bw
   Tile2D t = make_tile(C4, cw, rows, rpb);
   float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f}, ds = 0.f;
   ChanBN cb;
-  chan_bn_block(cb, cw, C4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, nullptr, nullptr);
+  chan_bn_block(cb, cw, C4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, nullptr, nullptr, p.chan);
   if (t.cok) {
     const bool has_act = mode & 2;
     const float slope = has_act ? __ldg(p.slope) : 0.f;
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(NT) bnact_bwd_apply_kernel(const scv_bnact_bwd
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (mode & 2) && p.dslope)
     p.dslope[0] += (float)p.sums[2 * C];
   ChanBN cb;
-  chan_bn_block(cb, cw, C4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, nullptr, nullptr);
+  chan_bn_block(cb, cw, C4, C, mode, p.stats, (int)p.fold, p.count, p.eps, p.gamma, p.beta, nullptr, nullptr, p.chan);
   if (!t.cok) return;
   const bool has_act = mode & 2;
   const bool train_bn = (mode & 5) == 5;

@@ -107,6 +107,13 @@ struct GemmTcParams {
   int sub;           // row tiles per work item (1 or 2): with 2 the CTA runs two 128-row tiles against ONE W tile per
                      // stage (two accumulators, no TMEM double buffering) - a third less shared-memory traffic per FLOP
   int epi_kind;      // which compiled epilogue variant serves (act, R, stats, round_out); see gemm_tc_body
+  // BatchNorm / PReLU backward reduction fused into a data-gradient epilogue (bnr_sums != nullptr): see scv_gemm_t
+  const float* bnr_x;
+  int64_t bnr_bs, bnr_ls;
+  const float* bnr_chan;
+  const float* bnr_slope;
+  int bnr_c;
+  double* bnr_sums;
   int ksplit;        // split-K: the reduction is cut into `ksplit` chunk ranges, one work item each, and the epilogue ADDS
                      // (red.global.add) into a pre-zeroed Y - for GEMMs with few output tiles and a long K (SCV_ACT_ACCUM)
   int kc_per;        // k chunks per split
@@ -148,14 +155,38 @@ __device__ __forceinline__ float act_apply(float v, int act, float r) {
 
 // Epilogue arithmetic of one 32x32 chunk for lane (rq, cq): rows 4 i + rq (i < 8), columns n .. n + 3.
 // ACT >= 0 / RD / ST / RND are compile-time; ACT = -1 is the generic path (activation, rounding from p at run time).
-template <int ACT, bool RD, bool ST, bool RND, bool ACC = false>
+// BNR: the stored value is the gradient w.r.t. the OUTPUT of a BatchNorm(+PReLU) layer whose pre-normalisation input X has
+// the same (row, column) addressing; its backward reduction (sum g', sum g' xhat per channel, PReLU slope gradient) is
+// accumulated here instead of in a separate pass over X and Y (s1 / s2 carry the two column sums, ds the slope term).
+template <int ACT, bool RD, bool ST, bool RND, bool ACC = false, bool BNR = false>
 __device__ __forceinline__ void epi_rows(const GemmTcParams& p, const float4* xp4, const int rq, const int cq, const bool col_ok,
                                          const int n, const float4 bv, const long long (&yoff)[8], const long long (&roff)[8],
-                                         const int (&ncap)[8], float4& s1, float4& s2) {
+                                         const int (&ncap)[8], float4& s1, float4& s2, const long long (&xoff)[8] = {},
+                                         float* ds = nullptr) {
   const int act = ACT >= 0 ? ACT : p.act;
   const bool rnd = ACT >= 0 ? RND : (p.round_out != 0);
   const float osc = p.out_scale;
   float4 rv[8];
+  float4 xv[BNR ? 8 : 1];
+  float4 c_sc = make_float4(1.f, 1.f, 1.f, 1.f), c_sh = make_float4(0.f, 0.f, 0.f, 0.f), c_mu = c_sh, c_rs = c_sc;
+  float slope = 0.f;
+  bool has_act = false;
+  if (BNR) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok && n < ncap[i]) xv[i] = __ldg(reinterpret_cast<const float4*>(p.bnr_x + xoff[i] + n));
+    }
+    if (p.bnr_chan && col_ok) {
+      const int ch = n % p.bnr_c, C = p.bnr_c;
+      c_sc = __ldg(reinterpret_cast<const float4*>(p.bnr_chan + ch));
+      c_sh = __ldg(reinterpret_cast<const float4*>(p.bnr_chan + C + ch));
+      c_mu = __ldg(reinterpret_cast<const float4*>(p.bnr_chan + 2 * C + ch));
+      c_rs = __ldg(reinterpret_cast<const float4*>(p.bnr_chan + 3 * C + ch));
+    }
+    has_act = p.bnr_slope != nullptr;
+    if (has_act) slope = __ldg(p.bnr_slope);
+  }
   if (RD) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -177,6 +208,22 @@ __device__ __forceinline__ void epi_rows(const GemmTcParams& p, const float4* xp
       if (ST) {
         s1.x += tv.x; s1.y += tv.y; s1.z += tv.z; s1.w += tv.w;
         s2.x = fmaf(tv.x, tv.x, s2.x); s2.y = fmaf(tv.y, tv.y, s2.y); s2.z = fmaf(tv.z, tv.z, s2.z); s2.w = fmaf(tv.w, tv.w, s2.w);
+      }
+      if (BNR) {
+        const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w}, gs[4] = {tv.x, tv.y, tv.z, tv.w};
+        const float sc[4] = {c_sc.x, c_sc.y, c_sc.z, c_sc.w}, sh[4] = {c_sh.x, c_sh.y, c_sh.z, c_sh.w};
+        const float mu[4] = {c_mu.x, c_mu.y, c_mu.z, c_mu.w}, rs[4] = {c_rs.x, c_rs.y, c_rs.z, c_rs.w};
+        float a1[4], a2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float v = fmaf(xs[q], sc[q], sh[q]);
+          float gg = gs[q];
+          if (has_act && v < 0.f) { *ds += gg * v; gg *= slope; }
+          a1[q] = gg;
+          a2[q] = gg * (xs[q] - mu[q]) * rs[q];
+        }
+        s1.x += a1[0]; s1.y += a1[1]; s1.z += a1[2]; s1.w += a1[3];
+        s2.x += a2[0]; s2.y += a2[1]; s2.z += a2[2]; s2.w += a2[3];
       }
       float4 yv = tv;
       if (act != SCV_ACT_NONE)
@@ -354,7 +401,12 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     const int rows_in_box = p.bl * p.nb;
     const int N = p.N;
     const int et = threadIdx.x - 128;
-    const bool has_stats = p.stats != nullptr;
+    const bool has_bnr = p.bnr_sums != nullptr;
+    const bool has_stats = p.stats != nullptr || has_bnr;  // column sums through the shared-memory accumulators
+    // where the column sums go: forward statistics stats[n], stats[N + n]; backward reduction sums[n % C], sums[C + n % C]
+    double* const sum_base = has_bnr ? p.bnr_sums : p.stats;
+    const int sum_mod = has_bnr ? p.bnr_c : p.N, sum_off2 = has_bnr ? p.bnr_c : p.N;
+    float ds_acc = 0.f;
     if (has_stats) {
       for (int c = et; c < 2 * kMaxBN; c += 32 * kEpiWarps) sacc[c] = 0.f;
       epi_bar();
@@ -372,8 +424,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
           epi_bar();
           const int pn0 = cur_nt * p.bn, pc = min(p.bn, N - pn0);
           for (int c = et; c < pc; c += 32 * kEpiWarps) {
-            atomicAdd(p.stats + pn0 + c, (double)sacc[c]);
-            atomicAdd(p.stats + N + pn0 + c, (double)sacc[kMaxBN + c]);
+            atomicAdd(sum_base + (pn0 + c) % sum_mod, (double)sacc[c]);
+            atomicAdd(sum_base + sum_off2 + (pn0 + c) % sum_mod, (double)sacc[kMaxBN + c]);
             sacc[c] = 0.f;
             sacc[kMaxBN + c] = 0.f;
           }
@@ -390,7 +442,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
      for (int sj = 0; sj < sub; ++sj) {
       const int mt = mt0 + sj;
       const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;
-      long long yoff[8], roff[8];
+      long long yoff[8], roff[8], xoff[8];
       int ncap[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -400,6 +452,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         const bool ok = row < rows_in_box && mt < p.m_tiles && b < p.B && l < p.Lo;
         yoff[i] = (long long)(b * p.y_bs + l * p.y_ls);
         roff[i] = (long long)(b * p.r_bs + l * p.r_ls);
+        xoff[i] = (long long)(b * p.bnr_bs + l * p.bnr_ls);
         ncap[i] = ok ? ((l == p.Lo - 1) ? p.n_last : N) : 0;
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub == 2 ? sj : acc) * kMaxBN;
@@ -438,6 +491,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
           case 4: epi_rows<SCV_ACT_NONE, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
           case 5: epi_rows<SCV_ACT_TANH, false, false, false>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
           case 6: epi_rows<SCV_ACT_NONE, false, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
+          case 7: epi_rows<SCV_ACT_NONE, false, false, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2, xoff, &ds_acc); break;
+          case 8: epi_rows<SCV_ACT_NONE, true, false, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2, xoff, &ds_acc); break;
           default:
             if (rd) epi_rows<-1, true, true, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2);
             else epi_rows<-1, false, true, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2);
@@ -473,9 +528,13 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
       epi_bar();
       const int pn0 = cur_nt * p.bn, pc = min(p.bn, N - pn0);
       for (int c = et; c < pc; c += 32 * kEpiWarps) {
-        atomicAdd(p.stats + pn0 + c, (double)sacc[c]);
-        atomicAdd(p.stats + N + pn0 + c, (double)sacc[kMaxBN + c]);
+        atomicAdd(sum_base + (pn0 + c) % sum_mod, (double)sacc[c]);
+        atomicAdd(sum_base + sum_off2 + (pn0 + c) % sum_mod, (double)sacc[kMaxBN + c]);
       }
+    }
+    if (has_bnr && p.bnr_slope != nullptr) {  // PReLU slope gradient: sum over everything this warp touched
+      const float d = scv::warp_sum(ds_acc);
+      if (lane == 0 && d != 0.f) atomicAdd(p.bnr_sums + 2 * p.bnr_c, (double)d);
     }
   }
   tc_fence_before();
@@ -848,6 +907,11 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   if (p->R && (p->r_bs % 4 || p->r_ls % 4 || !aligned16(p->R))) return decline("scv_gemm", "R rows not float4-aligned", M, p->N, p->K);
   if (p->bias && (p->bias_mod % 4 || p->bias_n % 4 || !aligned16(p->bias)))
     return decline("scv_gemm", "bias not float4-aligned", M, p->N, p->K);
+  const bool bnr = p->bnr_sums != nullptr;
+  if (bnr && ((p->act & 15) != SCV_ACT_NONE || (p->act & (SCV_ACT_ROUND_TF32 | SCV_ACT_ACCUM)) || p->stats || !p->bnr_x ||
+              p->bnr_c <= 0 || p->bnr_c % 4 || p->N % p->bnr_c || p->bnr_bs % 4 || p->bnr_ls % 4 || !aligned16(p->bnr_x) ||
+              (p->bnr_chan && !aligned16(p->bnr_chan))))
+    return decline("scv_gemm", "fused BatchNorm backward reduction needs a plain epilogue and float4-aligned X", M, p->N, p->K);
   const bool accum = (p->act & SCV_ACT_ACCUM) != 0;
   if (accum && ((p->act & 15) != SCV_ACT_NONE || (p->act & SCV_ACT_ROUND_TF32) || p->R || p->stats))
     return decline("scv_gemm", "SCV_ACT_ACCUM with an activation / residual / statistics", M, p->N, p->K);
@@ -889,7 +953,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
     if (q.m_tiles < 2) q.sub = 1;
   }
   const size_t fixed = 1024 + ((sizeof(SmemCtl) + 15) & ~size_t(15)) + kEpiWarps * kXposeFloats * 4 +
-                       (p->stats ? 2 * kMaxBN * sizeof(float) : 0);
+                       ((p->stats || p->bnr_sums) ? 2 * kMaxBN * sizeof(float) : 0);
   size_t stage_bytes = (size_t)kBM * kBK * 4 * q.sub + (size_t)(q.bn / ctas) * kBK * 4;
   if (q.sub == 2 && (kSmemLimit - fixed) / stage_bytes < 3 && force_sub != 2) {
     q.sub = 1;  // two stages cannot hide the TMA latency (measured: 256 x 256 items with 2 stages lose 30 %)
@@ -923,12 +987,15 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   q.act = (int)(p->act & 15); q.round_out = (p->act & SCV_ACT_ROUND_TF32) ? 1 : 0; q.out_scale = (float)p->out_scale; q.stats = p->stats;
   {
     const bool rd = q.R != nullptr, stt = q.stats != nullptr, rn = q.round_out != 0;
-    if (accum) q.epi_kind = 6;
+    if (bnr) q.epi_kind = rd ? 8 : 7;
+    else if (accum) q.epi_kind = 6;
     else if (q.act == SCV_ACT_NONE && !rn) q.epi_kind = (rd ? 2 : 0) + (stt ? 1 : 0);
     else if (q.act == SCV_ACT_NONE && rn && !rd && !stt) q.epi_kind = 4;
     else if (q.act == SCV_ACT_TANH && !rn && !rd && !stt) q.epi_kind = 5;
     else q.epi_kind = 99;  // generic
   }
+  q.bnr_x = p->bnr_x; q.bnr_bs = p->bnr_bs; q.bnr_ls = p->bnr_ls; q.bnr_chan = p->bnr_chan; q.bnr_slope = p->bnr_slope;
+  q.bnr_c = (int)p->bnr_c; q.bnr_sums = p->bnr_sums;
   q.trace = nullptr;
   if (const char* tr = getenv("SCV_TC_TRACE")) {  // debug: device buffer address (decimal) to receive CTA 0's timeline
     q.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 10));

@@ -503,9 +503,21 @@ class Plan:
             fn = lambda: ops.gemm(**kw)  # noqa: E731
             F.append(SideLaunch(fn) if role == "side" else AfterSide(fn) if role == "join" else fn)
 
+        # per-channel (scale, shift, mean, rstd) of every BatchNorm, written by its forward pass and read by the data-gradient
+        # GEMM whose epilogue carries that layer's backward reduction (scv_gemm_t bnr_*)
+        self.chan = torch.zeros(4 * nbn + 16, **f32)
+        self._chan_n = 0
+        chan_of: Dict[str, Ref] = {}
+        fuse_bnr = os.environ.get("SCV_FUSE_BNR", "1") != "0"
+
         def bnact_fwd(bn_name, slope_name, X, L, Cc, st_off, fold, H=None, U=None):
             kw = dict(X=X.at(0), x_bs=X.bs, x_ls=X.ls, B=B, L=L, Cc=Cc, fold=fold, count=float(B * L), eps=1e-4,
                       momentum=0.1, slope=eng.pref(slope_name) if slope_name else None)
+            if bn_name and bn_name not in chan_of:
+                chan_of[bn_name] = Ref(self.chan, self._chan_n)
+                self._chan_n += 4 * Cc
+            if bn_name:
+                kw.update(chan_out=chan_of[bn_name])
             if bn_name:
                 mod = m.get_submodule(bn_name)
                 kw.update(gamma=eng.pref(bn_name + ".weight"), beta=eng.pref(bn_name + ".bias"),
@@ -522,8 +534,18 @@ class Plan:
                 ops.bnact_fwd(mode=mode, stats=st_off if bn_name else None, **kw)
             F.append(run)
 
-        def bnact_bwd(bn_name, slope_name, X, L, Cc, st_off, fold, dO, dU, dX, sm_off):
-            """returns the two backward launches (reduce, apply) for the same geometry"""
+        def bnr_ctx(bn_name, slope_name, X, Cc, sm_off, ls):
+            """scv_gemm_t bnr_* arguments: the GEMM that produces the gradient w.r.t. this layer's output accumulates the
+            layer's backward reduction in its epilogue (X and the GEMM output share their row geometry, row stride ls)"""
+            if not fuse_bnr:
+                return {}
+            return dict(bnr_x=X.at(0), bnr_bs=X.bs, bnr_ls=ls, bnr_chan=chan_of[bn_name] if bn_name else None,
+                        bnr_slope=eng.pref(slope_name) if slope_name else None, bnr_c=Cc, bnr_sums=sm_off)
+
+        def bnact_bwd(bn_name, slope_name, X, L, Cc, st_off, fold, dO, dU, dX, sm_off, fused=False):
+            """returns the backward launches (reduce — unless the producing GEMM's epilogue did it —, apply) for the same
+            geometry"""
+            fused = fused and fuse_bnr
             mode = bn_mode(bool(bn_name), bool(slope_name)) | (TRAIN if bn_name else 0)
             kw = dict(X=X.at(0), x_bs=X.bs, x_ls=X.ls, B=B, L=L, Cc=Cc, mode=mode, fold=fold, count=float(B * L),
                       eps=1e-4, slope=eng.pref(slope_name) if slope_name else None)
@@ -535,7 +557,7 @@ class Plan:
             if dU is not None:
                 kw.update(dU=dU.at(0), u_bs=dU.bs, u_ls=dU.ls)
             out = []
-            if mode & 3:
+            if (mode & 3) and not fused:
                 out.append(lambda: ops.bnact_bwd_reduce(sums=sm_off, stats=st_off if bn_name else None, **kw))
             akw = dict(kw)
             akw.update(dX=dX.at(0) if dX is not None else None, d_bs=dX.bs if dX is not None else 0,
@@ -554,10 +576,10 @@ class Plan:
             return SideLaunch(lambda: ops.wgrad(**kw))
 
         def dgemm(g: GemmW, Aref, a_bs, a_ls, Lo, Y, y_bs, y_ls, n_last=None, R=None, r_bs=0, r_ls=0, act=ACT_NONE,
-                  out_scale=1.0):
+                  out_scale=1.0, bnr=None):
             kw = dict(A=Aref, a_bs=a_bs, a_ls=a_ls, B=B, Lo=Lo, K=g.dK, N=g.dN, W=eng.wdref(g), Y=Y, y_bs=y_bs,
                       y_ls=y_ls, n_last=n_last, R=R, r_bs=r_bs, r_ls=r_ls, act=act, out_scale=out_scale,
-                      precision=prec)
+                      precision=prec, **(bnr or {}))
             return lambda: ops.gemm(**kw)
 
         WG = eng.W
@@ -774,14 +796,18 @@ class Plan:
                                       dOut.at(0), dOut.bs, dOut.ls, B, W, round_tf32=rnd))
         Bw.append(wgrad(gout, Hlast.at(-ho), Hlast.bs, ch[0], W, dOut.at(0), dOut.bs, dOut.ls))
         dH = A(eng.l_dec, ch[0])
-        Bw.append(dgemm(gout, dOut.at(-3), dOut.bs, C0, eng.l_dec, dH.at(0), dH.bs, dH.ls))
+        lastb = dec_blocks[-1]
+        sm_next = sums(lastb["Co"])  # the gradient of conv_out goes straight into the last block's add.0 (no skip term)
+        Bw.append(dgemm(gout, dOut.at(-3), dOut.bs, C0, eng.l_dec, dH.at(0), dH.bs, dH.ls,
+                        bnr=bnr_ctx(lastb["pre"] + "add.0", lastb["pre"] + "add.1.weight", lastb["T"], lastb["Co"], sm_next,
+                                    dH.ls)))
         dU = None
         for blk in reversed(dec_blocks):
             Ci, Co, L, Lo2, pre = blk["Ci"], blk["Co"], blk["L"], blk["Lo2"], blk["pre"]
             gs, g0, g3 = blk["gs"], blk["g0"], blk["g3"]
             dT = Ao(Lo2, Co, k - p2, p2 + 1, even=True)
             lst = bnact_bwd(pre + "add.0", pre + "add.1.weight", blk["T"], Lo2, Co, blk["st2"], 2, dH, dU, dT,
-                            sums(Co))
+                            sm_next if dU is None else sums(Co), fused=dU is None)
             if dU is not None:
                 lst[0] = AfterSide(lst[0])  # dU comes from the previous block's skip dgrad on the side stream
             Bw += lst
@@ -794,10 +820,12 @@ class Plan:
             Bw.append(wgrad(g3, blk["R0a"].at(-wl), blk["R0a"].bs, Ci // 2, L, dT.at(0), dT.bs, 2 * Co,
                             bias_n=2 * Co))
             dR0a = A(L, Ci // 2)
-            Bw.append(dgemm(g3, dT.at(-p2), dT.bs, 2 * Co, L, dR0a.at(0), dR0a.bs, dR0a.ls))
+            sm1 = sums(Ci // 2)
+            Bw.append(dgemm(g3, dT.at(-p2), dT.bs, 2 * Co, L, dR0a.at(0), dR0a.bs, dR0a.ls,
+                            bnr=bnr_ctx(pre + "residual.1", pre + "residual.2.weight", blk["R0"], Ci // 2, sm1, dR0a.ls)))
             dR0 = Ao(L, Ci // 2, p2, p2)
             Bw += bnact_bwd(pre + "residual.1", pre + "residual.2.weight", blk["R0"], L, Ci // 2, blk["st1"], 1,
-                            dR0a, None, dR0, sums(Ci // 2))
+                            dR0a, None, dR0, sm1, fused=True)
             Bw.append(wgrad(g0, blk["H"].at(-p2), blk["H"].bs, Ci, L, dR0.at(0), dR0.bs, dR0.ls))
             dHin = A(L, Ci)
             Bw.append(dgemm(g0, dR0.at(-p2), dR0.bs, Ci // 2, L, dHin.at(0), dHin.bs, dHin.ls))
@@ -864,13 +892,16 @@ class Plan:
         # enqueued — (index in Bw after which gpacked[lo:hi] is final, lo, hi), last layers first
         self._bw_buckets = [(len(Bw), gfc.w, eng.gp_split)]
         dH = A(Ll, Cl)
-        Bw.append(dgemm(gfc, self.dms, eng.ms_ld, 0, 1, dH.at(0), dH.bs, 0))
+        laste = enc_blocks[-1]
+        sm_next = sums(laste["Co"])
+        Bw.append(dgemm(gfc, self.dms, eng.ms_ld, 0, 1, dH.at(0), dH.bs, 0,
+                        bnr=bnr_ctx(laste["pre"] + "add.0", laste["pre"] + "add.1.weight", laste["T"], laste["Co"], sm_next, 0)))
         for bi, blk in reversed(list(enumerate(enc_blocks))):
             Ci, Co, Lo, Lin, pre = blk["Ci"], blk["Co"], blk["Lo"], blk["Lin"], blk["pre"]
             gs, g0, g3 = blk["gs"], blk["g0"], blk["g3"]
             dT = Ao(Lo, Co, p2, p2)
             Bw += bnact_bwd(pre + "add.0", pre + "add.1.weight", blk["T"], Lo, Co, blk["st2"], 1, dH, None, dT,
-                            sums(Co))
+                            sm_next, fused=True)
             # the skip path's data gradient needs only dT: side stream, beside residual.3 dgrad -> BN backward
             dHin = A(blk["Lin"], Ci)
             Lg = (blk["Lin"] + 1) // 2
@@ -878,20 +909,30 @@ class Plan:
             Bw.append(SideData(dgemm(gs, dT.at(-wl), dT.bs, Co, Lg, dHin.at(0), dHin.bs, 2 * Ci, n_last=nlast)))
             Bw.append(wgrad(g3, blk["R0a"].at(-p2), blk["R0a"].bs, Co // 2, Lo, dT.at(0), dT.bs, dT.ls))
             dR0a = A(Lo, Co // 2)
-            Bw.append(dgemm(g3, dT.at(-(k - 1 - p2)), dT.bs, Co, Lo, dR0a.at(0), dR0a.bs, dR0a.ls))
+            sm1 = sums(Co // 2)
+            Bw.append(dgemm(g3, dT.at(-(k - 1 - p2)), dT.bs, Co, Lo, dR0a.at(0), dR0a.bs, dR0a.ls,
+                            bnr=bnr_ctx(pre + "residual.1", pre + "residual.2.weight", blk["R0"], Co // 2, sm1, dR0a.ls)))
             dR0 = Ao(Lo, Co // 2, hw, hw)
             Bw += bnact_bwd(pre + "residual.1", pre + "residual.2.weight", blk["R0"], Lo, Co // 2, blk["st1"], 1,
-                            dR0a, None, dR0, sums(Co // 2))
+                            dR0a, None, dR0, sm1, fused=True)
             Hin = blk["Hin"]
             Bw.append(wgrad(g0, Hin.at(-p2), Hin.bs, 2 * Ci, Lo, dR0.at(0), dR0.bs, dR0.ls))
             Bw.append(wgrad(gs, Hin.at(-p2), Hin.bs, 2 * Ci, Lo, dT.at(0), dT.bs, dT.ls))
+            # the block's input gradient is complete in this GEMM (skip path added as R): its epilogue carries the backward
+            # reduction of the layer that produced the input — the previous block's add.0, or the encoder's first PReLU
+            sm_next = sums(Ci)
+            if bi > 0:
+                prev = enc_blocks[bi - 1]
+                ctx = bnr_ctx(prev["pre"] + "add.0", prev["pre"] + "add.1.weight", prev["T"], Ci, sm_next, 2 * Ci)
+            else:
+                ctx = bnr_ctx(None, "encoder.activation.weight", enc_in["Y0"], Ci, sm_next, 2 * Ci)
             Bw.append(AfterSide(dgemm(g0, dR0.at(-wl), dR0.bs, Co // 2, Lg, dHin.at(0), dHin.bs, 2 * Ci, n_last=nlast,
-                                      R=dHin.at(0), r_bs=dHin.bs, r_ls=2 * Ci)))
+                                      R=dHin.at(0), r_bs=dHin.bs, r_ls=2 * Ci, bnr=ctx)))
             if bi >= eng.nblk - 2:  # the two widest blocks (6.5 M and 1.6 M weights at the default widths); the small rest goes last
                 self._bw_buckets.append((len(Bw), gs.w, self._bw_buckets[-1][1]))
             dH = dHin
         dY0 = Ao(W, ch[0])
-        Bw += bnact_bwd(None, "encoder.activation.weight", enc_in["Y0"], W, ch[0], None, 1, dH, None, dY0, sums(ch[0]))
+        Bw += bnact_bwd(None, "encoder.activation.weight", enc_in["Y0"], W, ch[0], None, 1, dH, None, dY0, sm_next, fused=True)
         g = enc_in["g"]
         Bw.append(wgrad(g, X0.at(-3), X0.bs, C0, W, dY0.at(0), dY0.bs, dY0.ls))
         # public-API path only: weight gradients back into the reference layout (p.grad views of gflat)

@@ -45,7 +45,8 @@ class EmuOps:
         return self.n
 
     def gemm(self, A, a_bs, a_ls, B, Lo, K, N, W, Y, y_bs, y_ls, bias=None, bias_mod=1, bias_n=0, n_last=None,
-             R=None, r_bs=0, r_ls=0, act=ACT_NONE, out_scale=1.0, stats=None, precision=0):
+             R=None, r_bs=0, r_ls=0, act=ACT_NONE, out_scale=1.0, stats=None, precision=0,
+             bnr_x=None, bnr_bs=0, bnr_ls=0, bnr_chan=None, bnr_slope=None, bnr_c=0, bnr_sums=None):
         self.n += 1
         rnd, accum, act = bool(act & ACT_ROUND_TF32), bool(act & ACT_ACCUM), act & 15
         n_last = N if n_last is None else n_last
@@ -78,6 +79,26 @@ class EmuOps:
             y = torch.where(torch.where(valid, r, torch.zeros(())) > 0, y, torch.zeros(()))
         if rnd:
             y = rtf32(y)
+        if bnr_sums is not None:  # fused BatchNorm(+PReLU) backward reduction (scv_gemm_t bnr_*)
+            C = bnr_c
+            x = _v(bnr_x, (B, Lo, N), (bnr_bs, bnr_ls, 1))
+            ch = torch.arange(N) % C
+            if bnr_chan is not None:
+                tb = _v(bnr_chan, (4, C), (C, 1))
+                sc, sh, mu, rs = tb[0][ch], tb[1][ch], tb[2][ch], tb[3][ch]
+            else:
+                sc, sh, mu, rs = torch.ones(N), torch.zeros(N), torch.zeros(N), torch.ones(N)
+            v = x * sc + sh
+            g = torch.where(valid, y, torch.zeros(()))
+            sm = _v(bnr_sums, (2 * C + 1,), (1,))
+            if bnr_slope is not None:
+                sl = _v(bnr_slope, (1,), (1,))
+                sm[2 * C] += torch.where(valid & (v < 0), g * v, torch.zeros(())).double().sum()
+                g = torch.where(v < 0, g * sl, g)
+            if bnr_chan is not None:
+                xh = torch.where(valid, (x - mu) * rs, torch.zeros(()))
+                sm[:C] += g.double().sum((0, 1)).reshape(N // C, C).sum(0)
+                sm[C:2 * C] += (g * xh).double().sum((0, 1)).reshape(N // C, C).sum(0)
         out = _v(Y, (B, Lo, N), (y_bs, y_ls, 1))
         if accum:
             y = y + out
@@ -149,9 +170,11 @@ class EmuOps:
 
     def bnact_fwd(self, X, x_bs, x_ls, B, L, Cc, mode, stats=None, fold=1, count=1.0, eps=1e-4, momentum=0.1,
                   gamma=None, beta=None, running_mean=None, running_var=None, slope=None,
-                  H=None, h_bs=0, h_ls=0, U=None, u_bs=0, u_ls=0):
+                  H=None, h_bs=0, h_ls=0, U=None, u_bs=0, u_ls=0, chan_out=None):
         self.n += 1
-        scale, shift, _, _ = self._chan(Cc, mode, stats, fold, count, eps, gamma, beta, running_mean, running_var)
+        scale, shift, mean_c, rstd_c = self._chan(Cc, mode, stats, fold, count, eps, gamma, beta, running_mean, running_var)
+        if chan_out is not None:
+            _v(chan_out, (4, Cc), (Cc, 1)).copy_(torch.stack([scale, shift, mean_c, rstd_c]))
         if (mode & 5) == 5 and running_mean is not None:
             st = _v(stats, (2, fold, Cc), (fold * Cc, Cc, 1))
             mean = st[0].sum(0) / count

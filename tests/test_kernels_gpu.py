@@ -335,3 +335,31 @@ def test_gen_features(ops, W):
     run_both(ops, T, lambda o, t: o.gen_features(t["xh"], ld, t["root"], t["off"], t["tree"], len(tree), t["parts"], B, W, J,
                                                  norm=t["norm"], pose_out=t["pose"], heading=t["head"], avg3=t["avg3"]),
              tol=2e-5, check=["pose", "head", "avg3"])
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("B,Lo,C,fold,taps,resid,bn,act_", [(300, 13, 64, 2, 3, True, True, True), (700, 1, 256, 4, 1, False, True, True),
+                                                            (260, 26, 32, 1, 5, False, True, True), (129, 7, 64, 2, 3, True, False, True),
+                                                            (64, 4, 128, 1, 5, False, True, False)])
+def test_gemm_fused_bn_backward_reduce(ops, B, Lo, C, fold, taps, resid, bn, act_, prec):
+    """scv_gemm with bnr_*: the data-gradient GEMM accumulates the BatchNorm / PReLU backward sums of the layer whose
+    output gradient it produces (tensor-core epilogue; FFMA path = GEMM + stand-alone reduction)."""
+    N, Cin = fold * C, 32
+    K = taps * Cin
+    rows = Lo + taps - 1
+    n_last = N - C if (fold == 2 and Lo > 1) else None
+    T = {"A": torch.randn(B * rows * Cin + K, generator=g(1)), "W": torch.randn(N * K, generator=g(2)) / math.sqrt(K),
+         "Y": torch.zeros(B * Lo * N), "R": torch.randn(B * Lo * N, generator=g(4)),
+         "X": torch.randn(B * Lo * N, generator=g(5)) * 1.5 + 0.2,
+         "chan": torch.cat([torch.rand(C, generator=g(6)) + 0.5, torch.randn(C, generator=g(7)) * 0.3,
+                            torch.randn(C, generator=g(8)) * 0.2, torch.rand(C, generator=g(9)) + 0.5]),
+         "slope": torch.tensor([0.25]), "sums": torch.zeros(2 * C + 1, dtype=torch.double)}
+    if prec:
+        T["A"], T["W"] = rtf32(T["A"]), rtf32(T["W"])
+
+    def call(o, t):
+        o.gemm(t["A"], rows * Cin, Cin, B, Lo, K, N, t["W"], t["Y"], Lo * N, N, n_last=n_last,
+               R=t["R"] if resid else None, r_bs=Lo * N, r_ls=N, precision=prec,
+               bnr_x=t["X"], bnr_bs=Lo * N, bnr_ls=N, bnr_chan=t["chan"] if bn else None,
+               bnr_slope=t["slope"] if act_ else None, bnr_c=C, bnr_sums=t["sums"])
+    run_both(ops, T, call, tol=2e-5, check=["Y", "sums"])
