@@ -78,7 +78,7 @@ typedef struct {
    * 146-147,172-180) whose pre-normalisation input is bnr_x, addressed like Y with (bnr_bs, bnr_ls), channel n % bnr_c.
    * With y = scale x + shift (bnr_chan = [scale | shift | mean | rstd] x bnr_c, as scv_bnact_fwd writes to chan_out;
    * NULL = no BatchNorm) and g' = (y < 0 ? slope : 1) g (bnr_slope NULL = no PReLU):
-   *   bnr_sums[c] += sum g',  bnr_sums[C + c] += sum g' (x - mean) rstd,  bnr_sums[2C] += sum_{y<0} g y
+   *   bnr_sums[c] += sum g',  bnr_sums[C + c] += sum g' (x - mean) rstd,  bnr_sums[2C] += sum over y < 0 of g y
    * i.e. exactly what scv_bnact_bwd_reduce accumulates, without its extra pass over X and Y. */
   const float* bnr_x; int64_t bnr_bs, bnr_ls;
   const float* bnr_chan; const float* bnr_slope; int64_t bnr_c;
@@ -209,18 +209,8 @@ typedef struct {
   double lr, beta1, beta2, eps, weight_decay; int64_t step;
   const double* hyper; /* optional device [lr, step]: overrides lr/step (CUDA-graph replay) */
   int64_t kind; /* 0 adam (L2 wd folded in grad), 1 adamw (decoupled), 2 sgd nesterov (m = momentum buf, beta1 = momentum) */
-  /* packed-gradient mode (inv_idx != NULL): the GEMM weight gradients are read where the wgrad kernels accumulated them,
-   * gpacked[inv_idx[i]] (g[i] where inv_idx[i] < 0: BatchNorm / PReLU gradients, zeroed once read) — no gradient-unpack
-   * pass.  (Round 2 also tried WRITING the packed weight copies from this kernel: 4-byte scattered stores made it 25x
-   * slower, 3.8 ms; the packed matrices are rebuilt by scv_gather, whose stores are coalesced.) */
-  const int32_t* inv_idx; const float* gpacked;
 } scv_optim_t;
 int scv_optim_step(const scv_optim_t* p, void* stream);
-/* global gradient norm in packed-weights mode: sumsq[0] += sum_{j < n_packed, pack_idx[j] >= 0} gpacked[j]^2
- * + sum_{i < n_direct} gdirect[i]^2; positions with pack_idx[j] < 0 (structural zeros / padding of the packed
- * layout, where the wgrad kernels deposit values nobody reads) are reset to 0. */
-int scv_sumsq_packed(float* gpacked, const int32_t* pack_idx, int64_t n_packed, const float* gdirect, int64_t n_direct,
-                     double* sumsq, void* stream);
 /* cudaMemsetAsync(p, 0, bytes) on `stream`: the per-step accumulators (BatchNorm sums, loss terms, grad norm) live in
  * one buffer and are cleared by one memset node of the step's CUDA graph. */
 int scv_zero(void* p, int64_t bytes, void* stream);

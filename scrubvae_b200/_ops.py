@@ -78,8 +78,7 @@ BnactBwdT = _struct("BnactBwdT", [
 OptimT = _struct("OptimT", [
     ("p", _vp), ("g", _vp), ("m", _vp), ("v", _vp), ("n", _i64), ("sumsq", _vp), ("max_norm", _f64),
     ("gscale", _f64), ("lr", _f64), ("beta1", _f64), ("beta2", _f64), ("eps", _f64),
-    ("weight_decay", _f64), ("step", _i64), ("hyper", _vp), ("kind", _i64),
-    ("inv_idx", _vp), ("gpacked", _vp)])
+    ("weight_decay", _f64), ("step", _i64), ("hyper", _vp), ("kind", _i64)])
 
 _SIGS = {
     "scv_version": (C.c_int, []),
@@ -103,7 +102,6 @@ _SIGS = {
     "scv_sumsq": (C.c_int, [_vp, _i64, _vp, _vp]),
     "scv_optim_step": (C.c_int, [C.POINTER(OptimT), _vp]),
     "scv_gen_features": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "scv_sumsq_packed": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "scv_zero": (C.c_int, [_vp, _i64, _vp]),
     "scv_d2f": (C.c_int, [_vp, _vp, _i64, _vp]),
     "scv_loss_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
@@ -251,14 +249,10 @@ class CudaOps:
         self._check(self.lib.scv_sumsq(_ptr(g), n, _ptr(out), self._stream()), "scv_sumsq")
 
     def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind,
-                   hyper=None, inv_idx=None, gpacked=None):
+                   hyper=None):
         s = OptimT(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, _ptr(sumsq), max_norm, gscale, lr, beta1, beta2, eps,
-                   weight_decay, step, _ptr(hyper), kind, _ptr(inv_idx), _ptr(gpacked))
+                   weight_decay, step, _ptr(hyper), kind)
         self._check(self.lib.scv_optim_step(C.byref(s), self._stream()), "scv_optim_step")
-
-    def sumsq_packed(self, gpacked, pack_idx, n_packed, gdirect, n_direct, out):
-        self._check(self.lib.scv_sumsq_packed(_ptr(gpacked), _ptr(pack_idx), n_packed, _ptr(gdirect), n_direct,
-                                              _ptr(out), self._stream()), "scv_sumsq_packed")
 
     def zero(self, t):
         """cudaMemsetAsync over a whole tensor (a memset node when captured)."""

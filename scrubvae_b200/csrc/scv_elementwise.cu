@@ -445,37 +445,6 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const float* __restrict__ g, 
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
-// packed-weights mode: global norm over the live positions of gpacked (+ the direct BatchNorm / PReLU gradients), junk
-// positions (structural zeros, padding) reset on the way
-__global__ void __launch_bounds__(NT) sumsq_packed_kernel(float* __restrict__ gp, const int32_t* __restrict__ idx, int64_t n,
-                                                          const float* __restrict__ gd, int64_t nd, double* out) {
-  __shared__ double sh[32];
-  float acc = 0.f;
-  double dacc = 0.0;
-  int cnt = 0;
-  const int64_t n4 = n >> 2;  // n is a multiple of 4 (every packed matrix is padded to 4 floats)
-  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (int64_t)gridDim.x * NT) {
-    const int4 j = __ldg(reinterpret_cast<const int4*>(idx) + i);
-    float4 v = *(reinterpret_cast<const float4*>(gp) + i);
-    if ((j.x | j.y | j.z | j.w) < 0) {  // some junk in this group: mask + write back
-      if (j.x < 0) v.x = 0.f;
-      if (j.y < 0) v.y = 0.f;
-      if (j.z < 0) v.z = 0.f;
-      if (j.w < 0) v.w = 0.f;
-      *(reinterpret_cast<float4*>(gp) + i) = v;
-    }
-    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    if (++cnt == 64) { dacc += (double)acc; acc = 0.f; cnt = 0; }
-  }
-  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < nd; i += (int64_t)gridDim.x * NT) {
-    const float v = gd[i];
-    acc += v * v;
-  }
-  dacc += (double)acc;
-  double s = scv::block_sum_d(dacc, sh);
-  if (threadIdx.x == 0) atomicAdd(out, s);
-}
-
 __global__ void __launch_bounds__(NT) optim_kernel(const scv_optim_t p) {
   // clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6))  (train/trainer.py:164)
   const float gs = (float)p.gscale;
@@ -493,35 +462,22 @@ __global__ void __launch_bounds__(NT) optim_kernel(const scv_optim_t p) {
   const float step_size = (float)(lrd / bc1d), bc2s = (float)sqrt(bc2d);
   const bool first = stepd < 1.5;
   const int kind = (int)p.kind;
-  const bool packed = p.inv_idx != nullptr;
-  float* gw = const_cast<float*>(p.g);
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * NT) {
-    float g, w = p.p[i];
-    int32_t j = -1;
-    if (packed) {
-      j = __ldg(p.inv_idx + i);
-      if (j >= 0) g = __ldg(p.gpacked + j);  // gathered READ: sector-mates are read by neighbouring threads, L2 absorbs it
-      else { g = gw[i]; gw[i] = 0.f; }
-    } else {
-      g = p.g[i];
-    }
-    g *= coef;
-    float wn;
+    float g = p.g[i] * coef, w = p.p[i];
     if (kind == 2) {  // SGD, momentum beta1, nesterov (torch.optim.SGD)
       float buf = first ? g : b1 * p.m[i] + g;
       p.m[i] = buf;
-      wn = w - lr * (g + b1 * buf);
-    } else {
-      if (kind == 1) w *= 1.f - lr * wd;
-      else if (wd != 0.f) g += wd * w;
-      float m = p.m[i] + (1.f - b1) * (g - p.m[i]);          // torch: exp_avg.lerp_(grad, 1-beta1)
-      float v = b2 * p.v[i] + (1.f - b2) * g * g;
-      p.m[i] = m;
-      p.v[i] = v;
-      float denom = sqrtf(v) / bc2s + eps;
-      wn = w - step_size * (m / denom);
+      p.p[i] = w - lr * (g + b1 * buf);
+      continue;
     }
-    p.p[i] = wn;
+    if (kind == 1) w *= 1.f - lr * wd;
+    else if (wd != 0.f) g += wd * w;
+    float m = p.m[i] + (1.f - b1) * (g - p.m[i]);          // torch: exp_avg.lerp_(grad, 1-beta1)
+    float v = b2 * p.v[i] + (1.f - b2) * g * g;
+    p.m[i] = m;
+    p.v[i] = v;
+    float denom = sqrtf(v) / bc2s + eps;
+    p.p[i] = w - step_size * (m / denom);
   }
 }
 
@@ -627,15 +583,6 @@ int scv_sumsq(const float* g, int64_t n, double* sumsq, void* stream) {
   return scv::check_launch("sumsq_kernel");
 }
 
-int scv_sumsq_packed(float* gpacked, const int32_t* pack_idx, int64_t n_packed, const float* gdirect, int64_t n_direct,
-                     double* sumsq, void* stream) {
-  SCV_REQUIRE(gpacked && pack_idx && sumsq && n_packed % 4 == 0 && scv::aligned16(gpacked) && scv::aligned16(pack_idx),
-              "scv_sumsq_packed: gpacked / pack_idx must be 16-byte aligned and n_packed a multiple of 4");
-  sumsq_packed_kernel<<<grid1d(n_packed / 4 + 1, 4), NT, 0, (cudaStream_t)stream>>>(gpacked, pack_idx, n_packed, gdirect,
-                                                                                  gdirect ? n_direct : 0, sumsq);
-  return scv::check_launch("sumsq_packed_kernel");
-}
-
 int scv_zero(void* p, int64_t bytes, void* stream) {
   if (bytes <= 0) return 0;
   cudaError_t e = cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream);
@@ -648,7 +595,6 @@ int scv_zero(void* p, int64_t bytes, void* stream) {
 
 int scv_optim_step(const scv_optim_t* p, void* stream) {
   SCV_REQUIRE(p->kind >= 0 && p->kind <= 2 && (p->hyper || p->step >= 1), "scv_optim_step: bad kind/step");
-  SCV_REQUIRE(!p->inv_idx || (p->gpacked && p->g), "scv_optim_step: packed-gradient mode needs gpacked and g");
   optim_kernel<<<grid1d(p->n, 8), NT, 0, (cudaStream_t)stream>>>(*p);
   return scv::check_launch("optim_kernel");
 }

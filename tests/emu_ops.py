@@ -422,34 +422,16 @@ class EmuOps:
         self.n += 1
         _v(out, (1,), (1,)).add_((_v(g, (n,), (1,)).double() ** 2).sum())
 
-    def sumsq_packed(self, gpacked, pack_idx, n_packed, gdirect, n_direct, out):
-        self.n += 1
-        G, I = _v(gpacked, (n_packed,), (1,)), _v(pack_idx, (n_packed,), (1,))
-        G[I < 0] = 0.0
-        tot = (G.double() ** 2).sum()
-        if gdirect is not None and n_direct:
-            tot = tot + (_v(gdirect, (n_direct,), (1,)).double() ** 2).sum()
-        _v(out, (1,), (1,)).add_(tot)
-
     def zero(self, t):
         t.zero_()
 
     def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind,
-                   hyper=None, inv_idx=None, gpacked=None):
+                   hyper=None):
         self.n += 1
         if hyper is not None:
             hy = _v(hyper, (2,), (1,))
             lr, step = float(hy[0]), int(round(float(hy[1])))
         P, G = _v(p, (n,), (1,)), _v(g, (n,), (1,))
-        if inv_idx is not None:  # packed-gradient mode: gather the weight gradients, zero the direct ones once read
-            inv = _v(inv_idx, (n,), (1,)).long()
-            live = inv >= 0
-            Gfull = G.clone()
-            Gfull[live] = _tail(gpacked)[inv[live]]
-            G[~live] = 0.0
-            self.optim_step(p, Gfull, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind)
-            self.n -= 1
-            return
         coef = gscale
         if sumsq is not None:
             norm = math.sqrt(float(_v(sumsq, (1,), (1,)))) * gscale
