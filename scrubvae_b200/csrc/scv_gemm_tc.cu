@@ -160,23 +160,17 @@ __device__ __forceinline__ float act_apply(float v, int act, float r) {
 // accumulated here instead of in a separate pass over X and Y (s1 / s2 carry the two column sums, ds the slope term).
 template <int ACT, bool RD, bool ST, bool RND, bool ACC = false, bool BNR = false>
 __device__ __forceinline__ void epi_rows(const GemmTcParams& p, const float4* xp4, const int rq, const int cq, const bool col_ok,
-                                         const int n, const float4 bv, const long long (&yoff)[8], const long long (&roff)[8],
-                                         const int (&ncap)[8], float4& s1, float4& s2, const long long (&xoff)[8] = {},
+                                         const int n, const float4 bv, const long long* __restrict__ yoff,
+                                         const long long* __restrict__ roff, const int* __restrict__ ncap, float4& s1,
+                                         float4& s2, const long long* __restrict__ xoff = nullptr,
                                          float* ds = nullptr) {
   const int act = ACT >= 0 ? ACT : p.act;
   const bool rnd = ACT >= 0 ? RND : (p.round_out != 0);
   const float osc = p.out_scale;
-  float4 rv[8];
-  float4 xv[BNR ? 8 : 1];
   float4 c_sc = make_float4(1.f, 1.f, 1.f, 1.f), c_sh = make_float4(0.f, 0.f, 0.f, 0.f), c_mu = c_sh, c_rs = c_sc;
   float slope = 0.f;
   bool has_act = false;
   if (BNR) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col_ok && n < ncap[i]) xv[i] = __ldg(reinterpret_cast<const float4*>(p.bnr_x + xoff[i] + n));
-    }
     if (p.bnr_chan && col_ok) {
       const int ch = n % p.bnr_c, C = p.bnr_c;
       c_sc = __ldg(reinterpret_cast<const float4*>(p.bnr_chan + ch));
@@ -187,51 +181,66 @@ __device__ __forceinline__ void epi_rows(const GemmTcParams& p, const float4* xp
     has_act = p.bnr_slope != nullptr;
     if (has_act) slope = __ldg(p.bnr_slope);
   }
-  if (RD) {
+  // global loads (residual R, BatchNorm input X) are issued G rows deep before the arithmetic; the BNR variants hold two
+  // operands per row and go 4 deep to stay inside the register budget
+  constexpr int G = BNR ? 4 : 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col_ok && n < ncap[i]) rv[i] = __ldg(reinterpret_cast<const float4*>(p.R + roff[i] + n));
+  for (int i0 = 0; i0 < 8; i0 += G) {
+    float4 rv[RD ? G : 1], xv[BNR ? G : 1];
+    if (RD) {
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && n < ncap[i0 + u]) rv[u] = __ldg(reinterpret_cast<const float4*>(p.R + roff[i0 + u] + n));
+      }
     }
-  }
+    if (BNR) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rq;
-    const float4 a = xp4[r * 8 + (cq ^ (r & 7))];
-    if (col_ok && n < ncap[i]) {
-      float4 tv = make_float4(fmaf(osc, a.x, bv.x), fmaf(osc, a.y, bv.y), fmaf(osc, a.z, bv.z), fmaf(osc, a.w, bv.w));
-      float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (RD) {
-        r4 = rv[i];
-        if (act != SCV_ACT_RELUMASK) { tv.x += r4.x; tv.y += r4.y; tv.z += r4.z; tv.w += r4.w; }
+      for (int u = 0; u < G; ++u) {
+        xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && n < ncap[i0 + u]) xv[u] = __ldg(reinterpret_cast<const float4*>(p.bnr_x + xoff[i0 + u] + n));
       }
-      if (ST) {
-        s1.x += tv.x; s1.y += tv.y; s1.z += tv.z; s1.w += tv.w;
-        s2.x = fmaf(tv.x, tv.x, s2.x); s2.y = fmaf(tv.y, tv.y, s2.y); s2.z = fmaf(tv.z, tv.z, s2.z); s2.w = fmaf(tv.w, tv.w, s2.w);
-      }
-      if (BNR) {
-        const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w}, gs[4] = {tv.x, tv.y, tv.z, tv.w};
-        const float sc[4] = {c_sc.x, c_sc.y, c_sc.z, c_sc.w}, sh[4] = {c_sh.x, c_sh.y, c_sh.z, c_sh.w};
-        const float mu[4] = {c_mu.x, c_mu.y, c_mu.z, c_mu.w}, rs[4] = {c_rs.x, c_rs.y, c_rs.z, c_rs.w};
-        float a1[4], a2[4];
+    }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float v = fmaf(xs[q], sc[q], sh[q]);
-          float gg = gs[q];
-          if (has_act && v < 0.f) { *ds += gg * v; gg *= slope; }
-          a1[q] = gg;
-          a2[q] = gg * (xs[q] - mu[q]) * rs[q];
+    for (int u = 0; u < G; ++u) {
+      const int i = i0 + u;
+      const int r = i * 4 + rq;
+      const float4 a = xp4[r * 8 + (cq ^ (r & 7))];
+      if (col_ok && n < ncap[i]) {
+        float4 tv = make_float4(fmaf(osc, a.x, bv.x), fmaf(osc, a.y, bv.y), fmaf(osc, a.z, bv.z), fmaf(osc, a.w, bv.w));
+        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (RD) {
+          r4 = rv[u];
+          if (act != SCV_ACT_RELUMASK) { tv.x += r4.x; tv.y += r4.y; tv.z += r4.z; tv.w += r4.w; }
         }
-        s1.x += a1[0]; s1.y += a1[1]; s1.z += a1[2]; s1.w += a1[3];
-        s2.x += a2[0]; s2.y += a2[1]; s2.z += a2[2]; s2.w += a2[3];
+        if (ST) {
+          s1.x += tv.x; s1.y += tv.y; s1.z += tv.z; s1.w += tv.w;
+          s2.x = fmaf(tv.x, tv.x, s2.x); s2.y = fmaf(tv.y, tv.y, s2.y); s2.z = fmaf(tv.z, tv.z, s2.z); s2.w = fmaf(tv.w, tv.w, s2.w);
+        }
+        if (BNR) {
+          const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, gs[4] = {tv.x, tv.y, tv.z, tv.w};
+          const float sc[4] = {c_sc.x, c_sc.y, c_sc.z, c_sc.w}, sh[4] = {c_sh.x, c_sh.y, c_sh.z, c_sh.w};
+          const float mu[4] = {c_mu.x, c_mu.y, c_mu.z, c_mu.w}, rs[4] = {c_rs.x, c_rs.y, c_rs.z, c_rs.w};
+          float a1[4], a2[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float v = fmaf(xs[q], sc[q], sh[q]);
+            float gg = gs[q];
+            if (has_act && v < 0.f) { *ds += gg * v; gg *= slope; }
+            a1[q] = gg;
+            a2[q] = gg * (xs[q] - mu[q]) * rs[q];
+          }
+          s1.x += a1[0]; s1.y += a1[1]; s1.z += a1[2]; s1.w += a1[3];
+          s2.x += a2[0]; s2.y += a2[1]; s2.z += a2[2]; s2.w += a2[3];
+        }
+        float4 yv = tv;
+        if (act != SCV_ACT_NONE)
+          yv = make_float4(act_apply(tv.x, act, r4.x), act_apply(tv.y, act, r4.y), act_apply(tv.z, act, r4.z),
+                           act_apply(tv.w, act, r4.w));
+        if (rnd) yv = scv::round_tf32(yv);
+        if (ACC) red_add_v4(p.Y + yoff[i] + n, yv);
+        else *reinterpret_cast<float4*>(p.Y + yoff[i] + n) = yv;
       }
-      float4 yv = tv;
-      if (act != SCV_ACT_NONE)
-        yv = make_float4(act_apply(tv.x, act, r4.x), act_apply(tv.y, act, r4.y), act_apply(tv.z, act, r4.z),
-                         act_apply(tv.w, act, r4.w));
-      if (rnd) yv = scv::round_tf32(yv);
-      if (ACC) red_add_v4(p.Y + yoff[i] + n, yv);
-      else *reinterpret_cast<float4*>(p.Y + yoff[i] + n) = yv;
     }
   }
 }
@@ -244,7 +253,10 @@ __device__ __forceinline__ void epi_rows(const GemmTcParams& p, const float4* xp
 // half of the W tile and MULTICASTS it into both shared memories, so W crosses the L2 -> SM fabric once per pair.  The
 // layers of this network are paced by that fabric (12.3 TB/s chip-wide, ~42 B/cycle per SM, against the 64-96 B/cycle a
 // 128x256 TF32 tile consumes), not by the tensor pipe.
-template <int kCtas, bool kMc = false, bool kBf16 = false>
+// kBnr: the epilogue variants with the fused BatchNorm backward reduction live in their own kernel instantiation — their
+// extra per-row offsets and per-channel constants cost registers (the combined kernel spilled 200 bytes and every GEMM of
+// the step slowed down by 8 %).
+template <int kCtas, bool kMc = false, bool kBf16 = false, bool kBnr = false>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmTcParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
@@ -401,7 +413,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     const int rows_in_box = p.bl * p.nb;
     const int N = p.N;
     const int et = threadIdx.x - 128;
-    const bool has_bnr = p.bnr_sums != nullptr;
+    const bool has_bnr = kBnr && p.bnr_sums != nullptr;
     const bool has_stats = p.stats != nullptr || has_bnr;  // column sums through the shared-memory accumulators
     // where the column sums go: forward statistics stats[n], stats[N + n]; backward reduction sums[n % C], sums[C + n % C]
     double* const sum_base = has_bnr ? p.bnr_sums : p.stats;
@@ -442,7 +454,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
      for (int sj = 0; sj < sub; ++sj) {
       const int mt = mt0 + sj;
       const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;
-      long long yoff[8], roff[8], xoff[8];
+      long long yoff[8], roff[kBnr ? 1 : 8];  // kBnr: X and R share Y's row geometry (checked on the host): one offset array
       int ncap[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -451,8 +463,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         const int64_t b = (int64_t)bt_i * p.nb + bi, l = (int64_t)lt_i * p.bl + li;
         const bool ok = row < rows_in_box && mt < p.m_tiles && b < p.B && l < p.Lo;
         yoff[i] = (long long)(b * p.y_bs + l * p.y_ls);
-        roff[i] = (long long)(b * p.r_bs + l * p.r_ls);
-        xoff[i] = (long long)(b * p.bnr_bs + l * p.bnr_ls);
+        if (!kBnr) roff[kBnr ? 0 : i] = (long long)(b * p.r_bs + l * p.r_ls);
         ncap[i] = ok ? ((l == p.Lo - 1) ? p.n_last : N) : 0;
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub == 2 ? sj : acc) * kMaxBN;
@@ -483,6 +494,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         // one instantiation per (activation, residual, sums, rounding) combination the step uses: the per-element
         // work is then a handful of instructions instead of a runtime-branching generic path (one epilogue warp
         // per scheduler: every instruction's latency is exposed)
+        if (kBnr) {
+          if (rd) epi_rows<SCV_ACT_NONE, true, false, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, yoff, ncap, s1, s2, yoff, &ds_acc);
+          else epi_rows<SCV_ACT_NONE, false, false, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, yoff, ncap, s1, s2, yoff, &ds_acc);
+        } else {
         switch (p.epi_kind) {
           case 0: epi_rows<SCV_ACT_NONE, false, false, false>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
           case 1: epi_rows<SCV_ACT_NONE, false, true, false>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
@@ -491,11 +506,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
           case 4: epi_rows<SCV_ACT_NONE, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
           case 5: epi_rows<SCV_ACT_TANH, false, false, false>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
           case 6: epi_rows<SCV_ACT_NONE, false, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2); break;
-          case 7: epi_rows<SCV_ACT_NONE, false, false, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2, xoff, &ds_acc); break;
-          case 8: epi_rows<SCV_ACT_NONE, true, false, false, false, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2, xoff, &ds_acc); break;
           default:
             if (rd) epi_rows<-1, true, true, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2);
             else epi_rows<-1, false, true, true>(p, xp4, rq, cq, col_ok, n, bv, yoff, roff, ncap, s1, s2);
+        }
         }
         if (has_stats) {
 #pragma unroll
@@ -548,6 +562,16 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcParams p) {
   gemm_tc_body<1>(tmA, tmW, p);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_bnr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcParams p) {
+  gemm_tc_body<1, false, false, true>(tmA, tmW, p);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_bnr_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcParams p) {
+  gemm_tc_body<1, false, true, true>(tmA, tmW, p);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -829,6 +853,8 @@ int ensure_attrs() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_bnr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_bnr_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e == cudaSuccess) {
@@ -909,9 +935,10 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
     return decline("scv_gemm", "bias not float4-aligned", M, p->N, p->K);
   const bool bnr = p->bnr_sums != nullptr;
   if (bnr && ((p->act & 15) != SCV_ACT_NONE || (p->act & (SCV_ACT_ROUND_TF32 | SCV_ACT_ACCUM)) || p->stats || !p->bnr_x ||
-              p->bnr_c <= 0 || p->bnr_c % 4 || p->N % p->bnr_c || p->bnr_bs % 4 || p->bnr_ls % 4 || !aligned16(p->bnr_x) ||
+              p->bnr_c <= 0 || p->bnr_c % 4 || p->N % p->bnr_c || p->bnr_bs != p->y_bs || (p->Lo > 1 && p->bnr_ls != p->y_ls) ||
+              (p->R && (p->r_bs != p->y_bs || (p->Lo > 1 && p->r_ls != p->y_ls))) || !aligned16(p->bnr_x) ||
               (p->bnr_chan && !aligned16(p->bnr_chan))))
-    return decline("scv_gemm", "fused BatchNorm backward reduction needs a plain epilogue and float4-aligned X", M, p->N, p->K);
+    return decline("scv_gemm", "fused BatchNorm backward reduction needs a plain epilogue and X (and R) laid out like Y", M, p->N, p->K);
   const bool accum = (p->act & SCV_ACT_ACCUM) != 0;
   if (accum && ((p->act & 15) != SCV_ACT_NONE || (p->act & SCV_ACT_ROUND_TF32) || p->R || p->stats))
     return decline("scv_gemm", "SCV_ACT_ACCUM with an activation / residual / statistics", M, p->N, p->K);
@@ -931,7 +958,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   // single-CTA kernel is the default; SCV_TC_PAIR=1 selects the pair kernel for experiments.
   static const int force_pair = [] { const char* e = getenv("SCV_TC_PAIR"); return e ? atoi(e) : 0; }();
   int ctas = force_pair ? 2 : 1;
-  if (q.m_tiles < 2 || pair_capacity() < 1 || bf16) ctas = 1;
+  if (q.m_tiles < 2 || pair_capacity() < 1 || bf16 || bnr) ctas = 1;
   // N tile: as wide as the MMA allows, balanced over the tiles, multiple of 16 (of 32 for a pair: each CTA holds half)
   const int ng = 16 * ctas;
   const int n16 = (int)cdiv(p->N, ng) * ng;
@@ -963,7 +990,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   // every layer (profiles/r02_multicast_vs_unicast.md): each SM still has to take delivery of the full W tile, and L2
   // already merges the two CTAs' unicast requests.  Off by default; SCV_TC_MC=1 selects it (the kernel tests cover both).
   const int mc_env = [] { const char* e = getenv("SCV_TC_MC"); return e ? atoi(e) : 0; }();  // read per call: tests toggle it
-  const bool mc = ctas == 1 && !bf16 && mc_env != 0 && g_mc_capacity >= 1 && q.m_tiles >= 2 * q.sub && q.bn % 16 == 0;
+  const bool mc = ctas == 1 && !bf16 && !bnr && mc_env != 0 && g_mc_capacity >= 1 && q.m_tiles >= 2 * q.sub && q.bn % 16 == 0;
   // split-K (accumulating GEMMs only): few output tiles, long reduction
   q.ksplit = 1;
   q.kc_per = q.k_chunks;
@@ -1031,6 +1058,11 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   }
   const int total = q.n_tiles * (int)cdiv(q.m_tiles, q.sub) * q.ksplit;
   const int grid = total < sm_count() ? total : sm_count();
+  if (bnr) {
+    if (bf16) gemm_tc_bnr_bf16_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, q);
+    else gemm_tc_bnr_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, q);
+    return check_launch("gemm_tc_bnr_kernel");
+  }
   if (bf16) {
     gemm_tc_bf16_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, q);
     return check_launch("gemm_tc_bf16_kernel");
