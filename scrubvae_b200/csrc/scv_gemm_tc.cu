@@ -414,7 +414,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     const int N = p.N;
     const int et = threadIdx.x - 128;
     const bool has_bnr = kBnr && p.bnr_sums != nullptr;
-    const bool has_stats = p.stats != nullptr || has_bnr;  // column sums through the shared-memory accumulators
+    // column sums through the shared-memory accumulators (a PReLU-only reduction, bnr_chan == nullptr, has none)
+    const bool has_stats = p.stats != nullptr || (has_bnr && p.bnr_chan != nullptr);
     // where the column sums go: forward statistics stats[n], stats[N + n]; backward reduction sums[n % C], sums[C + n % C]
     double* const sum_base = has_bnr ? p.bnr_sums : p.stats;
     const int sum_mod = has_bnr ? p.bnr_c : p.N, sum_off2 = has_bnr ? p.bnr_c : p.N;
