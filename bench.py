@@ -290,9 +290,11 @@ def hbm_kernel_table(step, hbm_gbs, reps=3):
         "recon_loss": lambda a, kw: B * W * (C0 + J * 3 * 2 + 3 + C0) * esz,
         "out_bwd": lambda a, kw: B * W * C0 * esz * 3,
         "unpack_root": lambda a, kw: B * W * 6 * esz,
-        "sumsq": lambda a, kw: eng.n_flat * esz,
+        "sumsq": lambda a, kw: a[1] * esz,
+        "sumsq_packed": lambda a, kw: a[2] * esz,
         "gather": lambda a, kw: a[3] * esz * 2,  # weight repack / gradient unpack: one read + one write per element
-        "optim_step": lambda a, kw: eng.n_flat * esz * 7,  # p, m, v read + write; gradient read
+        # p, m, v read + write; gradient read; resident mode also writes the operand copy
+        "optim_step": lambda a, kw: a[4] * esz * (8 if kw.get("pack_idx") is not None else 7),
     }
     recs = []
     saved = {}
@@ -390,7 +392,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         torch.cuda.manual_seed(1234 + rank)  # rank-distinct reparameterisation noise
     host = synth_host_batch(B, seed=1000 * rank, cfg=cfg)
     data = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-    step = TrainStep(m, opt, loss_scale, B, use_graph=not args.no_graph, comm=comm)
+    step = TrainStep(m, opt, loss_scale, B, use_graph=not args.no_graph, comm=comm, resident=not args.no_resident)
 
     def barrier():
         torch.cuda.synchronize()
@@ -595,6 +597,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-on-GPU comparator")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 3 s sustained leg")
+    ap.add_argument("--no-resident", action="store_true",
+                    help="rebuild the packed GEMM matrices from the parameter buffer every step (round-1 tail) instead of "
+                         "keeping the master weights resident in the packed layout")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))

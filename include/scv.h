@@ -209,8 +209,16 @@ typedef struct {
   double lr, beta1, beta2, eps, weight_decay; int64_t step;
   const double* hyper; /* optional device [lr, step]: overrides lr/step (CUDA-graph replay) */
   int64_t kind; /* 0 adam (L2 wd folded in grad), 1 adamw (decoupled), 2 sgd nesterov (m = momentum buf, beta1 = momentum) */
+  /* RESIDENT-PACKED mode (pack_idx != NULL): p, g, m, v are all in the packed K-major layout of the GEMM matrices (p = fp32
+   * master, g = what the wgrad kernels accumulated), so every access is coalesced; positions with pack_idx[j] < 0 (structural
+   * zeros / padding) are skipped.  The updated weight is also written as the operand copy the next forward GEMMs load:
+   * packed_out[j] (fp32, rounded to TF32 if flags & SCV_F_ROUND_TF32) and / or packed16_out[j] (bf16).  No repack pass and
+   * no gradient-unpack pass is left in the step. */
+  const int32_t* pack_idx; float* packed_out; void* packed16_out; int64_t flags;
 } scv_optim_t;
 int scv_optim_step(const scv_optim_t* p, void* stream);
+/* global gradient norm over the packed gradients: sumsq[0] += sum over j < n with pack_idx[j] >= 0 of gpacked[j]^2 */
+int scv_sumsq_packed(const float* gpacked, const int32_t* pack_idx, int64_t n, double* sumsq, void* stream);
 /* cudaMemsetAsync(p, 0, bytes) on `stream`: the per-step accumulators (BatchNorm sums, loss terms, grad norm) live in
  * one buffer and are cleared by one memset node of the step's CUDA graph. */
 int scv_zero(void* p, int64_t bytes, void* stream);

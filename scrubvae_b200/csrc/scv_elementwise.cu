@@ -445,6 +445,65 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const float* __restrict__ g, 
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
+__global__ void __launch_bounds__(NT) sumsq_packed_kernel(const float* __restrict__ gp, const int32_t* __restrict__ idx, int64_t n,
+                                                          double* out) {
+  __shared__ double sh[32];
+  float acc = 0.f;
+  double dacc = 0.0;
+  int cnt = 0;
+  const int64_t n4 = n >> 2;  // every packed matrix is padded to 4 floats
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (int64_t)gridDim.x * NT) {
+    const int4 j = __ldg(reinterpret_cast<const int4*>(idx) + i);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(gp) + i);
+    acc += (j.x >= 0 ? v.x * v.x : 0.f) + (j.y >= 0 ? v.y * v.y : 0.f) + (j.z >= 0 ? v.z * v.z : 0.f) + (j.w >= 0 ? v.w * v.w : 0.f);
+    if (++cnt == 64) { dacc += (double)acc; acc = 0.f; cnt = 0; }
+  }
+  dacc += (double)acc;
+  double s = scv::block_sum_d(dacc, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// resident-packed optimizer: same arithmetic as optim_kernel, every array in the packed layout, plus the operand copies
+__global__ void __launch_bounds__(NT) optim_packed_kernel(const scv_optim_t p) {
+  const float gs = (float)p.gscale;
+  float coef = gs;
+  if (p.sumsq) {
+    double norm = sqrt(p.sumsq[0]) * p.gscale;
+    double c = p.max_norm / (norm + 1e-6);
+    coef = (float)((c < 1.0 ? c : 1.0) * p.gscale);
+  }
+  const double lrd = p.hyper ? p.hyper[0] : p.lr;
+  const double stepd = p.hyper ? p.hyper[1] : (double)p.step;
+  const float lr = (float)lrd, b1 = (float)p.beta1, b2 = (float)p.beta2, eps = (float)p.eps, wd = (float)p.weight_decay;
+  const double bc1d = 1.0 - pow(p.beta1, stepd), bc2d = 1.0 - pow(p.beta2, stepd);
+  const float step_size = (float)(lrd / bc1d), bc2s = (float)sqrt(bc2d);
+  const bool first = stepd < 1.5;
+  const int kind = (int)p.kind;
+  const bool rnd = (p.flags & SCV_F_ROUND_TF32) != 0;
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(p.packed16_out);
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * NT) {
+    if (__ldg(p.pack_idx + i) < 0) continue;  // structural zero / padding of the packed layout
+    float g = p.g[i] * coef, w = p.p[i], wn;
+    if (kind == 2) {
+      float buf = first ? g : b1 * p.m[i] + g;
+      p.m[i] = buf;
+      wn = w - lr * (g + b1 * buf);
+    } else {
+      if (kind == 1) w *= 1.f - lr * wd;
+      else if (wd != 0.f) g += wd * w;
+      float m = p.m[i] + (1.f - b1) * (g - p.m[i]);
+      float v = b2 * p.v[i] + (1.f - b2) * g * g;
+      p.m[i] = m;
+      p.v[i] = v;
+      float denom = sqrtf(v) / bc2s + eps;
+      wn = w - step_size * (m / denom);
+    }
+    p.p[i] = wn;
+    if (p.packed_out) p.packed_out[i] = rnd ? scv::round_tf32(wn) : wn;
+    if (o16) o16[i] = __float2bfloat16_rn(wn);
+  }
+}
+
 __global__ void __launch_bounds__(NT) optim_kernel(const scv_optim_t p) {
   // clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6))  (train/trainer.py:164)
   const float gs = (float)p.gscale;
@@ -595,8 +654,21 @@ int scv_zero(void* p, int64_t bytes, void* stream) {
 
 int scv_optim_step(const scv_optim_t* p, void* stream) {
   SCV_REQUIRE(p->kind >= 0 && p->kind <= 2 && (p->hyper || p->step >= 1), "scv_optim_step: bad kind/step");
+  if (p->n <= 0) return 0;
+  if (p->pack_idx) {
+    optim_packed_kernel<<<grid1d(p->n, 8), NT, 0, (cudaStream_t)stream>>>(*p);
+    return scv::check_launch("optim_packed_kernel");
+  }
   optim_kernel<<<grid1d(p->n, 8), NT, 0, (cudaStream_t)stream>>>(*p);
   return scv::check_launch("optim_kernel");
+}
+
+int scv_sumsq_packed(const float* gpacked, const int32_t* pack_idx, int64_t n, double* sumsq, void* stream) {
+  SCV_REQUIRE(gpacked && pack_idx && sumsq && n % 4 == 0 && scv::aligned16(gpacked) && scv::aligned16(pack_idx),
+              "scv_sumsq_packed: gpacked / pack_idx must be 16-byte aligned and n a multiple of 4");
+  if (n <= 0) return 0;
+  sumsq_packed_kernel<<<grid1d(n / 4 + 1, 4), NT, 0, (cudaStream_t)stream>>>(gpacked, pack_idx, n, sumsq);
+  return scv::check_launch("sumsq_packed_kernel");
 }
 
 int scv_loss_finalize(const double* acc, const float* scale, float* out, int64_t n, void* stream) {

@@ -338,6 +338,15 @@ class Engine:
         self.gpacked = torch.zeros(self._n_fwd, device=dev)
         self.inv_idx = lay.inverse_map(fwd_idx, self.n_flat).to(torch.int32).to(dev)
         self.grads_dirty = False   # gpacked / gflat hold gradients of a piecewise backward (TrainStep zeroes them)
+        # RESIDENT-PACKED training state (TrainStep(resident=True)): during a run of fused steps the fp32 master of every
+        # GEMM weight / bias lives in the packed layout (`pmaster`), the optimizer updates it there with coalesced accesses
+        # and writes the operand copies itself — no weight repack and no gradient unpack in the step.  `flat` (the
+        # reference-layout buffer the nn.Parameters view) is refreshed on demand (ensure_flat).
+        self.pmaster = None
+        self.idx_d_from_p = None   # data-gradient layout -> position in pmaster
+        self.flat_valid = True     # `flat` holds the current weights
+        self.resident_valid = False  # `pmaster` (+ packed moments) hold the current weights
+        self._resident_opt = None
         del self._pack_parts, self._pack_parts_d
         self.max_k = max(max(g.K, g.dK if g.wd is not None else 0) for g in self.W.values())
         for gc in getattr(self, "gr_cat", {}).values():
@@ -353,6 +362,51 @@ class Engine:
 
     def wdref(self, g: GemmW) -> Ref:
         return Ref(self.packed16 if self.packed16 is not None else self.packed, self._n_fwd + g.wd)
+
+    # ---- resident-packed master (see __init__)
+    def resident_import(self, opt):
+        """flat -> pmaster / packed operand copies / packed moments (coalesced-store gathers)."""
+        ops, nf = self.ops, self._n_fwd
+        self.ensure_flat()
+        if self.pmaster is None:
+            self.pmaster = torch.zeros(nf, device=self.device)
+            d_idx = self.pack_idx[nf:].long()
+            comp = torch.where(d_idx >= 0, self.inv_idx.long()[d_idx.clamp_min(0)], torch.full_like(d_idx, -1))
+            self.idx_d_from_p = comp.to(torch.int32)
+        if getattr(opt, "mp", None) is None or opt.mp.numel() != nf:
+            opt.mp, opt.vp = torch.zeros(nf, device=self.device), torch.zeros(nf, device=self.device)
+        ops.gather(self.flat, self.pack_idx, self.pmaster, nf, False, round_tf32=0)
+        ops.gather(opt.m, self.pack_idx, opt.mp, nf, False, round_tf32=0)
+        ops.gather(opt.v, self.pack_idx, opt.vp, nf, False, round_tf32=0)
+        self.repack("fwd")
+        self.resident_valid = True
+        self._resident_opt = opt
+
+    def resident_dgrad_matrices(self):
+        """data-gradient matrices from the resident master (side stream, beside the forward pass)"""
+        nf = self._n_fwd
+        n = self.packed.numel() - nf
+        if n <= 0:
+            return
+        if self.packed16 is not None:
+            self.ops.gather(self.pmaster, self.idx_d_from_p, Ref(self.packed16, nf), n, False, round_tf32=2)
+            h0 = self._d_heads0
+            if n > h0:
+                self.ops.gather(self.pmaster, Ref(self.idx_d_from_p, h0), Ref(self.packed, nf + h0), n - h0, False, round_tf32=0)
+            return
+        self.ops.gather(self.pmaster, self.idx_d_from_p, Ref(self.packed, nf), n, False, round_tf32=self.rnd)
+
+    def ensure_flat(self):
+        """`flat` (and the optimizer moments in the reference layout) up to date: called by everything that reads
+        parameters outside the resident fused steps (state_dict, the piecewise API path, checkpoints, epoch ends)."""
+        if self.flat_valid:
+            return
+        ops, opt = self.ops, self._resident_opt
+        ops.gather(self.pmaster, self.inv_idx, self.flat, self.n_flat, True)
+        if opt is not None and getattr(opt, "mp", None) is not None:
+            ops.gather(opt.mp, self.inv_idx, opt.m, self.n_flat, True)
+            ops.gather(opt.vp, self.inv_idx, opt.v, self.n_flat, True)
+        self.flat_valid = True
 
     def wref32(self, g: GemmW) -> Ref:  # scrubber heads: fp32 FFMA kernels in every precision mode
         return Ref(self.packed, g.w)
@@ -970,6 +1024,7 @@ class Plan:
 
     def forward(self, data, training: bool, upto: Optional[str] = None, z_given=None):
         eng, m = self.eng, self.eng.m
+        eng.ensure_flat()  # this path packs the GEMM matrices from `flat`
         self._training = training
         if z_given is None:
             self.load_inputs(data, need_loss_inputs=False)
@@ -1140,8 +1195,13 @@ class TrainStep:
     `comm` (optional): callable(engine, phase) hook used by data parallelism (parallel.py) to launch the
     bucketed gradient all-reduce from inside the backward launch list (Plan.backward)."""
 
-    def __init__(self, model, optimizer, loss_scale, B, max_norm=1e6, use_graph=True, comm=None, keep_grads=False):
+    def __init__(self, model, optimizer, loss_scale, B, max_norm=1e6, use_graph=True, comm=None, keep_grads=False,
+                 resident=False):
         self.model, self.opt = model, optimizer
+        # resident=True: the weights' fp32 master stays in the packed GEMM layout between steps (Engine.resident_import /
+        # ensure_flat); nn.Parameter values are then refreshed only on demand — call sync() (or Engine.ensure_flat())
+        # before reading them, and nothing else may edit the parameters between the steps of one run
+        self.resident = resident
         # keep_grads (tests / debugging): the step's (all-reduced, unscaled) gradients are copied out in the reference
         # parameter layout before the optimizer consumes them — see named_grads()
         self.keep_grads = keep_grads
@@ -1169,46 +1229,64 @@ class TrainStep:
             else:
                 plan.eps.normal_()
             eng.nbt.add_(1)
-            # packed forward matrices first (coalesced-store gather from the flat parameters, 0.1 ms); the data-gradient
-            # matrices, which only backward reads, and the clearing of the weight-gradient accumulators run on a side
-            # stream beside the forward pass
-            eng.repack("fwd")
+            # packed forward matrices: resident mode — already current (the optimizer wrote them); otherwise gathered from
+            # the flat parameters (0.1 ms).  The data-gradient matrices, which only backward reads, and the clearing of the
+            # weight-gradient accumulators run on a side stream beside the forward pass.
+            res = self.resident
+            if not res:
+                eng.repack("fwd")
+
+            def side_work():
+                if res:
+                    eng.resident_dgrad_matrices()
+                else:
+                    eng.repack("dgrad")
+                ops.zero(eng.gpacked)
+                ops.zero(eng.gflat[:eng.n_direct])  # BatchNorm / PReLU gradients accumulate
             if plan.dside is not None:
                 main = torch.cuda.current_stream()
                 plan.dside.wait_stream(main)
                 with torch.cuda.stream(plan.dside):
-                    eng.repack("dgrad")
-                    ops.zero(eng.gpacked)
-                    ops.zero(eng.gflat[:eng.n_direct])  # BatchNorm / PReLU gradients accumulate
+                    side_work()
                 plan.run_forward()
                 for f in plan.Lk:
                     f()
                 main.wait_stream(plan.dside)
             else:
-                eng.repack("dgrad")
-                ops.zero(eng.gpacked)
-                ops.zero(eng.gflat[:eng.n_direct])
+                side_work()
                 plan.run_forward()
                 for f in plan.Lk:
                     f()
             plan.gscale.copy_(plan.loss_scale)
             plan.backward(self.comm)
-            # tail: weight gradients back to the parameter layout (coalesced-store gather), global norm, clip + optimizer.
-            # Measured alternatives (profiles/r02_optimizer_tail.md): an optimizer that WRITES the packed matrices with
-            # scattered 4-byte stores took 3.8 ms; one that only READS the packed gradients by gather 348 us against
-            # 110 (gather) + 132 (optimizer) here.
-            ops.gather(eng.gpacked, eng.inv_idx, eng.gflat, eng.n_flat, True)
-            if self.keep_grads:
-                if self.grad_snapshot is None:
-                    self.grad_snapshot = torch.zeros_like(eng.gflat)
-                self.grad_snapshot.copy_(eng.gflat)
-            ops.sumsq(eng.gflat, eng.n_flat, plan.sumsq)
             grp = opt.param_groups[0]
             from .train.optim import KIND
             b1 = grp["momentum"] if opt.kind == "sgd" else grp["betas"][0]
-            ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, eng.n_flat, plan.sumsq, self.max_norm, opt.grad_scale,
-                           float(grp["lr"]), b1, grp["betas"][1], grp["eps"], grp["weight_decay"], 1, KIND[opt.kind],
-                           hyper=opt.hyper)
+            hp = (self.max_norm, opt.grad_scale, float(grp["lr"]), b1, grp["betas"][1], grp["eps"], grp["weight_decay"], 1,
+                  KIND[opt.kind])
+            if self.keep_grads:  # tests: the step's gradients in the reference layout
+                if self.grad_snapshot is None:
+                    self.grad_snapshot = torch.zeros_like(eng.gflat)
+                self.grad_snapshot.copy_(eng.gflat)
+                ops.gather(eng.gpacked, eng.inv_idx, self.grad_snapshot, eng.n_flat, True)
+            if res:
+                # resident tail: global norm over the packed gradients + the direct ones, then the optimizer in the packed
+                # layout (writes master, moments and the operand copies; all coalesced) and on the small direct region
+                nf, nd = eng._n_fwd, eng.n_direct
+                ops.sumsq_packed(eng.gpacked, eng.pack_idx, nf, plan.sumsq)
+                ops.sumsq(eng.gflat, nd, plan.sumsq)
+                ops.optim_step(eng.pmaster, eng.gpacked, opt.mp, opt.vp, nf, plan.sumsq, *hp, hyper=opt.hyper,
+                               pack_idx=eng.pack_idx, packed_out=eng.packed,
+                               packed16_out=eng.packed16, round_tf32=eng.rnd == 1)
+                ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, nd, plan.sumsq, *hp, hyper=opt.hyper)
+            else:
+                # tail: weight gradients back to the parameter layout (coalesced-store gather), global norm, clip +
+                # optimizer.  Measured alternatives (profiles/r02_optimizer_tail.md): an optimizer that WRITES the packed
+                # matrices with scattered 4-byte stores took 3.8 ms; one that READS the packed gradients by gather 348 us
+                # against 110 (gather) + 132 (optimizer) here.
+                ops.gather(eng.gpacked, eng.inv_idx, eng.gflat, eng.n_flat, True)
+                ops.sumsq(eng.gflat, eng.n_flat, plan.sumsq)
+                ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, eng.n_flat, plan.sumsq, *hp, hyper=opt.hyper)
         finally:
             plan._fused_tail = False
 
@@ -1220,6 +1298,13 @@ class TrainStep:
             plan.load_targets(data)
         opt._steps += 1
         opt.push_hyper()  # ring of pinned slots: safe when the host runs several steps ahead of the device
+        if self.resident:
+            if not self.eng.resident_valid or self.eng._resident_opt is not opt:
+                self.eng.resident_import(opt)
+            self.eng.flat_valid = False  # from here on only the packed master is current
+        else:
+            self.eng.ensure_flat()
+            self.eng.resident_valid = False  # this step updates `flat`
         if not self.use_graph:
             n0 = self.eng.ops.launch_count()
             self._sequence()
@@ -1242,6 +1327,10 @@ class TrainStep:
         else:
             self.graph.replay()
         return plan.loss_out
+
+    def sync(self):
+        """nn.Parameter values (and the optimizer moments in the reference layout) up to date after resident steps."""
+        self.eng.ensure_flat()
 
     def named_grads(self):
         """{parameter name: gradient of the last step} (needs keep_grads=True); under data parallelism the SUM over ranks."""

@@ -195,6 +195,19 @@ class ResVAE(VAE):
             self._engine.invalidate()
         return out
 
+    # parameters may temporarily live in the packed GEMM layout (engine.TrainStep(resident=True)): refresh the
+    # reference-layout views before anything reads or replaces them through the nn.Module API
+    def state_dict(self, *a, **k):
+        if self._engine is not None:
+            self._engine.ensure_flat()
+        return super().state_dict(*a, **k)
+
+    def load_state_dict(self, *a, **k):
+        if self._engine is not None:
+            self._engine.ensure_flat()
+            self._engine.resident_valid = False
+        return super().load_state_dict(*a, **k)
+
     def normalize_root(self, root):
         return 2 * (root - self.arena_size[0]) / (self.arena_size[1] - self.arena_size[0]) - 1
 

@@ -28,7 +28,9 @@ def broadcast_parameters(model, src: int = 0):
     eng = getattr(model, "_engine", None)
     with torch.no_grad():
         if eng is not None:
+            eng.ensure_flat()
             dist.broadcast(eng.flat, src)
+            eng.resident_valid = False
         else:
             for p in model.parameters():
                 dist.broadcast(p.data, src)

@@ -77,9 +77,15 @@ class FusedOptimizer(torch.optim.Optimizer):
             ev.record()
             self.hyper_events[i] = ev
 
+    def state_dict(self):
+        eng = self._bind()
+        eng.ensure_flat()  # moments may live in the packed layout (engine.TrainStep(resident=True))
+        return super().state_dict()
+
     @torch.no_grad()
     def step(self, closure=None):
         eng = self._bind()
+        eng.ensure_flat()
         grp = self.param_groups[0]
         self._steps += 1
         self.push_hyper()
@@ -89,6 +95,7 @@ class FusedOptimizer(torch.optim.Optimizer):
                            clip[1] if clip else 0.0, self.grad_scale, float(grp["lr"]), b1, grp["betas"][1],
                            grp["eps"], grp["weight_decay"], self._steps, KIND[self.kind], hyper=self.hyper)
         eng.clip = None
+        eng.resident_valid = False  # `flat` was updated here: a resident TrainStep must re-import
         if self.kind != "sgd":
             for st in self.state.values():
                 if "step" in st:
@@ -97,6 +104,8 @@ class FusedOptimizer(torch.optim.Optimizer):
 
     def load_state_dict(self, state_dict):
         eng = self._bind()
+        eng.ensure_flat()
+        eng.resident_valid = False
         names = [n for n, _ in self.model.named_parameters()]
         sd_state = state_dict["state"]
         with torch.no_grad():

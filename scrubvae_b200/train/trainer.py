@@ -148,10 +148,14 @@ def _fused_train_epoch(config, model, loader, device, epoch, optimizer, schedule
         hit = steps.get(key)
         if hit is not None and hit[0]() is optimizer:
             return hit[1]
-        st = TrainStep(model, optimizer, config["loss"], B, max_norm=1e6, use_graph=True, comm=eng.comm)
+        st = TrainStep(model, optimizer, config["loss"], B, max_norm=1e6, use_graph=True, comm=eng.comm, resident=True)
         steps[key] = (weakref.ref(optimizer), st)
         return st
 
+    # the steps of this epoch keep the weights' master in the packed GEMM layout: import what the parameters hold now
+    # (reset_parameters, load_state_dict, a broadcast ... may have changed them since the last epoch), export at the end
+    eng.ensure_flat()
+    eng.resident_valid = False
     names = None
     acc = None
     n_batches = 0
@@ -182,6 +186,7 @@ def _fused_train_epoch(config, model, loader, device, epoch, optimizer, schedule
             scheduler.step(epoch + n_batches / len(loader))
         acc = vec.clone() if acc is None else acc + vec
         n_batches += 1
+    eng.ensure_flat()
     epoch_metrics = {}
     host = acc.cpu() if acc is not None else None
     for k in ["total"] + list(config["loss"].keys()):

@@ -422,12 +422,34 @@ class EmuOps:
         self.n += 1
         _v(out, (1,), (1,)).add_((_v(g, (n,), (1,)).double() ** 2).sum())
 
+    def sumsq_packed(self, gpacked, pack_idx, n, out):
+        self.n += 1
+        live = _v(pack_idx, (n,), (1,)) >= 0
+        _v(out, (1,), (1,)).add_((_v(gpacked, (n,), (1,))[live].double() ** 2).sum())
+
     def zero(self, t):
         t.zero_()
 
     def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind,
-                   hyper=None):
+                   hyper=None, pack_idx=None, packed_out=None, packed16_out=None, round_tf32=False):
         self.n += 1
+        if pack_idx is not None:  # resident-packed mode: only the live positions, plus the operand copies
+            live = _v(pack_idx, (n,), (1,)) >= 0
+            P, G, M = _v(p, (n,), (1,)), _v(g, (n,), (1,)), _v(m, (n,), (1,))
+            V = _v(v, (n,), (1,)) if v is not None else None
+            sub = [P[live].clone(), G[live].clone(), M[live].clone(), V[live].clone() if V is not None else None]
+            k = sub[0].numel()
+            self.optim_step(sub[0], sub[1], sub[2], sub[3], k, sumsq, max_norm, gscale, lr, beta1, beta2, eps,
+                            weight_decay, step, kind, hyper=hyper)
+            self.n -= 1
+            P[live], M[live] = sub[0], sub[2]
+            if V is not None:
+                V[live] = sub[3]
+            if packed_out is not None:
+                _v(packed_out, (n,), (1,))[live] = rtf32(sub[0]) if round_tf32 else sub[0]
+            if packed16_out is not None:
+                _v(packed16_out, (n,), (1,))[live] = sub[0].to(torch.bfloat16)
+            return
         if hyper is not None:
             hy = _v(hyper, (2,), (1,))
             lr, step = float(hy[0]), int(round(float(hy[1])))

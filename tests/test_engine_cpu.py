@@ -294,3 +294,57 @@ def test_test_epoch_and_generative_restrictiveness_on_emulation():
     for k in mr:
         tol = 1e-4 if k.startswith("r2_") else 2e-5
         assert abs(mo[k] - mr[k]) <= tol * max(1.0, abs(mr[k])), (k, mo[k], mr[k])
+
+
+@pytest.mark.parametrize("kind", ["adamw", "sgd"])
+def test_resident_packed_steps_equal_flat_steps(kind):
+    """TrainStep(resident=True) — master weights and moments kept in the packed GEMM layout, optimizer writing the operand
+    copies — gives the same weights, moments and losses as the flat-master path over several steps, also when the two
+    are interleaved with the piecewise API path and a mid-run parameter edit."""
+    from scrubvae_b200.engine import TrainStep
+    ch, zd, B = [8, 16, 32], 8, 6
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "heading_gr": 1.0}
+    data = orc.synth_batch(B, seed=3)
+    out = []
+    for resident in (False, True):
+        torch.manual_seed(6)
+        m, dcfg = build_model(ch, zd, ["heading"], ["heading"])
+        m._engine = Engine(m, ops=EmuOps())
+        m.train()
+        lr = 1e-9 if kind == "sgd" else 1e-3
+        opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": kind, "lr": lr, "lr_schedule": None})
+        step = TrainStep(m, opt, scale, B, use_graph=False, resident=resident)
+        losses = []
+        for i in range(3):
+            m._noise = orc.synth_eps(B, zd, seed=20 + i)
+            losses.append(step.run(data).clone())
+        step.sync()
+        # an edit through the nn.Module API between runs (what train() does with the scrubber heads every epoch)
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if "mlp1.0.weight" in n:
+                    p.mul_(0.5)
+        m.engine.resident_valid = False
+        # one piecewise step, then two more fused ones
+        m._noise = orc.synth_eps(B, zd, seed=30)
+        lo = sv.train.get_batch_loss(m, data, sv.train.predict_batch(m, data, m.disentangle_keys), scale, dcfg)
+        for p in m.parameters():
+            p.grad = None
+        lo["total"].backward()
+        sv.train.clip_grad_norm_(m, max_norm=1e6)
+        opt.step()
+        for i in range(2):
+            m._noise = orc.synth_eps(B, zd, seed=40 + i)
+            losses.append(step.run(data).clone())
+        step.sync()
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        osd = opt.state_dict()["state"]
+        out.append((losses, sd, {k: {kk: vv.clone() for kk, vv in st.items() if torch.is_tensor(vv)} for k, st in osd.items()}))
+    (la, sa, oa), (lb, sb, ob) = out
+    for x, y in zip(la, lb):
+        assert torch.allclose(x, y, rtol=1e-6, atol=1e-7)
+    for k in sa:
+        assert torch.allclose(sa[k].float(), sb[k].float(), rtol=1e-6, atol=1e-8), k
+    for k in oa:
+        for kk in oa[k]:
+            assert torch.allclose(oa[k][kk], ob[k][kk], rtol=1e-6, atol=1e-10), (k, kk)
