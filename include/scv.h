@@ -255,6 +255,19 @@ int scv_preprocess_windows(const double* pose, const int64_t* starts, const int6
                            int64_t window, int64_t J, const int32_t* tree, const int32_t* offset, const double* yaw,
                            int64_t mode, float* x6d, float* root, float* offsets, float* target_pose, void* stream);
 
+/* ---- "mcmi" scrubbing loss: kernel mutual-information estimate between the latent mean and the conditioning variables
+ * (MutInfoEstimator model/disentangle.py:234-317, loss train/losses.py:221-225, estimator rebuild after every optimizer
+ * step train/trainer.py:184-199).  Stored samples xs (S,z), ys (S,dy); var_s (S,z) for var_mode "diagonal" (NULL = "sphere":
+ * the scalar bandwidth); logAx (S) (diagonal) or (1) (sphere); valid: device flag, 0 = no estimator yet (loss 0, no gradient).
+ * scv_mi_loss: loss[0] += mean_b [LSE_s a_xy - LSE_s a_x - LSE_s a_y] (double, if loss != NULL); dx (B,z) += gscale[0] * d loss/d x
+ * (if dx != NULL; gscale NULL = 1).  y rows have stride y_ld.
+ * scv_mi_update: xs = mu, ys = var rows, var_s = diag(L)^2 + bandwidth, logAx, valid = 1. */
+int scv_mi_loss(const float* x, const float* y, int64_t y_ld, const float* xs, const float* ys, const float* var_s,
+                const float* logAx, double bandwidth, int64_t S, int64_t B, int64_t z, int64_t dy, const float* valid,
+                double* loss, const float* gscale, float* dx, void* stream);
+int scv_mi_update(const float* mu, const float* L, const float* var, int64_t var_ld, float* xs, float* ys, float* var_s,
+                  float* logAx, double bandwidth, int64_t S, int64_t z, int64_t dy, float* valid, void* stream);
+
 /* ---- generative restrictiveness (eval): reference eval/eval.py:22-120.  For B decoded windows (xh rows of ld floats: the
  * decoder output after tanh, 6-D channels first; root_hat (B*W,3) un-normalised root positions or NULL = 0; offsets
  * (B*W,J,3)): forward kinematics (fwd_kin_cont6d_torch data/dataset.py:83-116, eps 1e-8) and, per window,

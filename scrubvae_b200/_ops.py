@@ -102,6 +102,8 @@ _SIGS = {
     "scv_gather": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "scv_sumsq": (C.c_int, [_vp, _i64, _vp, _vp]),
     "scv_optim_step": (C.c_int, [C.POINTER(OptimT), _vp]),
+    "scv_mi_loss": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "scv_mi_update": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _vp, _vp]),
     "scv_gen_features": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "scv_zero": (C.c_int, [_vp, _i64, _vp]),
     "scv_sumsq_packed": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
@@ -287,6 +289,15 @@ class CudaOps:
         self._check(self.lib.scv_preprocess_windows(_ptr(pose), _ptr(starts), _ptr(keep), n_keep, window, J, _ptr(tree),
                                                     _ptr(offset), _ptr(yaw), mode, _ptr(x6d), _ptr(root), _ptr(offsets),
                                                     _ptr(target_pose), self._stream()), "scv_preprocess_windows")
+
+    def mi_loss(self, x, y, y_ld, xs, ys, var_s, logAx, bandwidth, S, B, z, dy, valid=None, loss=None, gscale=None, dx=None):
+        self._check(self.lib.scv_mi_loss(_ptr(x), _ptr(y), y_ld, _ptr(xs), _ptr(ys), _ptr(var_s), _ptr(logAx), float(bandwidth),
+                                         S, B, z, dy, _ptr(valid), _ptr(loss), _ptr(gscale), _ptr(dx), self._stream()),
+                    "scv_mi_loss")
+
+    def mi_update(self, mu, L, var, var_ld, xs, ys, var_s, logAx, bandwidth, S, z, dy, valid=None):
+        self._check(self.lib.scv_mi_update(_ptr(mu), _ptr(L), _ptr(var), var_ld, _ptr(xs), _ptr(ys), _ptr(var_s), _ptr(logAx),
+                                           float(bandwidth), S, z, dy, _ptr(valid), self._stream()), "scv_mi_update")
 
     def gen_features(self, xh, ld, root_hat, offsets, tree, n_tree, parts, B, W, J, norm=None, pose_out=None, heading=None,
                      avg3=None):

@@ -509,6 +509,9 @@ class Plan:
 
         # ---- loss bookkeeping: acc (double) / out (float): [jpe, root, prior, gr keys...]
         self.loss_names = ["jpe", "root", "prior"] + [kk + "_gr" for kk in eng.gr_keys]
+        if eng.cond_dim > 0:
+            self.loss_names.append("mcmi")  # kernel mutual-information scrubbing loss (needs conditioning variables)
+        self.mi = None  # estimator buffers, allocated by enable_mcmi()
         nl = len(self.loss_names)
         nbn = sum(mod.num_features for mod in m.modules() if isinstance(mod, nn.BatchNorm1d))
         n_stats, n_sums = 4 * nbn + 8, 2 * nbn + 2 * ch[0] + 64
@@ -830,6 +833,7 @@ class Plan:
             Lk.append(lambda preds=preds, ld=ld, key=key, ki=ki: ops.gr_loss(
                 preds, None, ld, self.gr_target.get(key), self.gr_labels.get(key), B, self.gr_dim[key],
                 len(eng.gr_keys), Ref(self.loss_acc, 3 + ki), None))
+        Lk.append(lambda: self._mi_launch(loss=True))
         Lk.append(lambda: ops.loss_finalize(self.loss_acc, self.loss_scale, self.loss_out, nl))
         self.Lk = Lk
 
@@ -939,6 +943,7 @@ class Plan:
         self.dL_kl = torch.zeros(B, z, z, **f32)
         self.dms = torch.zeros(B * eng.ms_ld + 64, **opd)[:B * eng.ms_ld].view(B, eng.ms_ld)
         Bw.append(lambda: ops.kl(self.mu, self.Lmat, None, Ref(self.gscale, 2), self.dmu_kl, self.dL_kl, B, z))
+        Bw.append(lambda: self._mi_launch(loss=False))  # adds d mcmi / d mu into dmu_kl
         Bw.append(lambda: ops.reparam_bwd(self.ms, eng.ms_ld, self.eps, self.dmu_kl, self.dmu_gr, 1.0, self.dzc,
                                           eng.zc_ld, self.dL_kl, self.dms, eng.ms_ld, B, z, round_tf32=rnd))
         Bw.append(wgrad(gfc, Hflat.at(0), Hflat.bs, 0, 1, self.dms, eng.ms_ld, 0))
@@ -992,6 +997,56 @@ class Plan:
         # public-API path only: weight gradients back into the reference layout (p.grad views of gflat)
         Bw.append(lambda: None if self._fused_tail else ops.gather(eng.gpacked, eng.inv_idx, eng.gflat, eng.n_flat, True))
         self.Bw = Bw
+
+    # ------------------------------------------------------------------ mcmi (MutInfoEstimator)
+    def enable_mcmi(self, bandwidth: float, var_mode: str = "sphere"):
+        """Allocates the estimator's stored-sample buffers (reference model/disentangle.py:234-275): S = this plan's batch."""
+        eng, m = self.eng, self.eng.m
+        if eng.cond_dim <= 0:
+            raise RuntimeError("scrubvae_b200: the mcmi loss needs conditional features (data_o['var'])")
+        key = (float(bandwidth), var_mode)
+        if self.mi is not None and self.mi["key"] == key:
+            return
+        if var_mode not in ("sphere", "diagonal"):
+            raise ValueError(var_mode)
+        f32 = dict(device=eng.device, dtype=torch.float32)
+        B, z = self.B, m.z_dim
+        self.mi = dict(key=key, bandwidth=float(bandwidth), diag=var_mode == "diagonal", xs=torch.zeros(B, z, **f32),
+                       ys=torch.zeros(B, eng.cond_dim, **f32), var_s=torch.zeros(B, z, **f32), logAx=torch.zeros(B, **f32),
+                       valid=torch.zeros(1, **f32))
+
+    def _mi_launch(self, loss: bool):
+        mi = self.mi
+        if mi is None:
+            return
+        eng, z = self.eng, self.eng.m.z_dim
+        idx = self.loss_names.index("mcmi")
+        self.eng.ops.mi_loss(self.mu, self.var, self.var.shape[1], mi["xs"], mi["ys"], mi["var_s"] if mi["diag"] else None,
+                             mi["logAx"], mi["bandwidth"], self.B, self.B, z, eng.cond_dim, valid=mi["valid"],
+                             loss=Ref(self.loss_acc, idx) if loss else None,
+                             gscale=None if loss else Ref(self.gscale, idx), dx=None if loss else self.dmu_kl)
+
+    def mi_update(self):
+        """Estimator rebuild from the plan's current mu / L / var (call after an encode with the UPDATED weights)."""
+        mi, eng = self.mi, self.eng
+        eng.ops.mi_update(self.mu, self.Lmat, self.var, self.var.shape[1], mi["xs"], mi["ys"],
+                          mi["var_s"] if mi["diag"] else None, mi["logAx"], mi["bandwidth"], self.B, eng.m.z_dim, eng.cond_dim,
+                          valid=mi["valid"])
+
+    def mi_set(self, est):
+        """Piecewise API path: the estimator object the trainer built (model.mi_estimator) or None."""
+        mi = self.mi
+        if est is None:
+            mi["valid"].zero_()
+            return
+        mi["xs"].copy_(est.x_s)
+        mi["ys"].copy_(est.y_s)
+        if mi["diag"]:
+            mi["var_s"].copy_(est.var_s)
+            mi["logAx"].copy_(est.logA_x.reshape(-1))
+        else:
+            mi["logAx"][:1].copy_(est.logA_x.reshape(-1)[:1])
+        mi["valid"].fill_(1.0)
 
     # ------------------------------------------------------------------ running
     def load_inputs(self, data, need_loss_inputs: bool):
@@ -1196,8 +1251,11 @@ class TrainStep:
     bucketed gradient all-reduce from inside the backward launch list (Plan.backward)."""
 
     def __init__(self, model, optimizer, loss_scale, B, max_norm=1e6, use_graph=True, comm=None, keep_grads=False,
-                 resident=False):
+                 resident=False, mi=None):
         self.model, self.opt = model, optimizer
+        # mi = dict(bandwidth=..., var_mode=...): the "mcmi" loss is active — after the optimizer the encoder runs once more
+        # with the updated weights and the mutual-information estimator is rebuilt from it (reference trainer.py:184-199)
+        self.mi = mi
         # resident=True: the weights' fp32 master stays in the packed GEMM layout between steps (Engine.resident_import /
         # ensure_flat); nn.Parameter values are then refreshed only on demand — call sync() (or Engine.ensure_flat())
         # before reading them, and nothing else may edit the parameters between the steps of one run
@@ -1210,6 +1268,8 @@ class TrainStep:
         self.plan = self.eng.plan(B)
         self.max_norm = float(max_norm)
         self.comm = comm
+        if self.mi is not None:
+            self.plan.enable_mcmi(self.mi["bandwidth"], self.mi.get("var_mode") or "sphere")
         self.plan.set_loss_scale(loss_scale)
         self.opt._bind()
         self.graph = None
@@ -1287,6 +1347,15 @@ class TrainStep:
                 ops.gather(eng.gpacked, eng.inv_idx, eng.gflat, eng.n_flat, True)
                 ops.sumsq(eng.gflat, eng.n_flat, plan.sumsq)
                 ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, eng.n_flat, plan.sumsq, *hp, hyper=opt.hyper)
+            if self.mi is not None:
+                # updated encode (train mode: batch statistics again, running statistics advance a second time, as the
+                # reference's model.encode(data) does) -> new stored samples of the estimator
+                if not res:
+                    eng.repack("fwd")
+                ops.zero(plan.stats)
+                eng.nbt.add_(eng.nbt_enc)
+                plan.run_forward(upto="encode")
+                plan.mi_update()
         finally:
             plan._fused_tail = False
 

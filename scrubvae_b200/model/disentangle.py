@@ -47,3 +47,39 @@ class GRScrubber(_EngineOnly):
             for head in mlp:
                 if isinstance(head, nn.Linear):
                     head.reset_parameters()
+
+
+class MutInfoEstimator(nn.Module):
+    """Reference model/disentangle.py:234-317: the stored samples of the kernel mutual-information estimate behind the
+    "mcmi" loss.  Same constructor; the pairwise log-sum-exps and their gradient run in scv_mi_loss (csrc/scv_mi.cu).
+    The trainer rebuilds it after every optimizer step from the UPDATED encoder (train/trainer.py:184-199)."""
+
+    def __init__(self, x_s, y_s, bandwidth, var_mode="sphere", model_var=None, device="cuda"):
+        super().__init__()
+        self.register_buffer("x_s", x_s.detach().to(torch.float32).contiguous())
+        self.register_buffer("y_s", y_s.detach().to(torch.float32).contiguous())
+        self.num_s = x_s.shape[0]
+        assert y_s.shape[0] == self.num_s
+        self.x_dim, self.y_dim = x_s.shape[1], y_s.shape[1]
+        self.var_mode = var_mode
+        self.gamma = float(bandwidth)
+        log2pi = float(torch.log(torch.tensor(2 * torch.pi)))
+        if var_mode == "sphere":
+            self.register_buffer("var_s", torch.tensor([self.gamma], device=x_s.device))
+            self.register_buffer("logA_x", self.x_dim * (log2pi + torch.log(self.var_s)))
+        elif var_mode == "diagonal":
+            self.register_buffer("var_s", (model_var.detach().diagonal(dim1=-2, dim2=-1) ** 2 + self.gamma).contiguous())
+            self.register_buffer("logA_x", (self.x_dim * log2pi + torch.sum(torch.log(self.var_s), dim=-1)).contiguous())
+        else:
+            raise ValueError(var_mode)
+
+    def forward(self, x, y):
+        """Value of the estimate (no autograd: inside the training step the loss and its gradient come from the
+        engine's launch lists, train/losses.get_batch_loss)."""
+        from .._ops import get_ops
+        ops = get_ops()
+        out = torch.zeros(1, dtype=torch.double, device=x.device)
+        x, y = x.detach().float().contiguous(), y.detach().float().contiguous()
+        ops.mi_loss(x, y, y.shape[1], self.x_s, self.y_s, self.var_s if self.var_mode == "diagonal" else None, self.logA_x,
+                    self.gamma, self.num_s, x.shape[0], self.x_dim, self.y_dim, loss=out)
+        return out[0].float()

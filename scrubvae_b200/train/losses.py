@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import torch
 
-UNSUPPORTED = ("rotation", "mcmi", "total_correlation")
+UNSUPPORTED = ("rotation", "total_correlation")
 
 
 class _StepLoss(torch.autograd.Function):
@@ -51,6 +51,9 @@ def get_batch_loss(model, data, data_o, loss_scale, disentangle_config):
     gr_keys = list(methods.get("grad_reversal", []))
     if gr_keys != plan.eng.gr_keys:
         raise RuntimeError("disentangle_config['method']['grad_reversal'] does not match the model's heads")
+    if "mcmi" in loss_scale.keys():  # reference :221-225: the estimator (or zero while there is none yet)
+        plan.enable_mcmi(disentangle_config["bandwidth"], disentangle_config.get("var_mode") or "sphere")
+        plan.mi_set(model.mi_estimator)
     plan.loss(data, loss_scale)
     if torch.is_grad_enabled():
         vec = _StepLoss.apply(plan.anchor, plan)
@@ -58,7 +61,7 @@ def get_batch_loss(model, data, data_o, loss_scale, disentangle_config):
         vec = plan.loss_out.clone()
     batch_loss = {}
     for i, name in enumerate(plan.loss_names):
-        if name in ("prior", "jpe", "root") and name not in loss_scale.keys():
+        if name in ("prior", "jpe", "root", "mcmi") and name not in loss_scale.keys():
             continue
         batch_loss[name] = vec[i]
     for k in batch_loss:

@@ -140,15 +140,28 @@ def _fused_train_epoch(config, model, loader, device, epoch, optimizer, schedule
             ev.record(copy_stream)
         return dev, ev, slot
 
+    mi_reset = set()
+
     def step_for(B):
         """The captured step for this batch size, optimizer and the hyper-parameters baked in at capture."""
         grp = optimizer.param_groups[0]
+        mikey = (config["disentangle"].get("bandwidth"), config["disentangle"].get("var_mode")) \
+            if "mcmi" in config["loss"].keys() else None
         key = (B, id(optimizer), optimizer.kind, tuple(grp["betas"]), grp["eps"], grp["weight_decay"], grp["momentum"],
-               optimizer.grad_scale)
+               optimizer.grad_scale, mikey)
         hit = steps.get(key)
         if hit is not None and hit[0]() is optimizer:
+            if mikey is not None and B not in mi_reset:
+                hit[1].plan.mi["valid"].zero_()  # model.mi_estimator = None at the start of every epoch (reference :124)
+                mi_reset.add(B)
             return hit[1]
-        st = TrainStep(model, optimizer, config["loss"], B, max_norm=1e6, use_graph=True, comm=eng.comm, resident=True)
+        mi_reset.add(B)
+        mi = None
+        if "mcmi" in config["loss"].keys():
+            mi = dict(bandwidth=config["disentangle"]["bandwidth"], var_mode=config["disentangle"].get("var_mode") or "sphere")
+        st = TrainStep(model, optimizer, config["loss"], B, max_norm=1e6, use_graph=True, comm=eng.comm, resident=True, mi=mi)
+        if mi is not None:
+            st.plan.mi["valid"].zero_()  # model.mi_estimator = None at the start of every epoch (reference :124)
         steps[key] = (weakref.ref(optimizer), st)
         return st
 
@@ -230,6 +243,14 @@ def train_test_epoch(config, model, loader, device, epoch, optimizer=None, sched
                 if scheduler is not None:
                     scheduler.step(epoch + batch_idx / len(loader))
             epoch_metrics = {k: v + batch_loss[k].detach() for k, v in epoch_metrics.items()}
+            if "mcmi" in config["loss"].keys():  # reference :184-199: estimator rebuilt from the updated encoder
+                from ..model.disentangle import MutInfoEstimator
+                var_y = data_o["var"].clone()
+                updated = model.encode(data)
+                model.mi_estimator = MutInfoEstimator(
+                    x_s=updated["mu"].detach().clone(), y_s=var_y, bandwidth=config["disentangle"]["bandwidth"],
+                    var_mode=config["disentangle"]["var_mode"],
+                    model_var=updated["L"].detach().clone() if "L" in updated.keys() else None, device=device)
             if step_callback is not None:
                 step_callback(batch_idx, batch_loss["total"].detach().reshape(1))
 

@@ -489,6 +489,45 @@ class EmuOps:
         nr = torch.as_strided(t, (F, 3), (ld, 1), off + nx)
         _v(root_hat, (F, 3), (3, 1)).copy_(0.5 * (nr + 1) * (a[1] - a[0]) + a[0])
 
+    def mi_loss(self, x, y, y_ld, xs, ys, var_s, logAx, bandwidth, S, B, z, dy, valid=None, loss=None, gscale=None, dx=None):
+        """MutInfoEstimator.forward (model/disentangle.py:277-317) and its gradient w.r.t. x"""
+        self.n += 1
+        if valid is not None and float(_v(valid, (1,), (1,))[0]) == 0.0:
+            return
+        X = _v(x, (B, z), (z, 1)).clone().requires_grad_(True)
+        Y = _v(y, (B, dy), (y_ld, 1))
+        XS, YS = _v(xs, (S, z), (z, 1)), _v(ys, (S, dy), (dy, 1))
+        VS = _v(var_s, (S, z), (z, 1)) if var_s is not None else torch.tensor([bandwidth])
+        LA = _v(logAx, (S,), (1,))[None, :] if var_s is not None else _v(logAx, (1,), (1,))
+        logAy = dy * (math.log(2 * math.pi) + math.log(bandwidth))
+        with torch.enable_grad():
+            dxm = X[:, None, :] - XS[None, :, :]
+            dym = Y[:, None, :] - YS[None, :, :]
+            sdx = ((dxm / VS) * dxm).sum(-1)
+            sdy = ((dym / bandwidth) * dym).sum(-1)
+            val = (torch.logsumexp(-0.5 * (LA + logAy + sdx + sdy), -1) - torch.logsumexp(-0.5 * (LA + sdx), -1)
+                   - torch.logsumexp(-0.5 * (logAy + sdy), -1)).mean()
+        if loss is not None:
+            _v(loss, (1,), (1,)).add_(val.detach().double())
+        if dx is not None:
+            g, = torch.autograd.grad(val, X)
+            sc = float(_v(gscale, (1,), (1,))[0]) if gscale is not None else 1.0
+            _v(dx, (B, z), (z, 1)).add_(sc * g)
+
+    def mi_update(self, mu, L, var, var_ld, xs, ys, var_s, logAx, bandwidth, S, z, dy, valid=None):
+        self.n += 1
+        _v(xs, (S, z), (z, 1)).copy_(_v(mu, (S, z), (z, 1)))
+        _v(ys, (S, dy), (dy, 1)).copy_(_v(var, (S, dy), (var_ld, 1)))
+        log2pi = math.log(2 * math.pi)
+        if var_s is not None:
+            v = torch.diagonal(_v(L, (S, z, z), (z * z, z, 1)), dim1=-2, dim2=-1) ** 2 + bandwidth
+            _v(var_s, (S, z), (z, 1)).copy_(v)
+            _v(logAx, (S,), (1,)).copy_(z * log2pi + torch.log(v).sum(-1))
+        else:
+            _v(logAx, (1,), (1,)).fill_(z * (log2pi + math.log(bandwidth)))
+        if valid is not None:
+            _v(valid, (1,), (1,)).fill_(1.0)
+
     def gen_features(self, xh, ld, root_hat, offsets, tree, n_tree, parts, B, W, J, norm=None, pose_out=None, heading=None,
                      avg3=None):
         """eval/eval.py:58-118 (FK through the oracle's fwd_kin, then the feature formulas)"""

@@ -348,3 +348,77 @@ def test_resident_packed_steps_equal_flat_steps(kind):
     for k in oa:
         for kk in oa[k]:
             assert torch.allclose(oa[k][kk], ob[k][kk], rtol=1e-6, atol=1e-10), (k, kk)
+
+
+@pytest.mark.parametrize("var_mode", ["sphere", "diagonal"])
+def test_mcmi_epoch_matches_reference(var_mode):
+    """The "mcmi" scrubbing loss (MutInfoEstimator, reference model/disentangle.py:234-317) through train_test_epoch:
+    zero on the first batch, estimator rebuilt from the updated encoder after every step (trainer.py:184-199) — epoch
+    metrics and final weights against the live reference, on both the piecewise and the fused path."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference not importable here")
+    from oracle import ref_runner as rr
+    refimport.import_reference()
+    from scrubvae.train import trainer as rtr
+    ch, zd, B = [8, 16, 32], 8, 6
+    ref, dc = rr.build_model("cpu", ch=ch, z_dim=zd, cond=["heading"], gr=[], seed=7)
+    dc = dict(dc, bandwidth=0.7, var_mode=var_mode)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "mcmi": 0.5}
+    batches = [{k: v for k, v in orc.synth_batch(B, seed=30 + i).items() if k in ("x6d", "root", "offsets", "target_pose", "heading")}
+               for i in range(3)]
+    noise = [orc.synth_eps(B, zd, seed=50 + i) for i in range(6)]
+
+    def patched_randn(seq):
+        it = iter(seq)
+        return lambda t, *a, **k: next(it).to(t)
+    import contextlib, io
+    orig = torch.randn_like
+    torch.randn_like = patched_randn(noise)  # forward draws; the updated encode() draws nothing (no sampling)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ropt, _ = rtr.get_optimizer_and_lr_scheduler(ref, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
+            mref = rtr.train_test_epoch({"loss": dict(scale), "disentangle": dc}, ref, batches, "cpu", 1, optimizer=ropt,
+                                        scheduler=None, mode="train")
+    finally:
+        torch.randn_like = orig
+    rsd = ref.state_dict()
+    for fused in (False, True):
+        m, dcfg = build_model(ch, zd, ["heading"], [])
+        dcfg = dict(dcfg, bandwidth=0.7, var_mode=var_mode)
+        m.load_state_dict(sd)
+        m._engine = Engine(m, ops=EmuOps())
+        opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
+        cfg = {"loss": dict(scale), "disentangle": dcfg, "train": {}}
+        if fused:  # the fused path is CUDA-only in train_test_epoch: drive TrainStep directly on the emulation
+            from scrubvae_b200.engine import TrainStep
+            st = TrainStep(m, opt, scale, B, use_graph=False, resident=True, mi=dict(bandwidth=0.7, var_mode=var_mode))
+            tot = None
+            for i, b in enumerate(batches):
+                m._noise = noise[i]
+                v = st.run(b).clone()
+                tot = v if tot is None else tot + v
+            st.sync()
+            mo = {n: float(tot[j]) / len(batches) for j, n in enumerate(st.plan.loss_names)}
+            mo["total"] = float(tot[-1]) / len(batches)
+        else:
+            seq = iter(noise)
+
+            def cb(i, vec):
+                m._noise = next(seq, None)
+            m._noise = next(seq)
+            with contextlib.redirect_stdout(io.StringIO()):
+                mo = sv.train.train_test_epoch(cfg, m, batches, "cpu", 1, optimizer=opt, scheduler=None, mode="train",
+                                               step_callback=cb)
+        for k in mref:
+            assert abs(mo[k] - mref[k]) <= 3e-5 * abs(mref[k]) + 1e-6, (fused, k, mo[k], mref[k])
+        osd = m.state_dict()
+        for k in rsd:
+            if k.startswith("mi_estimator."):
+                continue  # the reference registers the estimator as a submodule; here its samples live in the plan
+            if k.endswith("running_mean"):
+                # the convolution biases in front of a BatchNorm have zero true gradient; Adam turns their rounding noise
+                # into +-lr steps, and the post-step encode() folds those arbitrary bias shifts into running_mean
+                continue
+            assert _rel(osd[k].float(), rsd[k].float()) < 5e-3 or ZERO_GRAD_BIAS.search(k), (fused, k)

@@ -363,3 +363,24 @@ def test_gemm_fused_bn_backward_reduce(ops, B, Lo, C, fold, taps, resid, bn, act
                bnr_x=t["X"], bnr_bs=Lo * N, bnr_ls=N, bnr_chan=t["chan"] if bn else None,
                bnr_slope=t["slope"] if act_ else None, bnr_c=C, bnr_sums=t["sums"])
     run_both(ops, T, call, tol=2e-5, check=["Y", "sums"])
+
+
+@pytest.mark.parametrize("diag", [False, True])
+@pytest.mark.parametrize("B,S,z,dy", [(37, 50, 16, 2), (128, 128, 64, 9), (5, 300, 96, 3)])
+def test_mi_loss_and_update(ops, B, S, z, dy, diag):
+    """scv_mi_update + scv_mi_loss (MutInfoEstimator, "mcmi" loss): value, gradient into x, and the not-yet-valid case."""
+    T = {"mu": torch.randn(S, z, generator=g(1)), "L": torch.tril(torch.randn(S, z, z, generator=g(2)) * 0.3) + torch.eye(z) * 0.8,
+         "var": torch.randn(S, dy + 2, generator=g(3)), "xs": torch.zeros(S, z), "ys": torch.zeros(S, dy), "var_s": torch.zeros(S, z),
+         "logAx": torch.zeros(S), "valid": torch.zeros(1), "x": torch.randn(B, z, generator=g(4)),
+         "y": torch.randn(B, dy + 2, generator=g(5)), "loss": torch.zeros(2, dtype=torch.double), "gs": torch.tensor([0.7]),
+         "dx": torch.randn(B, z, generator=g(6))}
+
+    def call(o, t):
+        vs = t["var_s"] if diag else None
+        o.mi_loss(t["x"], t["y"], dy + 2, t["xs"], t["ys"], vs, t["logAx"], 0.6, S, B, z, dy, valid=t["valid"], loss=Ref(t["loss"], 1),
+                  gscale=t["gs"], dx=t["dx"])  # no estimator yet: nothing may change
+        o.mi_update(t["mu"], t["L"], t["var"], dy + 2, t["xs"], t["ys"], vs, t["logAx"], 0.6, S, z, dy, valid=t["valid"])
+        o.mi_loss(t["x"], t["y"], dy + 2, t["xs"], t["ys"], vs, t["logAx"], 0.6, S, B, z, dy, valid=t["valid"], loss=t["loss"])
+        o.mi_loss(t["x"], t["y"], dy + 2, t["xs"], t["ys"], vs, t["logAx"], 0.6, S, B, z, dy, valid=t["valid"], gscale=t["gs"],
+                  dx=t["dx"])
+    run_both(ops, T, call, tol=2e-5, check=["xs", "ys", "logAx", "valid", "loss", "dx"] + (["var_s"] if diag else []))
