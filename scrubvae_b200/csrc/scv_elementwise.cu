@@ -142,7 +142,7 @@ __device__ __forceinline__ float4 bn_prelu(float4 x, const ChanBN& cb, bool has_
   return make_float4(v[0], v[1], v[2], v[3]);
 }
 
-__global__ void __launch_bounds__(NT) bnact_fwd_kernel(const scv_bnact_t p, const int cw, const int64_t rpb) {
+__global__ void __launch_bounds__(NT, 3) bnact_fwd_kernel(const scv_bnact_t p, const int cw, const int64_t rpb) {
   const int C = (int)p.C, C4 = C >> 2;
   const int mode = (int)p.mode;
   const int64_t rows = p.B * p.L;
@@ -238,7 +238,7 @@ __device__ __forceinline__ float4 load_dout(const scv_bnact_bwd_t& p, int64_t b,
   return g;
 }
 
-__global__ void __launch_bounds__(NT) bnact_bwd_reduce_kernel(const scv_bnact_bwd_t p, const int cw,
+__global__ void __launch_bounds__(NT, 3) bnact_bwd_reduce_kernel(const scv_bnact_bwd_t p, const int cw,
                                                               const int64_t rpb) {
   __shared__ float red[8][32][9];
   __shared__ double shd[32];
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(NT) bnact_bwd_reduce_kernel(const scv_bnact_bw
   }
 }
 
-__global__ void __launch_bounds__(NT) bnact_bwd_apply_kernel(const scv_bnact_bwd_t p, const int cw,
+__global__ void __launch_bounds__(NT, 3) bnact_bwd_apply_kernel(const scv_bnact_bwd_t p, const int cw,
                                                              const int64_t rpb) {
   const int C = (int)p.C, C4 = C >> 2;
   const int mode = (int)p.mode;

@@ -130,6 +130,15 @@ def golden_preprocess(sv):
     path = os.path.join(HERE, "preprocess.npz")
     np.savez_compressed(path, **save)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB", out["x6d"].shape)
+    # the other two direction_process modes (dataset.py:383-413) on the same frames: "x360" (centred, not rotated) and None
+    modes = {}
+    for mode in ("x360", None):
+        o = ds.preprocess_save_data("", skel, "4_mice", 51, 2, keys, 2.25, mode)
+        for k in ("x6d", "root", "target_pose"):
+            modes[f"{mode}.{k}"] = o[k].numpy().astype(np.float32)
+    path = os.path.join(HERE, "preprocess_modes.npz")
+    np.savez_compressed(path, **modes)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
 if __name__ == "__main__":

@@ -94,6 +94,35 @@ def test_preprocess_matches_reference_golden(golden_dir):
             assert (bl - offs[:, :, b].norm(dim=-1)).abs().max().item() < 1e-3
 
 
+def _modes(golden_dir):
+    z = np.load(os.path.join(golden_dir, "preprocess_modes.npz"))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("mode", ["x360", None])
+def test_oracle_matches_reference_golden_other_modes(golden_dir, mode):
+    """direction_process "x360" (root centred on the mid frame, no rotation) and None (raw), reference dataset.py:383-413:
+    the oracle against fixtures generated from the unmodified reference (make_golden.py)."""
+    g, gm = _g(golden_dir), _modes(golden_dir)
+    ref = orc.preprocess(g["in.pose"], g["in.ids"], window=51, stride=2, speed_threshold=2.25, direction_process=mode)
+    for k in ("x6d", "root", "target_pose"):
+        want = torch.from_numpy(gm[f"{mode}.{k}"])
+        assert (torch.as_tensor(ref[k]).float() - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item()), (mode, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["x360", None])
+def test_preprocess_matches_reference_golden_other_modes(golden_dir, mode):
+    g, gm = _g(golden_dir), _modes(golden_dir)
+    out = sv.data.preprocess_windows(g["in.pose"], g["in.ids"], orc.KINEMATIC_TREE, orc.OFFSET, window=51, stride=2,
+                                     speed_threshold=2.25, direction_process=mode)
+    for k in ("x6d", "root", "target_pose"):
+        want = torch.from_numpy(gm[f"{mode}.{k}"])
+        got = out[k].float().cpu()
+        assert got.shape == want.shape, (mode, k)
+        assert (got - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item()), (mode, k)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode,thr,stride", [("midfwd", 2.25, 2), ("x360", None, 5), (None, 2.25, 1)])
 def test_preprocess_matches_oracle_large(mode, thr, stride):
