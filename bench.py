@@ -565,6 +565,10 @@ def run_ours(args, cfg, rank, world, local_rank):
         _shutdown(dist, parallel, m)
 
 
+def dist_rank_env():
+    return int(os.environ.get("RANK", "0"))
+
+
 def _shutdown(dist, parallel, model):
     """Leaves the process group cleanly: the captured graphs that hold NCCL kernels are released first (what stalled the
     teardown in round 1), every rank meets at a barrier (rank 0 alone ran the GEMM profile), then the group is destroyed.
@@ -572,12 +576,18 @@ def _shutdown(dist, parallel, model):
     import torch
     sys.stdout.flush()
     sys.stderr.flush()
-    threading.Timer(30.0, lambda: os._exit(0)).start()
+    t0 = time.time()
+
+    def _watchdog():
+        print("bench: teardown watchdog fired after 30 s", file=sys.stderr, flush=True)
+        os._exit(0)
+    threading.Timer(30.0, _watchdog).start()
     try:
         parallel.shutdown(model)
         dist.barrier()
         torch.cuda.synchronize()
         dist.destroy_process_group()
+        print(f"bench: rank {dist_rank_env()} left the process group cleanly in {time.time() - t0:.2f} s", file=sys.stderr)
     except Exception as ex:
         print("bench: teardown:", repr(ex)[:200], file=sys.stderr)
     sys.stdout.flush()

@@ -211,9 +211,10 @@ typedef struct {
   int64_t kind; /* 0 adam (L2 wd folded in grad), 1 adamw (decoupled), 2 sgd nesterov (m = momentum buf, beta1 = momentum) */
   /* RESIDENT-PACKED mode (pack_idx != NULL): p, g, m, v are all in the packed K-major layout of the GEMM matrices (p = fp32
    * master, g = what the wgrad kernels accumulated), so every access is coalesced; positions with pack_idx[j] < 0 (structural
-   * zeros / padding) are skipped.  The updated weight is also written as the operand copy the next forward GEMMs load:
-   * packed_out[j] (fp32, rounded to TF32 if flags & SCV_F_ROUND_TF32) and / or packed16_out[j] (bf16).  No repack pass and
-   * no gradient-unpack pass is left in the step. */
+   * zeros / padding) keep their p, m, v.  The master is also written as the operand copy the next forward GEMMs load, at
+   * EVERY position (padding holds zeros in the master): packed_out[j] (fp32, rounded to TF32 if flags & SCV_F_ROUND_TF32)
+   * and / or packed16_out[j] (bf16).  n must be a multiple of 4 and the arrays 16-byte aligned (packed16_out: 8).  No
+   * repack pass and no gradient-unpack pass is left in the step. */
   const int32_t* pack_idx; float* packed_out; void* packed16_out; int64_t flags;
 } scv_optim_t;
 int scv_optim_step(const scv_optim_t* p, void* stream);

@@ -481,26 +481,52 @@ __global__ void __launch_bounds__(NT) optim_packed_kernel(const scv_optim_t p) {
   const int kind = (int)p.kind;
   const bool rnd = (p.flags & SCV_F_ROUND_TF32) != 0;
   __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(p.packed16_out);
-  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * NT) {
-    if (__ldg(p.pack_idx + i) < 0) continue;  // structural zero / padding of the packed layout
-    float g = p.g[i] * coef, w = p.p[i], wn;
-    if (kind == 2) {
-      float buf = first ? g : b1 * p.m[i] + g;
-      p.m[i] = buf;
-      wn = w - lr * (g + b1 * buf);
-    } else {
-      if (kind == 1) w *= 1.f - lr * wd;
-      else if (wd != 0.f) g += wd * w;
-      float m = p.m[i] + (1.f - b1) * (g - p.m[i]);
-      float v = b2 * p.v[i] + (1.f - b2) * g * g;
-      p.m[i] = m;
-      p.v[i] = v;
-      float denom = sqrtf(v) / bc2s + eps;
-      wn = w - step_size * (m / denom);
+  // four elements per thread, every load issued before the mask is known (padding positions are real memory in
+  // all the packed arrays); masked lanes write their old values back, so the stores stay 16-byte vectors
+  const int64_t n4 = p.n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (int64_t)gridDim.x * NT) {
+    const int4 id = __ldg(reinterpret_cast<const int4*>(p.pack_idx) + i);
+    const float4 g4 = ld4(p.g + 4 * i), w4 = ld4(p.p + 4 * i), m4 = ld4(p.m + 4 * i);
+    const float4 v4 = kind == 2 ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(p.v + 4 * i);
+    const int idx[4] = {id.x, id.y, id.z, id.w};
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float ww[4] = {w4.x, w4.y, w4.z, w4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (idx[q] < 0) continue;  // structural zero / padding of the packed layout: left untouched
+      float g = gg[q] * coef, w = ww[q];
+      if (kind == 2) {
+        float buf = first ? g : b1 * mm[q] + g;
+        mm[q] = buf;
+        ww[q] = w - lr * (g + b1 * buf);
+      } else {
+        if (kind == 1) w *= 1.f - lr * wd;
+        else if (wd != 0.f) g += wd * w;
+        float m = mm[q] + (1.f - b1) * (g - mm[q]);
+        float v = b2 * vv[q] + (1.f - b2) * g * g;
+        mm[q] = m;
+        vv[q] = v;
+        float denom = sqrtf(v) / bc2s + eps;
+        ww[q] = w - step_size * (m / denom);
+      }
     }
-    p.p[i] = wn;
-    if (p.packed_out) p.packed_out[i] = rnd ? scv::round_tf32(wn) : wn;
-    if (o16) o16[i] = __float2bfloat16_rn(wn);
+    st4(p.p + 4 * i, make_float4(ww[0], ww[1], ww[2], ww[3]));
+    st4(p.m + 4 * i, make_float4(mm[0], mm[1], mm[2], mm[3]));
+    if (kind != 2) st4(p.v + 4 * i, make_float4(vv[0], vv[1], vv[2], vv[3]));
+    if (p.packed_out) {
+      if (rnd) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ww[q] = scv::round_tf32(ww[q]);
+      }
+      st4(p.packed_out + 4 * i, make_float4(ww[0], ww[1], ww[2], ww[3]));
+    }
+    if (o16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(ww[0], ww[1]), hi = __floats2bfloat162_rn(ww[2], ww[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(o16 + 4 * i) = pk;
+    }
   }
 }
 
@@ -656,7 +682,12 @@ int scv_optim_step(const scv_optim_t* p, void* stream) {
   SCV_REQUIRE(p->kind >= 0 && p->kind <= 2 && (p->hyper || p->step >= 1), "scv_optim_step: bad kind/step");
   if (p->n <= 0) return 0;
   if (p->pack_idx) {
-    optim_packed_kernel<<<grid1d(p->n, 8), NT, 0, (cudaStream_t)stream>>>(*p);
+    SCV_REQUIRE(p->n % 4 == 0 && scv::aligned16(p->pack_idx) && scv::aligned16(p->g) && scv::aligned16(p->p) &&
+                    scv::aligned16(p->m) && (p->kind == 2 || scv::aligned16(p->v)) &&
+                    (!p->packed_out || scv::aligned16(p->packed_out)) &&
+                    (!p->packed16_out || (reinterpret_cast<uintptr_t>(p->packed16_out) & 7) == 0),
+                "scv_optim_step: the packed arrays must be 16-byte aligned and n a multiple of 4");
+    optim_packed_kernel<<<grid1d(p->n / 4, 2), NT, 0, (cudaStream_t)stream>>>(*p);
     return scv::check_launch("optim_packed_kernel");
   }
   optim_kernel<<<grid1d(p->n, 8), NT, 0, (cudaStream_t)stream>>>(*p);

@@ -312,7 +312,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       for (int t = first; t < total; t += step) {
@@ -348,7 +348,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       const uint32_t idesc = kBf16 ? idesc_bf16(kBM, p.bn, 0, 0) : idesc_tf32(kBM * kCtas, p.bn, 0, 0);
       // K-major, 128B swizzle: LBO 16 B (unused), SBO 1024 B; the stage base addresses are 1024-byte aligned
       const uint64_t desc0 = smem_desc(smem_u32(smem), 16, 1024);
@@ -603,7 +603,18 @@ struct WgradTcParams {
   float* dW;
   float* dbias;  // bias gradient = column sums of dY: one extra N=16 MMA per 8 rows against a tile of ones (k tile 0 only)
   int bias_mod, bias_n;
+  long long* trace;  // debug (SCV_TC_TRACE): as GemmTcParams::trace
 };
+
+__device__ __forceinline__ void tc_trace_w(const WgradTcParams& p, int role, int ev, int tile) {
+  if (p.trace && blockIdx.x == 0) {
+    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(p.trace), 1ULL);
+    if (i < 4000) {
+      p.trace[1 + 2 * i] = ((long long)role << 40) | ((long long)ev << 32) | (unsigned)tile;
+      p.trace[2 + 2 * i] = clock64();
+    }
+  }
+}
 
 constexpr int kWgradMaxBNK = 224;  // k-tile width limit (whole 32-float slabs); 224 + 16 bias columns fit a 256-column TMEM buffer
 constexpr int kBiasCol = 240;      // TMEM column of the bias accumulator inside each 256-column buffer
@@ -683,16 +694,18 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       for (int t = first; t < total; t += step) {
         int nt, kt, g0, g1;
         decode(t, nt, kt, g0, g1);
+        tc_trace_w(p, 0, 0, t);
         for (int g = g0; g < g1; ++g) {
           const int bt_i = g / p.lt, lt_i = g - bt_i * p.lt;
           const int l0 = lt_i * p.bl, b0 = bt_i * p.nb;
           mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1);
+          if (g == g0 || g == g1 - 1) tc_trace_w(p, 0, 1 + (g != g0), t);
           const uint32_t fb = smem_u32(&ctl->full[s]);
           mbar_expect_tx(fb, stage_tx);
           const uint32_t sy = smem_u32(smem + (size_t)s * stage_bytes);
@@ -709,7 +722,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = kBf16 ? idesc_bf16(kBM, p.bnk, 1, 1) : idesc_tf32(kBM, p.bnk, 1, 1);
       const uint32_t idesc_b = kBf16 ? idesc_bf16(kBM, 16, 1, 1) : idesc_tf32(kBM, 16, 1, 1);
       const uint64_t ones_desc = kBf16 ? smem_desc(smem_u32(ones), 2048, 1024, 2) : smem_desc(smem_u32(ones), 1024, 512, 1);
@@ -727,12 +740,15 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
         decode(t, nt, kt, g0, g1);
         const bool do_bias = p.dbias != nullptr && kt == 0;
         const int acc = sub == 2 ? 0 : (it & 1);
+        tc_trace_w(p, 1, 0, t);
         mbar_wait(smem_u32(&ctl->tempty[acc]), (sub == 2 ? (it & 1) : ((it >> 1) & 1)) ^ 1);
         tc_fence_after();
+        tc_trace_w(p, 1, 1, t);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;
         for (int g = g0; g < g1; ++g) {
           mbar_wait(smem_u32(&ctl->full[s]), ph);
           tc_fence_after();
+          if (g == g0 || g == g1 - 1) tc_trace_w(p, 1, 2 + (g != g0), t);
           const uint32_t sy = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sa = sy + y_bytes;
           const uint32_t y_lo = ydesc_lo0 + (uint32_t)s * stage_units, a_lo = y_lo + (y_bytes >> 4);
@@ -764,8 +780,10 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
       int nt, kt, g0, g1;
       decode(t, nt, kt, g0, g1);
       const int acc = sub == 2 ? 0 : (it & 1);
+      if (ew == 0 && lane == 0) tc_trace_w(p, 2, 0, t);
       mbar_wait(smem_u32(&ctl->tfull[acc]), sub == 2 ? (it & 1) : ((it >> 1) & 1));
       tc_fence_after();
+      if (ew == 0 && lane == 0) tc_trace_w(p, 2, 1, t);
       const int kbase = kt * p.bnk;
       const int kcols = min(p.bnk, p.K - kbase);
      for (int sj = 0; sj < sub; ++sj) {
@@ -804,6 +822,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ctl->tempty[acc]));
+      if (ew == 0 && lane == 0) tc_trace_w(p, 2, 2, t);
     }
   }
   tc_fence_before();
@@ -1092,6 +1111,8 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.dbias = want_bias ? p->dbias : nullptr;
   q.bias_mod = (int)(want_bias ? p->bias_mod : 1);
   q.bias_n = (int)(want_bias ? p->bias_n : 0);
+  q.trace = nullptr;
+  if (const char* tr = getenv("SCV_TC_TRACE")) q.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 10));
   choose_box(p->Lo, p->B, bf16 ? 64 : 32, bf16 ? 16 : 8, q.bl, q.nb);
   q.lt = (int)cdiv(p->Lo, q.bl);
   q.bt = (int)cdiv(p->B, q.nb);
@@ -1112,9 +1133,11 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   const int wmc_env = [] { const char* e = getenv("SCV_TC_WMC"); return e ? atoi(e) : 0; }();
   const bool mc = wmc_env != 0 && !bf16 && g_mc_capacity >= 1 && q.sub == 1 && q.n_tiles >= 2 && q.bnk >= 64;
   const int tiles = (mc ? (q.n_tiles + 1) / 2 * 2 : q.n_tiles) * q.k_tiles;
-  // row splits: fill the SMs ~2x over (once over for the two-tile items: their epilogue is not overlapped, so
-  // fewer, longer items), but keep at least 4 row groups per item
-  int splits = (int)cdiv((q.sub == 2 ? 1 : 2) * sm_count(), tiles);
+  // row splits: fill the SMs ~4x over (measured on the 28 weight-gradient GEMMs of the default network, B = 2048:
+  // 1x 1800 us, 2x 1553 us, 3x 1554 us, 4x 1487 us; shorter items even out the tail), once over for the two-tile
+  // items (their epilogue is not overlapped, so fewer, longer items), but keep at least 4 row groups per item
+  const int wsplit_env = [] { const char* e = getenv("SCV_TC_WSPLIT"); return e ? atoi(e) : 0; }();  // experiments
+  int splits = (int)cdiv((wsplit_env > 0 ? wsplit_env : (q.sub == 2 ? 1 : 4)) * sm_count(), tiles);
   if (splits > q.groups / 4) splits = q.groups / 4;
   if (splits < 1) splits = 1;
   q.gps = (int)cdiv(q.groups, splits);
@@ -1124,6 +1147,8 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   const size_t fixed = 1024 + 2048 + ((sizeof(SmemCtlW) + 15) & ~size_t(15)) + kEpiWarps * kXposeFloats * 4;
   int stages = (int)((kSmemLimit - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  const int wstages_env = [] { const char* e = getenv("SCV_TC_WSTAGES"); return e ? atoi(e) : 0; }();  // experiments
+  if (wstages_env >= 2 && stages > wstages_env) stages = wstages_env;
   if (stages < 2) return decline("scv_wgrad", "a stage does not fit shared memory twice", M, p->N, p->K);
   q.stages = stages;
 

@@ -1268,6 +1268,8 @@ class TrainStep:
         self.plan = self.eng.plan(B)
         self.max_norm = float(max_norm)
         self.comm = comm
+        if comm is not None and hasattr(comm, "steps"):
+            comm.steps.add(self)
         if self.mi is not None:
             self.plan.enable_mcmi(self.mi["bandwidth"], self.mi.get("var_mode") or "sphere")
         self.plan.set_loss_scale(loss_scale)

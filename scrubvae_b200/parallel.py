@@ -18,6 +18,8 @@ The collective is NCCL over NVLink 5 / NVSwitch through torch.distributed (`gloo
 it is capturable in the step's CUDA graph."""
 from __future__ import annotations
 
+import weakref
+
 import torch
 import torch.distributed as dist
 
@@ -54,6 +56,7 @@ class GradAllReduce:
         self.stream = torch.cuda.Stream(device=engine.device) if self.cuda else None
         self.bytes_per_step = 4 * (engine.gpacked.numel() + engine.n_direct)
         self._lo = engine.gp_split  # gpacked[_lo:gp_split] of the encoder part is already reduced this step
+        self.steps = weakref.WeakSet()  # every TrainStep that captured this hook's all-reduces (shutdown releases them)
 
     def _reduce(self, t):
         if t.numel():
@@ -126,6 +129,9 @@ def shutdown(model=None):
             for _, st in list(eng.__dict__.get("_train_steps", {}).values()):
                 st.graph = None
             eng.__dict__.pop("_train_steps", None)
+            comm = getattr(eng, "comm", None)
+            for st in list(getattr(comm, "steps", ())):  # steps built outside the trainer's cache
+                st.graph = None
             eng.comm = None
     gc.collect()
     if torch.cuda.is_available():

@@ -445,10 +445,11 @@ class EmuOps:
             P[live], M[live] = sub[0], sub[2]
             if V is not None:
                 V[live] = sub[3]
+            # the operand copies mirror the master at EVERY position (padding included: the master holds zeros there)
             if packed_out is not None:
-                _v(packed_out, (n,), (1,))[live] = rtf32(sub[0]) if round_tf32 else sub[0]
+                _v(packed_out, (n,), (1,)).copy_(rtf32(P) if round_tf32 else P)
             if packed16_out is not None:
-                _v(packed16_out, (n,), (1,))[live] = sub[0].to(torch.bfloat16)
+                _v(packed16_out, (n,), (1,)).copy_(P.to(torch.bfloat16))
             return
         if hyper is not None:
             hy = _v(hyper, (2,), (1,))

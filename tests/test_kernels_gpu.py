@@ -310,6 +310,41 @@ def test_gather_sumsq_optim_finalize(ops):
         run_both(ops, T, call, tol=1e-5, check=["dst", "dst2", "ss", "p", "m", "v", "lout"])
 
 
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("rnd,bf16", [(False, False), (True, False), (False, True)])
+def test_resident_packed_optimizer(ops, kind, rnd, bf16):
+    """The optimizer in the packed GEMM layout (resident master): padding positions (pack_idx < 0) keep their values in
+    every array, live ones get the same update as the flat kernel, and the operand copies are written alongside."""
+    n = 4 * 25013
+    idx = torch.randint(-3, n, (n,), generator=g(1)).to(torch.int32)  # ~3/n negative would be too few: force a pattern
+    idx[::7] = -1
+    idx[5:40] = -1
+    T = {"g": torch.randn(n, generator=g(2)), "idx": idx, "p": torch.randn(n, generator=g(3)),
+         "m": torch.randn(n, generator=g(4)) * 0.01, "v": torch.rand(n, generator=g(5)) * 1e-4,
+         "po": torch.full((n,), 7.0), "ss": torch.zeros(1, dtype=torch.double),
+         "hyper": torch.tensor([3e-4, 7.0], dtype=torch.double)}
+    if bf16:
+        T["p16"] = torch.full((n,), 7.0).to(torch.bfloat16)
+
+    def call(o, t):
+        t["ss"].zero_()
+        o.sumsq_packed(t["g"], t["idx"], n, t["ss"])
+        o.optim_step(t["p"], t["g"], t["m"], t["v"], n, t["ss"], 10.0, 0.5, 1e-3, 0.9, 0.999, 1e-8, 0.01, 3, kind,
+                     hyper=t["hyper"] if kind == 1 else None, pack_idx=t["idx"], packed_out=t["po"],
+                     packed16_out=t.get("p16"), round_tf32=rnd)
+    run_both(ops, T, call, tol=1e-5, check=["ss", "p", "m", "v", "po"])
+    if bf16:
+        run_both(ops, T, call, tol=4e-3, check=["p16"])
+    # padding untouched on the device (bit-exact)
+    gpu = {k: v.clone().cuda() for k, v in T.items()}
+    call(ops, gpu)
+    torch.cuda.synchronize()
+    dead = (idx < 0)
+    for k in ("p", "m", "v"):
+        if not (kind == 2 and k == "v"):
+            assert torch.equal(gpu[k].cpu()[dead], T[k][dead]), k
+
+
 def test_library_fails_loudly_when_missing(tmp_path):
     from scrubvae_b200 import _ops
     with pytest.raises(RuntimeError, match="no CPU fallback"):

@@ -69,6 +69,7 @@ def _worker(rank, world, port, q):
     errs = {n: (_rel(g1[n], gavg[n]), (g1[n].double() - gavg[n].double()).norm().item() / gn) for n in gavg}
     finite = bool(torch.isfinite(flat).all())
     q.put((rank, same, errs, finite))
+    del step  # parallel.shutdown finds the step through the comm hook's registry and drops its captured graph
     dist.barrier()
     parallel.shutdown(m)
     dist.destroy_process_group()
@@ -85,7 +86,11 @@ def test_two_rank_nccl_graph_step():
     res = [q.get(timeout=600) for _ in range(world)]
     for p in procs:
         p.join(timeout=120)
-        assert p.exitcode == 0
+    codes = [p.exitcode for p in procs]
+    for p in procs:
+        if p.is_alive():  # never leave a worker behind: pytest would wait for it at exit
+            p.kill()
+    assert codes == [0] * world, f"teardown did not finish cleanly: exit codes {codes}"
     for rank, same, errs, finite in res:
         assert finite
         assert same, "replicas diverged after 4 data-parallel steps"

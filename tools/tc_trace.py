@@ -18,13 +18,18 @@ step = TrainStep(m, opt, bench.LOSS_SCALE, a.batch, use_graph=False); step.run(d
 eng, ops = step.eng, step.eng.ops
 names = {eng.packed.data_ptr() + 4 * g.w: g.name + ":fwd" for g in eng.W.values()}
 names.update({eng.packed.data_ptr() + 4 * (eng._n_fwd + g.wd): g.name + ":dgrad" for g in eng.W.values() if g.wd is not None})
+wnames = {eng.gpacked.data_ptr() + 4 * g.w: g.name + ":wgrad" for g in eng.W.values()}
 calls = []
-og = ops.gemm
+og, ow = ops.gemm, ops.wgrad
 def rg(**kw):
     calls.append((names.get(_ptr(kw["W"]), "?"), kw)); og(**kw)
-ops.gemm = rg; step._sequence(); del ops.gemm
+def rw(**kw):
+    calls.append((wnames.get(_ptr(kw["dW"]), "?"), kw)); ow(**kw)
+ops.gemm, ops.wgrad = rg, rw; step._sequence(); del ops.gemm, ops.wgrad
 torch.cuda.synchronize()
 kw = [c for c in calls if a.filter in c[0]][0][1]
+if a.filter.endswith(":wgrad"):
+    og = ow
 og(**kw); torch.cuda.synchronize()
 os.environ["SCV_TC_TRACE"] = str(buf.data_ptr())
 og(**kw); torch.cuda.synchronize()
