@@ -21,6 +21,8 @@
 // the same (32, bl, nb) boxes; work items (n tile, k tile, row split) are spread over the SMs and the
 // epilogue adds into dW with coalesced red.global.add.v4.f32.  The bias gradient (column sums of dY) rides
 // along as one extra N=16 MMA per 8 rows against a shared-memory tile of ones (k tile 0 items only).
+#include <atomic>
+
 #include "scv_tc.cuh"
 
 namespace scv {
@@ -118,6 +120,10 @@ struct GemmTcParams {
                      // (red.global.add) into a pre-zeroed Y - for GEMMs with few output tiles and a long K (SCV_ACT_ACCUM)
   int kc_per;        // k chunks per split
   long long* trace;  // debug (SCV_TC_TRACE=<n events>): CTA 0 appends (role, event, tile, clock) records
+  int* work;         // dynamic work distribution (nullptr: static round robin): work[0] = next item, work[1] = CTAs done.
+                     // CTAs that start late (SMs held by a concurrent NCCL kernel) or draw long items no longer decide the
+                     // launch's duration; the last CTA to leave resets both counters, so launches and graph replays are
+                     // self-cleaning
 };
 
 // debug timeline of CTA 0: role 0 producer / 1 mma / 2 epilogue warp 0; only active when p.trace != nullptr
@@ -133,9 +139,68 @@ __device__ __forceinline__ void tc_trace(const GemmTcParams& p, int role, int ev
 
 struct SmemCtl {  // lives after the operand stages
   uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
+  uint64_t sfull[2], sempty[2];  // dynamic scheduler: the producer publishes item indices through item[2]
+  int item[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
+
+// consumer side of the dynamic scheduler (MMA thread, epilogue warps): next item index, -1 = no more work
+struct ItemReader {
+  uint32_t sfull, sempty;  // shared-memory addresses of slot 0's barriers (slot 1: + 8)
+  const int* item;
+  int slot;
+  uint32_t phase;
+  template <typename Ctl>
+  __device__ __forceinline__ void init(Ctl* ctl) {
+    sfull = smem_u32(&ctl->sfull[0]);
+    sempty = smem_u32(&ctl->sempty[0]);
+    item = ctl->item; slot = 0; phase = 0;
+  }
+  // whole-warp callers pass warp_wide = true: every lane reads, one lane hands the slot back
+  __device__ __forceinline__ int next(bool warp_wide, int lane) {
+    mbar_wait(sfull + 8u * slot, phase);
+    const int t = *reinterpret_cast<const volatile int*>(item + slot);
+    if (warp_wide) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sempty + 8u * slot);
+    } else {
+      mbar_arrive(sempty + 8u * slot);
+    }
+    if (++slot == 2) { slot = 0; phase ^= 1; }
+    return t;
+  }
+};
+// producer side: publish item t (or -1)
+struct ItemWriter {
+  uint32_t sfull, sempty;
+  int* item;
+  int slot;
+  uint32_t phase;
+  template <typename Ctl>
+  __device__ __forceinline__ void init(Ctl* ctl) {
+    sfull = smem_u32(&ctl->sfull[0]);
+    sempty = smem_u32(&ctl->sempty[0]);
+    item = ctl->item; slot = 0; phase = 0;
+  }
+  __device__ __forceinline__ void put(int t) {
+    mbar_wait(sempty + 8u * slot, phase ^ 1);
+    *reinterpret_cast<volatile int*>(item + slot) = t;
+    mbar_arrive(sfull + 8u * slot);  // release: the store above is visible to whoever acquires the phase
+    if (++slot == 2) { slot = 0; phase ^= 1; }
+  }
+};
+// leaving a dynamically scheduled launch (called by the producer thread once it has drawn its sentinel): the last CTA
+// resets the counters - every CTA has made its last draw by then, and kernel boundaries order the reset against the
+// next launch that uses the slot
+__device__ __forceinline__ void work_leave(int* work) {
+  const int d = atomicAdd(work + 1, 1);
+  if (d == (int)gridDim.x - 1) {
+    work[0] = 0;
+    work[1] = 0;
+    __threadfence();
+  }
+}
 // BatchNorm column sums / sums of squares of this CTA's tiles (flushed when the n tile changes): 2 x kMaxBN floats placed
 // behind the transpose tiles ONLY for launches that collect statistics — 2 KB that decide whether a third 64 KB stage
 // fits for the 256 x 256 work items.
@@ -299,9 +364,16 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&ctl->tfull[i]), 1);
       mbar_init(smem_u32(&ctl->tempty[i]), kEpiWarps * kCtas);
+      mbar_init(smem_u32(&ctl->sfull[i]), 1);
+      mbar_init(smem_u32(&ctl->sempty[i]), 1 + kEpiWarps);
     }
     fence_barrier_init();
   }
+  // dynamic work distribution (single-CTA kernels): every CTA starts on item blockIdx.x and DRAWS the following ones
+  // (gridDim.x + counter).  A draw for the first item too was measured slower: 148 same-address atomics at launch
+  // serialise in L2 (~2 us for the last CTA), while later draws are staggered and hidden behind the item's loads.
+  const bool dyn = kCtas == 1 && !kMc && p.work != nullptr;
+  const int t_first = first;
   if (warp == 2) {
     if (kCtas == 2) tmem_alloc2(smem_u32(&ctl->tmem_base), kTmemCols);
     else tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
@@ -315,7 +387,15 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = first; t < total; t += step) {
+      ItemWriter iw;
+      iw.init(ctl);
+      for (int t = t_first;;) {
+        if (dyn) iw.put(t < total ? t : -1);
+        if (t >= total) {
+          if (dyn) work_leave(p.work);  // hidden behind the last item's MMAs and epilogue
+          break;
+        }
+        const int t_next = dyn ? step + atomicAdd(p.work, 1) : t + step;  // drawn now, needed after this item's loads
         const int ks = t / tiles, tt = t - ks * tiles;
         const int nt = tt / m_groups, mt = (tt - nt * m_groups) * mper + (kMc ? (int)crank * sub : (int)rank);
         const int bt_i = mt / p.lt, lt_i = mt - bt_i * p.lt;  // mt >= m_tiles (odd tail): box fully out of bounds -> zeros
@@ -344,6 +424,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+        t = t_next;
       }
     }
     __syncwarp();
@@ -356,7 +437,11 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
       const uint32_t stage_units = stage_bytes >> 4;
       int s = 0, it = 0;
       uint32_t ph = 0;
-      for (int t = first; t < total; t += step, ++it) {
+      ItemReader ir;
+      ir.init(ctl);
+      for (int t = first;; ++it) {
+        if (dyn) t = ir.next(false, 0); else if (it) t += step;
+        if (t < 0 || t >= total) break;
         const int acc = sub == 2 ? 0 : (it & 1);  // sub == 2: both TMEM halves hold this item's two accumulators
         tc_trace(p, 1, 0, t);
         mbar_wait(smem_u32(&ctl->tempty[acc]), (sub == 2 ? (it & 1) : ((it >> 1) & 1)) ^ 1);
@@ -427,7 +512,11 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     const uint32_t tempty_addr[2] = {kCtas == 2 ? mapa_rank(smem_u32(&ctl->tempty[0]), 0) : smem_u32(&ctl->tempty[0]),
                                      kCtas == 2 ? mapa_rank(smem_u32(&ctl->tempty[1]), 0) : smem_u32(&ctl->tempty[1])};
     int it = 0, cur_nt = -1;
-    for (int t = first; t < total; t += step, ++it) {
+    ItemReader ir;
+    ir.init(ctl);
+    for (int t = first;; ++it) {
+      if (dyn) t = ir.next(true, lane); else if (it) t += step;
+      if (t < 0 || t >= total) break;
       const int ks = t / tiles, tt = t - ks * tiles;
       const int nt = tt / m_groups, mt0 = (tt - nt * m_groups) * mper + (kMc ? (int)crank * sub : (int)rank);
       const int n0 = nt * p.bn;
@@ -604,6 +693,7 @@ struct WgradTcParams {
   float* dbias;  // bias gradient = column sums of dY: one extra N=16 MMA per 8 rows against a tile of ones (k tile 0 only)
   int bias_mod, bias_n;
   long long* trace;  // debug (SCV_TC_TRACE): as GemmTcParams::trace
+  int* work;         // dynamic work distribution, as GemmTcParams::work
 };
 
 __device__ __forceinline__ void tc_trace_w(const WgradTcParams& p, int role, int ev, int tile) {
@@ -621,6 +711,8 @@ constexpr int kBiasCol = 240;      // TMEM column of the bias accumulator inside
 
 struct SmemCtlW {
   uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
+  uint64_t sfull[2], sempty[2];
+  int item[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -668,9 +760,13 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&ctl->tfull[i]), 1);
       mbar_init(smem_u32(&ctl->tempty[i]), kEpiWarps);
+      mbar_init(smem_u32(&ctl->sfull[i]), 1);
+      mbar_init(smem_u32(&ctl->sempty[i]), 1 + kEpiWarps);
     }
     fence_barrier_init();
   }
+  const bool dyn = !kMc && p.work != nullptr;  // first item blockIdx.x, the following ones drawn (see gemm_tc_body)
+  const int t_first = first;
   if (warp == 2) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
   if (warp == 3) {
     if (kBf16) for (int i = lane; i < 512; i += 32) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;  // two bf16 1.0
@@ -697,7 +793,15 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = first; t < total; t += step) {
+      ItemWriter iw;
+      iw.init(ctl);
+      for (int t = t_first;;) {
+        if (dyn) iw.put(t < total ? t : -1);
+        if (t >= total) {
+          if (dyn) work_leave(p.work);
+          break;
+        }
+        const int t_next = dyn ? step + atomicAdd(p.work, 1) : t + step;
         int nt, kt, g0, g1;
         decode(t, nt, kt, g0, g1);
         tc_trace_w(p, 0, 0, t);
@@ -718,6 +822,7 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
           tma_load_4d(sy + y_bytes, &tmA, fb, 0, l0, b0, kt * (p.bnk / SW));
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+        t = t_next;
       }
     }
     __syncwarp();
@@ -735,7 +840,11 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
       const uint32_t stage_units = stage_bytes >> 4;
       int s = 0, it = 0;
       uint32_t ph = 0;
-      for (int t = first; t < total; t += step, ++it) {
+      ItemReader ir;
+      ir.init(ctl);
+      for (int t = first;; ++it) {
+        if (dyn) t = ir.next(false, 0); else if (it) t += step;
+        if (t < 0 || t >= total) break;
         int nt, kt, g0, g1;
         decode(t, nt, kt, g0, g1);
         const bool do_bias = p.dbias != nullptr && kt == 0;
@@ -776,7 +885,11 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& tmY, const CUte
     const int rq = lane >> 3, cq = lane & 7;
     float4* xp4 = reinterpret_cast<float4*>(xpose + ew * kXposeFloats);
     int it = 0;
-    for (int t = first; t < total; t += step, ++it) {
+    ItemReader ir;
+    ir.init(ctl);
+    for (int t = first;; ++it) {
+      if (dyn) t = ir.next(true, lane); else if (it) t += step;
+      if (t < 0 || t >= total) break;
       int nt, kt, g0, g1;
       decode(t, nt, kt, g0, g1);
       const int acc = sub == 2 ? 0 : (it & 1);
@@ -848,6 +961,22 @@ wgrad_tc_mc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
   wgrad_tc_body<true>(tmY, tmA, p);
 }
 
+// counters of the dynamically scheduled launches: a ring of (next item, CTAs done) pairs, zero at load and reset by the
+// last CTA of every launch; consecutive launches take consecutive slots, so kernels running concurrently on different
+// streams (or as parallel branches of one CUDA graph) never share one
+constexpr int kWorkSlots = 4096;
+__device__ int g_work_slots[2 * kWorkSlots];
+int* g_work_base[64] = {};
+
+int* work_slot() {
+  const char* e = getenv("SCV_TC_DYN");  // read per call: SCV_TC_DYN=0 selects the static round robin
+  if (e && atoi(e) == 0) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_work_base[dev]) return nullptr;
+  static std::atomic<unsigned> seq{0};
+  return g_work_base[dev] + 2 * (seq.fetch_add(1u) % (unsigned)kWorkSlots);
+}
+
 int g_attr_done = 0;
 int g_pair_capacity = -1;
 int g_mc_capacity = -1;
@@ -898,6 +1027,14 @@ int ensure_attrs() {
     scv::set_error("tensor-core GEMM: cannot opt in to %d B of shared memory: %s", kSmemLimit, cudaGetErrorString(e));
     cudaGetLastError();
     return (int)e;
+  }
+  {
+    int dev = 0;
+    void* sym = nullptr;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && cudaGetSymbolAddress(&sym, g_work_slots) == cudaSuccess)
+      g_work_base[dev] = static_cast<int*>(sym);
+    else
+      cudaGetLastError();  // no dynamic scheduling on this device: the static round robin still works
   }
   g_attr_done = 1;
   return 0;
@@ -1043,6 +1180,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   }
   q.bnr_x = p->bnr_x; q.bnr_bs = p->bnr_bs; q.bnr_ls = p->bnr_ls; q.bnr_chan = p->bnr_chan; q.bnr_slope = p->bnr_slope;
   q.bnr_c = (int)p->bnr_c; q.bnr_sums = p->bnr_sums;
+  q.work = nullptr;
   q.trace = nullptr;
   if (const char* tr = getenv("SCV_TC_TRACE")) {  // debug: device buffer address (decimal) to receive CTA 0's timeline
     q.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 10));
@@ -1078,6 +1216,7 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   }
   const int total = q.n_tiles * (int)cdiv(q.m_tiles, q.sub) * q.ksplit;
   const int grid = total < sm_count() ? total : sm_count();
+  q.work = total > grid ? work_slot() : nullptr;
   if (bnr) {
     if (bf16) gemm_tc_bnr_bf16_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, q);
     else gemm_tc_bnr_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, q);
@@ -1111,6 +1250,7 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.dbias = want_bias ? p->dbias : nullptr;
   q.bias_mod = (int)(want_bias ? p->bias_mod : 1);
   q.bias_n = (int)(want_bias ? p->bias_n : 0);
+  q.work = nullptr;
   q.trace = nullptr;
   if (const char* tr = getenv("SCV_TC_TRACE")) q.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 10));
   choose_box(p->Lo, p->B, bf16 ? 64 : 32, bf16 ? 16 : 8, q.bl, q.nb);
@@ -1179,6 +1319,7 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   }
   const int total = tiles * q.splits;
   const int grid = total < sm_count() ? total : sm_count();
+  q.work = total > grid ? work_slot() : nullptr;
   if (bf16) {
     wgrad_tc_bf16_kernel<<<grid, kThreads, smem, st>>>(tmY, tmA, q);
     return check_launch("wgrad_tc_bf16_kernel");

@@ -115,6 +115,32 @@ def test_wgrad_multitile(ops, case, mc, monkeypatch):
         test_wgrad(ops, case, 2)
 
 
+# more work items than SMs (148): several items per CTA, under the dynamic work distribution (items drawn from a global
+# counter, self-resetting: the second launch of each pair must find it clean) and the static round robin
+MANY_CASES = [
+    (5000, 4, 8, 64, 1, 5, 272, None, ACT_NONE, True, True),    # 157 row tiles x 2 n tiles, residual + statistics
+    (2600, 13, 18, 32, 1, 3, 48, None, ACT_RELU, False, False),  # 265 row tiles, narrow N
+]
+
+
+@pytest.mark.parametrize("dyn", ["0", "1"])
+@pytest.mark.parametrize("sub", ["1", "2"])
+@pytest.mark.parametrize("case", MANY_CASES)
+def test_gemm_many_items(ops, case, sub, dyn, monkeypatch):
+    monkeypatch.setenv("SCV_TC_DYN", dyn)
+    monkeypatch.setenv("SCV_TC_SUB", sub)
+    for prec in (1, 1, 2):
+        test_gemm(ops, case, prec)
+
+
+@pytest.mark.parametrize("dyn", ["0", "1"])
+@pytest.mark.parametrize("case", MANY_CASES)
+def test_wgrad_many_items(ops, case, dyn, monkeypatch):
+    monkeypatch.setenv("SCV_TC_DYN", dyn)
+    for prec in (1, 1, 2):
+        test_wgrad(ops, case, prec)
+
+
 @pytest.mark.parametrize("prec", [0, 1])
 @pytest.mark.parametrize("mc", ["0", "1"])
 @pytest.mark.parametrize("B,K,N", [(2048, 4096, 68), (300, 1024, 44), (64, 8192, 272)])

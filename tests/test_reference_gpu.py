@@ -24,7 +24,11 @@ from test_engine_cpu import build_model, _rel
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refimport.available(), reason="reference not staged (oracle/make_ref.sh)")]
 
 SCALE = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "heading_gr": 1.0}
-GRAD_FACTOR = 2.0   # per parameter tensor, plus 1e-3 of the global gradient norm for tensors that are tiny by chance
+# per parameter tensor, plus 1e-3 of the global gradient norm for tensors that are tiny by chance.  The per-tensor ratio is
+# one draw of rounding noise against another: measured median 0.84 over the 129 tensors, the largest 1.9 - 2.2 depending
+# on the summation order of the split weight-gradient reductions (run to run), global ratio 0.82 — hence 2.5 here and the
+# tighter 1.5 on the global sum below
+GRAD_FACTOR = 2.5
 GLOBAL_FACTOR = 1.5
 
 
