@@ -269,6 +269,26 @@ int scv_mi_loss(const float* x, const float* y, int64_t y_ld, const float* xs, c
 int scv_mi_update(const float* mu, const float* L, const float* var, int64_t var_ld, float* xs, float* ys, float* var_s,
                   float* logAx, double bandwidth, int64_t S, int64_t z, int64_t dy, float* valid, void* stream);
 
+/* ---- "moving_avg_lsq" scrubber (MovingAvgLeastSquares model/disentangle.py:393-538, polynomial order 1; loss
+ * train/losses.py:237-245; running-covariance update after the optimizer step train/trainer.py:169-178).
+ * x = mu rows (B,z) with an appended column of ones when bias != 0: nx = z + bias <= 136; y (B,ny), ny <= 16.
+ * scv_mals_solve: W_i = solve(Sxx_i + diag(l2_reg; the bias row excluded), Sxy_i), i = 0,1 (fp32, partial pivoting), W_i (nx,ny).
+ * scv_mals_loss: l01[0] += sum (y - x W0)^2, l01[1] += sum (y - x W1)^2 (double; if l01 != NULL); yhat0/yhat1 (B,ny) optional
+ *   outputs; dmu (B rows of d_ld) += gscale[0] / B * ((yhat0 - y) W0^T + (yhat1 - y) W1^T) over the first z rows (if dmu != NULL).
+ * scv_mals_finalize (evaluate_loss :505-538): the forgetting factors move by delta towards the better decoder
+ *   (l0 < l1: lam0 = clamp(lam0 - delta, 0, 1), lam1 = lam0 + lamdiff; else lam1 = clamp(lam1 + delta, 0, 1), lam0 = lam1 -
+ *   lamdiff) and loss[0] += (l0 + l1) / 2 / B (if loss != NULL).
+ * scv_mals_update (:489-503): Sxx_i = lam_i Sxx_i + x^T x, Sxy_i = lam_i Sxy_i + x^T y. */
+int scv_mals_solve(const float* Sxx0, const float* Sxy0, const float* Sxx1, const float* Sxy1, double l2_reg, int64_t bias,
+                   int64_t nx, int64_t ny, float* W0, float* W1, void* stream);
+int scv_mals_loss(const float* mu, int64_t mu_ld, const float* y, int64_t y_ld, const float* W0, const float* W1, int64_t bias,
+                  int64_t B, int64_t z, int64_t ny, double* l01, float* yhat0, float* yhat1, const float* gscale, float* dmu,
+                  int64_t d_ld, void* stream);
+int scv_mals_finalize(const double* l01, float* lam0, float* lam1, double delta, double lamdiff, int64_t B, double* loss,
+                      void* stream);
+int scv_mals_update(const float* mu, int64_t mu_ld, const float* y, int64_t y_ld, int64_t bias, int64_t B, int64_t z, int64_t ny,
+                    const float* lam0, const float* lam1, float* Sxx0, float* Sxy0, float* Sxx1, float* Sxy1, void* stream);
+
 /* ---- generative restrictiveness (eval): reference eval/eval.py:22-120.  For B decoded windows (xh rows of ld floats: the
  * decoder output after tanh, 6-D channels first; root_hat (B*W,3) un-normalised root positions or NULL = 0; offsets
  * (B*W,J,3)): forward kinematics (fwd_kin_cont6d_torch data/dataset.py:83-116, eps 1e-8) and, per window,

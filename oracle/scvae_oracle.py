@@ -580,3 +580,51 @@ def synth_state_dict(cfg: Cfg, seed: int = 1) -> Dict[str, torch.Tensor]:
                 bound = 1.0 / math.sqrt(int(np.prod(shp[1:])))
             sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * bound
     return sd
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# moving_avg_lsq scrubber (MovingAvgLeastSquares, reference model/disentangle.py:393-538), polynomial order 1
+# --------------------------------------------------------------------------------------------------------------------
+def mals_init(z: int, ny: int, bias: bool = False, lamdiff: float = 1e-1) -> Dict[str, torch.Tensor]:
+    """buffers as registered by the reference constructor (:417-433)"""
+    nx = z + int(bias)
+    return {"Sxx0": torch.eye(nx), "Sxy0": torch.zeros(nx, ny), "Sxx1": torch.eye(nx), "Sxy1": torch.zeros(nx, ny),
+            "lam0": torch.tensor([0.9]), "lam1": torch.tensor([0.9]) + lamdiff}
+
+
+def _mals_x(mu, bias):
+    return torch.column_stack((mu, torch.ones(mu.shape[0], 1))) if bias else mu
+
+
+def mals_forward(st, mu, bias=False, l2_reg=0.0):
+    """forward (:466-487): decoder weights from the normal equations, predictions of both decoders"""
+    x = _mals_x(mu, bias)
+    l2 = torch.ones(x.shape[1]) * l2_reg
+    if bias:
+        l2[-1] = 0
+    W0 = torch.linalg.solve(st["Sxx0"].diagonal_scatter(st["Sxx0"].diagonal() + l2), st["Sxy0"])
+    W1 = torch.linalg.solve(st["Sxx1"].diagonal_scatter(st["Sxx1"].diagonal() + l2), st["Sxy1"])
+    return x @ W0, x @ W1, W0, W1
+
+
+def mals_evaluate(st, yhat0, yhat1, y, delta=1e-4, lamdiff=1e-1):
+    """evaluate_loss (:505-538): mean of the two summed squared errors; the forgetting factors move towards the better one"""
+    l0, l1 = ((y - yhat0) ** 2).sum(), ((y - yhat1) ** 2).sum()
+    if l0 < l1:
+        st["lam0"] = torch.clamp(st["lam0"] - delta, 0.0, 1.0)
+        st["lam1"] = st["lam0"] + lamdiff
+    else:
+        st["lam1"] = torch.clamp(st["lam1"] + delta, 0.0, 1.0)
+        st["lam0"] = st["lam1"] - lamdiff
+    return (l0 + l1) * 0.5
+
+
+def mals_update(st, mu, y, bias=False):
+    """update (:489-503): exponentially weighted running covariances"""
+    x = _mals_x(mu, bias)
+    xx, xy = x.T @ x, x.T @ y
+    st["Sxx0"] = st["lam0"] * st["Sxx0"] + xx
+    st["Sxy0"] = st["lam0"] * st["Sxy0"] + xy
+    st["Sxx1"] = st["lam1"] * st["Sxx1"] + xx
+    st["Sxy1"] = st["lam1"] * st["Sxy1"] + xy
+    return st

@@ -104,6 +104,10 @@ _SIGS = {
     "scv_optim_step": (C.c_int, [C.POINTER(OptimT), _vp]),
     "scv_mi_loss": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "scv_mi_update": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _vp, _vp]),
+    "scv_mals_solve": (C.c_int, [_vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "scv_mals_loss": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "scv_mals_finalize": (C.c_int, [_vp, _vp, _vp, _f64, _f64, _i64, _vp, _vp]),
+    "scv_mals_update": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scv_gen_features": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "scv_zero": (C.c_int, [_vp, _i64, _vp]),
     "scv_sumsq_packed": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
@@ -298,6 +302,25 @@ class CudaOps:
     def mi_update(self, mu, L, var, var_ld, xs, ys, var_s, logAx, bandwidth, S, z, dy, valid=None):
         self._check(self.lib.scv_mi_update(_ptr(mu), _ptr(L), _ptr(var), var_ld, _ptr(xs), _ptr(ys), _ptr(var_s), _ptr(logAx),
                                            float(bandwidth), S, z, dy, _ptr(valid), self._stream()), "scv_mi_update")
+
+    def mals_solve(self, Sxx0, Sxy0, Sxx1, Sxy1, l2_reg, bias, nx, ny, W0, W1):
+        self._check(self.lib.scv_mals_solve(_ptr(Sxx0), _ptr(Sxy0), _ptr(Sxx1), _ptr(Sxy1), float(l2_reg), int(bias), nx, ny,
+                                            _ptr(W0), _ptr(W1), self._stream()), "scv_mals_solve")
+
+    def mals_loss(self, mu, mu_ld, y, y_ld, W0, W1, bias, B, z, ny, l01=None, yhat0=None, yhat1=None, gscale=None, dmu=None,
+                  d_ld=0):
+        self._check(self.lib.scv_mals_loss(_ptr(mu), mu_ld, _ptr(y), y_ld, _ptr(W0), _ptr(W1), int(bias), B, z, ny, _ptr(l01),
+                                           _ptr(yhat0), _ptr(yhat1), _ptr(gscale), _ptr(dmu), d_ld, self._stream()),
+                    "scv_mals_loss")
+
+    def mals_finalize(self, l01, lam0, lam1, delta, lamdiff, B, loss=None):
+        self._check(self.lib.scv_mals_finalize(_ptr(l01), _ptr(lam0), _ptr(lam1), float(delta), float(lamdiff), B, _ptr(loss),
+                                               self._stream()), "scv_mals_finalize")
+
+    def mals_update(self, mu, mu_ld, y, y_ld, bias, B, z, ny, lam0, lam1, Sxx0, Sxy0, Sxx1, Sxy1):
+        self._check(self.lib.scv_mals_update(_ptr(mu), mu_ld, _ptr(y), y_ld, int(bias), B, z, ny, _ptr(lam0), _ptr(lam1),
+                                             _ptr(Sxx0), _ptr(Sxy0), _ptr(Sxx1), _ptr(Sxy1), self._stream()),
+                    "scv_mals_update")
 
     def gen_features(self, xh, ld, root_hat, offsets, tree, n_tree, parts, B, W, J, norm=None, pose_out=None, heading=None,
                      avg3=None):

@@ -558,6 +558,13 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub == 2 ? sj : acc) * kMaxBN;
       for (int c0 = h * 32; c0 < ncols; c0 += kColStep) {
+        // the bias columns of this lane: loaded BEFORE the TMEM read so that the global-load latency hides behind it
+        // (ncu: the first FFMA of every chunk sat ~500 cycles on this load)
+        const int cc = c0 + cq * 4;
+        const int n = n0 + cc;
+        const bool col_ok = cc < ncols;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok && n < p.bias_n && ks == 0) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (n % p.bias_mod)));
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
@@ -574,11 +581,6 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
           xp4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         __syncwarp();
-        const int cc = c0 + cq * 4;
-        const int n = n0 + cc;
-        const bool col_ok = cc < ncols;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok && n < p.bias_n && ks == 0) bv = __ldg(reinterpret_cast<const float4*>(p.bias + (n % p.bias_mod)));
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
         const bool rd = p.R != nullptr;
         // one instantiation per (activation, residual, sums, rounding) combination the step uses: the per-element
@@ -1253,13 +1255,15 @@ int wgrad_tc(const scv_wgrad_t* p, cudaStream_t st) {
   q.work = nullptr;
   q.trace = nullptr;
   if (const char* tr = getenv("SCV_TC_TRACE")) q.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 10));
-  choose_box(p->Lo, p->B, bf16 ? 64 : 32, bf16 ? 16 : 8, q.bl, q.nb);
+  const int wrows_env = [] { const char* e = getenv("SCV_TC_WROWS"); return e ? atoi(e) : 0; }();  // experiments
+  choose_box(p->Lo, p->B, wrows_env >= 8 ? wrows_env : (bf16 ? 64 : 32), bf16 ? 16 : 8, q.bl, q.nb);
   q.lt = (int)cdiv(p->Lo, q.bl);
   q.bt = (int)cdiv(p->B, q.nb);
   q.groups = q.lt * q.bt;
   // k tile: whole 32-float slabs (the TMA box counts slabs), balanced over the tiles
   const int k32 = (int)cdiv(p->K, SW) * SW;
-  const int kt0 = (int)cdiv(k32, bf16 ? 192 : kWgradMaxBNK);
+  const int wbnk_env = [] { const char* e = getenv("SCV_TC_WBNK"); return e ? atoi(e) : 0; }();  // experiments
+  const int kt0 = (int)cdiv(k32, wbnk_env >= 32 ? wbnk_env : (bf16 ? 192 : kWgradMaxBNK));
   q.bnk = (int)cdiv(cdiv(k32, kt0), SW) * SW;
   q.k_tiles = (int)cdiv(p->K, q.bnk);
   // two n tiles per item (sharing the A slabs) measured 7-10 % SLOWER than one on every large layer

@@ -290,6 +290,15 @@ class Engine:
         self.gr_keys: List[str] = []
         self.gr_layers: Dict[str, List[List[GemmW]]] = {}
         self.gr_alpha: Dict[str, float] = {}
+        # moving-average least-squares scrubbers (model/disentangle.py:393-538): running covariances live in the modules'
+        # buffers (state_dict keys as in the reference); the kernels read and update them in place
+        self.mals_keys: List[str] = []
+        self.mals_mod: Dict[str, nn.Module] = {}
+        if "moving_avg_lsq" in m.disentangle:
+            for key, mod in m.disentangle["moving_avg_lsq"].items():
+                self.mals_keys.append(key)
+                self.mals_mod[key] = mod
+                mod._ops = self.ops
         if "grad_reversal" in m.disentangle:
             for key, scr in m.disentangle["grad_reversal"].items():
                 self.gr_keys.append(key)
@@ -511,15 +520,25 @@ class Plan:
         self.loss_names = ["jpe", "root", "prior"] + [kk + "_gr" for kk in eng.gr_keys]
         if eng.cond_dim > 0:
             self.loss_names.append("mcmi")  # kernel mutual-information scrubbing loss (needs conditioning variables)
+        self.loss_names += [kk + "_mals" for kk in eng.mals_keys]
         self.mi = None  # estimator buffers, allocated by enable_mcmi()
         nl = len(self.loss_names)
         nbn = sum(mod.num_features for mod in m.modules() if isinstance(mod, nn.BatchNorm1d))
         n_stats, n_sums = 4 * nbn + 8, 2 * nbn + 2 * ch[0] + 64
         # every per-step accumulator in ONE buffer: [BN statistics | BN backward sums | loss terms | grad norm^2];
         # the fused step clears it with one memset, the piecewise API path clears the parts as it reaches them
-        self.zbuf = torch.zeros(n_stats + n_sums + nl + 1, dtype=torch.double, device=dev)
+        n_mals = 2 * len(eng.mals_keys)  # squared-error sums of the two decoders of every moving_avg_lsq scrubber
+        self.zbuf = torch.zeros(n_stats + n_sums + nl + 1 + n_mals, dtype=torch.double, device=dev)
         self.loss_acc = self.zbuf[n_stats + n_sums:n_stats + n_sums + nl]
-        self.sumsq = self.zbuf[n_stats + n_sums + nl:]
+        self.sumsq = self.zbuf[n_stats + n_sums + nl:n_stats + n_sums + nl + 1]
+        self.mals_l01 = self.zbuf[n_stats + n_sums + nl + 1:]
+        self.mals = {}
+        for key in eng.mals_keys:
+            mod = eng.mals_mod[key]
+            nxm, nym = mod.Sxy0.shape
+            self.mals[key] = dict(mod=mod, nx=nxm, ny=nym, bias=bool(mod.bias), W0=torch.zeros(nxm, nym, **f32),
+                                  W1=torch.zeros(nxm, nym, **f32), yhat0=torch.zeros(B, nym, **f32),
+                                  yhat1=torch.zeros(B, nym, **f32), y=torch.zeros(B, nym, **f32))
         self._fused_tail = False  # True while TrainStep drives the plan (see TrainStep._sequence)
         self.loss_out = torch.zeros(nl + 1, **f32)
         self.anchor = torch.zeros((), device=dev, requires_grad=True)  # autograd attachment point
@@ -693,6 +712,8 @@ class Plan:
                             self.var if eng.cond_dim > 0 else None, eng.cond_dim, self.mu, self.Lmat, self.zc,
                             eng.zc_ld, B, z, round_tf32=rnd)
         F.append(reparam)
+        for key in eng.mals_keys:  # moving_avg_lsq: decoder weights from the running covariances, predictions from mu
+            F.append(lambda key=key: self._mals_forward(key))
         self._n_enc = len(F)
 
         # =============================================================== decoder
@@ -834,6 +855,8 @@ class Plan:
                 preds, None, ld, self.gr_target.get(key), self.gr_labels.get(key), B, self.gr_dim[key],
                 len(eng.gr_keys), Ref(self.loss_acc, 3 + ki), None))
         Lk.append(lambda: self._mi_launch(loss=True))
+        for ki, key in enumerate(eng.mals_keys):
+            Lk.append(lambda key=key, ki=ki: self._mals_loss(key, ki))
         Lk.append(lambda: ops.loss_finalize(self.loss_acc, self.loss_scale, self.loss_out, nl))
         self.Lk = Lk
 
@@ -944,6 +967,8 @@ class Plan:
         self.dms = torch.zeros(B * eng.ms_ld + 64, **opd)[:B * eng.ms_ld].view(B, eng.ms_ld)
         Bw.append(lambda: ops.kl(self.mu, self.Lmat, None, Ref(self.gscale, 2), self.dmu_kl, self.dL_kl, B, z))
         Bw.append(lambda: self._mi_launch(loss=False))  # adds d mcmi / d mu into dmu_kl
+        for ki, key in enumerate(eng.mals_keys):  # adds d <key>_mals / d mu into dmu_kl
+            Bw.append(lambda key=key, ki=ki: self._mals_backward(key, ki))
         Bw.append(lambda: ops.reparam_bwd(self.ms, eng.ms_ld, self.eps, self.dmu_kl, self.dmu_gr, 1.0, self.dzc,
                                           eng.zc_ld, self.dL_kl, self.dms, eng.ms_ld, B, z, round_tf32=rnd))
         Bw.append(wgrad(gfc, Hflat.at(0), Hflat.bs, 0, 1, self.dms, eng.ms_ld, 0))
@@ -997,6 +1022,39 @@ class Plan:
         # public-API path only: weight gradients back into the reference layout (p.grad views of gflat)
         Bw.append(lambda: None if self._fused_tail else ops.gather(eng.gpacked, eng.inv_idx, eng.gflat, eng.n_flat, True))
         self.Bw = Bw
+
+    # ------------------------------------------------------------------ moving_avg_lsq (MovingAvgLeastSquares)
+    def _mals_forward(self, key):
+        """reference model/disentangle.py:466-487 (forward): W_i = solve(Sxx_i + l2, Sxy_i), yhat_i = [mu | 1] W_i"""
+        st, ops, z = self.mals[key], self.eng.ops, self.eng.m.z_dim
+        mod = st["mod"]
+        ops.mals_solve(mod.Sxx0, mod.Sxy0, mod.Sxx1, mod.Sxy1, mod.l2_reg, st["bias"], st["nx"], st["ny"], st["W0"], st["W1"])
+        ops.mals_loss(self.mu, z, st["y"], st["ny"], st["W0"], st["W1"], st["bias"], self.B, z, st["ny"],
+                      yhat0=st["yhat0"], yhat1=st["yhat1"])
+
+    def _mals_loss(self, key, ki):
+        """evaluate_loss (:505-538) / batch_size (train/losses.py:237-245); also moves the forgetting factors"""
+        st, ops, z = self.mals[key], self.eng.ops, self.eng.m.z_dim
+        mod = st["mod"]
+        if not self._fused_tail:
+            self.mals_l01[2 * ki:2 * ki + 2].zero_()
+        l01 = Ref(self.mals_l01, 2 * ki)
+        ops.mals_loss(self.mu, z, st["y"], st["ny"], st["W0"], st["W1"], st["bias"], self.B, z, st["ny"], l01=l01)
+        ops.mals_finalize(l01, mod.lam0, mod.lam1, mod.delta, mod.lamdiff, self.B,
+                          loss=Ref(self.loss_acc, self.loss_names.index(key + "_mals")))
+
+    def _mals_backward(self, key, ki):
+        st, ops, z = self.mals[key], self.eng.ops, self.eng.m.z_dim
+        ops.mals_loss(self.mu, z, st["y"], st["ny"], st["W0"], st["W1"], st["bias"], self.B, z, st["ny"],
+                      gscale=Ref(self.gscale, self.loss_names.index(key + "_mals")), dmu=self.dmu_kl, d_ld=z)
+
+    def mals_update(self):
+        """MovingAvgLeastSquares.update (:489-503) with this step's mu and targets (train/trainer.py:169-178)"""
+        ops, z = self.eng.ops, self.eng.m.z_dim
+        for key, st in self.mals.items():
+            mod = st["mod"]
+            ops.mals_update(self.mu, z, st["y"], st["ny"], st["bias"], self.B, z, st["ny"], mod.lam0, mod.lam1, mod.Sxx0,
+                            mod.Sxy0, mod.Sxx1, mod.Sxy1)
 
     # ------------------------------------------------------------------ mcmi (MutInfoEstimator)
     def enable_mcmi(self, bandwidth: float, var_mode: str = "sphere"):
@@ -1071,6 +1129,8 @@ class Plan:
                 torch.cat(parts, dim=-1, out=self.var)
 
     def load_targets(self, data):
+        for key, st in self.mals.items():
+            st["y"].copy_(data[key].reshape(st["y"].shape), non_blocking=True)
         for key in self.eng.gr_keys:
             if key == "ids":
                 self.gr_labels[key].copy_(data[key].ravel(), non_blocking=True)
@@ -1131,6 +1191,8 @@ class Plan:
             if eng.gr_keys:
                 out["disentangle"]["grad_reversal"] = {
                     key: [a[-1][0].t[:, :self.gr_dim[key]] for a in self.gr_act[key]] for key in eng.gr_keys}
+            if eng.mals_keys:
+                out["disentangle"]["moving_avg_lsq"] = {key: [st["yhat0"], st["yhat1"]] for key, st in self.mals.items()}
             out["_plan"] = self
         return out
 
@@ -1349,6 +1411,8 @@ class TrainStep:
                 ops.gather(eng.gpacked, eng.inv_idx, eng.gflat, eng.n_flat, True)
                 ops.sumsq(eng.gflat, eng.n_flat, plan.sumsq)
                 ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, eng.n_flat, plan.sumsq, *hp, hyper=opt.hyper)
+            if plan.mals:  # running covariances of the moving_avg_lsq scrubbers: this step's mu (train/trainer.py:169-178)
+                plan.mals_update()
             if self.mi is not None:
                 # updated encode (train mode: batch statistics again, running statistics advance a second time, as the
                 # reference's model.encode(data) does) -> new stored samples of the estimator

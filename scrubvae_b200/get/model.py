@@ -1,5 +1,5 @@
 """`scrubvae_b200.get.model` — same signature and semantics as the reference factory
-get/model.py:4-151, restricted to the methods on the built hot path (conditional + grad_reversal)."""
+get/model.py:4-151, restricted to the methods on the built path (conditional, grad_reversal, moving_avg_lsq)."""
 import torch
 
 
@@ -20,7 +20,7 @@ def model(model_config, load_model, epoch, disentangle_config, n_keypts, directi
 
     methods = disentangle_config["method"]
     for m in methods:
-        if m not in ("conditional", "grad_reversal"):
+        if m not in ("conditional", "grad_reversal", "moving_avg_lsq"):
             raise NotImplementedError(
                 f"scrubvae_b200.get.model: method '{m}' is outside the built hot path (SURVEY.md §8)")
     disentangle = {}
@@ -37,6 +37,14 @@ def model(model_config, load_model, epoch, disentangle_config, n_keypts, directi
         for feat in methods["grad_reversal"]:
             disentangle["grad_reversal"][feat] = GRScrubber(
                 model_config["z_dim"], feat_dim_dict[feat], alpha=disentangle_config["alpha"], bound=bound)
+
+    if "moving_avg_lsq" in methods.keys():  # reference get/model.py:73-85
+        from ..model.disentangle import MovingAvgLeastSquares
+        disentangle["moving_avg_lsq"] = {}
+        for feat in methods["moving_avg_lsq"]:
+            disentangle["moving_avg_lsq"][feat] = MovingAvgLeastSquares(
+                model_config["z_dim"], feat_dim_dict[feat], bias=loss_config[feat + "_mals"] < 0,
+                polynomial_order=disentangle_config["polynomial"], l2_reg=disentangle_config["l2_reg"])
 
     if model_config["type"] != "rcnn":
         raise NotImplementedError("scrubvae_b200.get.model: only model type 'rcnn' exists (as in the reference)")

@@ -83,3 +83,70 @@ class MutInfoEstimator(nn.Module):
         ops.mi_loss(x, y, y.shape[1], self.x_s, self.y_s, self.var_s if self.var_mode == "diagonal" else None, self.logA_x,
                     self.gamma, self.num_s, x.shape[0], self.x_dim, self.y_dim, loss=out)
         return out[0].float()
+
+
+class MovingAvgLeastSquares(nn.Module):
+    """Reference model/disentangle.py:393-538, polynomial order 1: two linear decoders of the scrubbed variable from the
+    latent mean, fitted by exponentially weighted least squares with forgetting factors lam0 < lam1 that drift towards the
+    better one.  Same constructor, buffers (Sxx0, Sxy0, Sxx1, Sxy1, lam0, lam1: the reference's state_dict keys) and
+    methods; the solve, the predictions, the loss with its gradient into mu, the forgetting-factor rule and the covariance
+    update run in csrc/scv_mals.cu, sequenced by the engine for the training step.  The standalone methods below use the
+    same kernels (ops handed over by the engine that owns the model)."""
+
+    def __init__(self, nx, ny, lamdiff=1e-1, delta=1e-4, bias=False, polynomial_order=1, l2_reg=0):
+        super().__init__()
+        if polynomial_order != 1:
+            raise NotImplementedError("scrubvae_b200: moving_avg_lsq is built for polynomial order 1 "
+                                      "(order 2 is a 2145 x 2145 solve per step: SURVEY.md §8(f) rank 4, not built)")
+        self.bias = bool(bias)
+        self.polynomial_order = polynomial_order
+        self.z = int(nx)
+        nx = int(nx) + int(self.bias)
+        if nx > 136 or ny > 16:
+            raise NotImplementedError("scrubvae_b200: moving_avg_lsq kernels hold z <= 135 (+ bias) and ny <= 16")
+        self.l2_reg = 0 if l2_reg is None else l2_reg
+        print("Moving Avg Least Squares Bias: {}".format(self.bias))
+        self.register_buffer("Sxx0", torch.eye(nx))
+        self.register_buffer("Sxy0", torch.zeros(nx, ny))
+        self.register_buffer("Sxx1", torch.eye(nx))
+        self.register_buffer("Sxy1", torch.zeros(nx, ny))
+        self.register_buffer("lam0", torch.tensor([0.9]))
+        self.register_buffer("lam1", torch.tensor([0.9]) + lamdiff)
+        self.delta = delta
+        self.lamdiff = lamdiff
+        self._ops = None
+        self._l01 = None
+
+    def _need_ops(self):
+        if self._ops is None:
+            from .._ops import get_ops
+            self._ops = get_ops()
+        return self._ops
+
+    def forward(self, x):
+        ops = self._need_ops()
+        B, ny = x.shape[0], self.Sxy0.shape[1]
+        x = x.detach().to(torch.float32).contiguous()
+        W0, W1 = torch.empty_like(self.Sxy0), torch.empty_like(self.Sxy1)
+        ops.mals_solve(self.Sxx0, self.Sxy0, self.Sxx1, self.Sxy1, self.l2_reg, self.bias, self.Sxx0.shape[0], ny, W0, W1)
+        y0, y1 = torch.zeros(B, ny, device=x.device), torch.zeros(B, ny, device=x.device)
+        ops.mals_loss(x, x.shape[1], y0, ny, W0, W1, self.bias, B, self.z, ny, yhat0=y0, yhat1=y1)  # y0 doubles as a dummy y
+        return [y0, y1]
+
+    def update(self, x, y):
+        ops = self._need_ops()
+        x = x.detach().to(torch.float32).contiguous()
+        y = y.detach().to(torch.float32).reshape(x.shape[0], -1).contiguous()
+        ops.mals_update(x, x.shape[1], y, y.shape[1], self.bias, x.shape[0], self.z, y.shape[1], self.lam0, self.lam1,
+                        self.Sxx0, self.Sxy0, self.Sxx1, self.Sxy1)
+        return self
+
+    def evaluate_loss(self, yhat0, yhat1, y):
+        """Sum of squared errors of the two decoders, averaged; moves lam0 / lam1 (reference :505-538).  No gradient: the
+        training path gets d loss / d mu from the engine's backward."""
+        ops = self._need_ops()
+        y = y.detach().to(torch.float32).reshape(yhat0.shape)
+        l01 = torch.stack([((y - yhat0.detach()).double() ** 2).sum(), ((y - yhat1.detach()).double() ** 2).sum()])
+        out = torch.zeros(1, dtype=torch.double, device=y.device)
+        ops.mals_finalize(l01, self.lam0, self.lam1, self.delta, self.lamdiff, 1, loss=out)
+        return out[0].to(torch.float32)

@@ -242,6 +242,9 @@ def train_test_epoch(config, model, loader, device, epoch, optimizer=None, sched
                 optimizer.step()
                 if scheduler is not None:
                     scheduler.step(epoch + batch_idx / len(loader))
+                # reference :169-178: running covariances of the moving-average scrubbers, from this batch's mu
+                if "moving_avg_lsq" in model.disentangle.keys():
+                    data_o["_plan"].mals_update()
             epoch_metrics = {k: v + batch_loss[k].detach() for k, v in epoch_metrics.items()}
             if "mcmi" in config["loss"].keys():  # reference :184-199: estimator rebuilt from the updated encoder
                 from ..model.disentangle import MutInfoEstimator

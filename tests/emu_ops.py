@@ -529,6 +529,67 @@ class EmuOps:
         if valid is not None:
             _v(valid, (1,), (1,)).fill_(1.0)
 
+    # ---- moving_avg_lsq scrubber (reference model/disentangle.py:393-538, polynomial order 1)
+    @staticmethod
+    def _mals_x(mu, mu_ld, bias, B, z):
+        x = _v(mu, (B, z), (mu_ld, 1))
+        return torch.cat([x, torch.ones(B, 1, dtype=x.dtype)], 1) if bias else x
+
+    def mals_solve(self, Sxx0, Sxy0, Sxx1, Sxy1, l2_reg, bias, nx, ny, W0, W1):
+        self.n += 1
+        l2 = torch.ones(nx) * l2_reg
+        if bias:
+            l2[-1] = 0
+        for Sxx, Sxy, W in ((Sxx0, Sxy0, W0), (Sxx1, Sxy1, W1)):
+            A = _v(Sxx, (nx, nx), (nx, 1))
+            A = A.diagonal_scatter(A.diagonal() + l2)
+            _v(W, (nx, ny), (ny, 1)).copy_(torch.linalg.solve(A, _v(Sxy, (nx, ny), (ny, 1))))
+
+    def mals_loss(self, mu, mu_ld, y, y_ld, W0, W1, bias, B, z, ny, l01=None, yhat0=None, yhat1=None, gscale=None, dmu=None,
+                  d_ld=0):
+        self.n += 1
+        nx = z + (1 if bias else 0)
+        x = self._mals_x(mu, mu_ld, bias, B, z)
+        Y = _v(y, (B, ny), (y_ld, 1))
+        w0, w1 = _v(W0, (nx, ny), (ny, 1)), _v(W1, (nx, ny), (ny, 1))
+        p0, p1 = x @ w0, x @ w1
+        if l01 is not None:
+            acc = _v(l01, (2,), (1,))
+            acc[0] += ((Y - p0).double() ** 2).sum()
+            acc[1] += ((Y - p1).double() ** 2).sum()
+        if yhat0 is not None:
+            _v(yhat0, (B, ny), (ny, 1)).copy_(p0)
+        if yhat1 is not None:
+            _v(yhat1, (B, ny), (ny, 1)).copy_(p1)
+        if dmu is not None:
+            g = float(_v(gscale, (1,), (1,))) / B
+            _v(dmu, (B, z), (d_ld, 1)).add_(g * ((p0 - Y) @ w0[:z].T + (p1 - Y) @ w1[:z].T))
+
+    def mals_finalize(self, l01, lam0, lam1, delta, lamdiff, B, loss=None):
+        self.n += 1
+        acc = _v(l01, (2,), (1,))
+        a0, a1 = _v(lam0, (1,), (1,)), _v(lam1, (1,), (1,))
+        if float(acc[0].float()) < float(acc[1].float()):
+            a0.copy_(torch.clamp(a0 - delta, 0.0, 1.0))
+            a1.copy_(a0 + lamdiff)
+        else:
+            a1.copy_(torch.clamp(a1 + delta, 0.0, 1.0))
+            a0.copy_(a1 - lamdiff)
+        if loss is not None:
+            _v(loss, (1,), (1,)).add_((acc[0] + acc[1]) * 0.5 / B)
+
+    def mals_update(self, mu, mu_ld, y, y_ld, bias, B, z, ny, lam0, lam1, Sxx0, Sxy0, Sxx1, Sxy1):
+        self.n += 1
+        nx = z + (1 if bias else 0)
+        x = self._mals_x(mu, mu_ld, bias, B, z)
+        Y = _v(y, (B, ny), (y_ld, 1))
+        xx, xy = x.T @ x, x.T @ Y
+        for lam, Sxx, Sxy in ((lam0, Sxx0, Sxy0), (lam1, Sxx1, Sxy1)):
+            a = float(_v(lam, (1,), (1,)))
+            A, Bm = _v(Sxx, (nx, nx), (nx, 1)), _v(Sxy, (nx, ny), (ny, 1))
+            A.copy_(a * A + xx)
+            Bm.copy_(a * Bm + xy)
+
     def gen_features(self, xh, ld, root_hat, offsets, tree, n_tree, parts, B, W, J, norm=None, pose_out=None, heading=None,
                      avg3=None):
         """eval/eval.py:58-118 (FK through the oracle's fwd_kin, then the feature formulas)"""

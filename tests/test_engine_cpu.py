@@ -422,3 +422,84 @@ def test_mcmi_epoch_matches_reference(var_mode):
                 # into +-lr steps, and the post-step encode() folds those arbitrary bias shifts into running_mean
                 continue
             assert _rel(osd[k].float(), rsd[k].float()) < 5e-3 or ZERO_GRAD_BIAS.search(k), (fused, k)
+
+
+@pytest.mark.parametrize("l2_reg", [0, 0.05])
+def test_moving_avg_lsq_epoch_matches_reference(l2_reg):
+    """The moving_avg_lsq scrubber (MovingAvgLeastSquares, reference model/disentangle.py:393-538, polynomial order 1)
+    through train_test_epoch: normal-equation solve of both decoders, predictions in data_o, <key>_mals loss with its
+    gradient into mu, forgetting-factor drift, covariance update after the optimizer step (trainer.py:169-178) — epoch
+    metrics, final weights AND the scrubber's buffers against the live reference, piecewise and fused.
+    (bias=False: the reference's bias branch hard-codes device="cuda" in update(); the GPU suite covers bias=True.)"""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference not importable here")
+    import contextlib, io
+    rsv = refimport.import_reference()
+    from scrubvae.train import trainer as rtr
+    ch, zd, B = [8, 16, 32], 8, 6
+    mc = dict(type="rcnn", channel=list(ch), kernel=5, z_dim=zd, window=51, activation="prelu", diag=False,
+              init_dilation=None, prior="gaussian", load_model=None, start_epoch=None)
+    dc = dict(method={"conditional": ["heading"], "moving_avg_lsq": ["heading"]}, features=["heading"], alpha=1.0,
+              polynomial=1, l2_reg=l2_reg)
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "heading_mals": 0.7}
+    torch.manual_seed(11)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = rsv.get.model(mc, None, None, dc, 18, "midfwd", loss_config=scale, arena_size=torch.tensor(orc.ARENA),
+                            kinematic_tree=orc.KINEMATIC_TREE, discrete_classes={}, device="cpu", verbose=0)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    batches = [{k: v for k, v in orc.synth_batch(B, seed=30 + i).items() if k in ("x6d", "root", "offsets", "target_pose", "heading")}
+               for i in range(4)]
+    noise = [orc.synth_eps(B, zd, seed=50 + i) for i in range(4)]
+    it = iter(noise)
+    orig = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: next(it).to(t)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ropt, _ = rtr.get_optimizer_and_lr_scheduler(ref, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
+            mref = rtr.train_test_epoch({"loss": dict(scale), "disentangle": dc}, ref, batches, "cpu", 1, optimizer=ropt,
+                                        scheduler=None, mode="train")
+    finally:
+        torch.randn_like = orig
+    rsd = ref.state_dict()
+    assert "disentangle.moving_avg_lsq.heading.Sxx0" in rsd
+    for fused in (False, True):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = sv.get.model(mc, None, None, dc, 18, "midfwd", loss_config=scale, arena_size=torch.tensor(orc.ARENA),
+                             kinematic_tree=orc.KINEMATIC_TREE, discrete_classes={}, device="cpu", verbose=0)
+        m.precision = "fp32"
+        assert set(m.state_dict().keys()) == set(sd.keys())
+        m.load_state_dict(sd)
+        m._engine = Engine(m, ops=EmuOps())
+        m.train()
+        opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
+        cfg = {"loss": dict(scale), "disentangle": dc, "train": {}}
+        if fused:
+            from scrubvae_b200.engine import TrainStep
+            st = TrainStep(m, opt, scale, B, use_graph=False, resident=True)
+            tot = None
+            for i, b in enumerate(batches):
+                m._noise = noise[i]
+                v = st.run(b).clone()
+                tot = v if tot is None else tot + v
+            st.sync()
+            mo = {n: float(tot[j]) / len(batches) for j, n in enumerate(st.plan.loss_names)}
+            mo["total"] = float(tot[-1]) / len(batches)
+        else:
+            seq = iter(noise)
+
+            def cb(i, vec):
+                m._noise = next(seq, None)
+            m._noise = next(seq)
+            with contextlib.redirect_stdout(io.StringIO()):
+                mo = sv.train.train_test_epoch(cfg, m, batches, "cpu", 1, optimizer=opt, scheduler=None, mode="train",
+                                               step_callback=cb)
+        for k in mref:
+            assert abs(mo[k] - mref[k]) <= 3e-5 * abs(mref[k]) + 1e-6, (fused, k, mo[k], mref[k])
+        osd = m.state_dict()
+        for k in rsd:
+            if k.endswith("running_mean"):
+                continue  # zero-true-gradient conv biases take +-lr Adam steps on rounding noise and shift the batch means
+            tol = 2e-4 if "moving_avg_lsq" in k else 5e-3
+            assert _rel(osd[k].float(), rsd[k].float()) < tol or ZERO_GRAD_BIAS.search(k), (fused, k, _rel(osd[k].float(), rsd[k].float()))
+        assert abs(float(osd["disentangle.moving_avg_lsq.heading.lam1"]) - float(rsd["disentangle.moving_avg_lsq.heading.lam1"])) < 1e-6

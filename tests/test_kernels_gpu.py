@@ -371,6 +371,35 @@ def test_resident_packed_optimizer(ops, kind, rnd, bf16):
             assert torch.equal(gpu[k].cpu()[dead], T[k][dead]), k
 
 
+@pytest.mark.parametrize("z,ny,bias,l2", [(64, 2, True, 0.0), (128, 3, True, 0.05), (8, 2, False, 0.01), (64, 16, False, 0.0)])
+def test_moving_avg_lsq_kernels(ops, z, ny, bias, l2):
+    """scv_mals_solve / loss / finalize / update (csrc/scv_mals.cu) against the torch emulation (torch.linalg.solve):
+    well-conditioned running covariances as they look after a few hundred updates."""
+    B, nx = 300, z + int(bias)
+    gg = g(7)
+    X = torch.randn(900, nx, generator=gg)
+    if bias:
+        X[:, -1] = 1.0
+    Wt = torch.randn(nx, ny, generator=gg)
+    Yt = X @ Wt + 0.1 * torch.randn(900, ny, generator=gg)
+    T = {"Sxx0": 0.5 * torch.eye(nx) + X[:600].T @ X[:600], "Sxy0": X[:600].T @ Yt[:600],
+         "Sxx1": 0.7 * torch.eye(nx) + X.T @ X, "Sxy1": X.T @ Yt,
+         "W0": torch.zeros(nx, ny), "W1": torch.zeros(nx, ny), "mu": torch.randn(B, z, generator=gg),
+         "y": torch.randn(B, ny, generator=gg), "l01": torch.zeros(2, dtype=torch.double), "yh0": torch.zeros(B, ny),
+         "yh1": torch.zeros(B, ny), "gs": torch.tensor([0.37]), "dmu": torch.randn(B, z, generator=gg),
+         "lam0": torch.tensor([0.9]), "lam1": torch.tensor([1.0]), "loss": torch.zeros(1, dtype=torch.double)}
+    T["y"] = (torch.cat([T["mu"], torch.ones(B, 1)], 1) if bias else T["mu"]) @ Wt + 0.3 * T["y"]
+
+    def call(o, t):
+        o.mals_solve(t["Sxx0"], t["Sxy0"], t["Sxx1"], t["Sxy1"], l2, bias, nx, ny, t["W0"], t["W1"])
+        o.mals_loss(t["mu"], z, t["y"], ny, t["W0"], t["W1"], bias, B, z, ny, l01=t["l01"], yhat0=t["yh0"], yhat1=t["yh1"])
+        o.mals_loss(t["mu"], z, t["y"], ny, t["W0"], t["W1"], bias, B, z, ny, gscale=t["gs"], dmu=t["dmu"], d_ld=z)
+        o.mals_finalize(t["l01"], t["lam0"], t["lam1"], 1e-4, 0.1, B, loss=t["loss"])
+        o.mals_update(t["mu"], z, t["y"], ny, bias, B, z, ny, t["lam0"], t["lam1"], t["Sxx0"], t["Sxy0"], t["Sxx1"], t["Sxy1"])
+    run_both(ops, T, call, tol=2e-4, check=["W0", "W1", "yh0", "yh1", "l01", "dmu", "loss"])
+    run_both(ops, T, call, tol=1e-5, check=["lam0", "lam1", "Sxx0", "Sxy0", "Sxx1", "Sxy1"])
+
+
 def test_library_fails_loudly_when_missing(tmp_path):
     from scrubvae_b200 import _ops
     with pytest.raises(RuntimeError, match="no CPU fallback"):

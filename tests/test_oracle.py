@@ -136,3 +136,32 @@ def test_known_answers():
                        out["root"].reshape(-1, 3)).reshape(-1, 51, 18, 3)
     f = pose[:, 25, 1] - pose[:, 25, 0]
     assert torch.atan2(f[:, 1], f[:, 0]).abs().max() < 1e-4  # mid-frame SpineM->SpineF faces +x
+
+
+def test_oracle_moving_avg_lsq_matches_live_reference():
+    """oracle.mals_* against the reference's MovingAvgLeastSquares (model/disentangle.py:393-538) over a short sequence of
+    forward / evaluate_loss / update calls (bias=False: the reference's bias branch is CUDA-only)."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference not importable here")
+    import contextlib, io
+    refimport.import_reference()
+    from scrubvae.model.disentangle import MovingAvgLeastSquares
+    z, ny, B = 8, 2, 16
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = MovingAvgLeastSquares(z, ny, bias=False, polynomial_order=1, l2_reg=0.01)
+    st = orc.mals_init(z, ny)
+    g = torch.Generator().manual_seed(3)
+    Wtrue = torch.randn(z, ny, generator=g)
+    for i in range(5):
+        mu = torch.randn(B, z, generator=g)
+        y = mu @ Wtrue + 0.1 * torch.randn(B, ny, generator=g)
+        r0, r1 = ref(mu)
+        o0, o1, _, _ = orc.mals_forward(st, mu, False, 0.01)
+        assert torch.allclose(r0, o0, rtol=1e-5, atol=1e-6) and torch.allclose(r1, o1, rtol=1e-5, atol=1e-6)
+        lr_, lo = ref.evaluate_loss(r0, r1, y), orc.mals_evaluate(st, o0, o1, y)
+        assert torch.allclose(lr_, lo, rtol=1e-5)
+        ref.update(mu, y)
+        orc.mals_update(st, mu, y)
+        for k in ("Sxx0", "Sxy0", "Sxx1", "Sxy1", "lam0", "lam1"):
+            assert torch.allclose(getattr(ref, k), st[k], rtol=1e-5, atol=1e-6), (i, k)

@@ -19,10 +19,15 @@ for x in csv.DictReader(lines):
 starts = [i for i, r in enumerate(rows) if "pack_input" in r[1]]
 if len(starts) < 2:
     raise SystemExit("need at least two steps in the launch list")
-# a step = [noise draw, stats zeroing, counter add, weight repack] + pack_input ... optimizer
-PRE = 4
-s = starts[which] - PRE
-e = (starts[which + 1] - PRE) if which + 1 != 0 and which + 1 < len(starts) else len(rows)
+# a step = [noise draw, counter add, ... whatever precedes pack_input] + pack_input ... last optimizer launch:
+# it begins right after the previous step's last optimizer kernel
+def step_begin(i):
+    j = i - 1
+    while j >= 0 and "optim" not in rows[j][1]:
+        j -= 1
+    return j + 1 if j >= 0 else max(0, i - 4)
+s = step_begin(starts[which])
+e = step_begin(starts[which + 1]) if which + 1 != 0 and which + 1 < len(starts) else len(rows)
 step = rows[s:e]
 with open(out + "_step.csv", "w") as f:
     f.write("id,kernel,grid,block,us\n")
