@@ -289,6 +289,30 @@ int scv_mals_finalize(const double* l01, float* lam0, float* lam1, double delta,
 int scv_mals_update(const float* mu, int64_t mu_ld, const float* y, int64_t y_ld, int64_t bias, int64_t B, int64_t z, int64_t ny,
                     const float* lam0, const float* lam1, float* Sxx0, float* Sxy0, float* Sxx1, float* Sxy1, void* stream);
 
+/* ---- "qda" scrubber (QuadraticDiscriminantFilter model/disentangle.py:90-232; loss train/losses.py:247-251; update
+ * train/trainer.py:169-178).  Per class c (nc <= 16 labels in `classes`, int64) two one-vs-rest Gaussian classifiers A, B, each
+ * with (mean, covariance) of "label != c" (0) and "label == c" (1): m0a, m1a, m0b, m1b (nc,z), S0a, S1a, S0b, S1b (nc,z,z), z <= 128.
+ * scv_qda_factor: SinvT (4,nc,z,z) = transposed inverses (Gauss-Jordan, partial pivoting, fp32), logdet (4,nc) (NaN if det < 0).
+ * scv_qda_loss: x (B rows of x_ld), labels y (B, int64).  acc (double, 4 per class) += [lla, llb, llra, llrb] with
+ *   cgll_q(x) = -1/2 (logdet_q + (x - m_q)^T S_q^-1 (x - m_q)), lla = sum_b cgll_{[y_b == c] a}, llra = sum_b s_b (cgll_1a - cgll_0a),
+ *   s_b = +-1 (if acc != NULL); dx (B rows of d_ld) += gscale[0] / (2 nc B) sum_c s_b [(t_0a - t_1a) + (t_0b - t_1b)],
+ *   t_q = S_q^-1 (x_b - m_q) (if dx != NULL).
+ * scv_qda_finalize (evaluate_loss :173-232): per class lla > llb ? (lama = clamp(lama - delta), lamb = lama + lamdiff)
+ *   : (lamb = clamp(lamb + delta), lama = lamb - lamdiff); loss[0] += sum_c (llra + llrb) / 2 / nc / B (if loss != NULL).
+ * scv_qda_update (:133-171): class-conditional batch means and covariances (correction 0; an empty subset gives NaN, as
+ *   torch.mean of an empty selection) blended into the running buffers with lama (A) and lamb (B); stat: scratch of
+ *   2 nc (z + 1) floats. */
+int scv_qda_factor(const float* S0a, const float* S1a, const float* S0b, const float* S1b, int64_t nc, int64_t z, float* SinvT,
+                   float* logdet, void* stream);
+int scv_qda_loss(const float* x, int64_t x_ld, const int64_t* y, const int64_t* classes, const float* m0a, const float* m1a,
+                 const float* m0b, const float* m1b, const float* SinvT, const float* logdet, int64_t nc, int64_t z, int64_t B,
+                 double* acc, const float* gscale, float* dx, int64_t d_ld, void* stream);
+int scv_qda_finalize(const double* acc, float* lama, float* lamb, double delta, double lamdiff, int64_t nc, int64_t B, double* loss,
+                     void* stream);
+int scv_qda_update(const float* x, int64_t x_ld, const int64_t* y, const int64_t* classes, int64_t nc, int64_t z, int64_t B,
+                   const float* lama, const float* lamb, float* m0a, float* m1a, float* m0b, float* m1b, float* S0a, float* S1a,
+                   float* S0b, float* S1b, float* stat, void* stream);
+
 /* ---- generative restrictiveness (eval): reference eval/eval.py:22-120.  For B decoded windows (xh rows of ld floats: the
  * decoder output after tanh, 6-D channels first; root_hat (B*W,3) un-normalised root positions or NULL = 0; offsets
  * (B*W,J,3)): forward kinematics (fwd_kin_cont6d_torch data/dataset.py:83-116, eps 1e-8) and, per window,

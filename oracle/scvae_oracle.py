@@ -628,3 +628,53 @@ def mals_update(st, mu, y, bias=False):
     st["Sxx1"] = st["lam1"] * st["Sxx1"] + xx
     st["Sxy1"] = st["lam1"] * st["Sxy1"] + xy
     return st
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# qda scrubber (QuadraticDiscriminantFilter, reference model/disentangle.py:90-232)
+# --------------------------------------------------------------------------------------------------------------------
+def qda_init(z: int, n_classes: int, lamdiff: float = 1e-2) -> Dict[str, torch.Tensor]:
+    """buffers as registered by the reference constructor (:104-125)"""
+    st = {}
+    for name in ("0a", "1a", "0b", "1b"):
+        st["m" + name] = torch.zeros(n_classes, z)
+        st["S" + name] = torch.eye(z)[None, :].repeat(n_classes, 1, 1)
+    st["lama"] = torch.ones(n_classes) * 0.2
+    st["lamb"] = st["lama"] + lamdiff
+    return st
+
+
+def _cgll(x, m, S):
+    """Gaussian log likelihood up to a constant (:130-135)"""
+    r = x - m
+    return -0.5 * (torch.logdet(S) + torch.sum(r * torch.linalg.solve(S, r.T).T, axis=1))
+
+
+def qda_evaluate(st, x, y, classes, delta=1e-3, lamdiff=1e-2, update=True):
+    """evaluate_loss (:173-232): average log-likelihood ratio of the two classifiers; forgetting factors drift"""
+    loss = 0
+    for i, label in enumerate(classes):
+        i0, i1 = (y != label).ravel(), (y == label).ravel()
+        lla0, lla1 = _cgll(x, st["m0a"][i:i + 1], st["S0a"][i]), _cgll(x, st["m1a"][i:i + 1], st["S1a"][i])
+        llb0, llb1 = _cgll(x, st["m0b"][i:i + 1], st["S0b"][i]), _cgll(x, st["m1b"][i:i + 1], st["S1b"][i])
+        lla, llb = torch.sum(i0 * lla0 + i1 * lla1), torch.sum(i0 * llb0 + i1 * llb1)
+        if update and lla > llb:
+            st["lama"][i] = torch.clamp(st["lama"][i] - delta, 0.0, 1.0)
+            st["lamb"][i] = st["lama"][i] + lamdiff
+        elif update:
+            st["lamb"][i] = torch.clamp(st["lamb"][i] + delta, 0.0, 1.0)
+            st["lama"][i] = st["lamb"][i] - lamdiff
+        s = (i1 * 2 - 1).float()
+        loss = loss + (s @ (lla1 - lla0) + s @ (llb1 - llb0)) * 0.5
+    return loss / len(classes)
+
+
+def qda_update(st, x, y, classes):
+    """update (:137-171): class-conditional batch mean / covariance (correction 0) blended with lama (A) and lamb (B)"""
+    for i, label in enumerate(classes):
+        for side, sel in ((0, (y != label).ravel()), (1, (y == label).ravel())):
+            mean, cov = torch.mean(x[sel], axis=0), torch.cov(x[sel].T, correction=0)
+            for lam, ab in ((st["lama"][i], "a"), (st["lamb"][i], "b")):
+                st[f"m{side}{ab}"][i] = (1 - lam) * st[f"m{side}{ab}"][i] + lam * mean
+                st[f"S{side}{ab}"][i] = (1 - lam) * st[f"S{side}{ab}"][i] + lam * cov
+    return st

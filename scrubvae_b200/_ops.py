@@ -104,6 +104,10 @@ _SIGS = {
     "scv_optim_step": (C.c_int, [C.POINTER(OptimT), _vp]),
     "scv_mi_loss": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "scv_mi_update": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _vp, _vp]),
+    "scv_qda_factor": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "scv_qda_loss": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "scv_qda_finalize": (C.c_int, [_vp, _vp, _vp, _f64, _f64, _i64, _i64, _vp, _vp]),
+    "scv_qda_update": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp] + [_vp] * 8 + [_vp, _vp]),
     "scv_mals_solve": (C.c_int, [_vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "scv_mals_loss": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "scv_mals_finalize": (C.c_int, [_vp, _vp, _vp, _f64, _f64, _i64, _vp, _vp]),
@@ -302,6 +306,24 @@ class CudaOps:
     def mi_update(self, mu, L, var, var_ld, xs, ys, var_s, logAx, bandwidth, S, z, dy, valid=None):
         self._check(self.lib.scv_mi_update(_ptr(mu), _ptr(L), _ptr(var), var_ld, _ptr(xs), _ptr(ys), _ptr(var_s), _ptr(logAx),
                                            float(bandwidth), S, z, dy, _ptr(valid), self._stream()), "scv_mi_update")
+
+    def qda_factor(self, S4, nc, z, SinvT, logdet):
+        self._check(self.lib.scv_qda_factor(*[_ptr(t) for t in S4], nc, z, _ptr(SinvT), _ptr(logdet), self._stream()),
+                    "scv_qda_factor")
+
+    def qda_loss(self, x, x_ld, y, classes, m4, SinvT, logdet, nc, z, B, acc=None, gscale=None, dx=None, d_ld=0):
+        self._check(self.lib.scv_qda_loss(_ptr(x), x_ld, _ptr(y), _ptr(classes), *[_ptr(t) for t in m4], _ptr(SinvT),
+                                          _ptr(logdet), nc, z, B, _ptr(acc), _ptr(gscale), _ptr(dx), d_ld, self._stream()),
+                    "scv_qda_loss")
+
+    def qda_finalize(self, acc, lama, lamb, delta, lamdiff, nc, B, loss=None):
+        self._check(self.lib.scv_qda_finalize(_ptr(acc), _ptr(lama), _ptr(lamb), float(delta), float(lamdiff), nc, B, _ptr(loss),
+                                              self._stream()), "scv_qda_finalize")
+
+    def qda_update(self, x, x_ld, y, classes, nc, z, B, lama, lamb, m4, S4, stat):
+        self._check(self.lib.scv_qda_update(_ptr(x), x_ld, _ptr(y), _ptr(classes), nc, z, B, _ptr(lama), _ptr(lamb),
+                                            *[_ptr(t) for t in m4], *[_ptr(t) for t in S4], _ptr(stat), self._stream()),
+                    "scv_qda_update")
 
     def mals_solve(self, Sxx0, Sxy0, Sxx1, Sxy1, l2_reg, bias, nx, ny, W0, W1):
         self._check(self.lib.scv_mals_solve(_ptr(Sxx0), _ptr(Sxy0), _ptr(Sxx1), _ptr(Sxy1), float(l2_reg), int(bias), nx, ny,

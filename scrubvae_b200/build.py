@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libscv.so")
-SOURCES = ["scv_api.cu", "scv_gemm_ffma.cu", "scv_gemm_tc.cu", "scv_elementwise.cu", "scv_loss.cu", "scv_preprocess.cu", "scv_eval.cu", "scv_mi.cu", "scv_mals.cu"]
+SOURCES = ["scv_api.cu", "scv_gemm_ffma.cu", "scv_gemm_tc.cu", "scv_elementwise.cu", "scv_loss.cu", "scv_preprocess.cu", "scv_eval.cu", "scv_mi.cu", "scv_mals.cu", "scv_qda.cu"]
 EXTRA_FLAGS = {"scv_preprocess.cu": ["-fmad=false"]}  # fp32 products and sums round separately, like the reference's torch ops
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

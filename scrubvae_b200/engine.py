@@ -299,6 +299,13 @@ class Engine:
                 self.mals_keys.append(key)
                 self.mals_mod[key] = mod
                 mod._ops = self.ops
+        self.qda_keys: List[str] = []  # quadratic discriminant filters (model/disentangle.py:90-232)
+        self.qda_mod: Dict[str, nn.Module] = {}
+        if "qda" in m.disentangle:
+            for key, mod in m.disentangle["qda"].items():
+                self.qda_keys.append(key)
+                self.qda_mod[key] = mod
+                mod._ops = self.ops
         if "grad_reversal" in m.disentangle:
             for key, scr in m.disentangle["grad_reversal"].items():
                 self.gr_keys.append(key)
@@ -520,18 +527,29 @@ class Plan:
         self.loss_names = ["jpe", "root", "prior"] + [kk + "_gr" for kk in eng.gr_keys]
         if eng.cond_dim > 0:
             self.loss_names.append("mcmi")  # kernel mutual-information scrubbing loss (needs conditioning variables)
-        self.loss_names += [kk + "_mals" for kk in eng.mals_keys]
+        self.loss_names += [kk + "_mals" for kk in eng.mals_keys] + [kk + "_qda" for kk in eng.qda_keys]
         self.mi = None  # estimator buffers, allocated by enable_mcmi()
         nl = len(self.loss_names)
         nbn = sum(mod.num_features for mod in m.modules() if isinstance(mod, nn.BatchNorm1d))
         n_stats, n_sums = 4 * nbn + 8, 2 * nbn + 2 * ch[0] + 64
         # every per-step accumulator in ONE buffer: [BN statistics | BN backward sums | loss terms | grad norm^2];
         # the fused step clears it with one memset, the piecewise API path clears the parts as it reaches them
-        n_mals = 2 * len(eng.mals_keys)  # squared-error sums of the two decoders of every moving_avg_lsq scrubber
+        n_qda = sum(4 * len(eng.qda_mod[kk].classes) for kk in eng.qda_keys)  # (lla, llb, llra, llrb) per class
+        n_mals = 2 * len(eng.mals_keys) + n_qda  # + squared-error sums of the two decoders of every moving_avg_lsq scrubber
         self.zbuf = torch.zeros(n_stats + n_sums + nl + 1 + n_mals, dtype=torch.double, device=dev)
         self.loss_acc = self.zbuf[n_stats + n_sums:n_stats + n_sums + nl]
         self.sumsq = self.zbuf[n_stats + n_sums + nl:n_stats + n_sums + nl + 1]
         self.mals_l01 = self.zbuf[n_stats + n_sums + nl + 1:]
+        self.qda = {}
+        off = 2 * len(eng.mals_keys)
+        for key in eng.qda_keys:
+            mod = eng.qda_mod[key]
+            ncq = len(mod.classes)
+            self.qda[key] = dict(mod=mod, nc=ncq, off=off, SinvT=torch.zeros(4, ncq, z, z, **f32),
+                                 logdet=torch.zeros(4, ncq, **f32), y=torch.zeros(B, dtype=torch.long, device=dev),
+                                 classes=torch.tensor([int(c) for c in mod.classes], dtype=torch.long, device=dev),
+                                 stat=torch.zeros(2 * ncq * (z + 1), **f32))
+            off += 4 * ncq
         self.mals = {}
         for key in eng.mals_keys:
             mod = eng.mals_mod[key]
@@ -857,6 +875,8 @@ class Plan:
         Lk.append(lambda: self._mi_launch(loss=True))
         for ki, key in enumerate(eng.mals_keys):
             Lk.append(lambda key=key, ki=ki: self._mals_loss(key, ki))
+        for key in eng.qda_keys:
+            Lk.append(lambda key=key: self._qda_loss(key))
         Lk.append(lambda: ops.loss_finalize(self.loss_acc, self.loss_scale, self.loss_out, nl))
         self.Lk = Lk
 
@@ -969,6 +989,8 @@ class Plan:
         Bw.append(lambda: self._mi_launch(loss=False))  # adds d mcmi / d mu into dmu_kl
         for ki, key in enumerate(eng.mals_keys):  # adds d <key>_mals / d mu into dmu_kl
             Bw.append(lambda key=key, ki=ki: self._mals_backward(key, ki))
+        for key in eng.qda_keys:  # adds d <key>_qda / d mu into dmu_kl
+            Bw.append(lambda key=key: self._qda_backward(key))
         Bw.append(lambda: ops.reparam_bwd(self.ms, eng.ms_ld, self.eps, self.dmu_kl, self.dmu_gr, 1.0, self.dzc,
                                           eng.zc_ld, self.dL_kl, self.dms, eng.ms_ld, B, z, round_tf32=rnd))
         Bw.append(wgrad(gfc, Hflat.at(0), Hflat.bs, 0, 1, self.dms, eng.ms_ld, 0))
@@ -1056,6 +1078,33 @@ class Plan:
             ops.mals_update(self.mu, z, st["y"], st["ny"], st["bias"], self.B, z, st["ny"], mod.lam0, mod.lam1, mod.Sxx0,
                             mod.Sxy0, mod.Sxx1, mod.Sxy1)
 
+    # ------------------------------------------------------------------ qda (QuadraticDiscriminantFilter)
+    def _qda_loss(self, key):
+        """evaluate_loss (reference model/disentangle.py:173-232) / batch_size (train/losses.py:247-251)"""
+        st, ops, z = self.qda[key], self.eng.ops, self.eng.m.z_dim
+        mod = st["mod"]
+        acc = Ref(self.mals_l01, st["off"])
+        if not self._fused_tail:
+            self.mals_l01[st["off"]:st["off"] + 4 * st["nc"]].zero_()
+        ops.qda_factor(mod.S4(), st["nc"], z, st["SinvT"], st["logdet"])
+        ops.qda_loss(self.mu, z, st["y"], st["classes"], mod.m4(), st["SinvT"], st["logdet"], st["nc"], z, self.B, acc=acc)
+        ops.qda_finalize(acc, mod.lama, mod.lamb, mod.delta, mod.lamdiff, st["nc"], self.B,
+                         loss=Ref(self.loss_acc, self.loss_names.index(key + "_qda")))
+
+    def _qda_backward(self, key):
+        st, ops, z = self.qda[key], self.eng.ops, self.eng.m.z_dim
+        mod = st["mod"]
+        ops.qda_loss(self.mu, z, st["y"], st["classes"], mod.m4(), st["SinvT"], st["logdet"], st["nc"], z, self.B,
+                     gscale=Ref(self.gscale, self.loss_names.index(key + "_qda")), dx=self.dmu_kl, d_ld=z)
+
+    def qda_update(self):
+        """QuadraticDiscriminantFilter.update (:133-171) with this step's mu and labels (train/trainer.py:169-178)"""
+        ops, z = self.eng.ops, self.eng.m.z_dim
+        for key, st in self.qda.items():
+            mod = st["mod"]
+            ops.qda_update(self.mu, z, st["y"], st["classes"], st["nc"], z, self.B, mod.lama, mod.lamb, mod.m4(), mod.S4(),
+                           st["stat"])
+
     # ------------------------------------------------------------------ mcmi (MutInfoEstimator)
     def enable_mcmi(self, bandwidth: float, var_mode: str = "sphere"):
         """Allocates the estimator's stored-sample buffers (reference model/disentangle.py:234-275): S = this plan's batch."""
@@ -1107,7 +1156,7 @@ class Plan:
         mi["valid"].fill_(1.0)
 
     # ------------------------------------------------------------------ running
-    def load_inputs(self, data, need_loss_inputs: bool):
+    def load_inputs(self, data, need_loss_inputs: bool, need_cond: bool = True):
         """Copies the batch into the static input buffers (skipped for tensors that already ARE them)."""
         eng, m = self.eng, self.eng.m
         for kname in ("x6d", "root") + (("offsets", "target_pose") if need_loss_inputs else ()):
@@ -1115,7 +1164,9 @@ class Plan:
                 src = data[kname]
                 if src.data_ptr() != self.inp[kname].data_ptr():
                     self.inp[kname].copy_(src.reshape(self.inp[kname].shape), non_blocking=True)
-        if eng.cond_dim > 0:
+        # encode(data) needs x6d and root only (reference model/residual.py:437-459): the conditioning variables are
+        # loaded when the batch carries them
+        if eng.cond_dim > 0 and (need_cond or all(kk in data for kk in m.conditional_keys)):
             parts = []
             for kk in m.conditional_keys:
                 if kk in m.discrete_classes:
@@ -1131,6 +1182,8 @@ class Plan:
     def load_targets(self, data):
         for key, st in self.mals.items():
             st["y"].copy_(data[key].reshape(st["y"].shape), non_blocking=True)
+        for key, st in self.qda.items():
+            st["y"].copy_(data[key].ravel(), non_blocking=True)
         for key in self.eng.gr_keys:
             if key == "ids":
                 self.gr_labels[key].copy_(data[key].ravel(), non_blocking=True)
@@ -1142,7 +1195,7 @@ class Plan:
         eng.ensure_flat()  # this path packs the GEMM matrices from `flat`
         self._training = training
         if z_given is None:
-            self.load_inputs(data, need_loss_inputs=False)
+            self.load_inputs(data, need_loss_inputs=False, need_cond=upto != "encode")
             if training:
                 if m._noise is not None:
                     self.eps.copy_(m._noise)
@@ -1413,6 +1466,8 @@ class TrainStep:
                 ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, eng.n_flat, plan.sumsq, *hp, hyper=opt.hyper)
             if plan.mals:  # running covariances of the moving_avg_lsq scrubbers: this step's mu (train/trainer.py:169-178)
                 plan.mals_update()
+            if plan.qda:
+                plan.qda_update()
             if self.mi is not None:
                 # updated encode (train mode: batch statistics again, running statistics advance a second time, as the
                 # reference's model.encode(data) does) -> new stored samples of the estimator

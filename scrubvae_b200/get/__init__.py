@@ -1,1 +1,2 @@
 from .model import model
+from .eval import latents

@@ -1,5 +1,5 @@
 """`scrubvae_b200.get.model` — same signature and semantics as the reference factory
-get/model.py:4-151, restricted to the methods on the built path (conditional, grad_reversal, moving_avg_lsq)."""
+get/model.py:4-151, restricted to the methods on the built path (conditional, grad_reversal, moving_avg_lsq, qda)."""
 import torch
 
 
@@ -20,7 +20,7 @@ def model(model_config, load_model, epoch, disentangle_config, n_keypts, directi
 
     methods = disentangle_config["method"]
     for m in methods:
-        if m not in ("conditional", "grad_reversal", "moving_avg_lsq"):
+        if m not in ("conditional", "grad_reversal", "moving_avg_lsq", "qda"):
             raise NotImplementedError(
                 f"scrubvae_b200.get.model: method '{m}' is outside the built hot path (SURVEY.md §8)")
     disentangle = {}
@@ -45,6 +45,12 @@ def model(model_config, load_model, epoch, disentangle_config, n_keypts, directi
             disentangle["moving_avg_lsq"][feat] = MovingAvgLeastSquares(
                 model_config["z_dim"], feat_dim_dict[feat], bias=loss_config[feat + "_mals"] < 0,
                 polynomial_order=disentangle_config["polynomial"], l2_reg=disentangle_config["l2_reg"])
+
+    if "qda" in methods.keys():  # reference get/model.py:86-94
+        from ..model.disentangle import QuadraticDiscriminantFilter
+        disentangle["qda"] = {}
+        for feat in methods["qda"]:
+            disentangle["qda"][feat] = QuadraticDiscriminantFilter(model_config["z_dim"], discrete_classes[feat])
 
     if model_config["type"] != "rcnn":
         raise NotImplementedError("scrubvae_b200.get.model: only model type 'rcnn' exists (as in the reference)")

@@ -150,3 +150,36 @@ class MovingAvgLeastSquares(nn.Module):
         out = torch.zeros(1, dtype=torch.double, device=y.device)
         ops.mals_finalize(l01, self.lam0, self.lam1, self.delta, self.lamdiff, 1, loss=out)
         return out[0].to(torch.float32)
+
+
+class QuadraticDiscriminantFilter(nn.Module):
+    """Reference model/disentangle.py:90-232: per class two one-vs-rest quadratic (Gaussian) classifiers of the latent mean
+    with streaming means / covariances and self-tuning forgetting factors lama < lamb.  Same constructor and buffers (m0a,
+    S0a, m1a, S1a, m0b, S0b, m1b, S1b, lama, lamb: the reference's state_dict keys and registration order); the inverses and
+    log-determinants, the log-likelihood-ratio loss with its gradient into mu, the forgetting-factor rule and the
+    class-conditional update run in csrc/scv_qda.cu, sequenced by the engine."""
+
+    def __init__(self, nx, classes, lamdiff=1e-2, delta=1e-3):
+        super().__init__()
+        self.classes = classes
+        n_classes = len(classes)
+        if nx > 128 or n_classes > 16:
+            raise NotImplementedError("scrubvae_b200: the qda kernels hold z <= 128 and <= 16 classes")
+        for name in ["0a", "1a", "0b", "1b"]:
+            self.register_buffer("m{}".format(name), torch.zeros(n_classes, nx))
+            self.register_buffer("S{}".format(name), torch.eye(nx)[None, :].repeat(n_classes, 1, 1))
+        self.register_buffer("lama", torch.ones(n_classes) * 0.2)
+        self.register_buffer("lamb", torch.ones(n_classes) * 0.2 + lamdiff)
+        self.delta = delta
+        self.lamdiff = lamdiff
+        self.z = int(nx)
+        self._ops = None
+
+    def forward(self, *args, **kwargs):
+        return
+
+    def m4(self):
+        return [self.m0a, self.m1a, self.m0b, self.m1b]
+
+    def S4(self):
+        return [self.S0a, self.S1a, self.S0b, self.S1b]

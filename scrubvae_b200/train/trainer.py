@@ -245,6 +245,8 @@ def train_test_epoch(config, model, loader, device, epoch, optimizer=None, sched
                 # reference :169-178: running covariances of the moving-average scrubbers, from this batch's mu
                 if "moving_avg_lsq" in model.disentangle.keys():
                     data_o["_plan"].mals_update()
+                if "qda" in model.disentangle.keys():
+                    data_o["_plan"].qda_update()
             epoch_metrics = {k: v + batch_loss[k].detach() for k, v in epoch_metrics.items()}
             if "mcmi" in config["loss"].keys():  # reference :184-199: estimator rebuilt from the updated encoder
                 from ..model.disentangle import MutInfoEstimator

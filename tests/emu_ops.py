@@ -529,6 +529,72 @@ class EmuOps:
         if valid is not None:
             _v(valid, (1,), (1,)).fill_(1.0)
 
+    # ---- qda scrubber (reference model/disentangle.py:90-232)
+    def qda_factor(self, S4, nc, z, SinvT, logdet):
+        self.n += 1
+        out, ld = _v(SinvT, (4, nc, z, z), (nc * z * z, z * z, z, 1)), _v(logdet, (4, nc), (nc, 1))
+        for q in range(4):
+            S = _v(S4[q], (nc, z, z), (z * z, z, 1))
+            out[q] = torch.linalg.inv(S).transpose(-1, -2)
+            ld[q] = torch.logdet(S)
+
+    def qda_loss(self, x, x_ld, y, classes, m4, SinvT, logdet, nc, z, B, acc=None, gscale=None, dx=None, d_ld=0):
+        self.n += 1
+        X = _v(x, (B, z), (x_ld, 1))
+        Y = _v(y, (B,), (1,))
+        cls = _v(classes, (nc,), (1,))
+        Si, ld = _v(SinvT, (4, nc, z, z), (nc * z * z, z * z, z, 1)), _v(logdet, (4, nc), (nc, 1))
+        g = torch.zeros(B, z)
+        for c in range(nc):
+            i1 = (Y == cls[c])
+            s = (i1.float() * 2 - 1)
+            ll, t = [], []
+            for q in range(4):
+                r = X - _v(m4[q], (nc, z), (z, 1))[c:c + 1]
+                tq = r @ Si[q, c]  # rows: (S^-1 r_b)^T = r_b^T S^-T ; Si holds S^-T
+                t.append(tq)
+                ll.append(-0.5 * (ld[q, c] + (r * tq).sum(1)))
+            if acc is not None:
+                a = _v(acc, (nc, 4), (4, 1))
+                a[c, 0] += torch.where(i1, ll[1], ll[0]).double().sum()
+                a[c, 1] += torch.where(i1, ll[3], ll[2]).double().sum()
+                a[c, 2] += (s * (ll[1] - ll[0])).double().sum()
+                a[c, 3] += (s * (ll[3] - ll[2])).double().sum()
+            g += s[:, None] * ((t[0] - t[1]) + (t[2] - t[3]))
+        if dx is not None:
+            _v(dx, (B, z), (d_ld, 1)).add_(float(_v(gscale, (1,), (1,))) * 0.5 / (nc * B) * g)
+
+    def qda_finalize(self, acc, lama, lamb, delta, lamdiff, nc, B, loss=None):
+        self.n += 1
+        a = _v(acc, (nc, 4), (4, 1))
+        la, lb = _v(lama, (nc,), (1,)), _v(lamb, (nc,), (1,))
+        for c in range(nc):
+            if float(a[c, 0].float()) > float(a[c, 1].float()):
+                la[c] = torch.clamp(la[c] - delta, 0.0, 1.0)
+                lb[c] = la[c] + lamdiff
+            else:
+                lb[c] = torch.clamp(lb[c] + delta, 0.0, 1.0)
+                la[c] = lb[c] - lamdiff
+        if loss is not None:
+            _v(loss, (1,), (1,)).add_(((a[:, 2] + a[:, 3]) * 0.5).sum() / nc / B)
+
+    def qda_update(self, x, x_ld, y, classes, nc, z, B, lama, lamb, m4, S4, stat):
+        self.n += 1
+        X = _v(x, (B, z), (x_ld, 1))
+        Y = _v(y, (B,), (1,))
+        cls = _v(classes, (nc,), (1,))
+        la, lb = _v(lama, (nc,), (1,)), _v(lamb, (nc,), (1,))
+        M = [_v(t, (nc, z), (z, 1)) for t in m4]
+        S = [_v(t, (nc, z, z), (z * z, z, 1)) for t in S4]
+        for c in range(nc):
+            for side in (0, 1):
+                sel = X[(Y == cls[c]) if side else (Y != cls[c])]
+                mean = sel.mean(0)
+                cov = torch.cov(sel.T, correction=0) if sel.shape[0] else torch.full((z, z), float("nan"))
+                for lam, off in ((la[c], 0), (lb[c], 2)):
+                    M[off + side][c] = (1 - lam) * M[off + side][c] + lam * mean
+                    S[off + side][c] = (1 - lam) * S[off + side][c] + lam * cov
+
     # ---- moving_avg_lsq scrubber (reference model/disentangle.py:393-538, polynomial order 1)
     @staticmethod
     def _mals_x(mu, mu_ld, bias, B, z):

@@ -400,6 +400,33 @@ def test_moving_avg_lsq_kernels(ops, z, ny, bias, l2):
     run_both(ops, T, call, tol=1e-5, check=["lam0", "lam1", "Sxx0", "Sxy0", "Sxx1", "Sxy1"])
 
 
+@pytest.mark.parametrize("z,nc,B", [(64, 4, 300), (128, 2, 130), (8, 3, 37)])
+def test_qda_kernels(ops, z, nc, B):
+    """scv_qda_factor / loss / finalize / update (csrc/scv_qda.cu) against the torch emulation (torch.linalg.inv, logdet,
+    torch.cov): running covariances as they look after some updates (identity blended with class covariances)."""
+    gg = g(9)
+    def spd():
+        A = torch.randn(nc, z, 3 * z, generator=gg)
+        return 0.6 * torch.eye(z)[None] + 0.4 * (A @ A.transpose(1, 2)) / (3 * z)
+    T = {"x": torch.randn(B, z, generator=gg), "y": (torch.arange(B) % nc).to(torch.long), "cls": torch.arange(nc, dtype=torch.long),
+         "SinvT": torch.zeros(4, nc, z, z), "logdet": torch.zeros(4, nc), "acc": torch.zeros(4 * nc, dtype=torch.double),
+         "gs": torch.tensor([0.41]), "dx": torch.randn(B, z, generator=gg), "lama": torch.full((nc,), 0.2),
+         "lamb": torch.full((nc,), 0.21), "loss": torch.zeros(1, dtype=torch.double), "stat": torch.zeros(2 * nc * (z + 1))}
+    for q in range(4):
+        T[f"m{q}"] = 0.3 * torch.randn(nc, z, generator=gg)
+        T[f"S{q}"] = spd()
+
+    def call(o, t):
+        m4, S4 = [t[f"m{q}"] for q in range(4)], [t[f"S{q}"] for q in range(4)]
+        o.qda_factor(S4, nc, z, t["SinvT"], t["logdet"])
+        o.qda_loss(t["x"], z, t["y"], t["cls"], m4, t["SinvT"], t["logdet"], nc, z, B, acc=t["acc"])
+        o.qda_loss(t["x"], z, t["y"], t["cls"], m4, t["SinvT"], t["logdet"], nc, z, B, gscale=t["gs"], dx=t["dx"], d_ld=z)
+        o.qda_finalize(t["acc"], t["lama"], t["lamb"], 1e-3, 1e-2, nc, B, loss=t["loss"])
+        o.qda_update(t["x"], z, t["y"], t["cls"], nc, z, B, t["lama"], t["lamb"], m4, S4, t["stat"])
+    run_both(ops, T, call, tol=2e-4, check=["SinvT", "logdet", "acc", "dx", "loss"])
+    run_both(ops, T, call, tol=2e-5, check=["lama", "lamb"] + [f"m{q}" for q in range(4)] + [f"S{q}" for q in range(4)])
+
+
 def test_library_fails_loudly_when_missing(tmp_path):
     from scrubvae_b200 import _ops
     with pytest.raises(RuntimeError, match="no CPU fallback"):

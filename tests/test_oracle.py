@@ -165,3 +165,26 @@ def test_oracle_moving_avg_lsq_matches_live_reference():
         orc.mals_update(st, mu, y)
         for k in ("Sxx0", "Sxy0", "Sxx1", "Sxy1", "lam0", "lam1"):
             assert torch.allclose(getattr(ref, k), st[k], rtol=1e-5, atol=1e-6), (i, k)
+
+
+def test_oracle_qda_matches_live_reference():
+    """oracle.qda_* against the reference's QuadraticDiscriminantFilter (model/disentangle.py:90-232) over a short sequence
+    of evaluate_loss / update calls."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference not importable here")
+    refimport.import_reference()
+    from scrubvae.model.disentangle import QuadraticDiscriminantFilter
+    z, classes, B = 6, [0, 1, 2], 18
+    ref = QuadraticDiscriminantFilter(z, classes)
+    st = orc.qda_init(z, len(classes))
+    g = torch.Generator().manual_seed(4)
+    for i in range(5):
+        y = ((torch.arange(B) + i) % 3).reshape(B, 1)
+        x = torch.randn(B, z, generator=g) + 0.5 * y.float()
+        lr_, lo = ref.evaluate_loss(x, y), orc.qda_evaluate(st, x, y, classes)
+        assert torch.allclose(lr_, lo, rtol=1e-5, atol=1e-6), (i, lr_, lo)
+        ref.update(x, y)
+        orc.qda_update(st, x, y, classes)
+        for k in st:
+            assert torch.allclose(getattr(ref, k), st[k], rtol=1e-5, atol=1e-6), (i, k)

@@ -252,3 +252,68 @@ def test_moving_avg_lsq_epoch_against_reference_on_gpu(scale_sign):
         for k in ("Sxx0", "Sxy0", "Sxx1", "Sxy1", "lam0", "lam1"):
             a, b = osd[pre + k].float().cpu(), rsd[pre + k].float().cpu()
             assert (a - b).norm() <= 1e-3 * b.norm() + 1e-6, (fused, k, (a - b).norm().item(), b.norm().item())
+
+
+def test_qda_epoch_against_reference_on_gpu():
+    """qda scrubber (reference model/disentangle.py:90-232) on the device against the unmodified reference on the same GPU
+    (fp32): epoch metrics within 1e-3, the filter's running means / covariances / forgetting factors after 4 steps."""
+    import contextlib, io
+    rsv = refimport.import_reference()
+    from scrubvae.train import trainer as rtr
+    from oracle import ref_runner as rr
+    dev = torch.device("cuda", 0)
+    ch, zd, B = [16, 32, 64, 128, 256], 32, 96
+    mc = dict(type="rcnn", channel=list(ch), kernel=5, z_dim=zd, window=51, activation="prelu", diag=False,
+              init_dilation=None, prior="gaussian", load_model=None, start_epoch=None, precision="fp32")
+    dc = dict(method={"conditional": ["heading"], "qda": ["ids"]}, features=["heading", "ids"], alpha=1.0)
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "ids_qda": 0.2}
+    classes = {"ids": [0, 1, 2, 3]}
+    torch.manual_seed(6)
+    with contextlib.redirect_stdout(io.StringIO()), rr.precision("fp32"):
+        ref = rsv.get.model({k: v for k, v in mc.items() if k != "precision"}, None, None, dc, 18, "midfwd", loss_config=scale,
+                            arena_size=torch.tensor(orc.ARENA), kinematic_tree=orc.KINEMATIC_TREE, discrete_classes=classes,
+                            device="cuda", verbose=0)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    keys = ("x6d", "root", "offsets", "target_pose", "heading")
+    batches = []
+    for i in range(4):
+        b = {k: v.to(dev) for k, v in orc.synth_batch(B, seed=30 + i).items() if k in keys}
+        b["ids"] = ((torch.arange(B, device=dev) + i) % 4).reshape(B, 1)
+        batches.append(b)
+    noise = [orc.synth_eps(B, zd, seed=50 + i).to(dev) for i in range(4)]
+    it = iter(noise)
+    orig = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: next(it).to(t)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()), rr.precision("fp32"):
+            ropt, _ = rtr.get_optimizer_and_lr_scheduler(ref, {"optimizer": "adamw", "lr": 1e-4, "lr_schedule": None})
+            mref = rtr.train_test_epoch({"loss": dict(scale), "disentangle": dc}, ref, batches, dev, 1, optimizer=ropt,
+                                        scheduler=None, mode="train")
+    finally:
+        torch.randn_like = orig
+    rsd = ref.state_dict()
+    for fused in (False, True):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = sv.get.model(mc, None, None, dc, 18, "midfwd", loss_config=scale, arena_size=torch.tensor(orc.ARENA),
+                             kinematic_tree=orc.KINEMATIC_TREE, discrete_classes=classes, device=dev, verbose=0)
+        assert list(m.state_dict().keys()) == list(sd.keys())
+        m.load_state_dict(sd)
+        opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-4, "lr_schedule": None})
+        cfg = {"loss": dict(scale), "disentangle": dc, "train": {"fused_step": fused}}
+        seq = iter(noise)
+
+        def cb(i, vec, m=m, seq=seq):
+            nxt = next(seq, None)
+            if nxt is not None:
+                m._noise.copy_(nxt)
+        m._noise = next(seq).clone()
+        with contextlib.redirect_stdout(io.StringIO()):
+            mo = sv.train.train_test_epoch(cfg, m, batches, dev, 1, optimizer=opt, scheduler=None, mode="train",
+                                           step_callback=cb)
+        for k in mref:
+            assert abs(mo[k] - mref[k]) <= 1e-3 * abs(mref[k]) + 1e-5, (fused, k, mo[k], mref[k])
+        osd = m.state_dict()
+        pre = "disentangle.qda.ids."
+        for k in ("m0a", "S0a", "m1a", "S1a", "m0b", "S0b", "m1b", "S1b", "lama", "lamb"):
+            a, b = osd[pre + k].float().cpu(), rsd[pre + k].float().cpu()
+            assert (a - b).norm() <= 1e-3 * b.norm() + 1e-6, (fused, k, (a - b).norm().item(), b.norm().item())
