@@ -142,7 +142,8 @@ __device__ __forceinline__ float4 bn_prelu(float4 x, const ChanBN& cb, bool has_
   return make_float4(v[0], v[1], v[2], v[3]);
 }
 
-__global__ void __launch_bounds__(NT, 3) bnact_fwd_kernel(const scv_bnact_t p, const int cw, const int64_t rpb) {
+template <int OCC, bool UP>
+__global__ void __launch_bounds__(NT, OCC) bnact_fwd_kernel(const scv_bnact_t p, const int cw, const int64_t rpb) {
   const int C = (int)p.C, C4 = C >> 2;
   const int mode = (int)p.mode;
   const int64_t rows = p.B * p.L;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(NT, 3) bnact_fwd_kernel(const scv_bnact_t p, c
   RowIt it;
   it.init(t.r0, t.rstep, L);
   for (int64_t r = t.r0; r < t.rend; r += 4 * (int64_t)t.rstep) {
-    float4 xc[4], xm[4], xp[4];
+    float4 xc[4], xm[UP ? 4 : 1], xp[UP ? 4 : 1];
     uint32_t bb[4], ll[4];
     bool ok[4];
 #pragma unroll
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(NT, 3) bnact_fwd_kernel(const scv_bnact_t p, c
       if (ok[u]) {
         const float* xr = p.X + (int64_t)bb[u] * p.x_bs + (int64_t)ll[u] * p.x_ls + t.c * 4;
         xc[u] = ld4(xr);
-        if (p.U) {
+        if (UP && p.U) {
           xm[u] = ll[u] > 0 ? ld4(xr - p.x_ls) : xc[u];
           xp[u] = ll[u] < L - 1 ? ld4(xr + p.x_ls) : xc[u];
         }
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(NT, 3) bnact_fwd_kernel(const scv_bnact_t p, c
       if (!ok[u]) continue;
       const float4 a = bn_prelu(xc[u], cb, has_act, slope);
       if (p.H) scv::store_out4(p.H, (int64_t)bb[u] * p.h_bs + (int64_t)ll[u] * p.h_ls + t.c * 4, a, om);
-      if (p.U) {
+      if (UP && p.U) {
         const float4 am = bn_prelu(xm[u], cb, has_act, slope), ap = bn_prelu(xp[u], cb, has_act, slope);
         float4 e, o;
         e.x = 0.25f * am.x + 0.75f * a.x; e.y = 0.25f * am.y + 0.75f * a.y;
@@ -221,10 +222,11 @@ __global__ void __launch_bounds__(NT, 3) bnact_fwd_kernel(const scv_bnact_t p, c
 }
 
 // gradient w.r.t. the activated output at (b,l): direct part + transpose of the x2 linear upsample
+template <bool UP = true>
 __device__ __forceinline__ float4 load_dout(const scv_bnact_bwd_t& p, int64_t b, int64_t l, int c4) {
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.dO) g = ld4(p.dO + b * p.o_bs + l * p.o_ls + c4 * 4);
-  if (p.dU) {
+  if (UP && p.dU) {
     const int64_t L = p.L;
     const float* u = p.dU + b * p.u_bs + c4 * 4;
     float4 e = ld4(u + (2 * l) * p.u_ls), o = ld4(u + (2 * l + 1) * p.u_ls);
@@ -314,7 +316,8 @@ __global__ void __launch_bounds__(NT, 3) bnact_bwd_reduce_kernel(const scv_bnact
   }
 }
 
-__global__ void __launch_bounds__(NT, 3) bnact_bwd_apply_kernel(const scv_bnact_bwd_t p, const int cw,
+template <int OCC, bool UP>
+__global__ void __launch_bounds__(NT, OCC) bnact_bwd_apply_kernel(const scv_bnact_bwd_t p, const int cw,
                                                              const int64_t rpb) {
   const int C = (int)p.C, C4 = C >> 2;
   const int mode = (int)p.mode;
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(NT, 3) bnact_bwd_apply_kernel(const scv_bnact_
       it.next();
       if (ok[u]) {
         xv[u] = ld4(p.X + (int64_t)bb[u] * p.x_bs + (int64_t)ll[u] * p.x_ls + t.c * 4);
-        gv[u] = load_dout(p, bb[u], ll[u], t.c);
+        gv[u] = load_dout<UP>(p, bb[u], ll[u], t.c);
       }
     }
 #pragma unroll
@@ -620,6 +623,17 @@ static int check_rows(const char* who, int64_t C, const void* ptr, int64_t bs, i
   return 0;
 }
 
+// resident CTAs per SM of the BN / PReLU streaming kernels: 3 (80 registers) by default; SCV_BNACT_OCC=4 (64 registers)
+static int bnact_occ() {
+  const char* e = getenv("SCV_BNACT_OCC");
+  return (e && atoi(e) == 4) ? 4 : 3;
+}
+
+static bool bnact_nospec() {  // experiments: SCV_BNACT_SPEC=0 runs every launch through the upsample-capable variants
+  const char* e = getenv("SCV_BNACT_SPEC");
+  return e && atoi(e) == 0;
+}
+
 int scv_bnact_fwd(const scv_bnact_t* p, void* stream) {
   if (check_rows("scv_bnact_fwd X", p->C, p->X, p->x_bs, p->x_ls)) return -1;
   if (p->H && check_rows("scv_bnact_fwd H", p->C, p->H, p->h_bs, p->h_ls)) return -1;
@@ -628,8 +642,11 @@ int scv_bnact_fwd(const scv_bnact_t* p, void* stream) {
   SCV_REQUIRE(!((p->mode & 5) == 5) || p->stats, "scv_bnact_fwd: training BN needs stats");
   SCV_REQUIRE(!((p->mode & 5) == 1) || (p->running_mean && p->running_var), "scv_bnact_fwd: eval BN needs running stats");
   SCV_REQUIRE(p->B * p->L < (1LL << 31), "scv_bnact_fwd: more than 2^31 rows");
-  Launch2D l = plan2d(p->C / 4, p->B * p->L, 3);
-  bnact_fwd_kernel<<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
+  const int occ = bnact_occ();
+  Launch2D l = plan2d(p->C / 4, p->B * p->L, occ);
+  if (occ == 4) bnact_fwd_kernel<4, true><<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
+  else if (p->U || bnact_nospec()) bnact_fwd_kernel<3, true><<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
+  else bnact_fwd_kernel<3, false><<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
   return scv::check_launch("bnact_fwd_kernel");
 }
 
@@ -651,8 +668,11 @@ int scv_bnact_bwd_apply(const scv_bnact_bwd_t* p, void* stream) {
   if (p->dX && check_rows("scv_bnact_bwd dX", p->C, p->dX, p->d_bs, p->d_ls)) return -1;
   SCV_REQUIRE(!(p->mode & 3) || p->sums, "scv_bnact_bwd_apply: sums required");
   SCV_REQUIRE(p->B * p->L < (1LL << 31), "scv_bnact_bwd_apply: more than 2^31 rows");
-  Launch2D l = plan2d(p->C / 4, p->B * p->L, 3);
-  bnact_bwd_apply_kernel<<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
+  const int occ = bnact_occ();
+  Launch2D l = plan2d(p->C / 4, p->B * p->L, occ);
+  if (occ == 4) bnact_bwd_apply_kernel<4, true><<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
+  else if (p->dU || bnact_nospec()) bnact_bwd_apply_kernel<3, true><<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
+  else bnact_bwd_apply_kernel<3, false><<<l.grid, NT, 0, (cudaStream_t)stream>>>(*p, l.cw, l.rows_per_block);
   return scv::check_launch("bnact_bwd_apply_kernel");
 }
 

@@ -19,3 +19,6 @@ echo "== step gaps"; timeout 300 python tools/step_gaps.py 2>&1 | tail -40 > $OU
 echo "== gemm table"; timeout 600 python tools/gemm_bench.py --json $OUT/gemm_${TAG}.json > $OUT/gemm_${TAG}.txt 2>&1; tail -5 $OUT/gemm_${TAG}.txt
 echo "== ncu launch list"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches_$TAG.csv python bench.py --no-graph --no-cpu --no-gpu-eager --no-sustained --steps 2 --warmup 3 > $OUT/ncu_launches_$TAG.log 2>&1; echo "rc=$?"; wc -l $OUT/launches_$TAG.csv
 echo "== ncu full"; bash tools/gpu_ncu.sh $TAG enc.2.r3:fwd dec.0.skip:dgrad enc.3.r3:wgrad
+echo "== ncu elementwise"; timeout 300 python tools/ew_once.py > $OUT/plain_ew.log 2>&1 && timeout 600 ncu --set full --clock-control none --nvtx --nvtx-include "once/" -k regex:"optim_packed_kernel|recon_loss_chain_kernel|sumsq_packed_kernel|pack_input_kernel" -c 4 -o $OUT/prof_ew1_$TAG -f python tools/ew_once.py > $OUT/ncu_ew1.log 2>&1; tail -1 $OUT/ncu_ew1.log
+timeout 600 ncu --set full --clock-control none --nvtx --nvtx-include "once/" -k regex:"bnact_fwd_kernel|bnact_bwd_apply_kernel" --launch-skip 14 -c 8 -o $OUT/prof_ew2_$TAG -f python tools/ew_once.py > $OUT/ncu_ew2.log 2>&1; tail -1 $OUT/ncu_ew2.log
+ls -la $OUT/prof_ew*_$TAG.ncu-rep; du -sh $OUT
