@@ -525,7 +525,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                                             "from the committed ncu pass (profiles/gemm_family_dram.json), not re-measured "
                                             "in this run; ncu counts a launch's DRAM writes only while it runs, so dirty "
                                             "L2 lines written back later are under-counted",
-                            "kernel": "tcgen05 overlapping-row GEMM family (gemm_tc[_mc]_kernel + wgrad_tc[_mc]_kernel): all "
+                            "kernel": "tcgen05 overlapping-row GEMM family (gemm_tc[_bnr]_kernel + wgrad_tc_kernel): all "
                                       "its launches of one step replayed back to back from one CUDA graph, CUDA events",
                             "launches_per_step": gp["launches"], "gemm_seconds_per_step": gp["seconds"],
                             "gemm_share_of_step": gp["seconds"] / (dt / args.steps),

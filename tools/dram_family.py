@@ -1,7 +1,7 @@
 """DRAM traffic of the tensor-core GEMM family over one training step, from an ncu metrics pass:
    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 900 --csv \
        --log-file gpurun_out/dram.csv python bench.py --no-graph --no-cpu --no-gpu-eager --no-sustained --steps 2 --warmup 3
-   python tools/dram_family.py gpurun_out/dram.csv profiles/gemm_family_dram.json [step_index]"""
+   python tools/dram_family.py gpurun_out/dram.csv profiles/gemm_family_dram.json [step_index] [bench config key]"""
 import csv, json, sys
 src, out = sys.argv[1], sys.argv[2]
 which = int(sys.argv[3]) if len(sys.argv) > 3 else 2
@@ -36,5 +36,11 @@ doc = {"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram
        "per_kernel": {n: {"launches": sum(1 for r in fam if r["name"] == n),
                           "dram_bytes": sum(r.get("dram__bytes_read.sum", 0.0) + r.get("dram__bytes_write.sum", 0.0) for r in fam if r["name"] == n),
                           "us": sum(r["us"] for r in fam if r["name"] == n)} for n in sorted({r["name"] for r in fam})}}
-json.dump(doc, open(out, "w"), indent=1)
+cfg = sys.argv[4] if len(sys.argv) > 4 else "2"
+try:
+    full = json.load(open(out))
+except Exception:
+    full = {}
+full[cfg] = doc  # bench.py reads profiles/gemm_family_dram.json[<--config>]["dram_bytes_per_step"]
+json.dump(full, open(out, "w"), indent=1)
 print(json.dumps(doc, indent=1))
