@@ -465,6 +465,15 @@ class Engine:
         B = data["x6d"].shape[0]
         return self.plan(B).forward(data, training)
 
+    # ---- dp_bn "sync": BatchNorm statistics over the global batch (set by parallel.setup(..., bn_sync=True))
+    def bn_sync_world(self) -> int:
+        grp = self.__dict__.get("_bn_sync")
+        return grp[0] if grp else 1
+
+    def bn_sync_reduce(self, t):
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._bn_sync[1])
+
     def encode(self, data, training: bool):
         B = data["x6d"].shape[0]
         return self.plan(B).forward(data, training, upto="encode")
@@ -623,8 +632,17 @@ class Plan:
                 kw.update(U=U.at(0), u_bs=U.bs, u_ls=U.ls)
             base = bn_mode(bool(bn_name), bool(slope_name))
 
+            n_st = 2 * Cc * fold
+
             def run():
                 mode = base | (TRAIN if (self._training and bn_name) else 0)
+                world = eng.bn_sync_world()
+                if world > 1 and (mode & TRAIN):
+                    # dp_bn "sync" (SURVEY.md §8e caveat 1): batch statistics over the GLOBAL batch — the layer's column
+                    # sums are all-reduced before they are finalised, the count grows by the world size
+                    eng.bn_sync_reduce(st_off.t[st_off.off:st_off.off + n_st])
+                    ops.bnact_fwd(mode=mode, stats=st_off, **dict(kw, count=kw["count"] * world))
+                    return
                 ops.bnact_fwd(mode=mode, stats=st_off if bn_name else None, **kw)
             F.append(run)
 
@@ -652,15 +670,29 @@ class Plan:
                 kw.update(dU=dU.at(0), u_bs=dU.bs, u_ls=dU.ls)
             out = []
             if (mode & 3) and not fused:
-                out.append(lambda: ops.bnact_bwd_reduce(sums=sm_off, stats=st_off if bn_name else None, **kw))
+                def reduce():
+                    world = eng.bn_sync_world()  # dp_bn "sync": `stats` holds the global sums
+                    ops.bnact_bwd_reduce(sums=sm_off, stats=st_off if bn_name else None,
+                                         **(dict(kw, count=kw["count"] * world) if world > 1 else kw))
+                out.append(reduce)
             akw = dict(kw)
             akw.update(dX=dX.at(0) if dX is not None else None, d_bs=dX.bs if dX is not None else 0,
                        d_ls=dX.ls if dX is not None else 0,
                        dgamma=eng.gref(bn_name + ".weight") if bn_name else None,
                        dbeta=eng.gref(bn_name + ".bias") if bn_name else None,
                        dslope=eng.gref(slope_name) if slope_name else None)
-            out.append(lambda: ops.bnact_bwd_apply(sums=sm_off if (mode & 3) else None,
-                                                   stats=st_off if bn_name else None, **akw))
+            n_sm = 2 * Cc + 1
+
+            def apply():
+                world = eng.bn_sync_world()
+                if world > 1 and (mode & 3):
+                    # the backward reduction over the global batch too; the BatchNorm / PReLU parameter gradients this
+                    # launch writes are then global sums on every rank (parallel.GradAllReduce leaves them alone)
+                    eng.bn_sync_reduce(sm_off.t[sm_off.off:sm_off.off + n_sm])
+                    ops.bnact_bwd_apply(sums=sm_off, stats=st_off if bn_name else None, **dict(akw, count=akw["count"] * world))
+                    return
+                ops.bnact_bwd_apply(sums=sm_off if (mode & 3) else None, stats=st_off if bn_name else None, **akw)
+            out.append(apply)
             return out
 
         def wgrad(g: GemmW, Aref, a_bs, a_ls, Lo, dY, y_bs, y_ls, bias_n=None):

@@ -72,7 +72,8 @@ class GradAllReduce:
             self._lo = lo
         elif phase == "encoder_done":
             self._reduce(eng.gpacked[:self._lo])
-            self._reduce(eng.gflat[:eng.n_direct])
+            if eng.bn_sync_world() == 1:  # dp_bn "sync": the BatchNorm / PReLU gradients are already global sums
+                self._reduce(eng.gflat[:eng.n_direct])
             self._lo = eng.gp_split
 
     def __call__(self, eng, phase: str, wait=(), lo=None, hi=None):
@@ -80,7 +81,10 @@ class GradAllReduce:
         if self.world == 1:
             return
         if phase == "post_backward":
-            self._reduce(eng.gflat)
+            if eng.bn_sync_world() == 1:
+                self._reduce(eng.gflat)
+            else:
+                self._reduce(eng.gflat[eng.n_direct:])
             return
         if not self.cuda:
             self._run(eng, phase, lo, hi)
@@ -95,11 +99,16 @@ class GradAllReduce:
             main.wait_stream(self.stream)
 
 
-def setup(model, optimizer=None, group=None):
+def setup(model, optimizer=None, group=None, bn_sync=False):
     """Public entry of data parallelism (call once per process after torch.distributed is initialised and the model is
     on its device): identical replicas (rank 0's parameters and buffers), the bucketed gradient all-reduce hooked into
     the engine's backward (both the fused TrainStep path and `total.backward()`), 1/world folded into the optimizer's
-    gradient scale.  Returns the GradAllReduce hook (None when the world is one process)."""
+    gradient scale.  Returns the GradAllReduce hook (None when the world is one process).
+
+    bn_sync=True selects the dp_bn "sync" mode of SURVEY.md §8e (caveat 1): every BatchNorm's batch statistics (and the
+    matching backward sums) are all-reduced, so the replicas together compute exactly what ONE device would on the
+    global batch — parity with the single-device reference at world x B windows — at the price of 33 small latency-bound
+    all-reduces per step.  Default is per-replica statistics (standard DDP semantics)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return None
@@ -107,6 +116,7 @@ def setup(model, optimizer=None, group=None):
     eng = model.engine
     comm = GradAllReduce(eng, world, group)
     eng.comm = comm
+    eng._bn_sync = (world, group) if bn_sync else None
     if optimizer is not None:
         optimizer.grad_scale = 1.0 / world
     return comm

@@ -100,3 +100,72 @@ def test_two_rank_step_matches_sharded_oracle():
             assert e < 5e-3 or ZERO_GRAD_BIAS.search(n), (rank, n, e)
         assert same, "replicas diverged after the update"
         assert nbytes > 0
+
+
+SCALE_NOGR = {"prior": 1e-4, "jpe": 1.0, "root": 1.0}
+
+
+def _worker_sync(rank, world, port, q):
+    """dp_bn "sync": the two replicas together must reproduce ONE device on the concatenated batch."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import scrubvae_b200 as sv
+    from scrubvae_b200.engine import Engine, TrainStep
+    from scrubvae_b200 import parallel
+    from oracle import scvae_oracle as orc
+    from emu_ops import EmuOps
+    from test_engine_cpu import build_model, _rel
+    torch.manual_seed(10 + rank)
+    m, dcfg = build_model(CH, Z, ["heading"], [])
+    m._engine = Engine(m, ops=EmuOps())
+    m.train()
+    opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
+    comm = parallel.setup(m, opt, bn_sync=True)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    shards = [orc.synth_batch(BL, seed=100 + r) for r in range(world)]
+    epss = [orc.synth_eps(BL, Z, seed=200 + r) for r in range(world)]
+    m._noise = epss[rank]
+    step = TrainStep(m, opt, SCALE_NOGR, BL, use_graph=False, comm=comm, keep_grads=True)
+    step.run(shards[rank])
+    losses = {k: v.item() for k, v in step.losses().items()}
+    lsum = torch.tensor([losses[k] for k in sorted(losses)], dtype=torch.double)
+    dist.all_reduce(lsum)
+    lmean = dict(zip(sorted(losses), (lsum / world).tolist()))
+    # ONE device on the global batch
+    cfg = orc.Cfg(ch=CH, z_dim=Z, grad_reversal=())
+    glob = {k: torch.cat([s[k] for s in shards], 0) for k in shards[0]}
+    l, g, _, sd1, _ = orc.train_step(sd0, glob, cfg, SCALE_NOGR, torch.cat(epss, 0))
+    lref = {k: v.item() for k, v in l.items()}
+    gn = sum(float((v.double() ** 2).sum()) for v in g.values()) ** 0.5
+    errs = {n: (_rel(gv / world, g[n]), ((gv / world).double() - g[n].double()).norm().item() / gn)
+            for n, gv in step.named_grads().items() if n in g}
+    bufs = {k: v for k, v in m.state_dict().items() if k.endswith("running_mean") or k.endswith("running_var")}
+    berr = {k: _rel(v.float(), sd1[k].float()) for k, v in bufs.items() if k in sd1}
+    q.put((rank, lmean, lref, errs, berr))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sync_batchnorm_matches_one_device_on_the_global_batch():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_sync, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, lmean, lref, errs, berr in res:
+        for k, v in lref.items():  # mean of the local losses = the global-batch loss
+            if k in lmean:
+                assert abs(lmean[k] - v) <= 3e-5 * abs(v) + 1e-6, (rank, k, lmean[k], v)
+        assert len(errs) > 50
+        for n, (rel, glob) in errs.items():  # reduced gradient = the single-device gradient on the global batch
+            assert rel < 3e-4 or glob < 2e-6, (rank, n, rel, glob)
+        for k, e in berr.items():  # running statistics of the global batch on every rank
+            assert e < 1e-5, (rank, k, e)
