@@ -175,11 +175,13 @@ int scv_kl(const float* mu, const float* L, double* loss, const float* gscale, f
  *   root : train/losses.py:216-219 with inv_normalize_root model/residual.py:433-436;
  *          loss[1] += sum (root_hat-root)^2 / B;  root_hat (F,3) is written out.
  * dxh rows get the UNIT gradients d jpe/d xh[..nx) and d root/d xh[nx..nx+3) (pad columns 0).
- * parents[j] = parent joint (-1 root); chain_id/chain_pos describe kinematic_tree. */
+ * tree = [n_chains, len_0, joints_0..., len_1, ...] (int32, device).  tree_kind: 0 = both kernels are launched and decide on the
+ * device which one serves this skeleton (the other exits at once); 1 = the caller knows the lane-per-chain kernel serves it
+ * (<= 8 chains of <= 5 joints, every chain starting at joint 0 or at a joint an earlier chain placed, J <= 32); 2 = generic. */
 int scv_recon_loss(const float* xh, int64_t ld, const float* offsets, const float* target,
                    const float* root, const float* arena, const int32_t* tree, int64_t n_tree,
                    double* loss, float* root_hat, float* dxh, int64_t F, int64_t B, int64_t J,
-                   void* stream);
+                   int64_t tree_kind, void* stream);
 
 /* draw[b][halo+w][c] = (g_jpe*dxh[c<nx] | g_root*dxh[nx<=c<nx+3]) * (1 - xh^2); g_* are device
  * scalars (NULL = 0).  Backward of tanh at model/residual.py:291 fused with the loss scales. */

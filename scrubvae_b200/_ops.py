@@ -96,7 +96,7 @@ _SIGS = {
     "scv_reparam_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "scv_reparam_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _f64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "scv_kl": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
-    "scv_recon_loss": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "scv_recon_loss": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "scv_out_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "scv_gr_loss": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "scv_gather": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
@@ -233,10 +233,10 @@ class CudaOps:
         self._check(self.lib.scv_kl(_ptr(mu), _ptr(L), _ptr(loss), _ptr(gscale), _ptr(dmu), _ptr(dL), B, z,
                                     self._stream()), "scv_kl")
 
-    def recon_loss(self, xh, ld, offsets, target, root, arena, tree, n_tree, loss, root_hat, dxh, F, B, J):
+    def recon_loss(self, xh, ld, offsets, target, root, arena, tree, n_tree, loss, root_hat, dxh, F, B, J, tree_kind=0):
         self._check(self.lib.scv_recon_loss(_ptr(xh), ld, _ptr(offsets), _ptr(target), _ptr(root), _ptr(arena),
                                             _ptr(tree), n_tree, _ptr(loss), _ptr(root_hat), _ptr(dxh), F, B, J,
-                                            self._stream()), "scv_recon_loss")
+                                            int(tree_kind), self._stream()), "scv_recon_loss")
 
     def out_bwd(self, xh, dxh, ld, g_jpe, g_root, nx, draw, d_bs, d_ls, B, W, round_tf32=False):
         self._check(self.lib.scv_out_bwd(_ptr(xh), _ptr(dxh), ld, _ptr(g_jpe), _ptr(g_root), nx, _ptr(draw), d_bs,

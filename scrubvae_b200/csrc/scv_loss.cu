@@ -641,8 +641,9 @@ int scv_kl(const float* mu, const float* L, double* loss, const float* gscale, f
 
 int scv_recon_loss(const float* xh, int64_t ld, const float* offsets, const float* target, const float* root,
                    const float* arena, const int32_t* tree, int64_t n_tree, double* loss, float* root_hat, float* dxh,
-                   int64_t F, int64_t B, int64_t J, void* stream) {
+                   int64_t F, int64_t B, int64_t J, int64_t tree_kind, void* stream) {
   SCV_REQUIRE(J <= SCV_MAX_J && n_tree <= SCV_MAX_J * 3 && ld >= J * 6 + 3, "scv_recon_loss: bad J/tree/ld");
+  SCV_REQUIRE(tree_kind >= 0 && tree_kind <= 2, "scv_recon_loss: tree_kind is 0 (decide on the device), 1 or 2");
   if (F <= 0) return 0;
   int64_t blocks = (F + FK_WARPS - 1) / FK_WARPS;
   const int64_t cap = (int64_t)scv::sm_count() * 8;
@@ -650,10 +651,16 @@ int scv_recon_loss(const float* xh, int64_t ld, const float* offsets, const floa
   // fast path first (lane per chain); the generic kernel exits at once when the fast path took the skeleton
   int64_t cblocks = (F + FK_WARPS * 4 - 1) / (FK_WARPS * 4);
   if (cblocks > cap) cblocks = cap;
-  recon_loss_chain_kernel<<<(unsigned)cblocks, FK_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      xh, ld, offsets, target, root, arena, tree, loss, root_hat, dxh, F, (int)B, (int)J);
-  int rc0 = scv::check_launch("recon_loss_chain_kernel");
-  if (rc0) return rc0;
+  // tree_kind: the tree lives on the device and the library never synchronises, so by default BOTH kernels are launched
+  // and each decides for itself (the one that does not serve the skeleton exits at once, ~12 us of empty launch); a
+  // caller that knows the tree says which one serves it: 1 = lane per chain, 2 = lane per joint
+  if (tree_kind != 2) {
+    recon_loss_chain_kernel<<<(unsigned)cblocks, FK_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        xh, ld, offsets, target, root, arena, tree, loss, root_hat, dxh, F, (int)B, (int)J);
+    int rc0 = scv::check_launch("recon_loss_chain_kernel");
+    if (rc0) return rc0;
+  }
+  if (tree_kind == 1) return 0;
   recon_loss_kernel<<<(unsigned)blocks, FK_WARPS * 32, 0, (cudaStream_t)stream>>>(
       xh, ld, offsets, target, root, arena, tree, (int)n_tree, loss, root_hat, dxh, F, (int)B, (int)J);
   return scv::check_launch("recon_loss_kernel");

@@ -483,6 +483,21 @@ class Engine:
         return self.plan(B).forward(data, training, z_given=z)
 
 
+def _chain_tree_ok(tree, J) -> bool:
+    """Host twin of chain_tree_ok + the start-joint check of csrc/scv_loss.cu: can the lane-per-chain FK kernel serve this
+    kinematic tree (<= 8 chains of 1..5 joints, every chain starting at joint 0 or at a joint an earlier chain placed)?"""
+    if len(tree) > 8 or J > 32:
+        return False
+    placed = set()
+    for chain in tree:
+        if not 1 <= len(chain) <= 5:
+            return False
+        if chain[0] != 0 and chain[0] not in placed:
+            return False
+        placed.update(int(j) for j in chain[1:])
+    return True
+
+
 class Plan:
     """Static buffers + launch lists for one batch size."""
 
@@ -528,8 +543,10 @@ class Plan:
             for chain in m.kinematic_tree:
                 tr += [len(chain)] + [int(j) for j in chain]
             self.tree = torch.tensor(tr, dtype=torch.int32, device=dev)
+            self.tree_kind = 1 if _chain_tree_ok(m.kinematic_tree, self.J) else 2  # which scv_recon_loss kernel serves it
         else:
             self.tree = None
+            self.tree_kind = 0
         arena = m.arena_size
 
         # ---- loss bookkeeping: acc (double) / out (float): [jpe, root, prior, gr keys...]
@@ -895,9 +912,14 @@ class Plan:
             if self.tree is None:
                 raise RuntimeError("scrubvae_b200: the jpe loss needs model.kinematic_tree")
             ops.recon_loss(self.xh, C0, self.inp["offsets"], self.inp["target_pose"], self.inp["root"], arena,
-                           self.tree, self.tree.numel(), self.loss_acc, None, self.dxh, B * W, B, self.J)
+                           self.tree, self.tree.numel(), self.loss_acc, None, self.dxh, B * W, B, self.J,
+                           tree_kind=self.tree_kind)
         Lk.append(recon)
-        Lk.append(lambda: ops.kl(self.mu, self.Lmat, Ref(self.loss_acc, 2), None, None, None, B, z))
+        # fused step: the loss scales are known up front, so ONE pass over L gives the KL term and its gradients
+        # (the backward launch below is then skipped); the piecewise path learns d total / d prior only in backward
+        Lk.append(lambda: ops.kl(self.mu, self.Lmat, Ref(self.loss_acc, 2), Ref(self.loss_scale, 2), self.dmu_kl, self.dL_kl,
+                                 B, z) if self._fused_tail else
+                  ops.kl(self.mu, self.Lmat, Ref(self.loss_acc, 2), None, None, None, B, z))
         for ki, key in enumerate(eng.gr_keys):
             preds = [a[-1][0] for a in self.gr_act[key]]
             ld = self.gr_act[key][0][-1][1]
@@ -1017,7 +1039,8 @@ class Plan:
         self.dmu_kl = torch.zeros(B, z, **f32)
         self.dL_kl = torch.zeros(B, z, z, **f32)
         self.dms = torch.zeros(B * eng.ms_ld + 64, **opd)[:B * eng.ms_ld].view(B, eng.ms_ld)
-        Bw.append(lambda: ops.kl(self.mu, self.Lmat, None, Ref(self.gscale, 2), self.dmu_kl, self.dL_kl, B, z))
+        Bw.append(lambda: None if self._fused_tail else
+                  ops.kl(self.mu, self.Lmat, None, Ref(self.gscale, 2), self.dmu_kl, self.dL_kl, B, z))
         Bw.append(lambda: self._mi_launch(loss=False))  # adds d mcmi / d mu into dmu_kl
         for ki, key in enumerate(eng.mals_keys):  # adds d <key>_mals / d mu into dmu_kl
             Bw.append(lambda key=key, ki=ki: self._mals_backward(key, ki))

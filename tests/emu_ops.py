@@ -336,7 +336,7 @@ class EmuOps:
 
     # ---- reconstruction
     @torch.enable_grad()
-    def recon_loss(self, xh, ld, offsets, target, root, arena, tree, n_tree, loss, root_hat, dxh, F, B, J):
+    def recon_loss(self, xh, ld, offsets, target, root, arena, tree, n_tree, loss, root_hat, dxh, F, B, J, tree_kind=0):
         self.n += 1
         from oracle import scvae_oracle as orc  # test infrastructure may use the oracle
         tr = _v(tree, (n_tree,), (1,)).tolist()

@@ -153,9 +153,20 @@ def test_fused_epoch_over_device_loader_equals_piecewise_path():
         assert abs(ma[k] - mb[k]) <= 1e-5 * abs(mb[k]) + 1e-6, (k, ma[k], mb[k])
     # five AdamW steps: every step moves an element by ~lr * sign(g), so elements whose gradient is rounding noise (the two
     # paths order their floating-point sums differently: split-K atomics, fused optimizer) differ by a few lr
+    # — which is a large RELATIVE difference only for parameters that start at zero (BatchNorm beta), and which of those
+    # elements flip depends on the order of the atomics (dynamic tile scheduling).  So: relative 5e-3, OR the Adam bound —
+    # no element further apart than 2 lr per step and fewer than 5 % of a tensor's elements apart by more than lr / 5.
     from test_engine_cpu import ZERO_GRAD_BIAS
-    bad = {k: _rel(sa[k].float().cpu(), sb[k].float().cpu()) for k in sa
-           if _rel(sa[k].float().cpu(), sb[k].float().cpu()) >= 5e-3 and not ZERO_GRAD_BIAS.search(k)}
+    lr, steps = 1e-5, len(loader)
+    bad = {}
+    for k in sa:
+        a, b = sa[k].float().cpu(), sb[k].float().cpu()
+        if _rel(a, b) < 5e-3 or ZERO_GRAD_BIAS.search(k):
+            continue
+        d = (a - b).abs()
+        if d.max().item() <= 2.2 * lr * steps and (d > 0.2 * lr).float().mean().item() < 0.05 and "running" not in k:
+            continue
+        bad[k] = (_rel(a, b), d.max().item(), (d > 0.2 * lr).float().mean().item())
     assert not bad, bad
 
 
