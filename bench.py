@@ -294,7 +294,7 @@ def hbm_kernel_table(step, hbm_gbs, reps=3):
         "sumsq_packed": lambda a, kw: a[2] * esz,
         "gather": lambda a, kw: a[3] * esz * 2,  # weight repack / gradient unpack: one read + one write per element
         # p, m, v read + write; gradient read; resident mode also writes the operand copy
-        "optim_step": lambda a, kw: a[4] * esz * (8 if kw.get("pack_idx") is not None else 7),
+        "optim_step": lambda a, kw: a[4] * esz * (8 if (kw.get("pack_idx") is not None or kw.get("pack_mask") is not None) else 7),
     }
     recs = []
     saved = {}

@@ -218,10 +218,15 @@ typedef struct {
    * and / or packed16_out[j] (bf16).  n must be a multiple of 4 and the arrays 16-byte aligned (packed16_out: 8).  No
    * repack pass and no gradient-unpack pass is left in the step. */
   const int32_t* pack_idx; float* packed_out; void* packed16_out; int64_t flags;
+  /* optional liveness bitmask of the packed positions (bit j of word w: position 32 w + j is live), ceil(n / 32) words:
+   * when given it replaces the sign test on pack_idx (which may then be NULL) - 1/32 of the index array's traffic */
+  const uint32_t* pack_mask;
 } scv_optim_t;
 int scv_optim_step(const scv_optim_t* p, void* stream);
-/* global gradient norm over the packed gradients: sumsq[0] += sum over j < n with pack_idx[j] >= 0 of gpacked[j]^2 */
-int scv_sumsq_packed(const float* gpacked, const int32_t* pack_idx, int64_t n, double* sumsq, void* stream);
+/* global gradient norm over the packed gradients: sumsq[0] += sum over the live j < n (pack_mask bit, or pack_idx[j] >= 0 when
+ * pack_mask is NULL) of gpacked[j]^2 */
+int scv_sumsq_packed(const float* gpacked, const int32_t* pack_idx, const uint32_t* pack_mask, int64_t n, double* sumsq,
+                     void* stream);
 /* cudaMemsetAsync(p, 0, bytes) on `stream`: the per-step accumulators (BatchNorm sums, loss terms, grad norm) live in
  * one buffer and are cleared by one memset node of the step's CUDA graph. */
 int scv_zero(void* p, int64_t bytes, void* stream);

@@ -79,7 +79,7 @@ OptimT = _struct("OptimT", [
     ("p", _vp), ("g", _vp), ("m", _vp), ("v", _vp), ("n", _i64), ("sumsq", _vp), ("max_norm", _f64),
     ("gscale", _f64), ("lr", _f64), ("beta1", _f64), ("beta2", _f64), ("eps", _f64),
     ("weight_decay", _f64), ("step", _i64), ("hyper", _vp), ("kind", _i64),
-    ("pack_idx", _vp), ("packed_out", _vp), ("packed16_out", _vp), ("flags", _i64)])
+    ("pack_idx", _vp), ("packed_out", _vp), ("packed16_out", _vp), ("flags", _i64), ("pack_mask", _vp)])
 
 _SIGS = {
     "scv_version": (C.c_int, []),
@@ -114,7 +114,7 @@ _SIGS = {
     "scv_mals_update": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scv_gen_features": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "scv_zero": (C.c_int, [_vp, _i64, _vp]),
-    "scv_sumsq_packed": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "scv_sumsq_packed": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "scv_d2f": (C.c_int, [_vp, _vp, _i64, _vp]),
     "scv_loss_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "scv_unpack_root": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _i64, _vp]),
@@ -261,14 +261,14 @@ class CudaOps:
         self._check(self.lib.scv_sumsq(_ptr(g), n, _ptr(out), self._stream()), "scv_sumsq")
 
     def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind,
-                   hyper=None, pack_idx=None, packed_out=None, packed16_out=None, round_tf32=False):
+                   hyper=None, pack_idx=None, packed_out=None, packed16_out=None, round_tf32=False, pack_mask=None):
         s = OptimT(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, _ptr(sumsq), max_norm, gscale, lr, beta1, beta2, eps,
                    weight_decay, step, _ptr(hyper), kind, _ptr(pack_idx), _ptr(packed_out), _ptr(packed16_out),
-                   int(bool(round_tf32)))
+                   int(bool(round_tf32)), _ptr(pack_mask))
         self._check(self.lib.scv_optim_step(C.byref(s), self._stream()), "scv_optim_step")
 
-    def sumsq_packed(self, gpacked, pack_idx, n, out):
-        self._check(self.lib.scv_sumsq_packed(_ptr(gpacked), _ptr(pack_idx), n, _ptr(out), self._stream()),
+    def sumsq_packed(self, gpacked, pack_idx, n, out, pack_mask=None):
+        self._check(self.lib.scv_sumsq_packed(_ptr(gpacked), _ptr(pack_idx), _ptr(pack_mask), n, _ptr(out), self._stream()),
                     "scv_sumsq_packed")
 
     def zero(self, t):

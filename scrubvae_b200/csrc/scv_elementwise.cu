@@ -448,18 +448,40 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const float* __restrict__ g, 
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
-__global__ void __launch_bounds__(NT) sumsq_packed_kernel(const float* __restrict__ gp, const int32_t* __restrict__ idx, int64_t n,
-                                                          double* out) {
+// liveness of 4 consecutive packed positions starting at float4 index i: from the bitmask (bit j of word w = position
+// 32 w + j is live; 1/32 of the index array's traffic) when given, else from the sign of the index entries
+__device__ __forceinline__ uint32_t live4(const int32_t* __restrict__ idx, const uint32_t* __restrict__ mask, int64_t i) {
+  if (mask) return (__ldg(mask + (i >> 3)) >> (((uint32_t)i & 7u) * 4u)) & 0xFu;
+  const int4 j = __ldg(reinterpret_cast<const int4*>(idx) + i);
+  return (j.x >= 0 ? 1u : 0u) | (j.y >= 0 ? 2u : 0u) | (j.z >= 0 ? 4u : 0u) | (j.w >= 0 ? 8u : 0u);
+}
+
+__global__ void __launch_bounds__(NT) sumsq_packed_kernel(const float* __restrict__ gp, const int32_t* __restrict__ idx,
+                                                          const uint32_t* __restrict__ mask, int64_t n, double* out) {
   __shared__ double sh[32];
   float acc = 0.f;
   double dacc = 0.0;
   int cnt = 0;
   const int64_t n4 = n >> 2;  // every packed matrix is padded to 4 floats
-  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (int64_t)gridDim.x * NT) {
-    const int4 j = __ldg(reinterpret_cast<const int4*>(idx) + i);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(gp) + i);
-    acc += (j.x >= 0 ? v.x * v.x : 0.f) + (j.y >= 0 ? v.y * v.y : 0.f) + (j.z >= 0 ? v.z * v.z : 0.f) + (j.w >= 0 ? v.w * v.w : 0.f);
-    if (++cnt == 64) { dacc += (double)acc; acc = 0.f; cnt = 0; }
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  for (int64_t i0 = (int64_t)blockIdx.x * NT + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+    float4 v[4];
+    uint32_t lv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // four independent 16-byte loads in flight per thread
+      const int64_t i = i0 + u * stride;
+      lv[u] = 0u;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n4) {
+        lv[u] = live4(idx, mask, i);
+        v[u] = __ldg(reinterpret_cast<const float4*>(gp) + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      acc += ((lv[u] & 1u) ? v[u].x * v[u].x : 0.f) + ((lv[u] & 2u) ? v[u].y * v[u].y : 0.f) +
+             ((lv[u] & 4u) ? v[u].z * v[u].z : 0.f) + ((lv[u] & 8u) ? v[u].w * v[u].w : 0.f);
+    if (++cnt == 16) { dacc += (double)acc; acc = 0.f; cnt = 0; }
   }
   dacc += (double)acc;
   double s = scv::block_sum_d(dacc, sh);
@@ -488,15 +510,14 @@ __global__ void __launch_bounds__(NT) optim_packed_kernel(const scv_optim_t p) {
   // all the packed arrays); masked lanes write their old values back, so the stores stay 16-byte vectors
   const int64_t n4 = p.n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (int64_t)gridDim.x * NT) {
-    const int4 id = __ldg(reinterpret_cast<const int4*>(p.pack_idx) + i);
+    const uint32_t lv = live4(p.pack_idx, p.pack_mask, i);
     const float4 g4 = ld4(p.g + 4 * i), w4 = ld4(p.p + 4 * i), m4 = ld4(p.m + 4 * i);
     const float4 v4 = kind == 2 ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(p.v + 4 * i);
-    const int idx[4] = {id.x, id.y, id.z, id.w};
     const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
     float ww[4] = {w4.x, w4.y, w4.z, w4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (idx[q] < 0) continue;  // structural zero / padding of the packed layout: left untouched
+      if (!((lv >> q) & 1u)) continue;  // structural zero / padding of the packed layout: left untouched
       float g = gg[q] * coef, w = ww[q];
       if (kind == 2) {
         float buf = first ? g : b1 * mm[q] + g;
@@ -701,8 +722,8 @@ int scv_zero(void* p, int64_t bytes, void* stream) {
 int scv_optim_step(const scv_optim_t* p, void* stream) {
   SCV_REQUIRE(p->kind >= 0 && p->kind <= 2 && (p->hyper || p->step >= 1), "scv_optim_step: bad kind/step");
   if (p->n <= 0) return 0;
-  if (p->pack_idx) {
-    SCV_REQUIRE(p->n % 4 == 0 && scv::aligned16(p->pack_idx) && scv::aligned16(p->g) && scv::aligned16(p->p) &&
+  if (p->pack_idx || p->pack_mask) {
+    SCV_REQUIRE(p->n % 4 == 0 && (p->pack_mask || scv::aligned16(p->pack_idx)) && scv::aligned16(p->g) && scv::aligned16(p->p) &&
                     scv::aligned16(p->m) && (p->kind == 2 || scv::aligned16(p->v)) &&
                     (!p->packed_out || scv::aligned16(p->packed_out)) &&
                     (!p->packed16_out || (reinterpret_cast<uintptr_t>(p->packed16_out) & 7) == 0),
@@ -714,11 +735,13 @@ int scv_optim_step(const scv_optim_t* p, void* stream) {
   return scv::check_launch("optim_kernel");
 }
 
-int scv_sumsq_packed(const float* gpacked, const int32_t* pack_idx, int64_t n, double* sumsq, void* stream) {
-  SCV_REQUIRE(gpacked && pack_idx && sumsq && n % 4 == 0 && scv::aligned16(gpacked) && scv::aligned16(pack_idx),
+int scv_sumsq_packed(const float* gpacked, const int32_t* pack_idx, const uint32_t* pack_mask, int64_t n, double* sumsq,
+                     void* stream) {
+  SCV_REQUIRE(gpacked && (pack_idx || pack_mask) && sumsq && n % 4 == 0 && scv::aligned16(gpacked) &&
+                  (pack_mask || scv::aligned16(pack_idx)),
               "scv_sumsq_packed: gpacked / pack_idx must be 16-byte aligned and n a multiple of 4");
   if (n <= 0) return 0;
-  sumsq_packed_kernel<<<grid1d(n / 4 + 1, 4), NT, 0, (cudaStream_t)stream>>>(gpacked, pack_idx, n, sumsq);
+  sumsq_packed_kernel<<<grid1d(n / 4 + 1, 4), NT, 0, (cudaStream_t)stream>>>(gpacked, pack_idx, pack_mask, n, sumsq);
   return scv::check_launch("sumsq_packed_kernel");
 }
 

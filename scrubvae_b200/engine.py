@@ -347,6 +347,13 @@ class Engine:
         d_idx = torch.cat(self._pack_parts_d) if self._pack_parts_d else torch.zeros(0, dtype=torch.long)
         assert fwd_idx.numel() == self._n_fwd and d_idx.numel() == self._n_d
         self.pack_idx = torch.cat([fwd_idx, d_idx]).to(torch.int32).to(dev)
+        # liveness bitmask of the forward matrices' positions (bit j of word w: position 32 w + j holds a parameter): what the
+        # resident optimizer and the packed gradient norm read instead of the 4-byte index entries
+        live = torch.zeros((int(fwd_idx.numel()) + 31) // 32 * 32, dtype=torch.int64)
+        live[:fwd_idx.numel()] = (fwd_idx >= 0).to(torch.int64)
+        words = (live.view(-1, 32) << torch.arange(32, dtype=torch.int64)[None, :]).sum(1)
+        words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)  # two's complement into int32 storage
+        self.pack_mask = words.to(torch.int32).to(dev)
         self.packed = torch.zeros(self._n_fwd + self._n_d, device=dev)
         # bf16 mode: the GEMMs read bf16 copies of the packed matrices (same element offsets); `packed` (fp32) then only
         # serves the biases, which the epilogues add in fp32
@@ -1505,10 +1512,10 @@ class TrainStep:
                 # resident tail: global norm over the packed gradients + the direct ones, then the optimizer in the packed
                 # layout (writes master, moments and the operand copies; all coalesced) and on the small direct region
                 nf, nd = eng._n_fwd, eng.n_direct
-                ops.sumsq_packed(eng.gpacked, eng.pack_idx, nf, plan.sumsq)
+                ops.sumsq_packed(eng.gpacked, None, nf, plan.sumsq, pack_mask=eng.pack_mask)
                 ops.sumsq(eng.gflat, nd, plan.sumsq)
                 ops.optim_step(eng.pmaster, eng.gpacked, opt.mp, opt.vp, nf, plan.sumsq, *hp, hyper=opt.hyper,
-                               pack_idx=eng.pack_idx, packed_out=eng.packed,
+                               pack_mask=eng.pack_mask, packed_out=eng.packed,
                                packed16_out=eng.packed16, round_tf32=eng.rnd == 1)
                 ops.optim_step(eng.flat, eng.gflat, opt.m, opt.v, nd, plan.sumsq, *hp, hyper=opt.hyper)
             else:

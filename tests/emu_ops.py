@@ -422,19 +422,28 @@ class EmuOps:
         self.n += 1
         _v(out, (1,), (1,)).add_((_v(g, (n,), (1,)).double() ** 2).sum())
 
-    def sumsq_packed(self, gpacked, pack_idx, n, out):
+    @staticmethod
+    def _live(pack_idx, pack_mask, n):
+        """liveness of the packed positions: the bitmask (bit j of word w = position 32 w + j) when given, else idx >= 0"""
+        if pack_mask is not None:
+            words = _v(pack_mask, ((n + 31) // 32,), (1,)).to(torch.int64) & 0xFFFFFFFF
+            bits = (words[:, None] >> torch.arange(32)[None, :]) & 1
+            return bits.reshape(-1)[:n].bool()
+        return _v(pack_idx, (n,), (1,)) >= 0
+
+    def sumsq_packed(self, gpacked, pack_idx, n, out, pack_mask=None):
         self.n += 1
-        live = _v(pack_idx, (n,), (1,)) >= 0
+        live = self._live(pack_idx, pack_mask, n)
         _v(out, (1,), (1,)).add_((_v(gpacked, (n,), (1,))[live].double() ** 2).sum())
 
     def zero(self, t):
         t.zero_()
 
     def optim_step(self, p, g, m, v, n, sumsq, max_norm, gscale, lr, beta1, beta2, eps, weight_decay, step, kind,
-                   hyper=None, pack_idx=None, packed_out=None, packed16_out=None, round_tf32=False):
+                   hyper=None, pack_idx=None, packed_out=None, packed16_out=None, round_tf32=False, pack_mask=None):
         self.n += 1
-        if pack_idx is not None:  # resident-packed mode: only the live positions, plus the operand copies
-            live = _v(pack_idx, (n,), (1,)) >= 0
+        if pack_idx is not None or pack_mask is not None:  # resident-packed mode: only the live positions + operand copies
+            live = self._live(pack_idx, pack_mask, n)
             P, G, M = _v(p, (n,), (1,)), _v(g, (n,), (1,)), _v(m, (n,), (1,))
             V = _v(v, (n,), (1,)) if v is not None else None
             sub = [P[live].clone(), G[live].clone(), M[live].clone(), V[live].clone() if V is not None else None]

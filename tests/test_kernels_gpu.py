@@ -336,9 +336,10 @@ def test_gather_sumsq_optim_finalize(ops):
         run_both(ops, T, call, tol=1e-5, check=["dst", "dst2", "ss", "p", "m", "v", "lout"])
 
 
+@pytest.mark.parametrize("use_mask", [False, True])
 @pytest.mark.parametrize("kind", [0, 1, 2])
 @pytest.mark.parametrize("rnd,bf16", [(False, False), (True, False), (False, True)])
-def test_resident_packed_optimizer(ops, kind, rnd, bf16):
+def test_resident_packed_optimizer(ops, kind, rnd, bf16, use_mask):
     """The optimizer in the packed GEMM layout (resident master): padding positions (pack_idx < 0) keep their values in
     every array, live ones get the same update as the flat kernel, and the operand copies are written alongside."""
     n = 4 * 25013
@@ -351,13 +352,18 @@ def test_resident_packed_optimizer(ops, kind, rnd, bf16):
          "hyper": torch.tensor([3e-4, 7.0], dtype=torch.double)}
     if bf16:
         T["p16"] = torch.full((n,), 7.0).to(torch.bfloat16)
+    if use_mask:  # the liveness bitmask instead of the index array (bit j of word w: position 32 w + j)
+        live = torch.zeros((n + 31) // 32 * 32, dtype=torch.int64)
+        live[:n] = (idx >= 0).to(torch.int64)
+        words = (live.view(-1, 32) << torch.arange(32, dtype=torch.int64)[None, :]).sum(1)
+        T["mask"] = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
 
     def call(o, t):
         t["ss"].zero_()
-        o.sumsq_packed(t["g"], t["idx"], n, t["ss"])
+        o.sumsq_packed(t["g"], None if use_mask else t["idx"], n, t["ss"], pack_mask=t.get("mask"))
         o.optim_step(t["p"], t["g"], t["m"], t["v"], n, t["ss"], 10.0, 0.5, 1e-3, 0.9, 0.999, 1e-8, 0.01, 3, kind,
-                     hyper=t["hyper"] if kind == 1 else None, pack_idx=t["idx"], packed_out=t["po"],
-                     packed16_out=t.get("p16"), round_tf32=rnd)
+                     hyper=t["hyper"] if kind == 1 else None, pack_idx=None if use_mask else t["idx"], packed_out=t["po"],
+                     packed16_out=t.get("p16"), round_tf32=rnd, pack_mask=t.get("mask"))
     run_both(ops, T, call, tol=1e-5, check=["ss", "p", "m", "v", "po"])
     if bf16:
         run_both(ops, T, call, tol=4e-3, check=["p16"])
