@@ -463,25 +463,11 @@ __global__ void __launch_bounds__(NT) sumsq_packed_kernel(const float* __restric
   double dacc = 0.0;
   int cnt = 0;
   const int64_t n4 = n >> 2;  // every packed matrix is padded to 4 floats
-  const int64_t stride = (int64_t)gridDim.x * NT;
-  for (int64_t i0 = (int64_t)blockIdx.x * NT + threadIdx.x; i0 < n4; i0 += 4 * stride) {
-    float4 v[4];
-    uint32_t lv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {  // four independent 16-byte loads in flight per thread
-      const int64_t i = i0 + u * stride;
-      lv[u] = 0u;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < n4) {
-        lv[u] = live4(idx, mask, i);
-        v[u] = __ldg(reinterpret_cast<const float4*>(gp) + i);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      acc += ((lv[u] & 1u) ? v[u].x * v[u].x : 0.f) + ((lv[u] & 2u) ? v[u].y * v[u].y : 0.f) +
-             ((lv[u] & 4u) ? v[u].z * v[u].z : 0.f) + ((lv[u] & 8u) ? v[u].w * v[u].w : 0.f);
-    if (++cnt == 16) { dacc += (double)acc; acc = 0.f; cnt = 0; }
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (int64_t)gridDim.x * NT) {
+    const uint32_t lv = live4(idx, mask, i);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(gp) + i);
+    acc += ((lv & 1u) ? v.x * v.x : 0.f) + ((lv & 2u) ? v.y * v.y : 0.f) + ((lv & 4u) ? v.z * v.z : 0.f) + ((lv & 8u) ? v.w * v.w : 0.f);
+    if (++cnt == 64) { dacc += (double)acc; acc = 0.f; cnt = 0; }
   }
   dacc += (double)acc;
   double s = scv::block_sum_d(dacc, sh);
