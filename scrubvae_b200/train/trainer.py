@@ -320,17 +320,30 @@ def train(config, model, loader_dict, run=None, device="cuda"):
             config["loss"]["prior"] = beta_scheduler.get(epoch)
             print("Beta schedule: {:.3f}".format(config["loss"]["prior"]))
         t0 = time.time()
-        metrics = train_epoch(config, model, loader_dict["train"], device, optimizer, scheduler, epoch)
+        train_metrics = train_epoch(config, model, loader_dict["train"], device, optimizer, scheduler, epoch)
+        metrics = {"{}_train".format(k): v for k, v in train_metrics.items()}  # reference :351-361
         if "grad_reversal" in model.disentangle.keys():
             for key in model.disentangle["grad_reversal"].keys():
                 model.disentangle["grad_reversal"][key].reset_parameters()
             from ..parallel import resync
             resync(model)  # data parallelism: every rank drew its own re-initialisation; rank 0's everywhere
+        # automatically tuned forgetting factors of the moving-average scrubbers (reference :372-384)
+        if "moving_avg_lsq" in model.disentangle.keys():
+            for key in model.disentangle["moving_avg_lsq"].keys():
+                metrics["lambda_mals_{}".format(key)] = model.disentangle["moving_avg_lsq"][key].lam1.detach().cpu().numpy()
+        if "qda" in model.disentangle.keys():
+            for key in model.disentangle["qda"].keys():
+                metrics["lambda_qda_{}".format(key)] = model.disentangle["qda"][key].lama.detach().cpu().numpy()
         metrics["time"] = time.time() - t0
         if epoch % 5 == 0:
             Path("{}/weights".format(config["out_path"])).mkdir(parents=True, exist_ok=True)
             torch.save({k: v.cpu() for k, v in model.state_dict().items()},
                        "{}/weights/epoch_{}.pth".format(config["out_path"], epoch))
+            # validation metrics every 5 epochs from epoch 50 on (reference :400-414; its sklearn decodability scores and
+            # wandb logging that follow are outside the built path)
+            if epoch >= 50 and loader_dict.get("val") is not None:
+                test_metrics, _ = test_epoch(config, model, loader_dict["val"], device, epoch)
+                metrics.update({"{}_test".format(k): v for k, v in test_metrics.items()})
         if epoch % 20 == 0:
             Path("{}/checkpoints".format(config["out_path"])).mkdir(parents=True, exist_ok=True)
             torch.save({"optimizer": optimizer.state_dict(), "lr_scheduler": scheduler},
