@@ -276,6 +276,23 @@ int scv_mi_loss(const float* x, const float* y, int64_t y_ld, const float* xs, c
 int scv_mi_update(const float* mu, const float* L, const float* var, int64_t var_ld, float* xs, float* ys, float* var_s,
                   float* logAx, double bandwidth, int64_t S, int64_t z, int64_t dy, float* valid, void* stream);
 
+/* ---- "moving_avg" scrubber (MovingAverageFilter model/disentangle.py:9-88; loss train/losses.py:286-289; update
+ * train/trainer.py:169-178): per class c two running means m1, m2 (nc,z) of the latent mean with forgetting factors lam1 < lam2.
+ * scv_ma_loss (evaluate_loss :32-74): class means xbar_c of x over the members of class c (stat: scratch nc (z + 1) floats, the
+ *   member count last; an empty class gives NaN as torch.mean of an empty selection); ||xbar_c - m1_c|| < ||xbar_c - m2_c|| ?
+ *   (lam1 = clamp(lam1 - delta), lam2 = lam1 + lamdiff) : (lam2 = clamp(lam2 + delta), lam1 = lam2 - lamdiff); estimates
+ *   e_c = ((1 - lam1) xbar + lam1 m1 + (1 - lam2) xbar + lam2 m2) / 2; loss[0] += sqrt(sum_{c < c'} |e_c - e_c'|^2) (NOT divided by
+ *   the batch size, as the reference); coef (nc,z) = d loss / d x_b for a member b of class c.
+ * scv_ma_backward: dx (B rows of d_ld) += gscale[0] * coef[class of y_b].
+ * scv_ma_update (:76-88): m_i = (1 - lam_i) xbar + lam_i m_i. */
+int scv_ma_loss(const float* x, int64_t x_ld, const int64_t* y, const int64_t* classes, int64_t nc, int64_t z, int64_t B,
+                const float* m1, const float* m2, float* lam1, float* lam2, double delta, double lamdiff, float* stat, float* coef,
+                double* loss, void* stream);
+int scv_ma_backward(const int64_t* y, const int64_t* classes, const float* coef, const float* gscale, int64_t nc, int64_t z,
+                    int64_t B, float* dx, int64_t d_ld, void* stream);
+int scv_ma_update(const float* x, int64_t x_ld, const int64_t* y, const int64_t* classes, int64_t nc, int64_t z, int64_t B,
+                  const float* lam1, const float* lam2, float* m1, float* m2, float* stat, void* stream);
+
 /* ---- "moving_avg_lsq" scrubber (MovingAvgLeastSquares model/disentangle.py:393-538, polynomial order 1; loss
  * train/losses.py:237-245; running-covariance update after the optimizer step train/trainer.py:169-178).
  * x = mu rows (B,z) with an appended column of ones when bias != 0: nx = z + bias <= 136; y (B,ny), ny <= 16.

@@ -678,3 +678,38 @@ def qda_update(st, x, y, classes):
                 st[f"m{side}{ab}"][i] = (1 - lam) * st[f"m{side}{ab}"][i] + lam * mean
                 st[f"S{side}{ab}"][i] = (1 - lam) * st[f"S{side}{ab}"][i] + lam * cov
     return st
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# moving_avg scrubber (MovingAverageFilter, reference model/disentangle.py:9-88)
+# --------------------------------------------------------------------------------------------------------------------
+def ma_init(z: int, n_classes: int, lamdiff: float = 1e-2) -> Dict[str, torch.Tensor]:
+    lam1 = torch.ones(n_classes) * 0.5
+    return {"m1": torch.zeros(n_classes, z), "m2": torch.zeros(n_classes, z), "lam1": lam1, "lam2": lam1 + lamdiff}
+
+
+def ma_evaluate(st, x, y, classes, delta=1e-3, lamdiff=1e-2):
+    """evaluate_loss (:32-74): forgetting factors drift towards the running mean closer to the batch mean; the loss is the
+    norm of the upper-triangular pairwise differences between the classes' mean estimates"""
+    m1, m2 = torch.zeros_like(st["m1"]), torch.zeros_like(st["m2"])
+    for i, label in enumerate(classes):
+        xbar = torch.mean(x[(y == label).ravel(), :], axis=0)
+        if torch.linalg.norm(xbar - st["m1"][i]) < torch.linalg.norm(xbar - st["m2"][i]):
+            st["lam1"][i] = torch.clamp(st["lam1"][i] - delta, 0.0, 1.0)
+            st["lam2"][i] = st["lam1"][i] + lamdiff
+        else:
+            st["lam2"][i] = torch.clamp(st["lam2"][i] + delta, 0.0, 1.0)
+            st["lam1"][i] = st["lam2"][i] - lamdiff
+        m1[i] = (1 - st["lam1"][i]) * xbar + st["lam1"][i] * st["m1"][i]
+        m2[i] = (1 - st["lam2"][i]) * xbar + st["lam2"][i] * st["m2"][i]
+    est = 0.5 * (m1 + m2)
+    return torch.linalg.norm(torch.triu(est.T[..., None] - est.T[..., None, :], diagonal=1))
+
+
+def ma_update(st, x, y, classes):
+    """update (:76-88)"""
+    for i, label in enumerate(classes):
+        xbar = torch.mean(x[(y == label).ravel(), :], axis=0)
+        st["m1"][i] = (1 - st["lam1"][i]) * xbar + st["lam1"][i] * st["m1"][i]
+        st["m2"][i] = (1 - st["lam2"][i]) * xbar + st["lam2"][i] * st["m2"][i]
+    return st

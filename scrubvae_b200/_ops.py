@@ -108,6 +108,9 @@ _SIGS = {
     "scv_qda_loss": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "scv_qda_finalize": (C.c_int, [_vp, _vp, _vp, _f64, _f64, _i64, _i64, _vp, _vp]),
     "scv_qda_update": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp] + [_vp] * 8 + [_vp, _vp]),
+    "scv_ma_loss": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _f64, _f64, _vp, _vp, _vp, _vp]),
+    "scv_ma_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "scv_ma_update": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scv_mals_solve": (C.c_int, [_vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "scv_mals_loss": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "scv_mals_finalize": (C.c_int, [_vp, _vp, _vp, _f64, _f64, _i64, _vp, _vp]),
@@ -324,6 +327,19 @@ class CudaOps:
         self._check(self.lib.scv_qda_update(_ptr(x), x_ld, _ptr(y), _ptr(classes), nc, z, B, _ptr(lama), _ptr(lamb),
                                             *[_ptr(t) for t in m4], *[_ptr(t) for t in S4], _ptr(stat), self._stream()),
                     "scv_qda_update")
+
+    def ma_loss(self, x, x_ld, y, classes, nc, z, B, m1, m2, lam1, lam2, delta, lamdiff, stat, coef, loss=None):
+        self._check(self.lib.scv_ma_loss(_ptr(x), x_ld, _ptr(y), _ptr(classes), nc, z, B, _ptr(m1), _ptr(m2), _ptr(lam1),
+                                         _ptr(lam2), float(delta), float(lamdiff), _ptr(stat), _ptr(coef), _ptr(loss),
+                                         self._stream()), "scv_ma_loss")
+
+    def ma_backward(self, y, classes, coef, gscale, nc, z, B, dx, d_ld):
+        self._check(self.lib.scv_ma_backward(_ptr(y), _ptr(classes), _ptr(coef), _ptr(gscale), nc, z, B, _ptr(dx), d_ld,
+                                             self._stream()), "scv_ma_backward")
+
+    def ma_update(self, x, x_ld, y, classes, nc, z, B, lam1, lam2, m1, m2, stat):
+        self._check(self.lib.scv_ma_update(_ptr(x), x_ld, _ptr(y), _ptr(classes), nc, z, B, _ptr(lam1), _ptr(lam2), _ptr(m1),
+                                           _ptr(m2), _ptr(stat), self._stream()), "scv_ma_update")
 
     def mals_solve(self, Sxx0, Sxy0, Sxx1, Sxy1, l2_reg, bias, nx, ny, W0, W1):
         self._check(self.lib.scv_mals_solve(_ptr(Sxx0), _ptr(Sxy0), _ptr(Sxx1), _ptr(Sxy1), float(l2_reg), int(bias), nx, ny,

@@ -276,6 +276,118 @@ __global__ void __launch_bounds__(NT) qda_update_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// "moving_avg" scrubber (MovingAverageFilter, reference model/disentangle.py:9-88; loss train/losses.py:286-289; update
+// train/trainer.py:169-178): per class two running means m1, m2 of the latent mean with forgetting factors lam1 < lam2.
+//   xbar_c = mean of x over the members of class c;  ||xbar_c - m1_c|| < ||xbar_c - m2_c|| ? (lam1 -= delta, lam2 = lam1 +
+//   lamdiff) : (lam2 += delta, lam1 = lam2 - lamdiff);  e_c = ((1-lam1) xbar + lam1 m1 + (1-lam2) xbar + lam2 m2) / 2
+//   loss = sqrt(sum_{c<c'} ||e_c - e_c'||^2);  d loss / d x_b = (2 - lam1 - lam2)/2 (nc e_c - sum_c' e_c') / loss / n_c
+// ---------------------------------------------------------------------------------------------------------------------
+// class means: block per class, thread per feature; stat[c*(z+1) + j], member count at [z]
+__global__ void __launch_bounds__(NT) ma_mean_kernel(const float* __restrict__ x, int64_t x_ld, const int64_t* __restrict__ y,
+                                                     const int64_t* __restrict__ classes, int z, int B, float* __restrict__ stat) {
+  const int64_t label = classes[blockIdx.x];
+  float* out = stat + (size_t)blockIdx.x * (z + 1);
+  for (int j = threadIdx.x; j <= z; j += NT) {
+    float s = 0.f;
+    int n = 0;
+    for (int b = 0; b < B; ++b)
+      if (y[b] == label) { ++n; if (j < z) s += x[(int64_t)b * x_ld + j]; }
+    out[j] = j < z ? s / (float)n : (float)n;
+  }
+}
+
+// one block: forgetting factors, estimates, loss, per-class gradient rows coef (nc, z)
+__global__ void __launch_bounds__(NT) ma_eval_kernel(const float* __restrict__ stat, const float* __restrict__ m1,
+                                                     const float* __restrict__ m2, float* lam1, float* lam2, float delta,
+                                                     float lamdiff, int nc, int z, float* __restrict__ coef, double* loss) {
+  __shared__ float est[MAXC][MAXZ];
+  __shared__ float red[NT / 32][2];
+  __shared__ float l1s[MAXC], l2s[MAXC], tot[1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = 0; c < nc; ++c) {
+    const float* xb = stat + (size_t)c * (z + 1);
+    float d1 = 0.f, d2 = 0.f;
+    for (int j = threadIdx.x; j < z; j += NT) {
+      const float a = xb[j] - m1[c * z + j], b = xb[j] - m2[c * z + j];
+      d1 += a * a;
+      d2 += b * b;
+    }
+    d1 = scv::warp_sum(d1);
+    d2 = scv::warp_sum(d2);
+    if (lane == 0) { red[warp][0] = d1; red[warp][1] = d2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int w = 0; w < NT / 32; ++w) { s1 += red[w][0]; s2 += red[w][1]; }
+      float a = lam1[c], b = lam2[c];
+      if (sqrtf(s1) < sqrtf(s2)) {
+        a = fminf(fmaxf(a - delta, 0.f), 1.f);
+        b = a + lamdiff;
+      } else {
+        b = fminf(fmaxf(b + delta, 0.f), 1.f);
+        a = b - lamdiff;
+      }
+      lam1[c] = a; lam2[c] = b;
+      l1s[c] = a; l2s[c] = b;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < z; j += NT)
+      est[c][j] = 0.5f * (((1.f - l1s[c]) * xb[j] + l1s[c] * m1[c * z + j]) + ((1.f - l2s[c]) * xb[j] + l2s[c] * m2[c * z + j]));
+    __syncthreads();
+  }
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < z; j += NT)
+    for (int a = 0; a < nc; ++a)
+      for (int b = a + 1; b < nc; ++b) {
+        const float d = est[a][j] - est[b][j];
+        acc += d * d;
+      }
+  acc = scv::warp_sum(acc);
+  if (lane == 0) red[warp][0] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < NT / 32; ++w) t += red[w][0];
+    tot[0] = sqrtf(t);
+    if (loss) loss[0] += (double)tot[0];
+  }
+  __syncthreads();
+  const float nrm = tot[0];
+  for (int j = threadIdx.x; j < z; j += NT) {
+    float sum = 0.f;
+    for (int c = 0; c < nc; ++c) sum += est[c][j];
+    for (int c = 0; c < nc; ++c) {
+      const float n = stat[(size_t)c * (z + 1) + z];
+      coef[c * z + j] = 0.5f * (2.f - l1s[c] - l2s[c]) * ((float)nc * est[c][j] - sum) / nrm / n;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) ma_bwd_kernel(const int64_t* __restrict__ y, const int64_t* __restrict__ classes,
+                                                    const float* __restrict__ coef, const float* __restrict__ gscale, int nc, int z,
+                                                    int B, float* __restrict__ dx, int64_t d_ld) {
+  const float g = gscale ? gscale[0] : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < (int64_t)B * z; i += (int64_t)gridDim.x * NT) {
+    const int b = (int)(i / z), j = (int)(i - (int64_t)b * z);
+    const int64_t yb = y[b];
+    int c = -1;
+    for (int k = 0; k < nc; ++k)
+      if (classes[k] == yb) c = k;
+    if (c >= 0) dx[(int64_t)b * d_ld + j] += g * coef[c * z + j];
+  }
+}
+
+__global__ void __launch_bounds__(NT) ma_update_kernel(const float* __restrict__ stat, const float* __restrict__ lam1,
+                                                       const float* __restrict__ lam2, int nc, int z, float* m1, float* m2) {
+  for (int i = threadIdx.x + blockIdx.x * NT; i < nc * z; i += gridDim.x * NT) {
+    const int c = i / z, j = i - c * z;
+    const float xb = stat[(size_t)c * (z + 1) + j];
+    m1[i] = (1.f - lam1[c]) * xb + lam1[c] * m1[i];
+    m2[i] = (1.f - lam2[c]) * xb + lam2[c] * m2[i];
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -339,6 +451,38 @@ int scv_qda_update(const float* x, int64_t x_ld, const int64_t* y, const int64_t
   qda_update_kernel<<<dim3((unsigned)z, (unsigned)(2 * nc)), NT, 0, (cudaStream_t)stream>>>(x, x_ld, y, classes, (int)z, (int)B, stat,
                                                                                           lama, lamb, P);
   return scv::check_launch("qda_update_kernel");
+}
+
+int scv_ma_loss(const float* x, int64_t x_ld, const int64_t* y, const int64_t* classes, int64_t nc, int64_t z, int64_t B,
+                const float* m1, const float* m2, float* lam1, float* lam2, double delta, double lamdiff, float* stat, float* coef,
+                double* loss, void* stream) {
+  SCV_REQUIRE(z >= 1 && z <= MAXZ && nc >= 1 && nc <= MAXC, "scv_ma_loss: z <= 128, classes <= 16");
+  ma_mean_kernel<<<(unsigned)nc, NT, 0, (cudaStream_t)stream>>>(x, x_ld, y, classes, (int)z, (int)B, stat);
+  int rc = scv::check_launch("ma_mean_kernel");
+  if (rc) return rc;
+  ma_eval_kernel<<<1, NT, 0, (cudaStream_t)stream>>>(stat, m1, m2, lam1, lam2, (float)delta, (float)lamdiff, (int)nc, (int)z, coef,
+                                                    loss);
+  return scv::check_launch("ma_eval_kernel");
+}
+
+int scv_ma_backward(const int64_t* y, const int64_t* classes, const float* coef, const float* gscale, int64_t nc, int64_t z,
+                    int64_t B, float* dx, int64_t d_ld, void* stream) {
+  if (B <= 0) return 0;
+  int blocks = (int)((B * z + NT - 1) / NT);
+  const int cap = scv::sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  ma_bwd_kernel<<<blocks, NT, 0, (cudaStream_t)stream>>>(y, classes, coef, gscale, (int)nc, (int)z, (int)B, dx, d_ld);
+  return scv::check_launch("ma_bwd_kernel");
+}
+
+int scv_ma_update(const float* x, int64_t x_ld, const int64_t* y, const int64_t* classes, int64_t nc, int64_t z, int64_t B,
+                  const float* lam1, const float* lam2, float* m1, float* m2, float* stat, void* stream) {
+  SCV_REQUIRE(z >= 1 && z <= MAXZ && nc >= 1 && nc <= MAXC, "scv_ma_update: z <= 128, classes <= 16");
+  ma_mean_kernel<<<(unsigned)nc, NT, 0, (cudaStream_t)stream>>>(x, x_ld, y, classes, (int)z, (int)B, stat);
+  int rc = scv::check_launch("ma_mean_kernel");
+  if (rc) return rc;
+  ma_update_kernel<<<(unsigned)((nc * z + NT - 1) / NT), NT, 0, (cudaStream_t)stream>>>(stat, lam1, lam2, (int)nc, (int)z, m1, m2);
+  return scv::check_launch("ma_update_kernel");
 }
 
 }  // extern "C"

@@ -299,6 +299,13 @@ class Engine:
                 self.mals_keys.append(key)
                 self.mals_mod[key] = mod
                 mod._ops = self.ops
+        self.ma_keys: List[str] = []  # moving-average class-mean filters (model/disentangle.py:9-88)
+        self.ma_mod: Dict[str, nn.Module] = {}
+        if "moving_avg" in m.disentangle:
+            for key, mod in m.disentangle["moving_avg"].items():
+                self.ma_keys.append(key)
+                self.ma_mod[key] = mod
+                mod._ops = self.ops
         self.qda_keys: List[str] = []  # quadratic discriminant filters (model/disentangle.py:90-232)
         self.qda_mod: Dict[str, nn.Module] = {}
         if "qda" in m.disentangle:
@@ -560,7 +567,8 @@ class Plan:
         self.loss_names = ["jpe", "root", "prior"] + [kk + "_gr" for kk in eng.gr_keys]
         if eng.cond_dim > 0:
             self.loss_names.append("mcmi")  # kernel mutual-information scrubbing loss (needs conditioning variables)
-        self.loss_names += [kk + "_mals" for kk in eng.mals_keys] + [kk + "_qda" for kk in eng.qda_keys]
+        self.loss_names += ([kk + "_mals" for kk in eng.mals_keys] + [kk + "_qda" for kk in eng.qda_keys] +
+                            [kk + "_ma" for kk in eng.ma_keys])
         self.mi = None  # estimator buffers, allocated by enable_mcmi()
         nl = len(self.loss_names)
         nbn = sum(mod.num_features for mod in m.modules() if isinstance(mod, nn.BatchNorm1d))
@@ -583,6 +591,13 @@ class Plan:
                                  classes=torch.tensor([int(c) for c in mod.classes], dtype=torch.long, device=dev),
                                  stat=torch.zeros(2 * ncq * (z + 1), **f32))
             off += 4 * ncq
+        self.ma = {}
+        for key in eng.ma_keys:
+            mod = eng.ma_mod[key]
+            ncm = len(mod.classes)
+            self.ma[key] = dict(mod=mod, nc=ncm, y=torch.zeros(B, dtype=torch.long, device=dev),
+                                classes=torch.tensor([int(c) for c in mod.classes], dtype=torch.long, device=dev),
+                                stat=torch.zeros(ncm * (z + 1), **f32), coef=torch.zeros(ncm, z, **f32))
         self.mals = {}
         for key in eng.mals_keys:
             mod = eng.mals_mod[key]
@@ -938,6 +953,8 @@ class Plan:
             Lk.append(lambda key=key, ki=ki: self._mals_loss(key, ki))
         for key in eng.qda_keys:
             Lk.append(lambda key=key: self._qda_loss(key))
+        for key in eng.ma_keys:
+            Lk.append(lambda key=key: self._ma_loss(key))
         Lk.append(lambda: ops.loss_finalize(self.loss_acc, self.loss_scale, self.loss_out, nl))
         self.Lk = Lk
 
@@ -1053,6 +1070,8 @@ class Plan:
             Bw.append(lambda key=key, ki=ki: self._mals_backward(key, ki))
         for key in eng.qda_keys:  # adds d <key>_qda / d mu into dmu_kl
             Bw.append(lambda key=key: self._qda_backward(key))
+        for key in eng.ma_keys:  # adds d <key>_ma / d mu into dmu_kl
+            Bw.append(lambda key=key: self._ma_backward(key))
         Bw.append(lambda: ops.reparam_bwd(self.ms, eng.ms_ld, self.eps, self.dmu_kl, self.dmu_gr, 1.0, self.dzc,
                                           eng.zc_ld, self.dL_kl, self.dms, eng.ms_ld, B, z, round_tf32=rnd))
         Bw.append(wgrad(gfc, Hflat.at(0), Hflat.bs, 0, 1, self.dms, eng.ms_ld, 0))
@@ -1139,6 +1158,26 @@ class Plan:
             mod = st["mod"]
             ops.mals_update(self.mu, z, st["y"], st["ny"], st["bias"], self.B, z, st["ny"], mod.lam0, mod.lam1, mod.Sxx0,
                             mod.Sxy0, mod.Sxx1, mod.Sxy1)
+
+    # ------------------------------------------------------------------ moving_avg (MovingAverageFilter)
+    def _ma_loss(self, key):
+        """evaluate_loss (reference model/disentangle.py:32-74; train/losses.py:286-289: not divided by the batch size)"""
+        st, ops, z = self.ma[key], self.eng.ops, self.eng.m.z_dim
+        mod = st["mod"]
+        ops.ma_loss(self.mu, z, st["y"], st["classes"], st["nc"], z, self.B, mod.m1, mod.m2, mod.lam1, mod.lam2, mod.delta,
+                    mod.lamdiff, st["stat"], st["coef"], loss=Ref(self.loss_acc, self.loss_names.index(key + "_ma")))
+
+    def _ma_backward(self, key):
+        st, ops, z = self.ma[key], self.eng.ops, self.eng.m.z_dim
+        ops.ma_backward(st["y"], st["classes"], st["coef"], Ref(self.gscale, self.loss_names.index(key + "_ma")), st["nc"], z,
+                        self.B, self.dmu_kl, z)
+
+    def ma_update(self):
+        """MovingAverageFilter.update (:76-88) with this step's mu and labels (train/trainer.py:169-178)"""
+        ops, z = self.eng.ops, self.eng.m.z_dim
+        for key, st in self.ma.items():
+            mod = st["mod"]
+            ops.ma_update(self.mu, z, st["y"], st["classes"], st["nc"], z, self.B, mod.lam1, mod.lam2, mod.m1, mod.m2, st["stat"])
 
     # ------------------------------------------------------------------ qda (QuadraticDiscriminantFilter)
     def _qda_loss(self, key):
@@ -1245,6 +1284,8 @@ class Plan:
         for key, st in self.mals.items():
             st["y"].copy_(data[key].reshape(st["y"].shape), non_blocking=True)
         for key, st in self.qda.items():
+            st["y"].copy_(data[key].ravel(), non_blocking=True)
+        for key, st in self.ma.items():
             st["y"].copy_(data[key].ravel(), non_blocking=True)
         for key in self.eng.gr_keys:
             if key == "ids":
@@ -1530,6 +1571,8 @@ class TrainStep:
                 plan.mals_update()
             if plan.qda:
                 plan.qda_update()
+            if plan.ma:
+                plan.ma_update()
             if self.mi is not None:
                 # updated encode (train mode: batch statistics again, running statistics advance a second time, as the
                 # reference's model.encode(data) does) -> new stored samples of the estimator

@@ -1,5 +1,5 @@
 """`scrubvae_b200.get.model` — same signature and semantics as the reference factory
-get/model.py:4-151, restricted to the methods on the built path (conditional, grad_reversal, moving_avg_lsq, qda)."""
+get/model.py:4-151, restricted to the methods on the built path (conditional, grad_reversal, moving_avg_lsq, qda, moving_avg)."""
 import torch
 
 
@@ -20,7 +20,7 @@ def model(model_config, load_model, epoch, disentangle_config, n_keypts, directi
 
     methods = disentangle_config["method"]
     for m in methods:
-        if m not in ("conditional", "grad_reversal", "moving_avg_lsq", "qda"):
+        if m not in ("conditional", "grad_reversal", "moving_avg_lsq", "qda", "moving_avg"):
             raise NotImplementedError(
                 f"scrubvae_b200.get.model: method '{m}' is outside the built hot path (SURVEY.md §8)")
     disentangle = {}
@@ -51,6 +51,12 @@ def model(model_config, load_model, epoch, disentangle_config, n_keypts, directi
         disentangle["qda"] = {}
         for feat in methods["qda"]:
             disentangle["qda"][feat] = QuadraticDiscriminantFilter(model_config["z_dim"], discrete_classes[feat])
+
+    if "moving_avg" in methods.keys():  # reference get/model.py:96-104
+        from ..model.disentangle import MovingAverageFilter
+        disentangle["moving_avg"] = {}
+        for feat in methods["moving_avg"]:
+            disentangle["moving_avg"][feat] = MovingAverageFilter(model_config["z_dim"], discrete_classes[feat])
 
     if model_config["type"] != "rcnn":
         raise NotImplementedError("scrubvae_b200.get.model: only model type 'rcnn' exists (as in the reference)")

@@ -183,3 +183,25 @@ class QuadraticDiscriminantFilter(nn.Module):
 
     def S4(self):
         return [self.S0a, self.S1a, self.S0b, self.S1b]
+
+
+class MovingAverageFilter(nn.Module):
+    """Reference model/disentangle.py:9-88: per class two running means of the latent mean with self-tuning forgetting
+    factors; the loss is the norm of the pairwise differences between the classes' mean estimates.  Same constructor and
+    buffers (m1, m2, lam1, lam2); kernels scv_ma_* (csrc/scv_qda.cu), sequenced by the engine."""
+
+    def __init__(self, nx, classes, lamdiff=1e-2, delta=1e-3):
+        super().__init__()
+        self.classes = classes
+        if nx > 128 or len(classes) > 16:
+            raise NotImplementedError("scrubvae_b200: the moving_avg kernels hold z <= 128 and <= 16 classes")
+        self.register_buffer("m1", torch.zeros(len(self.classes), nx))
+        self.register_buffer("m2", torch.zeros(len(self.classes), nx))
+        self.register_buffer("lam1", torch.ones(len(self.classes)) * 0.5)
+        self.register_buffer("lam2", torch.ones(len(self.classes)) * 0.5 + lamdiff)
+        self.delta = delta
+        self.lamdiff = lamdiff
+        self._ops = None
+
+    def forward(self, *args, **kwargs):
+        return

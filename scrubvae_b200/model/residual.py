@@ -173,10 +173,10 @@ class ResVAE(VAE):
         else:
             self.disentangle = nn.ModuleDict()
         for method in self.disentangle.keys():
-            if method not in ("grad_reversal", "moving_avg_lsq", "qda"):
+            if method not in ("grad_reversal", "moving_avg_lsq", "qda", "moving_avg"):
                 raise NotImplementedError(
                     f"scrubvae_b200: scrubber method '{method}' is outside the built hot path "
-                    "(conditional, grad_reversal, moving_avg_lsq, qda; SURVEY.md §8)")
+                    "(conditional, grad_reversal, moving_avg_lsq, qda, moving_avg; SURVEY.md §8)")
         self.mi_estimator = None
         self._engine = None
         self._noise = None  # test hook: injected reparameterisation noise (B, z)

@@ -247,6 +247,8 @@ def train_test_epoch(config, model, loader, device, epoch, optimizer=None, sched
                     data_o["_plan"].mals_update()
                 if "qda" in model.disentangle.keys():
                     data_o["_plan"].qda_update()
+                if "moving_avg" in model.disentangle.keys():
+                    data_o["_plan"].ma_update()
             epoch_metrics = {k: v + batch_loss[k].detach() for k, v in epoch_metrics.items()}
             if "mcmi" in config["loss"].keys():  # reference :184-199: estimator rebuilt from the updated encoder
                 from ..model.disentangle import MutInfoEstimator

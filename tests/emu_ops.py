@@ -538,6 +538,51 @@ class EmuOps:
         if valid is not None:
             _v(valid, (1,), (1,)).fill_(1.0)
 
+    # ---- moving_avg scrubber (reference model/disentangle.py:9-88)
+    @staticmethod
+    def _ma_means(x, x_ld, y, classes, nc, z, B):
+        X, Y, cls = _v(x, (B, z), (x_ld, 1)), _v(y, (B,), (1,)), _v(classes, (nc,), (1,))
+        sel = [(Y == cls[c]) for c in range(nc)]
+        return torch.stack([X[s].mean(0) for s in sel]), torch.stack([s.sum() for s in sel]).float(), sel
+
+    def ma_loss(self, x, x_ld, y, classes, nc, z, B, m1, m2, lam1, lam2, delta, lamdiff, stat, coef, loss=None):
+        self.n += 1
+        xbar, cnt, _ = self._ma_means(x, x_ld, y, classes, nc, z, B)
+        M1, M2 = _v(m1, (nc, z), (z, 1)), _v(m2, (nc, z), (z, 1))
+        l1, l2 = _v(lam1, (nc,), (1,)), _v(lam2, (nc,), (1,))
+        for c in range(nc):
+            if torch.linalg.norm(xbar[c] - M1[c]) < torch.linalg.norm(xbar[c] - M2[c]):
+                l1[c] = torch.clamp(l1[c] - delta, 0.0, 1.0)
+                l2[c] = l1[c] + lamdiff
+            else:
+                l2[c] = torch.clamp(l2[c] + delta, 0.0, 1.0)
+                l1[c] = l2[c] - lamdiff
+        est = 0.5 * (((1 - l1)[:, None] * xbar + l1[:, None] * M1) + ((1 - l2)[:, None] * xbar + l2[:, None] * M2))
+        d = torch.triu(est.T[..., None] - est.T[..., None, :], diagonal=1)
+        nrm = torch.linalg.norm(d)
+        if loss is not None:
+            _v(loss, (1,), (1,)).add_(nrm.double())
+        _v(coef, (nc, z), (z, 1)).copy_(0.5 * (2 - l1 - l2)[:, None] * (nc * est - est.sum(0, keepdim=True)) / nrm / cnt[:, None])
+        st = _v(stat, (nc, z + 1), (z + 1, 1))
+        st[:, :z] = xbar
+        st[:, z] = cnt
+
+    def ma_backward(self, y, classes, coef, gscale, nc, z, B, dx, d_ld):
+        self.n += 1
+        Y, cls = _v(y, (B,), (1,)), _v(classes, (nc,), (1,))
+        g = float(_v(gscale, (1,), (1,))) if gscale is not None else 1.0
+        D, Cf = _v(dx, (B, z), (d_ld, 1)), _v(coef, (nc, z), (z, 1))
+        for c in range(nc):
+            D[Y == cls[c]] += g * Cf[c]
+
+    def ma_update(self, x, x_ld, y, classes, nc, z, B, lam1, lam2, m1, m2, stat):
+        self.n += 1
+        xbar, cnt, _ = self._ma_means(x, x_ld, y, classes, nc, z, B)
+        M1, M2 = _v(m1, (nc, z), (z, 1)), _v(m2, (nc, z), (z, 1))
+        l1, l2 = _v(lam1, (nc,), (1,)), _v(lam2, (nc,), (1,))
+        M1.copy_((1 - l1)[:, None] * xbar + l1[:, None] * M1)
+        M2.copy_((1 - l2)[:, None] * xbar + l2[:, None] * M2)
+
     # ---- qda scrubber (reference model/disentangle.py:90-232)
     def qda_factor(self, S4, nc, z, SinvT, logdet):
         self.n += 1

@@ -672,3 +672,84 @@ def test_scrubbers_in_test_mode_match_reference():
         if ".moving_avg_lsq." in k or ".qda." in k:
             assert _rel(osd[k].float(), rsd[k].float()) < 1e-6, (k, _rel(osd[k].float(), rsd[k].float()))
     assert float(rsd["disentangle.moving_avg_lsq.heading.lam1"]) != float(sd["disentangle.moving_avg_lsq.heading.lam1"])
+
+
+def test_moving_avg_epoch_matches_reference():
+    """The moving_avg scrubber (MovingAverageFilter, reference model/disentangle.py:9-88) through train_test_epoch: class
+    means of mu, forgetting-factor drift by distance, the norm of the pairwise differences between the classes' mean estimates
+    as the <key>_ma loss (not divided by the batch size) with its gradient into mu, running-mean update after the optimizer
+    step — epoch metrics, weights and the filter's buffers against the live reference, piecewise and fused."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference not importable here")
+    import contextlib, io
+    rsv = refimport.import_reference()
+    from scrubvae.train import trainer as rtr
+    ch, zd, B = [8, 16, 32], 8, 12
+    mc = dict(type="rcnn", channel=list(ch), kernel=5, z_dim=zd, window=51, activation="prelu", diag=False,
+              init_dilation=None, prior="gaussian", load_model=None, start_epoch=None)
+    dc = dict(method={"conditional": ["heading"], "moving_avg": ["ids"]}, features=["heading", "ids"], alpha=1.0)
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "ids_ma": 2.0}
+    classes = {"ids": [0, 1, 2]}
+    torch.manual_seed(19)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = rsv.get.model(mc, None, None, dc, 18, "midfwd", loss_config=scale, arena_size=torch.tensor(orc.ARENA),
+                            kinematic_tree=orc.KINEMATIC_TREE, discrete_classes=classes, device="cpu", verbose=0)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    batches = []
+    for i in range(4):
+        b = {k: v for k, v in orc.synth_batch(B, seed=30 + i).items() if k in ("x6d", "root", "offsets", "target_pose", "heading")}
+        b["ids"] = ((torch.arange(B) + i) % 3).reshape(B, 1)
+        batches.append(b)
+    noise = [orc.synth_eps(B, zd, seed=50 + i) for i in range(4)]
+    it = iter(noise)
+    orig = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: next(it).to(t)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ropt, _ = rtr.get_optimizer_and_lr_scheduler(ref, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
+            mref = rtr.train_test_epoch({"loss": dict(scale), "disentangle": dc}, ref, batches, "cpu", 1, optimizer=ropt,
+                                        scheduler=None, mode="train")
+    finally:
+        torch.randn_like = orig
+    rsd = ref.state_dict()
+    assert "disentangle.moving_avg.ids.m2" in rsd
+    for fused in (False, True):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = sv.get.model(mc, None, None, dc, 18, "midfwd", loss_config=scale, arena_size=torch.tensor(orc.ARENA),
+                             kinematic_tree=orc.KINEMATIC_TREE, discrete_classes=classes, device="cpu", verbose=0)
+        m.precision = "fp32"
+        assert list(m.state_dict().keys()) == list(sd.keys())
+        m.load_state_dict(sd)
+        m._engine = Engine(m, ops=EmuOps())
+        m.train()
+        opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
+        cfg = {"loss": dict(scale), "disentangle": dc, "train": {}}
+        if fused:
+            from scrubvae_b200.engine import TrainStep
+            st = TrainStep(m, opt, scale, B, use_graph=False, resident=True)
+            tot = None
+            for i, b in enumerate(batches):
+                m._noise = noise[i]
+                v = st.run(b).clone()
+                tot = v if tot is None else tot + v
+            st.sync()
+            mo = {n: float(tot[j]) / len(batches) for j, n in enumerate(st.plan.loss_names)}
+            mo["total"] = float(tot[-1]) / len(batches)
+        else:
+            seq = iter(noise)
+
+            def cb(i, vec):
+                m._noise = next(seq, None)
+            m._noise = next(seq)
+            with contextlib.redirect_stdout(io.StringIO()):
+                mo = sv.train.train_test_epoch(cfg, m, batches, "cpu", 1, optimizer=opt, scheduler=None, mode="train",
+                                               step_callback=cb)
+        for k in mref:
+            assert abs(mo[k] - mref[k]) <= 5e-5 * abs(mref[k]) + 1e-6, (fused, k, mo[k], mref[k])
+        osd = m.state_dict()
+        for k in rsd:
+            if k.endswith("running_mean"):
+                continue  # zero-true-gradient conv biases take +-lr Adam steps on rounding noise and shift the batch means
+            tol = 5e-4 if ".moving_avg." in k else 5e-3
+            assert _rel(osd[k].float(), rsd[k].float()) < tol or ZERO_GRAD_BIAS.search(k), (fused, k, _rel(osd[k].float(), rsd[k].float()))

@@ -433,6 +433,25 @@ def test_qda_kernels(ops, z, nc, B):
     run_both(ops, T, call, tol=2e-5, check=["lama", "lamb"] + [f"m{q}" for q in range(4)] + [f"S{q}" for q in range(4)])
 
 
+@pytest.mark.parametrize("z,nc,B", [(64, 4, 300), (128, 3, 131), (8, 2, 9)])
+def test_moving_avg_kernels(ops, z, nc, B):
+    """scv_ma_loss / backward / update (csrc/scv_qda.cu) against the torch emulation of MovingAverageFilter."""
+    gg = g(11)
+    T = {"x": torch.randn(B, z, generator=gg), "y": (torch.arange(B) % nc).to(torch.long), "cls": torch.arange(nc, dtype=torch.long),
+         "m1": 0.3 * torch.randn(nc, z, generator=gg), "m2": 0.3 * torch.randn(nc, z, generator=gg),
+         "lam1": torch.full((nc,), 0.5), "lam2": torch.full((nc,), 0.51), "stat": torch.zeros(nc * (z + 1)),
+         "coef": torch.zeros(nc, z), "loss": torch.zeros(1, dtype=torch.double), "gs": torch.tensor([1.7]),
+         "dx": torch.randn(B, z, generator=gg)}
+    T["x"] += 0.5 * T["y"][:, None].float()
+
+    def call(o, t):
+        o.ma_loss(t["x"], z, t["y"], t["cls"], nc, z, B, t["m1"], t["m2"], t["lam1"], t["lam2"], 1e-3, 1e-2, t["stat"], t["coef"],
+                  loss=t["loss"])
+        o.ma_backward(t["y"], t["cls"], t["coef"], t["gs"], nc, z, B, t["dx"], z)
+        o.ma_update(t["x"], z, t["y"], t["cls"], nc, z, B, t["lam1"], t["lam2"], t["m1"], t["m2"], t["stat"])
+    run_both(ops, T, call, tol=2e-5, check=["loss", "coef", "dx", "lam1", "lam2", "m1", "m2"])
+
+
 def test_library_fails_loudly_when_missing(tmp_path):
     from scrubvae_b200 import _ops
     with pytest.raises(RuntimeError, match="no CPU fallback"):

@@ -188,3 +188,24 @@ def test_oracle_qda_matches_live_reference():
         orc.qda_update(st, x, y, classes)
         for k in st:
             assert torch.allclose(getattr(ref, k), st[k], rtol=1e-5, atol=1e-6), (i, k)
+
+
+def test_oracle_moving_avg_matches_live_reference():
+    """oracle.ma_* against the reference's MovingAverageFilter (model/disentangle.py:9-88)."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference not importable here")
+    refimport.import_reference()
+    from scrubvae.model.disentangle import MovingAverageFilter
+    z, classes, B = 6, [0, 1, 2], 18
+    ref = MovingAverageFilter(z, classes)
+    st = orc.ma_init(z, len(classes))
+    g = torch.Generator().manual_seed(5)
+    for i in range(5):
+        y = ((torch.arange(B) + i) % 3).reshape(B, 1)
+        x = torch.randn(B, z, generator=g) + 0.5 * y.float()
+        assert torch.allclose(ref.evaluate_loss(x, y), orc.ma_evaluate(st, x, y, classes), rtol=1e-6)
+        ref.update(x, y)
+        orc.ma_update(st, x, y, classes)
+        for k in st:
+            assert torch.allclose(getattr(ref, k), st[k], rtol=1e-6, atol=1e-7), (i, k)
