@@ -1111,13 +1111,16 @@ int gemm_tc(const scv_gemm_t* p, cudaStream_t st) {
   q.bt = (int)cdiv(p->B, q.nb);
   q.m_tiles = q.lt * q.bt;
   q.k_chunks = (int)cdiv(p->K, bf16 ? 64 : kBK);
-  // CTA pairs (cta_group::2, gemm_tc2_kernel) are correct (kernel tests pass with SCV_TC_PAIR=1) but measured
-  // SLOWER on every layer of the step (profiles/r01_pair_vs_single.md: the M=256 pair MMA issues at the same
-  // 162 cycles as two M=128 MMAs, tools/cu/mma_rate2.cu, and the cross-SM operand fetch costs on top), so the
-  // single-CTA kernel is the default; SCV_TC_PAIR=1 selects the pair kernel for experiments.
-  static const int force_pair = [] { const char* e = getenv("SCV_TC_PAIR"); return e ? atoi(e) : 0; }();
-  int ctas = force_pair ? 2 : 1;
-  if (q.m_tiles < 2 || pair_capacity() < 1 || bf16 || bnr) ctas = 1;
+  // CTA pairs (cta_group::2, gemm_tc2_kernel).  Round 1 measured them slower on every layer (a pipeline bug: the peer CTA
+  // arrived on the leader's barrier every chunk) and left them off.
+  // Round 2: with the issue paths on elect.sync (and the peer's per-chunk remote arrive gone) the pair kernel wins on the
+  // large layers — a CTA pair ingests a third less operand data per FLOP.  Measured per layer (gpurun_out/gemm_r2q*.json,
+  // profiles/r02_pair_vs_single.md): N >= 128 and K >= 1024 picks every layer with a gain (-115 of 2524 us per step over
+  // the forward + data-gradient GEMMs) and none that loses more than 1 us.  SCV_TC_PAIR=0 / 1 forces never / always.
+  const char* pair_env = getenv("SCV_TC_PAIR");  // read per call (tests switch it)
+  const int force_pair = pair_env ? atoi(pair_env) : -1;
+  int ctas = force_pair == 1 ? 2 : (force_pair == 0 ? 1 : ((p->N >= 128 && p->K >= 1024) ? 2 : 1));
+  if (q.m_tiles < 2 || pair_capacity() < 1 || bf16 || bnr || accum) ctas = 1;
   // N tile: as wide as the MMA allows, balanced over the tiles, multiple of 16 (of 32 for a pair: each CTA holds half)
   const int ng = 16 * ctas;
   const int n16 = (int)cdiv(p->N, ng) * ng;

@@ -84,6 +84,11 @@ def test_gemm(ops, case, prec):
     run_both(ops, T, call, tol=1e-5 if prec == 0 else 2e-5, check=["Y", "stats"])
 
 
+# more work items than CTA pairs, long K: the pair kernel walks several items per pair
+MANY_CASES_FWD = [
+    (2600, 4, 8, 256, 1, 5, 272, None, ACT_NONE, True, True),   # 82 row tiles x 2 n tiles, K = 1280, residual + statistics
+]
+
 # many row tiles: the cluster-multicast kernels (two CTAs share the W tile / the A slabs), odd tile counts (one CTA of
 # the last pair has nothing to store), two row tiles per item, several n tiles, ragged edges
 BIG_CASES = [
@@ -101,9 +106,22 @@ BIG_CASES = [
 def test_gemm_multitile(ops, case, sub, mc, monkeypatch):
     monkeypatch.setenv("SCV_TC_MC", mc)
     monkeypatch.setenv("SCV_TC_SUB", sub)
+    monkeypatch.setenv("SCV_TC_PAIR", "0")  # the CTA-pair kernel (chosen by default for N >= 128, K >= 1024) has its own test
     test_gemm(ops, case, 1)
     if mc == "0":
         test_gemm(ops, case, 2)
+
+
+@pytest.mark.parametrize("pair", ["1", "auto"])
+@pytest.mark.parametrize("case", BIG_CASES + MANY_CASES_FWD)
+def test_gemm_cta_pairs(ops, case, pair, monkeypatch):
+    """gemm_tc2_kernel (cta_group::2): forced on every eligible shape, and as the default rule picks it."""
+    if pair == "auto":
+        monkeypatch.delenv("SCV_TC_PAIR", raising=False)
+    else:
+        monkeypatch.setenv("SCV_TC_PAIR", pair)
+    test_gemm(ops, case, 1)
+    test_gemm(ops, case, 1)
 
 
 @pytest.mark.parametrize("mc", ["0", "1"])
