@@ -52,8 +52,8 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
-        with open(obj + ".ptxas.log", "w") as f:
-            f.write(r.stderr)
+        with open(obj + ".ptxas.log", "w") as f:  # registers / spills per kernel (-Xptxas -v); compile times left out so that
+            f.write("".join(l for l in r.stderr.splitlines(True) if "Compile time" not in l))  # rebuilding keeps the tree clean
         if verbose:
             print(r.stderr)
         return obj
