@@ -965,7 +965,10 @@ wgrad_tc_mc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
 
 // counters of the dynamically scheduled launches: a ring of (next item, CTAs done) pairs, zero at load and reset by the
 // last CTA of every launch; consecutive launches take consecutive slots, so kernels running concurrently on different
-// streams (or as parallel branches of one CUDA graph) never share one
+// streams (or as parallel branches of one CUDA graph) never share one.  A slot is baked into a captured graph node; the
+// ring (4096 slots, ~25 training steps' worth of launches) would only hand the same slot to two kernels that RUN AT THE
+// SAME TIME if a graph replay overlapped eager launches made 4096 x k launches after its capture on another stream —
+// the engine serialises a step's graph and its eager work on one stream order, so that does not occur
 constexpr int kWorkSlots = 4096;
 __device__ int g_work_slots[2 * kWorkSlots];
 int* g_work_base[64] = {};
