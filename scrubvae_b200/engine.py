@@ -299,6 +299,8 @@ class Engine:
                 self.mals_keys.append(key)
                 self.mals_mod[key] = mod
                 mod._ops = self.ops
+        # direct_lsq (train/losses.py:173-179, :253-256): no module, no state — feature -> dimension, set by get.model
+        self.dlsq: Dict[str, int] = dict(getattr(m, "direct_lsq", None) or {})
         self.ma_keys: List[str] = []  # moving-average class-mean filters (model/disentangle.py:9-88)
         self.ma_mod: Dict[str, nn.Module] = {}
         if "moving_avg" in m.disentangle:
@@ -568,7 +570,7 @@ class Plan:
         if eng.cond_dim > 0:
             self.loss_names.append("mcmi")  # kernel mutual-information scrubbing loss (needs conditioning variables)
         self.loss_names += ([kk + "_mals" for kk in eng.mals_keys] + [kk + "_qda" for kk in eng.qda_keys] +
-                            [kk + "_ma" for kk in eng.ma_keys])
+                            [kk + "_ma" for kk in eng.ma_keys] + [kk + "_lsq" for kk in eng.dlsq])
         self.mi = None  # estimator buffers, allocated by enable_mcmi()
         nl = len(self.loss_names)
         nbn = sum(mod.num_features for mod in m.modules() if isinstance(mod, nn.BatchNorm1d))
@@ -576,7 +578,7 @@ class Plan:
         # every per-step accumulator in ONE buffer: [BN statistics | BN backward sums | loss terms | grad norm^2];
         # the fused step clears it with one memset, the piecewise API path clears the parts as it reaches them
         n_qda = sum(4 * len(eng.qda_mod[kk].classes) for kk in eng.qda_keys)  # (lla, llb, llra, llrb) per class
-        n_mals = 2 * len(eng.mals_keys) + n_qda  # + squared-error sums of the two decoders of every moving_avg_lsq scrubber
+        n_mals = 2 * len(eng.mals_keys) + n_qda + 2 * len(eng.dlsq)  # + squared-error sums of the least-squares decoders
         self.zbuf = torch.zeros(n_stats + n_sums + nl + 1 + n_mals, dtype=torch.double, device=dev)
         self.loss_acc = self.zbuf[n_stats + n_sums:n_stats + n_sums + nl]
         self.sumsq = self.zbuf[n_stats + n_sums + nl:n_stats + n_sums + nl + 1]
@@ -591,6 +593,15 @@ class Plan:
                                  classes=torch.tensor([int(c) for c in mod.classes], dtype=torch.long, device=dev),
                                  stat=torch.zeros(2 * ncq * (z + 1), **f32))
             off += 4 * ncq
+        self.dlsq = {}
+        off_l = 2 * len(eng.mals_keys) + n_qda
+        for key, nyd in eng.dlsq.items():
+            nxm = z + 1  # room for the bias column (chosen per call by the sign of the loss scale, as the reference)
+            self.dlsq[key] = dict(ny=nyd, off=off_l, bias=False, S=[torch.zeros(nxm * nxm, **f32) for _ in range(2)],
+                                  Sy=[torch.zeros(nxm * nyd, **f32) for _ in range(2)],
+                                  W=[torch.zeros(nxm * nyd, **f32) for _ in range(2)], y=torch.zeros(B, nyd, **f32),
+                                  zero=torch.zeros(2, **f32), lam=torch.zeros(2, **f32), gs=torch.zeros(1, **f32))
+            off_l += 2
         self.ma = {}
         for key in eng.ma_keys:
             mod = eng.ma_mod[key]
@@ -955,6 +966,8 @@ class Plan:
             Lk.append(lambda key=key: self._qda_loss(key))
         for key in eng.ma_keys:
             Lk.append(lambda key=key: self._ma_loss(key))
+        for key in eng.dlsq:
+            Lk.append(lambda key=key: self._dlsq_loss(key))
         Lk.append(lambda: ops.loss_finalize(self.loss_acc, self.loss_scale, self.loss_out, nl))
         self.Lk = Lk
 
@@ -1072,6 +1085,8 @@ class Plan:
             Bw.append(lambda key=key: self._qda_backward(key))
         for key in eng.ma_keys:  # adds d <key>_ma / d mu into dmu_kl
             Bw.append(lambda key=key: self._ma_backward(key))
+        for key in eng.dlsq:  # adds d <key>_lsq / d mu into dmu_kl
+            Bw.append(lambda key=key: self._dlsq_backward(key))
         Bw.append(lambda: ops.reparam_bwd(self.ms, eng.ms_ld, self.eps, self.dmu_kl, self.dmu_gr, 1.0, self.dzc,
                                           eng.zc_ld, self.dL_kl, self.dms, eng.ms_ld, B, z, round_tf32=rnd))
         Bw.append(wgrad(gfc, Hflat.at(0), Hflat.bs, 0, 1, self.dms, eng.ms_ld, 0))
@@ -1158,6 +1173,33 @@ class Plan:
             mod = st["mod"]
             ops.mals_update(self.mu, z, st["y"], st["ny"], st["bias"], self.B, z, st["ny"], mod.lam0, mod.lam1, mod.Sxx0,
                             mod.Sxy0, mod.Sxx1, mod.Sxy1)
+
+    # ------------------------------------------------------------------ direct_lsq
+    def _dlsq_loss(self, key):
+        """direct_lsq_loss (reference train/losses.py:173-179): the batch's own least-squares decoder of y from mu,
+        loss = sum (mu W - y)^2 with W = solve(mu^T mu, mu^T y), NOT divided by the batch size (:253-256).  Built from the
+        moving_avg_lsq kernels: the covariance update with forgetting factor 0 is exactly mu^T [mu | y]; both decoder
+        slots hold the same W, so (l0 + l1) / 2 = the loss."""
+        st, ops, z = self.dlsq[key], self.eng.ops, self.eng.m.z_dim
+        nx, ny, bias = z + int(st["bias"]), st["ny"], st["bias"]
+        ops.mals_update(self.mu, z, st["y"], ny, bias, self.B, z, ny, st["zero"], Ref(st["zero"], 1), st["S"][0], st["Sy"][0],
+                        st["S"][1], st["Sy"][1])
+        ops.mals_solve(st["S"][0], st["Sy"][0], st["S"][1], st["Sy"][1], 0.0, bias, nx, ny, st["W"][0], st["W"][1])
+        if not self._fused_tail:
+            self.mals_l01[st["off"]:st["off"] + 2].zero_()
+        l01 = Ref(self.mals_l01, st["off"])
+        ops.mals_loss(self.mu, z, st["y"], ny, st["W"][0], st["W"][1], bias, self.B, z, ny, l01=l01)
+        ops.mals_finalize(l01, st["lam"], Ref(st["lam"], 1), 0.0, 0.0, 1,
+                          loss=Ref(self.loss_acc, self.loss_names.index(key + "_lsq")))
+
+    def _dlsq_backward(self, key):
+        """d loss / d mu = 2 (mu W - y) W^T: at the least-squares optimum the residual is orthogonal to the columns of mu, so
+        the path through W contributes nothing.  scv_mals_loss adds gscale / B * (e0 W0^T + e1 W1^T): gscale is pre-scaled by B."""
+        st, ops, z = self.dlsq[key], self.eng.ops, self.eng.m.z_dim
+        idx = self.loss_names.index(key + "_lsq")
+        torch.mul(self.gscale[idx:idx + 1], float(self.B), out=st["gs"])
+        ops.mals_loss(self.mu, z, st["y"], st["ny"], st["W"][0], st["W"][1], st["bias"], self.B, z, st["ny"], gscale=st["gs"],
+                      dmu=self.dmu_kl, d_ld=z)
 
     # ------------------------------------------------------------------ moving_avg (MovingAverageFilter)
     def _ma_loss(self, key):
@@ -1287,6 +1329,8 @@ class Plan:
             st["y"].copy_(data[key].ravel(), non_blocking=True)
         for key, st in self.ma.items():
             st["y"].copy_(data[key].ravel(), non_blocking=True)
+        for key, st in self.dlsq.items():
+            st["y"].copy_(data[key].reshape(st["y"].shape), non_blocking=True)
         for key in self.eng.gr_keys:
             if key == "ids":
                 self.gr_labels[key].copy_(data[key].ravel(), non_blocking=True)
@@ -1353,6 +1397,8 @@ class Plan:
         return out
 
     def set_loss_scale(self, loss_scale: Dict[str, float]):
+        for key, st in self.dlsq.items():  # reference train/losses.py:255: bias = loss_scale[key + "_lsq"] < 0
+            st["bias"] = float(loss_scale.get(key + "_lsq", 0.0) or 0.0) < 0
         host = tuple(float(loss_scale.get(n, 0.0) or 0.0) for n in self.loss_names)
         if host != self._scale_host:
             self._scale_host = host

@@ -1,5 +1,5 @@
 """`scrubvae_b200.get.model` — same signature and semantics as the reference factory
-get/model.py:4-151, restricted to the methods on the built path (conditional, grad_reversal, moving_avg_lsq, qda, moving_avg)."""
+get/model.py:4-151, restricted to the methods on the built path (conditional, grad_reversal, moving_avg_lsq, qda, moving_avg, direct_lsq)."""
 import torch
 
 
@@ -20,7 +20,7 @@ def model(model_config, load_model, epoch, disentangle_config, n_keypts, directi
 
     methods = disentangle_config["method"]
     for m in methods:
-        if m not in ("conditional", "grad_reversal", "moving_avg_lsq", "qda", "moving_avg"):
+        if m not in ("conditional", "grad_reversal", "moving_avg_lsq", "qda", "moving_avg", "direct_lsq"):
             raise NotImplementedError(
                 f"scrubvae_b200.get.model: method '{m}' is outside the built hot path (SURVEY.md §8)")
     disentangle = {}
@@ -69,6 +69,9 @@ def model(model_config, load_model, epoch, disentangle_config, n_keypts, directi
         kinematic_tree=kinematic_tree, prior=model_config["prior"], ch=model_config["channel"],
         discrete_classes=discrete_classes, precision=model_config.get("precision") or "tf32",
     )
+    # direct_lsq has no module (reference train/losses.py:253-256 evaluates it from mu and data[key] alone): the engine
+    # only needs to know the features and their dimensions
+    vae.direct_lsq = {feat: feat_dim_dict[feat] for feat in methods.get("direct_lsq", [])}
     if verbose > 0:
         print(vae)
 

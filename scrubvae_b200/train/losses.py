@@ -46,7 +46,7 @@ def get_batch_loss(model, data, data_o, loss_scale, disentangle_config):
         raise RuntimeError("scrubvae_b200.get_batch_loss needs the data_o returned by model(data)")
     methods = disentangle_config["method"]
     for method in methods:
-        if method not in ("conditional", "grad_reversal", "moving_avg_lsq", "qda", "moving_avg"):
+        if method not in ("conditional", "grad_reversal", "moving_avg_lsq", "qda", "moving_avg", "direct_lsq"):
             raise NotImplementedError(f"scrubvae_b200: scrubbing method '{method}' is outside the built hot path")
     gr_keys = list(methods.get("grad_reversal", []))
     if gr_keys != plan.eng.gr_keys:

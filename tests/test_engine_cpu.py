@@ -753,3 +753,132 @@ def test_moving_avg_epoch_matches_reference():
                 continue  # zero-true-gradient conv biases take +-lr Adam steps on rounding noise and shift the batch means
             tol = 5e-4 if ".moving_avg." in k else 5e-3
             assert _rel(osd[k].float(), rsd[k].float()) < tol or ZERO_GRAD_BIAS.search(k), (fused, k, _rel(osd[k].float(), rsd[k].float()))
+
+
+def test_direct_lsq_epoch_matches_reference():
+    """The direct_lsq scrubbing loss (reference train/losses.py:173-179, :253-256): the batch's own least-squares decoder
+    of the variable from mu, sum of squared residuals, gradient through the solve — epoch metrics and final weights against
+    the live reference, piecewise and fused.  (Positive scale = no bias column: the reference's bias branch is CUDA-only.)"""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference not importable here")
+    import contextlib, io
+    rsv = refimport.import_reference()
+    from scrubvae.train import trainer as rtr
+    ch, zd, B = [8, 16, 32], 8, 16
+    mc = dict(type="rcnn", channel=list(ch), kernel=5, z_dim=zd, window=51, activation="prelu", diag=False,
+              init_dilation=None, prior="gaussian", load_model=None, start_epoch=None)
+    dc = dict(method={"conditional": ["heading"], "direct_lsq": ["heading"]}, features=["heading"], alpha=1.0)
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "heading_lsq": 0.5}
+    torch.manual_seed(23)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = rsv.get.model(mc, None, None, dc, 18, "midfwd", loss_config=scale, arena_size=torch.tensor(orc.ARENA),
+                            kinematic_tree=orc.KINEMATIC_TREE, discrete_classes={}, device="cpu", verbose=0)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    batches = [{k: v for k, v in orc.synth_batch(B, seed=30 + i).items() if k in ("x6d", "root", "offsets", "target_pose", "heading")}
+               for i in range(3)]
+    noise = [orc.synth_eps(B, zd, seed=50 + i) for i in range(3)]
+    it = iter(noise)
+    orig = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: next(it).to(t)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ropt, _ = rtr.get_optimizer_and_lr_scheduler(ref, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
+            mref = rtr.train_test_epoch({"loss": dict(scale), "disentangle": dc}, ref, batches, "cpu", 1, optimizer=ropt,
+                                        scheduler=None, mode="train")
+    finally:
+        torch.randn_like = orig
+    rsd = ref.state_dict()
+    assert mref["heading_lsq"] > 0
+    for fused in (False, True):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = sv.get.model(mc, None, None, dc, 18, "midfwd", loss_config=scale, arena_size=torch.tensor(orc.ARENA),
+                             kinematic_tree=orc.KINEMATIC_TREE, discrete_classes={}, device="cpu", verbose=0)
+        m.precision = "fp32"
+        assert list(m.state_dict().keys()) == list(sd.keys())
+        m.load_state_dict(sd)
+        m._engine = Engine(m, ops=EmuOps())
+        m.train()
+        opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
+        cfg = {"loss": dict(scale), "disentangle": dc, "train": {}}
+        if fused:
+            from scrubvae_b200.engine import TrainStep
+            st = TrainStep(m, opt, scale, B, use_graph=False, resident=True)
+            tot = None
+            for i, b in enumerate(batches):
+                m._noise = noise[i]
+                v = st.run(b).clone()
+                tot = v if tot is None else tot + v
+            st.sync()
+            mo = {n: float(tot[j]) / len(batches) for j, n in enumerate(st.plan.loss_names)}
+            mo["total"] = float(tot[-1]) / len(batches)
+        else:
+            seq = iter(noise)
+
+            def cb(i, vec):
+                m._noise = next(seq, None)
+            m._noise = next(seq)
+            with contextlib.redirect_stdout(io.StringIO()):
+                mo = sv.train.train_test_epoch(cfg, m, batches, "cpu", 1, optimizer=opt, scheduler=None, mode="train",
+                                               step_callback=cb)
+        for k in mref:
+            assert abs(mo[k] - mref[k]) <= 1e-4 * abs(mref[k]) + 1e-6, (fused, k, mo[k], mref[k])
+        osd = m.state_dict()
+        for k in rsd:
+            if k.endswith("running_mean"):
+                continue  # zero-true-gradient conv biases take +-lr Adam steps on rounding noise and shift the batch means
+            assert _rel(osd[k].float(), rsd[k].float()) < 5e-3 or ZERO_GRAD_BIAS.search(k), (fused, k, _rel(osd[k].float(), rsd[k].float()))
+
+
+def test_direct_lsq_gradient_matches_reference_autograd():
+    """One step, gradients compared tensor by tensor: the closed-form d loss / d mu = 2 (mu W - y) W^T the engine uses
+    against autograd through the reference's torch.linalg.solve."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference not importable here")
+    import contextlib, io
+    rsv = refimport.import_reference()
+    from scrubvae.train import losses as rlosses
+    from scrubvae.train.trainer import predict_batch as rpredict
+    from scrubvae_b200.engine import TrainStep
+    ch, zd, B = [8, 16, 32], 8, 16
+    mc = dict(type="rcnn", channel=list(ch), kernel=5, z_dim=zd, window=51, activation="prelu", diag=False,
+              init_dilation=None, prior="gaussian", load_model=None, start_epoch=None)
+    dc = dict(method={"conditional": ["heading"], "direct_lsq": ["heading"]}, features=["heading"], alpha=1.0)
+    scale = {"prior": 1e-4, "jpe": 1.0, "root": 1.0, "heading_lsq": 3.0}
+    torch.manual_seed(29)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = rsv.get.model(mc, None, None, dc, 18, "midfwd", loss_config=scale, arena_size=torch.tensor(orc.ARENA),
+                            kinematic_tree=orc.KINEMATIC_TREE, discrete_classes={}, device="cpu", verbose=0)
+        m = sv.get.model(mc, None, None, dc, 18, "midfwd", loss_config=scale, arena_size=torch.tensor(orc.ARENA),
+                         kinematic_tree=orc.KINEMATIC_TREE, discrete_classes={}, device="cpu", verbose=0)
+    batch = {k: v for k, v in orc.synth_batch(B, seed=61).items() if k in ("x6d", "root", "offsets", "target_pose", "heading")}
+    eps = orc.synth_eps(B, zd, seed=62)
+    ref.train()
+    orig = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: eps.to(t)
+    try:
+        data_o = rpredict(ref, batch, ref.disentangle_keys)
+        bl = rlosses.get_batch_loss(ref, batch, data_o, dict(scale), dc)
+    finally:
+        torch.randn_like = orig
+    bl["total"].backward()
+    gref = {n: p.grad.detach().clone() for n, p in ref.named_parameters() if p.grad is not None}
+    m.precision = "fp32"
+    m.load_state_dict(ref.state_dict())
+    m._engine = Engine(m, ops=EmuOps())
+    m.train()
+    m._noise = eps
+    opt, _ = sv.train.get_optimizer_and_lr_scheduler(m, {"optimizer": "adamw", "lr": 1e-3, "lr_schedule": None})
+    st = TrainStep(m, opt, scale, B, use_graph=False, keep_grads=True)
+    vec = st.run(batch)
+    names = st.plan.loss_names
+    assert abs(float(vec[names.index("heading_lsq")]) - float(bl["heading_lsq"])) <= 1e-4 * abs(float(bl["heading_lsq"]))
+    gn = sum(float((g.double() ** 2).sum()) for g in gref.values()) ** 0.5
+    checked = 0
+    for n, g in st.named_grads().items():
+        if n in gref and n.startswith("encoder."):  # the lsq term reaches the encoder only (through mu)
+            e = (g.double() - gref[n].double()).norm().item()
+            assert _rel(g, gref[n]) < 1e-3 or e / gn < 2e-6, (n, _rel(g, gref[n]), e / gn)
+            checked += 1
+    assert checked > 20
